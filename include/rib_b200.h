@@ -1,0 +1,121 @@
+/* rib_b200 — C ABI of the B200-native pose-guided rendering hot path.
+ *
+ * The reference (azuxmioy/Render-In-Between) is pure Python/PyTorch and has no FFI; these entry
+ * points are what a binding for its hot path would call.  Each one names the reference interface
+ * it replaces (paths relative to Pose_Guided_Neural_Rendering/).
+ *
+ * Conventions: plain pointers and sizes only; every tensor pointer is a CUDA device pointer owned
+ * by the caller unless stated otherwise; every call is asynchronous on `stream` (a cudaStream_t
+ * passed as void*), allocates no device memory (except rib_generator_create) and returns 0 on
+ * success or a negative code, with the message available from rib_last_error().  No CPU fallback.
+ */
+#ifndef RIB_B200_H_
+#define RIB_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RIB_ABI_VERSION 1
+
+/* Message of the last failing call on this host thread ("" if none). */
+const char* rib_last_error(void);
+int rib_abi_version(void);
+/* Total number of rib kernels launched by this process (all entry points). */
+long long rib_kernel_launch_count(void);
+
+/* ---- A1: pose rasterisation ------------------------------------------------------------------
+ * Replaces HSMAutoDataset._generate_skeleton + _generate_pose_map + to_tensor_norm and the label
+ * concatenation (datasets/HSM_auto_dataset.py:205-251, :73-75; utils/keypoint2img.py:36-173;
+ * models/evaluator.py:222-229, :250).  Bit-exact.
+ *   joints      device  f64 [B][19][3]  (x, y, confidence), model-pixel coordinates
+ *   gauss_taps  HOST    f64 [41]        normalised Gaussian taps (sigma 5, radius 20)
+ *   label       device  f32 [B][22][H][W]  = [skeleton RGB normalised to [-1,1] | 19 heat-maps]
+ */
+int rib_rasterize(const double* joints, int B, int H, int W, const double* gauss_taps, double skeleton_thres,
+                  double foot_thres, float* label, void* stream);
+
+/* ---- A3: flow-based bilinear resampling ------------------------------------------------------
+ * No call site in the reference tree; semantics of imaginaire's resample():
+ * out = grid_sample(src, identity + flow, bilinear, padding_mode='border', align_corners=True).
+ *   src f32 [B][C][H][W], flow f32 [B][2][H][W] (pixels; channel 0 = x), out f32 [B][C][H][W]
+ */
+int rib_warp(const float* src, const float* flow, float* out, int B, int C, int H, int W, void* stream);
+
+/* ---- A4: mask-blend composite ----------------------------------------------------------------
+ * Replaces models/evaluator.py:256-258 (fuse = pred*mask + dain*(1-mask)) and, when out_u8 is not
+ * NULL, utils/utils.py:122-147 tensor2images (uint8 HWC frame, truncating).
+ *   img, dain f32 [B][3][H][W]; mask f32 [B][1][H][W]; out_f32 f32 [B][3][H][W] (may be NULL);
+ *   out_u8 u8 [B][H][W][3] (may be NULL)
+ */
+int rib_composite(const float* img, const float* mask, const float* dain, float* out_f32, uint8_t* out_u8, int B,
+                  int H, int W, void* stream);
+
+/* ---- A2: generator ---------------------------------------------------------------------------
+ * Replaces models.generator.Generator (models/generator.py:35-302), LabelEmbedder (:306-410) and
+ * MaskGenerator (:415-510) in eval mode.
+ */
+typedef struct rib_gen_config {
+  int label_nc, img_nc;          /* gen.input_label_nc, gen.input_image_nc */
+  int nf, maxf, n_down, n_res;   /* gen.num_filters, max_num_filters, num_downsamples_img, derived num_res_blocks */
+  int emb_nf, emb_max, emb_down; /* gen.embed.* */
+  int mask_nf, mask_max, mask_down, mask_res; /* gen.mask.* */
+} rib_gen_config;
+
+/* One state-dict entry: the reference's key, a device fp32 pointer and the element count. */
+typedef struct rib_tensor {
+  const char* name;
+  const float* data;
+  long long numel;
+} rib_tensor;
+
+typedef struct rib_generator rib_generator;
+
+/* Folds spectral norm (W / (u . W v), weight_norm.py:84-85), repacks every conv into its K-major
+ * 16-bit GEMM operand and keeps the packed copy on the device.  `tensors` must hold the reference
+ * state-dict (372 entries for configs/HSM.yaml; unused label_embedding.* / conv_mask.* are ignored).
+ * Synchronises `stream` before returning. */
+int rib_generator_create(const rib_gen_config* cfg, const rib_tensor* tensors, int n_tensors, void* stream,
+                         rib_generator** out);
+void rib_generator_destroy(rib_generator* g);
+
+/* Bytes of caller-provided scratch needed by rib_generator_forward for a (B, H, W) batch. */
+long long rib_generator_workspace_bytes(rib_generator* g, int B, int H, int W);
+
+/* Generator.forward(label, label_prev, img_fake, img_prev) -> (img_final, mask)
+ * (models/generator.py:181-234; label_prev is dead in the reference and is not taken).
+ *   label f32 [B][22][H][W]; img_fake, img_prev f32 [B][3][H][W]; H, W multiples of 16
+ *   out_img f32 [B][3][H][W] in (-1,1); out_mask f32 [B][1][H][W] in (0,1)
+ * The workspace must stay bound to this generator between calls with the same (B, H, W). */
+int rib_generator_forward(rib_generator* g, int B, int H, int W, const float* label, const float* img_fake,
+                          const float* img_prev, float* out_img, float* out_mask, void* workspace,
+                          long long workspace_bytes, void* stream);
+
+/* ---- bring-up / test hooks (not part of the drop-in surface) ----------------------------------
+ * rib_debug_set_simt(1) replaces the tcgen05 main loop by a plain-FMA loop (same tiles and
+ * epilogues); used by the tests to bisect tensor-core problems.  Never set by bench.py. */
+void rib_debug_set_simt(int enable);
+int rib_debug_get_simt(void);
+/* Looks up an intermediate activation of the last forward plan by name.  16-bit NHWC storage:
+ * element (n, y, x, c) at ptr[((n*H + y)*W + x)*ld + c].  Returns 0 if found. */
+int rib_generator_debug_tensor(rib_generator* g, const char* name, const void** ptr, int* B, int* H, int* W, int* C,
+                               int* ld);
+/* 1 if activations are stored as IEEE fp16, 0 for bf16. */
+int rib_act_is_fp16(void);
+/* Stand-alone launch of the implicit-GEMM convolution for unit tests:
+ *   x    16-bit NHWC [B][Hin][Win][Cin]   (Cin multiple of 16)
+ *   w    f32 [Cout][Cin][k][k], bias f32 [Cout] (may be NULL), k in {1,3}, stride in {1,2}, pad k/2
+ *   out  16-bit NHWC [B][Hout][Wout][Cout] (Cout multiple of 16), act: 0 none, 1 leaky-relu 0.2
+ *   stats f64 [B][Cout][2] (may be NULL; accumulated into)
+ *   scratch: device buffer of at least rib_conv_test_scratch_bytes() bytes */
+long long rib_conv_test_scratch_bytes(int Cin, int Cout, int k);
+int rib_conv_test(const void* x, const float* w, const float* bias, void* out, double* stats, int B, int Hin, int Win,
+                  int Cin, int Cout, int k, int stride, int act, void* scratch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RIB_B200_H_ */

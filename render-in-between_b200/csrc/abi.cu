@@ -1,0 +1,118 @@
+// extern "C" surface of librib_b200.so (see include/rib_b200.h).  Nothing throws across this boundary.
+#include <string>
+
+#include "conv_gemm.cuh"
+#include "elementwise.cuh"
+#include "generator.cuh"
+#include "raster.cuh"
+
+namespace rib {
+static thread_local std::string t_error;
+void set_error(const std::string& msg) { t_error = msg; }
+const char* last_error() { return t_error.c_str(); }
+}  // namespace rib
+
+using namespace rib;
+
+#define RIB_GUARD_BEGIN try {
+#define RIB_GUARD_END                                      \
+  }                                                        \
+  catch (const std::exception& e) {                        \
+    rib::set_error(std::string("exception: ") + e.what()); \
+    return -9;                                             \
+  }                                                        \
+  catch (...) {                                            \
+    rib::set_error("unknown exception");                   \
+    return -9;                                             \
+  }
+
+extern "C" {
+
+const char* rib_last_error(void) { return rib::last_error(); }
+int rib_abi_version(void) { return RIB_ABI_VERSION; }
+long long rib_kernel_launch_count(void) { return conv_gemm_launch_count() + misc_launch_count(); }
+
+int rib_rasterize(const double* joints, int B, int H, int W, const double* gauss_taps, double skeleton_thres,
+                  double foot_thres, float* label, void* stream) {
+  RIB_GUARD_BEGIN
+  RIB_REQUIRE(joints && gauss_taps && label, "rib_rasterize: null argument");
+  int rc = launch_rasterize(joints, B, H, W, gauss_taps, skeleton_thres, foot_thres, label, (cudaStream_t)stream);
+  if (!rc) count_misc_launch(2);
+  return rc;
+  RIB_GUARD_END
+}
+
+int rib_warp(const float* src, const float* flow, float* out, int B, int C, int H, int W, void* stream) {
+  RIB_GUARD_BEGIN
+  RIB_REQUIRE(src && flow && out && B > 0 && C > 0 && H > 0 && W > 0, "rib_warp: bad argument");
+  int rc = launch_warp(src, flow, out, B, C, H, W, (cudaStream_t)stream);
+  if (!rc) count_misc_launch(1);
+  return rc;
+  RIB_GUARD_END
+}
+
+int rib_composite(const float* img, const float* mask, const float* dain, float* out_f32, uint8_t* out_u8, int B,
+                  int H, int W, void* stream) {
+  RIB_GUARD_BEGIN
+  RIB_REQUIRE(img && mask && dain && (out_f32 || out_u8) && B > 0 && H > 0 && W > 0, "rib_composite: bad argument");
+  int rc = launch_composite(img, mask, dain, out_f32, out_u8, B, H, W, (cudaStream_t)stream);
+  if (!rc) count_misc_launch(1);
+  return rc;
+  RIB_GUARD_END
+}
+
+int rib_generator_create(const rib_gen_config* cfg, const rib_tensor* tensors, int n_tensors, void* stream,
+                         rib_generator** out) {
+  RIB_GUARD_BEGIN
+  return generator_create(cfg, tensors, n_tensors, (cudaStream_t)stream, reinterpret_cast<Generator**>(out));
+  RIB_GUARD_END
+}
+
+void rib_generator_destroy(rib_generator* g) { generator_destroy(reinterpret_cast<Generator*>(g)); }
+
+long long rib_generator_workspace_bytes(rib_generator* g, int B, int H, int W) {
+  RIB_GUARD_BEGIN
+  RIB_REQUIRE(g, "rib_generator_workspace_bytes: null generator");
+  return generator_workspace_bytes(reinterpret_cast<Generator*>(g), B, H, W);
+  RIB_GUARD_END
+}
+
+int rib_generator_forward(rib_generator* g, int B, int H, int W, const float* label, const float* img_fake,
+                          const float* img_prev, float* out_img, float* out_mask, void* workspace,
+                          long long workspace_bytes, void* stream) {
+  RIB_GUARD_BEGIN
+  return generator_forward(reinterpret_cast<Generator*>(g), B, H, W, label, img_fake, img_prev, out_img, out_mask,
+                           workspace, workspace_bytes, (cudaStream_t)stream);
+  RIB_GUARD_END
+}
+
+void rib_debug_set_simt(int enable) { rib::g_debug_simt = enable ? 1 : 0; }
+int rib_debug_get_simt(void) { return rib::g_debug_simt; }
+
+int rib_generator_debug_tensor(rib_generator* g, const char* name, const void** ptr, int* B, int* H, int* W, int* C,
+                               int* ld) {
+  RIB_GUARD_BEGIN
+  RIB_REQUIRE(g && name && ptr && B && H && W && C && ld, "rib_generator_debug_tensor: null argument");
+  return generator_debug_tensor(reinterpret_cast<Generator*>(g), name, ptr, B, H, W, C, ld);
+  RIB_GUARD_END
+}
+
+int rib_act_is_fp16(void) {
+#ifdef RIB_ACT_FP16
+  return 1;
+#else
+  return 0;
+#endif
+}
+
+long long rib_conv_test_scratch_bytes(int Cin, int Cout, int k) { return conv_test_scratch_bytes(Cin, Cout, k); }
+
+int rib_conv_test(const void* x, const float* w, const float* bias, void* out, double* stats, int B, int Hin, int Win,
+                  int Cin, int Cout, int k, int stride, int act, void* scratch, void* stream) {
+  RIB_GUARD_BEGIN
+  RIB_REQUIRE(x && w && out && scratch, "rib_conv_test: null argument");
+  return conv_test(x, w, bias, out, stats, B, Hin, Win, Cin, Cout, k, stride, act, scratch, (cudaStream_t)stream);
+  RIB_GUARD_END
+}
+
+}  // extern "C"

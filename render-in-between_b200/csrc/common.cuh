@@ -1,0 +1,199 @@
+// Shared device/host helpers for the rib_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+namespace rib {
+
+// ---------------------------------------------------------------------------------------------
+// Activation storage type. Tensor-core operands are 16-bit with fp32 accumulation in TMEM.
+// RIB_ACT_FP16 selects IEEE half (10-bit mantissa) instead of bf16; both run at the same
+// tcgen05 kind::f16 rate.
+// ---------------------------------------------------------------------------------------------
+#ifdef RIB_ACT_FP16
+typedef __half act_t;
+#define RIB_UMMA_FMT 0u
+#define RIB_TMAP_DTYPE CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+__device__ __forceinline__ act_t f2act(float v) { return __float2half_rn(v); }
+__device__ __forceinline__ float act2f(act_t v) { return __half2float(v); }
+#else
+typedef __nv_bfloat16 act_t;
+#define RIB_UMMA_FMT 1u
+#define RIB_TMAP_DTYPE CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+__device__ __forceinline__ act_t f2act(float v) { return __float2bfloat16_rn(v); }
+__device__ __forceinline__ float act2f(act_t v) { return __bfloat162float(v); }
+#endif
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  act_t x = f2act(a), y = f2act(b);
+  return (uint32_t)(*reinterpret_cast<uint16_t*>(&x)) | ((uint32_t)(*reinterpret_cast<uint16_t*>(&y)) << 16);
+}
+__device__ __forceinline__ void unpack2(uint32_t u, float& a, float& b) {
+  uint16_t lo = (uint16_t)(u & 0xffffu), hi = (uint16_t)(u >> 16);
+  a = act2f(*reinterpret_cast<act_t*>(&lo));
+  b = act2f(*reinterpret_cast<act_t*>(&hi));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Error plumbing: every C-ABI entry returns 0 or a negative code; the message is kept per thread.
+// ---------------------------------------------------------------------------------------------
+void set_error(const std::string& msg);
+const char* last_error();
+
+#define RIB_CHECK_CUDA(expr)                                                                   \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      rib::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ +    \
+                     ":" + std::to_string(__LINE__) + ")");                                   \
+      return -2;                                                                               \
+    }                                                                                          \
+  } while (0)
+
+#define RIB_REQUIRE(cond, msg)                                                                 \
+  do {                                                                                         \
+    if (!(cond)) {                                                                             \
+      rib::set_error(std::string(msg) + " [" #cond "] (" + __FILE__ + ":" +                    \
+                     std::to_string(__LINE__) + ")");                                         \
+      return -1;                                                                               \
+    }                                                                                          \
+  } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers: mbarrier, TMA, tcgen05 / TMEM.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Bounded wait: a protocol bug becomes a trap (reported as a launch failure) instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) {
+      printf("rib: mbarrier timeout block=(%d,%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x, blockIdx.y,
+             blockIdx.z, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void prefetch_tmap(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, kind::f16 (bf16/fp16 operands, fp32 accumulate).
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns: thread i of the warp receives lane (base+i).
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor for a K-major tile whose rows are `row_bytes` (32/64/128) wide and
+// were written by TMA with the matching swizzle mode; 8-row groups are densely packed.
+//   bits [0,14) start address >> 4, [16,30) LBO >> 4 (unused for swizzled K-major: 1),
+//   [32,46) SBO >> 4 (= 8 rows * row_bytes), [46,48) version = 1 (sm_100), [61,64) layout type.
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_t row_bytes) {
+  uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(((8u * row_bytes) >> 4) & 0x3fffu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+
+// kind::f16 instruction descriptor: fp32 accumulate, A/B format from RIB_UMMA_FMT, both K-major.
+static inline uint32_t make_idesc_f16(int m, int n) {
+  uint32_t d = 0;
+  d |= 1u << 4;                      // c_format = F32
+  d |= (uint32_t)RIB_UMMA_FMT << 7;  // a_format
+  d |= (uint32_t)RIB_UMMA_FMT << 10; // b_format
+  d |= (uint32_t)(n >> 3) << 17;     // n_dim
+  d |= (uint32_t)(m >> 4) << 24;     // m_dim
+  return d;
+}
+
+__device__ __forceinline__ float lrelu02(float v) { return v > 0.f ? v : 0.2f * v; }
+
+}  // namespace rib

@@ -1,0 +1,342 @@
+// Bandwidth-bound kernels of the rendering path (sm_100a).  All are single-pass, 16-byte vectorised
+// and sized so that consecutive threads touch consecutive addresses.
+#include "elementwise.cuh"
+
+namespace rib {
+
+// ---------------------------------------------------------------------------------------------
+// NCHW fp32 -> NHWC 16-bit
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_nchw_kernel(const float* __restrict__ src, int C, act_t* __restrict__ dst, int ld, int c_off,
+                                 int HW, size_t total) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // pixel index over B*H*W
+  if (i >= total) return;
+  const size_t n = i / HW, hw = i - n * HW;
+  const float* s = src + n * (size_t)C * HW + hw;
+  act_t* d = dst + i * ld + c_off;
+  for (int c = 0; c < C; ++c) d[c] = f2act(__ldg(s + (size_t)c * HW));
+}
+
+int launch_pack_nchw(const float* src, int C, act_t* dst, int ld, int c_off, int B, int H, int W, cudaStream_t s) {
+  const size_t total = (size_t)B * H * W;
+  const int threads = 256;
+  pack_nchw_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(src, C, dst, ld, c_off, H * W,
+                                                                                   total);
+  RIB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Instance-norm application
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void in_coeffs(const double* stats, const float* w, const float* b, int n, int C, int c,
+                                          double cnt, float eps, float* scale, float* shift) {
+  const double s = stats[((size_t)n * C + c) * 2], ss = stats[((size_t)n * C + c) * 2 + 1];
+  const double mean = s / cnt;
+  double var = ss / cnt - mean * mean;
+  var = var < 0.0 ? 0.0 : var;
+  const double rstd = 1.0 / sqrt(var + (double)eps);
+  const double g = w ? (double)w[c] : 1.0, be = b ? (double)b[c] : 0.0;
+  *scale = (float)(g * rstd);
+  *shift = (float)(be - mean * g * rstd);
+}
+
+__global__ void in_apply_kernel(const InApplyParams p) {
+  extern __shared__ float s_coef[];  // [4][C]: scale_a, shift_a, scale_b, shift_b
+  const int n = blockIdx.y;
+  const double cnt = (double)p.H * (double)p.W;
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    in_coeffs(p.astats, p.aw, p.ab, n, p.C, c, cnt, p.eps, &s_coef[c], &s_coef[p.C + c]);
+    if (p.b != nullptr && p.bstats != nullptr)
+      in_coeffs(p.bstats, p.bw, p.bb, n, p.C, c, cnt, p.eps, &s_coef[2 * p.C + c], &s_coef[3 * p.C + c]);
+  }
+  __syncthreads();
+  const int vec_per_pix = p.C / 8;
+  const size_t nvec = (size_t)p.H * p.W * vec_per_pix;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t pix = i / vec_per_pix;
+    const int c0 = (int)(i - pix * vec_per_pix) * 8;
+    const size_t gp = (size_t)n * p.H * p.W + pix;
+    const uint4 av = *reinterpret_cast<const uint4*>(p.a + gp * p.lda + c0);
+    const uint32_t au[4] = {av.x, av.y, av.z, av.w};
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) unpack2(au[k], v[2 * k], v[2 * k + 1]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      v[k] = v[k] * s_coef[c0 + k] + s_coef[p.C + c0 + k];
+      if (p.act) v[k] = lrelu02(v[k]);
+    }
+    if (p.b != nullptr) {
+      const uint4 bv = *reinterpret_cast<const uint4*>(p.b + gp * p.ldb + c0);
+      const uint32_t bu[4] = {bv.x, bv.y, bv.z, bv.w};
+      float w[8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) unpack2(bu[k], w[2 * k], w[2 * k + 1]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        v[k] += p.bstats ? (w[k] * s_coef[2 * p.C + c0 + k] + s_coef[3 * p.C + c0 + k]) : w[k];
+    }
+    const uint4 o = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+    if (!p.ups) {
+      *reinterpret_cast<uint4*>(p.out + gp * p.ldo + c0) = o;
+    } else {
+      const int y = (int)(pix / p.W), x = (int)(pix - (size_t)y * p.W);
+      const int W2 = 2 * p.W;
+      const size_t base = ((size_t)n * 2 * p.H + 2 * y) * W2 + 2 * x;
+      *reinterpret_cast<uint4*>(p.out + base * p.ldo + c0) = o;
+      *reinterpret_cast<uint4*>(p.out + (base + 1) * p.ldo + c0) = o;
+      *reinterpret_cast<uint4*>(p.out + (base + W2) * p.ldo + c0) = o;
+      *reinterpret_cast<uint4*>(p.out + (base + W2 + 1) * p.ldo + c0) = o;
+    }
+  }
+}
+
+int launch_in_apply(const InApplyParams& p, cudaStream_t s) {
+  RIB_REQUIRE(p.C % 8 == 0 && p.lda % 8 == 0 && p.ldo % 8 == 0, "in_apply: channels must be a multiple of 8");
+  const size_t nvec = (size_t)p.H * p.W * (p.C / 8);
+  const int threads = 256;
+  unsigned gx = (unsigned)((nvec + threads - 1) / threads);
+  if (gx > 148u * 16u) gx = 148u * 16u;
+  dim3 grid(gx, (unsigned)p.B);
+  in_apply_kernel<<<grid, threads, 4 * p.C * sizeof(float), s>>>(p);
+  RIB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// AvgPool 3x3 s2 p1 + statistics
+// ---------------------------------------------------------------------------------------------
+__global__ void avgpool3s2_kernel(const act_t* __restrict__ src, int lds, act_t* __restrict__ dst, int ldd,
+                                  double* __restrict__ stats, int H, int W, int C) {
+  extern __shared__ float s_red[];  // [2][C]
+  const int n = blockIdx.y;
+  const int Ho = H / 2, Wo = W / 2;
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) s_red[c] = 0.f;
+  __syncthreads();
+  const int vec_per_pix = C / 8;
+  const size_t nvec = (size_t)Ho * Wo * vec_per_pix;
+  // consecutive threads of a block share the channel group pattern: blockDim % vec_per_pix == 0 or vice versa
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t pix = i / vec_per_pix;
+    const int c0 = (int)(i - pix * vec_per_pix) * 8;
+    const int oy = (int)(pix / Wo), ox = (int)(pix - (size_t)oy * Wo);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int iy = 2 * oy + dy;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int ix = 2 * ox + dx;
+        if (ix < 0 || ix >= W) continue;
+        const uint4 v = *reinterpret_cast<const uint4*>(src + (((size_t)n * H + iy) * W + ix) * lds + c0);
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float a, b;
+          unpack2(u[k], a, b);
+          acc[2 * k] += a;
+          acc[2 * k + 1] += b;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = acc[k] / 9.0f;
+    *reinterpret_cast<uint4*>(dst + (((size_t)n * Ho + oy) * Wo + ox) * ldd + c0) =
+        make_uint4(pack2(acc[0], acc[1]), pack2(acc[2], acc[3]), pack2(acc[4], acc[5]), pack2(acc[6], acc[7]));
+    if (stats != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        atomicAdd(&s_red[c0 + k], acc[k]);
+        atomicAdd(&s_red[C + c0 + k], acc[k] * acc[k]);
+      }
+    }
+  }
+  if (stats != nullptr) {
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      atomicAdd(&stats[((size_t)n * C + c) * 2 + 0], (double)s_red[c]);
+      atomicAdd(&stats[((size_t)n * C + c) * 2 + 1], (double)s_red[C + c]);
+    }
+  }
+}
+
+int launch_avgpool3s2(const act_t* src, int lds, act_t* dst, int ldd, double* stats, int B, int H, int W, int C,
+                      cudaStream_t s) {
+  RIB_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "avgpool: bad shape");
+  const size_t nvec = (size_t)(H / 2) * (W / 2) * (C / 8);
+  const int threads = 256;
+  unsigned gx = (unsigned)((nvec + threads - 1) / threads);
+  if (gx > 148u * 8u) gx = 148u * 8u;
+  dim3 grid(gx, (unsigned)B);
+  avgpool3s2_kernel<<<grid, threads, 2 * C * sizeof(float), s>>>(src, lds, dst, ldd, stats, H, W, C);
+  RIB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Composite
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint8_t to_u8(float x) {
+  double v = (double)x * 0.5 + 0.5;  // tensor2images multiplies a float32 array by float64 std/mean arrays
+  v = v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v);
+  return (uint8_t)(v * 255.0);
+}
+
+__global__ void composite_kernel(const float* __restrict__ img, const float* __restrict__ mask,
+                                 const float* __restrict__ dain, float* __restrict__ out_f32,
+                                 uint8_t* __restrict__ out_u8, int HW4, int HW, size_t total) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over B * HW/4
+  if (i >= total) return;
+  const size_t n = i / HW4, q = i - n * HW4;
+  const float4 m = __ldg(reinterpret_cast<const float4*>(mask + n * HW) + q);
+  const float mm[4] = {m.x, m.y, m.z, m.w};
+  float res[3][4];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const size_t off = (n * 3 + c) * (size_t)HW;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(img + off) + q);
+    const float4 d = __ldg(reinterpret_cast<const float4*>(dain + off) + q);
+    const float aa[4] = {a.x, a.y, a.z, a.w}, dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)  // separate roundings, as the reference's three elementwise ops
+      res[c][k] = __fadd_rn(__fmul_rn(aa[k], mm[k]), __fmul_rn(dd[k], __fsub_rn(1.0f, mm[k])));
+    if (out_f32 != nullptr)
+      reinterpret_cast<float4*>(out_f32 + off)[q] = make_float4(res[c][0], res[c][1], res[c][2], res[c][3]);
+  }
+  if (out_u8 != nullptr) {
+    uint8_t px[12];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) px[3 * k + c] = to_u8(res[c][k]);
+    uint32_t* o = reinterpret_cast<uint32_t*>(out_u8 + (n * (size_t)HW + q * 4) * 3);
+    o[0] = px[0] | (px[1] << 8) | (px[2] << 16) | ((uint32_t)px[3] << 24);
+    o[1] = px[4] | (px[5] << 8) | (px[6] << 16) | ((uint32_t)px[7] << 24);
+    o[2] = px[8] | (px[9] << 8) | (px[10] << 16) | ((uint32_t)px[11] << 24);
+  }
+}
+
+int launch_composite(const float* img, const float* mask, const float* dain, float* out_f32, uint8_t* out_u8, int B,
+                     int H, int W, cudaStream_t s) {
+  RIB_REQUIRE((H * W) % 4 == 0, "composite: H*W must be a multiple of 4");
+  const int HW = H * W;
+  const size_t total = (size_t)B * (HW / 4);
+  const int threads = 256;
+  composite_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(img, mask, dain, out_f32, out_u8,
+                                                                                   HW / 4, HW, total);
+  RIB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Flow warp (bilinear, border, align_corners=True)
+// ---------------------------------------------------------------------------------------------
+__global__ void warp_kernel(const float* __restrict__ src, const float* __restrict__ flow, float* __restrict__ out,
+                            int C, int H, int W, float sx, float sy, size_t total) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over B*H*W
+  if (i >= total) return;
+  const int HW = H * W;
+  const size_t n = i / HW;
+  const int hw = (int)(i - n * HW);
+  const int y = hw / W, x = hw - y * W;
+  const float fx = __ldg(flow + (n * 2 + 0) * (size_t)HW + hw);
+  const float fy = __ldg(flow + (n * 2 + 1) * (size_t)HW + hw);
+  // same float sequence as building the normalised grid and un-normalising it in grid_sample
+  const float gx = __fsub_rn(__fmul_rn(__fadd_rn((float)x, fx), sx), 1.0f);
+  const float gy = __fsub_rn(__fmul_rn(__fadd_rn((float)y, fy), sy), 1.0f);
+  float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.0f), 2.0f), (float)(W - 1));
+  float iy = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.0f), 2.0f), (float)(H - 1));
+  ix = fminf(fmaxf(ix, 0.f), (float)(W - 1));
+  iy = fminf(fmaxf(iy, 0.f), (float)(H - 1));
+  const float x0f = floorf(ix), y0f = floorf(iy);
+  const int x0 = (int)x0f, y0 = (int)y0f, x1 = x0 + 1, y1 = y0 + 1;
+  const float tx = ix - x0f, ty = iy - y0f;
+  const float wnw = (1.f - tx) * (1.f - ty), wne = tx * (1.f - ty), wsw = (1.f - tx) * ty, wse = tx * ty;
+  for (int c = 0; c < C; ++c) {
+    const float* s = src + (n * C + c) * (size_t)HW;
+    float acc = __ldg(s + y0 * W + x0) * wnw;
+    if (x1 < W) acc += __ldg(s + y0 * W + x1) * wne;
+    if (y1 < H) acc += __ldg(s + y1 * W + x0) * wsw;
+    if (x1 < W && y1 < H) acc += __ldg(s + y1 * W + x1) * wse;
+    out[(n * C + c) * (size_t)HW + hw] = acc;
+  }
+}
+
+int launch_warp(const float* src, const float* flow, float* out, int B, int C, int H, int W, cudaStream_t s) {
+  const size_t total = (size_t)B * H * W;
+  const int threads = 256;
+  const float sx = (float)(2.0 / (double)(W > 1 ? W - 1 : 1)), sy = (float)(2.0 / (double)(H > 1 ? H - 1 : 1));
+  warp_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(src, flow, out, C, H, W, sx, sy, total);
+  RIB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Weight folding / packing (runs once at model creation)
+// ---------------------------------------------------------------------------------------------
+__global__ void sn_sigma_inv_kernel(const float* __restrict__ w, const float* __restrict__ u,
+                                    const float* __restrict__ v, int Cout, int K, float* sigma_inv) {
+  __shared__ double s_part[256];
+  double acc = 0.0;
+  for (size_t i = threadIdx.x; i < (size_t)Cout * K; i += blockDim.x) {
+    const int r = (int)(i / K), c = (int)(i - (size_t)r * K);
+    acc += (double)u[r] * (double)w[i] * (double)v[c];
+  }
+  s_part[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) s_part[threadIdx.x] += s_part[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) sigma_inv[0] = (float)(1.0 / s_part[0]);
+}
+
+int launch_sn_sigma_inv(const float* w, const float* u, const float* v, int Cout, int K, float* sigma_inv,
+                        cudaStream_t s) {
+  sn_sigma_inv_kernel<<<1, 256, 0, s>>>(w, u, v, Cout, K, sigma_inv);
+  RIB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__device__ __forceinline__ int pack_row(const PackWeightParams& p, int co) {
+  if (p.spade_C == 0) return p.row_off + co;
+  const int half = co / p.spade_C, c = co - half * p.spade_C;
+  return p.row_off + (c / p.spade_CT) * 2 * p.spade_CT + half * p.spade_CT + c % p.spade_CT;
+}
+
+__global__ void pack_weight_kernel(const PackWeightParams p) {
+  const float scale = p.sigma_inv ? p.sigma_inv[0] : 1.f;
+  const size_t total = (size_t)p.Cout * p.Cin * p.taps;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % p.taps);
+    const size_t r = i / p.taps;
+    const int ci = (int)(r % p.Cin), co = (int)(r / p.Cin);
+    // the reference divides the fp32 weight by sigma (W / sigma), then the conv runs on that weight
+    const float wv = p.sigma_inv ? p.w[i] * scale : p.w[i];
+    p.dst[(size_t)pack_row(p, co) * p.ktotal + p.koff + tap * p.cin_pad + ci] = f2act(wv);
+  }
+  if (p.bias_dst != nullptr) {
+    for (int co = blockIdx.x * blockDim.x + threadIdx.x; co < p.Cout; co += gridDim.x * blockDim.x) {
+      float b = p.bias ? p.bias[co] : 0.f;
+      if (p.spade_C != 0 && co < p.spade_C) b += 1.0f;  // (1 + gamma)
+      const int row = pack_row(p, co);
+      if (p.bias_accumulate) p.bias_dst[row] += b;
+      else p.bias_dst[row] = b;
+    }
+  }
+}
+
+int launch_pack_weight(const PackWeightParams& p, cudaStream_t s) {
+  const size_t total = (size_t)p.Cout * p.Cin * p.taps;
+  unsigned blocks = (unsigned)((total + 255) / 256);
+  if (blocks > 2048u) blocks = 2048u;
+  pack_weight_kernel<<<blocks, 256, 0, s>>>(p);
+  RIB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace rib

@@ -1,0 +1,56 @@
+// Bandwidth-bound kernels of the rendering path (declarations).
+#pragma once
+#include "common.cuh"
+
+namespace rib {
+
+// NCHW fp32 -> NHWC 16-bit, channels [c_off, c_off + C) of a buffer with `ld` channels per pixel.
+int launch_pack_nchw(const float* src, int C, act_t* dst, int ld, int c_off, int B, int H, int W, cudaStream_t s);
+
+// Instance-norm (affine) application for the C-N-A blocks of the mask network
+// (conv.py:56-69 with order 'CNA'; residual.py:146-151 for the two-term form):
+//   out = act(IN_a(a)) [+ IN_b(b) | + b]   with optional nearest x2 up-sampling on the store
+struct InApplyParams {
+  const act_t* a; int lda; const double* astats; const float* aw; const float* ab;
+  const act_t* b; int ldb; const double* bstats; const float* bw; const float* bb;  // b optional
+  act_t* out; int ldo;
+  int B, H, W, C;  // input spatial size
+  int act;         // 0 none, 1 leaky-relu(0.2) on the first term
+  int ups;         // 1: write each pixel to the 2x2 block of a (2H, 2W) output
+  float eps;
+};
+int launch_in_apply(const InApplyParams& p, cudaStream_t s);
+
+// AvgPool2d(3, stride 2, pad 1, count_include_pad) (generator.py:127,208) + instance-norm statistics
+// of the pooled map (sum, sum of squares per (n, c), fp64 atomics).
+int launch_avgpool3s2(const act_t* src, int lds, act_t* dst, int ldd, double* stats, int B, int H, int W, int C,
+                      cudaStream_t s);
+
+// fuse = img * mask + dain * (1 - mask)   (evaluator.py:256-258); optional uint8 HWC frame
+// (utils.py:137-142: clip(x*0.5+0.5, 0, 1)*255 truncated, float64 arithmetic).
+int launch_composite(const float* img, const float* mask, const float* dain, float* out_f32, uint8_t* out_u8, int B,
+                     int H, int W, cudaStream_t s);
+
+// out = bilinear sample of src at (x + flow_x, y + flow_y), border padding, align_corners=True.
+int launch_warp(const float* src, const float* flow, float* out, int B, int C, int H, int W, cudaStream_t s);
+
+// sigma_inv[0] = 1 / (u . (W v)),  W = [Cout, K] fp32 (torch.nn.utils.spectral_norm, eval mode).
+int launch_sn_sigma_inv(const float* w, const float* u, const float* v, int Cout, int K, float* sigma_inv,
+                        cudaStream_t s);
+
+// Repack a conv weight [Cout][Cin][taps] fp32 into the K-major 16-bit GEMM operand:
+//   dst[row(co) * ktotal + koff + tap * cin_pad + ci] = w[co][ci][tap] * (sigma_inv ? *sigma_inv : 1)
+//   bias_dst[row(co)] (+)= bias[co] (+ 1 for SPADE gamma rows)
+// row(co) = row_off + co for plain convs; for SPADE ([gamma(C) | beta(C)] -> per-tile [gamma(CT) | beta(CT)]):
+//   c = co % C, half = co / C, row = row_off + (c / CT) * 2 * CT + half * CT + c % CT.
+struct PackWeightParams {
+  const float* w; const float* bias; const float* sigma_inv;
+  int Cout, Cin, taps;
+  act_t* dst; float* bias_dst;
+  int ktotal, koff, cin_pad, row_off;
+  int spade_C, spade_CT;  // 0 for plain convs
+  int bias_accumulate;    // add into bias_dst instead of overwriting (fused shortcut)
+};
+int launch_pack_weight(const PackWeightParams& p, cudaStream_t s);
+
+}  // namespace rib

@@ -1,0 +1,914 @@
+// Generator forward plan: weight folding/packing at creation, then one static list of kernel
+// launches per (B, H, W).  Restates the dataflow of PGNR/models/generator.py:181-234 (Generator),
+// :360-387 (LabelEmbedder, arch 'encoder'), :493-510 (MaskGenerator) with these fusions
+// (all parity-neutral):
+//   * spectral norm folded once (weight_norm.py:84-85)
+//   * the 34 same-size F.interpolate calls of SPADE dropped (activation_norm.py:224)
+//   * per SPADE res-block: the gamma/beta 1x1 convs of conv_block_0 and conv_block_s share one
+//     GEMM over the same cond map, the instance-norm + modulation + LeakyReLU are its epilogue
+//   * conv_block_1 (3x3) and the learned 1x1 shortcut accumulate into one TMEM tile (K = 9*hid + cin)
+//   * instance-norm statistics come out of the producing conv's epilogue (fp64 atomics)
+//   * nearest x2 up-sampling is a gather in the consumer (main branch) or the producer's store (mask net)
+//   * torch.cat never materialises: producers write channel slices
+#include "generator.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <map>
+#include <unordered_map>
+#include <vector>
+
+#include "conv_gemm.cuh"
+#include "elementwise.cuh"
+
+namespace rib {
+
+int g_debug_simt = 0;
+
+namespace {
+
+struct View {  // NHWC 16-bit activation (or a channel slice of one)
+  act_t* p = nullptr;
+  int B = 0, H = 0, W = 0, C = 0, ld = 0;
+};
+
+struct GemmLayer {
+  std::string name;
+  int n_pad = 0, n_valid = 0, ktotal = 0;
+  int cin0 = 0, taps = 0, cin1 = 0;  // padded input channels of source 0, its taps, source 1 (1x1) channels
+  act_t* w = nullptr;
+  float* bias = nullptr;
+  size_t w_off = 0, b_off = 0;
+};
+
+enum OpKind { OP_MEMSET, OP_PACK, OP_GEMM, OP_IN_APPLY, OP_POOL };
+enum ExtPtr { EXT_NONE = 0, EXT_LABEL, EXT_FAKE, EXT_PREV, EXT_OUT_IMG, EXT_OUT_MASK };
+
+struct Op {
+  OpKind kind;
+  // memset
+  void* ms_ptr = nullptr;
+  size_t ms_bytes = 0;
+  // pack
+  int ext = EXT_NONE;
+  int pk_C = 0, pk_ld = 0, pk_coff = 0;
+  act_t* pk_dst = nullptr;
+  // gemm
+  ConvGemmParams g;
+  int mode = 0;
+  // in_apply
+  InApplyParams ia;
+  // pool
+  const act_t* pl_src = nullptr;
+  act_t* pl_dst = nullptr;
+  double* pl_stats = nullptr;
+  int pl_lds = 0, pl_ldd = 0, pl_H = 0, pl_W = 0, pl_C = 0;
+};
+
+struct Bump {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Bump(void* b) : base(static_cast<uint8_t*>(b)) {}
+  void* take(size_t bytes) {
+    off = align_up(off, 1024);
+    void* p = base ? base + off : nullptr;
+    off += bytes;
+    return p;
+  }
+};
+
+}  // namespace
+
+struct Generator {
+  rib_gen_config cfg;
+  std::map<std::string, GemmLayer> layers;
+  std::unordered_map<std::string, const float*> in_affine;  // IN weight / bias device pointers (caller-owned fp32)
+  uint8_t* arena = nullptr;
+  size_t arena_bytes = 0;
+  // cached plan
+  int pB = 0, pH = 0, pW = 0;
+  void* pws = nullptr;
+  size_t ws_bytes_needed = 0;
+  std::vector<Op> ops;
+  std::map<std::string, View> debug_views;
+  bool plan_simt = false;
+};
+
+namespace {
+
+int nfilt(const rib_gen_config& c, int i) { return std::min(c.maxf, c.nf << i); }
+int mask_nfilt(const rib_gen_config& c, int i) { return std::min(c.mask_max, c.mask_nf << i); }
+int emb_ch(const rib_gen_config& c, int i) { return std::min(c.emb_max, c.emb_nf << i); }
+int pad16(int c) { return (c + 15) / 16 * 16; }
+
+struct BlockDef {
+  std::string name;
+  int cin, hid, cout, lvl;
+  bool shortcut;
+};
+
+std::vector<BlockDef> res_blocks(const rib_gen_config& c) {
+  std::vector<BlockDef> v;
+  for (int i = 0; i <= c.n_down; ++i) {
+    int ci = nfilt(c, i), co = nfilt(c, i + 1);
+    v.push_back({"down_" + std::to_string(i), ci, std::min(ci, co), co, std::min(c.emb_down, i), ci != co});
+  }
+  int ch = nfilt(c, c.n_down + 1);
+  for (int i = 0; i < c.n_res; ++i)
+    v.push_back({"res_" + std::to_string(i), ch, ch, ch, std::min(c.emb_down, c.n_down + 1), false});
+  for (int i = c.n_down; i >= 0; --i) {
+    int ci = nfilt(c, i + 1), co = nfilt(c, i);
+    v.push_back({"up_" + std::to_string(i), ci, std::min(ci, co), co, std::min(i, c.emb_down), ci != co});
+  }
+  return v;
+}
+
+// ---- model creation -------------------------------------------------------------------------
+struct Source {
+  std::unordered_map<std::string, std::pair<const float*, long long>> t;
+  const float* get(const std::string& k, long long numel, int* err) const {
+    auto it = t.find(k);
+    if (it == t.end()) {
+      set_error("state-dict entry missing: " + k);
+      *err = -3;
+      return nullptr;
+    }
+    if (it->second.second != numel) {
+      set_error("state-dict entry has wrong size: " + k);
+      *err = -3;
+      return nullptr;
+    }
+    return it->second.first;
+  }
+};
+
+struct PackJob {  // one reference conv placed inside a GEMM layer
+  std::string layer, prefix;
+  bool sn;
+  int cout, cin, taps, koff, cin_pad, row_off, spade_C, spade_CT;
+  bool bias_acc;
+};
+
+void add_layer(Generator* G, const std::string& name, int n_valid, int n_pad, int cin0_pad, int taps, int cin1) {
+  GemmLayer L;
+  L.name = name;
+  L.n_valid = n_valid;
+  L.n_pad = n_pad;
+  L.cin0 = cin0_pad;
+  L.taps = taps;
+  L.cin1 = cin1;
+  L.ktotal = cin0_pad * taps + cin1;
+  G->layers[name] = L;
+}
+
+int spade_ct(int C) { return std::min(C, 64); }
+
+}  // namespace
+
+int generator_create(const rib_gen_config* cfg, const rib_tensor* tensors, int n, cudaStream_t stream,
+                     Generator** out) {
+  RIB_REQUIRE(cfg && tensors && out, "generator_create: null argument");
+  const rib_gen_config& c = *cfg;
+  RIB_REQUIRE(c.nf % 16 == 0 && c.emb_nf % 16 == 0 && c.mask_nf % 16 == 0, "channel counts must be multiples of 16");
+  RIB_REQUIRE(c.label_nc <= 32 && c.img_nc == 3, "unsupported input channel counts");
+  Source src;
+  for (int i = 0; i < n; ++i) src.t[tensors[i].name] = {tensors[i].data, tensors[i].numel};
+
+  Generator* G = new Generator();
+  G->cfg = c;
+  std::vector<PackJob> jobs;
+  const int lab_pad = 32, emb_in_pad = 16, mask_in_pad = 16;
+
+  // ref_embedding
+  add_layer(G, "emb_0", emb_ch(c, 0), emb_ch(c, 0), emb_in_pad, 9, 0);
+  jobs.push_back({"emb_0", "ref_embedding.conv_first.layers.conv", true, emb_ch(c, 0), 2 * c.img_nc, 9, 0, emb_in_pad, 0, 0, 0, false});
+  for (int i = 0; i < c.emb_down; ++i) {
+    std::string ln = "emb_" + std::to_string(i + 1);
+    add_layer(G, ln, emb_ch(c, i + 1), emb_ch(c, i + 1), emb_ch(c, i), 9, 0);
+    jobs.push_back({ln, "ref_embedding.down_" + std::to_string(i) + ".layers.conv", true, emb_ch(c, i + 1), emb_ch(c, i), 9, 0, emb_ch(c, i), 0, 0, 0, false});
+  }
+  // down_first
+  add_layer(G, "down_first", c.nf, c.nf, lab_pad, 9, 0);
+  jobs.push_back({"down_first", "down_first.layers.conv", false, c.nf, c.label_nc, 9, 0, lab_pad, 0, 0, 0, false});
+  // SPADE res-blocks
+  for (const BlockDef& b : res_blocks(c)) {
+    const int cond = emb_ch(c, b.lvl);
+    const int nq = b.shortcut ? 2 : 1;
+    add_layer(G, b.name + ".spadeA", nq * 2 * b.cin, nq * 2 * b.cin, cond, 1, 0);
+    jobs.push_back({b.name + ".spadeA", b.name + ".conv_block_0.layers.norm.mlps.0.0.layers.conv", false, 2 * b.cin, cond, 1, 0, cond, 0, b.cin, spade_ct(b.cin), false});
+    if (b.shortcut)
+      jobs.push_back({b.name + ".spadeA", b.name + ".conv_block_s.layers.norm.mlps.0.0.layers.conv", false, 2 * b.cin, cond, 1, 0, cond, 2 * b.cin, b.cin, spade_ct(b.cin), false});
+    add_layer(G, b.name + ".conv0", b.hid, b.hid, b.cin, 9, 0);
+    jobs.push_back({b.name + ".conv0", b.name + ".conv_block_0.layers.conv", true, b.hid, b.cin, 9, 0, b.cin, 0, 0, 0, false});
+    add_layer(G, b.name + ".spadeB", 2 * b.hid, 2 * b.hid, cond, 1, 0);
+    jobs.push_back({b.name + ".spadeB", b.name + ".conv_block_1.layers.norm.mlps.0.0.layers.conv", false, 2 * b.hid, cond, 1, 0, cond, 0, b.hid, spade_ct(b.hid), false});
+    add_layer(G, b.name + ".conv1", b.cout, b.cout, b.hid, 9, b.shortcut ? b.cin : 0);
+    jobs.push_back({b.name + ".conv1", b.name + ".conv_block_1.layers.conv", true, b.cout, b.hid, 9, 0, b.hid, 0, 0, 0, false});
+    if (b.shortcut)
+      jobs.push_back({b.name + ".conv1", b.name + ".conv_block_s.layers.conv", true, b.cout, b.cin, 1, 9 * b.hid, b.cin, 0, 0, 0, true});
+  }
+  add_layer(G, "conv_img", c.img_nc, 16, c.nf, 9, 0);
+  jobs.push_back({"conv_img", "conv_img.layers.conv", false, c.img_nc, c.nf, 9, 0, c.nf, 0, 0, 0, false});
+  // mask network
+  const std::string f = "flow_network_temp.";
+  for (int br = 0; br < 2; ++br) {
+    const std::string bn = br == 0 ? "down_lbl" : "down_img";
+    const int cin = br == 0 ? c.label_nc : 3 * c.img_nc, cpad = br == 0 ? lab_pad : mask_in_pad;
+    add_layer(G, "mask." + bn + ".0", c.mask_nf, c.mask_nf, cpad, 9, 0);
+    jobs.push_back({"mask." + bn + ".0", f + bn + ".0.layers.conv", true, c.mask_nf, cin, 9, 0, cpad, 0, 0, 0, false});
+    for (int i = 0; i < c.mask_down; ++i) {
+      std::string ln = "mask." + bn + "." + std::to_string(i + 1);
+      add_layer(G, ln, mask_nfilt(c, i + 1), mask_nfilt(c, i + 1), mask_nfilt(c, i), 9, 0);
+      jobs.push_back({ln, f + bn + "." + std::to_string(i + 1) + ".layers.conv", true, mask_nfilt(c, i + 1), mask_nfilt(c, i), 9, 0, mask_nfilt(c, i), 0, 0, 0, false});
+    }
+  }
+  const int mch = mask_nfilt(c, c.mask_down);
+  for (int i = 0; i < c.mask_res; ++i) {
+    const int ci = i == 0 ? 2 * mch : mch;
+    const std::string rn = "mask.res." + std::to_string(i), rp = f + "res_flow." + std::to_string(i);
+    add_layer(G, rn + ".conv0", mch, mch, ci, 9, 0);
+    jobs.push_back({rn + ".conv0", rp + ".conv_block_0.layers.conv", true, mch, ci, 9, 0, ci, 0, 0, 0, false});
+    add_layer(G, rn + ".conv1", mch, mch, mch, 9, 0);
+    jobs.push_back({rn + ".conv1", rp + ".conv_block_1.layers.conv", true, mch, mch, 9, 0, mch, 0, 0, 0, false});
+    if (i == 0) {
+      add_layer(G, rn + ".convs", mch, mch, ci, 1, 0);
+      jobs.push_back({rn + ".convs", rp + ".conv_block_s.layers.conv", true, mch, ci, 1, 0, ci, 0, 0, 0, false});
+    }
+  }
+  for (int k = 0; k < c.mask_down; ++k) {
+    const int i = c.mask_down - 1 - k;
+    const std::string ln = "mask.up." + std::to_string(k);
+    add_layer(G, ln, mask_nfilt(c, i), mask_nfilt(c, i), mask_nfilt(c, i + 1), 9, 0);
+    jobs.push_back({ln, f + "up_flow." + std::to_string(2 * k + 1) + ".layers.conv", true, mask_nfilt(c, i), mask_nfilt(c, i + 1), 9, 0, mask_nfilt(c, i + 1), 0, 0, 0, false});
+  }
+  add_layer(G, "mask.conv_mask", 1, 16, c.mask_nf, 9, 0);
+  jobs.push_back({"mask.conv_mask", f + "conv_mask.0.layers.conv", false, 1, c.mask_nf, 9, 0, c.mask_nf, 0, 0, 0, false});
+
+  // arena: packed weights + biases + one sigma scalar per job
+  size_t off = 0;
+  for (auto& kv : G->layers) {
+    GemmLayer& L = kv.second;
+    off = align_up(off, 256);
+    L.w_off = off;
+    off += (size_t)L.n_pad * L.ktotal * sizeof(act_t);
+    off = align_up(off, 256);
+    L.b_off = off;
+    off += (size_t)L.n_pad * sizeof(float);
+  }
+  off = align_up(off, 256);
+  const size_t sigma_off = off;
+  off += jobs.size() * sizeof(float);
+  G->arena_bytes = off;
+  cudaError_t ce = cudaMalloc(&G->arena, G->arena_bytes);
+  if (ce != cudaSuccess) {
+    set_error(std::string("cudaMalloc(weights arena): ") + cudaGetErrorString(ce));
+    delete G;
+    return -2;
+  }
+  int rc = 0;
+  auto fail = [&](int code) {
+    cudaFree(G->arena);
+    delete G;
+    return code;
+  };
+  if (cudaMemsetAsync(G->arena, 0, G->arena_bytes, stream) != cudaSuccess) return fail(-2);
+  for (auto& kv : G->layers) {
+    kv.second.w = reinterpret_cast<act_t*>(G->arena + kv.second.w_off);
+    kv.second.bias = reinterpret_cast<float*>(G->arena + kv.second.b_off);
+  }
+  float* sigmas = reinterpret_cast<float*>(G->arena + sigma_off);
+  for (size_t j = 0; j < jobs.size(); ++j) {
+    const PackJob& pj = jobs[j];
+    GemmLayer& L = G->layers[pj.layer];
+    int err = 0;
+    const long long wn = (long long)pj.cout * pj.cin * pj.taps;
+    const float* w = src.get(pj.prefix + (pj.sn ? ".weight_orig" : ".weight"), wn, &err);
+    const float* bias = src.get(pj.prefix + ".bias", pj.cout, &err);
+    const float* sig = nullptr;
+    if (pj.sn && !err) {
+      const float* u = src.get(pj.prefix + ".weight_u", pj.cout, &err);
+      const float* v = src.get(pj.prefix + ".weight_v", (long long)pj.cin * pj.taps, &err);
+      if (!err) {
+        rc = launch_sn_sigma_inv(w, u, v, pj.cout, pj.cin * pj.taps, sigmas + j, stream);
+        if (rc) return fail(rc);
+        sig = sigmas + j;
+      }
+    }
+    if (err) return fail(err);
+    PackWeightParams pp;
+    pp.w = w;
+    pp.bias = bias;
+    pp.sigma_inv = sig;
+    pp.Cout = pj.cout;
+    pp.Cin = pj.cin;
+    pp.taps = pj.taps;
+    pp.dst = L.w;
+    pp.bias_dst = L.bias;
+    pp.ktotal = L.ktotal;
+    pp.koff = pj.koff;
+    pp.cin_pad = pj.cin_pad;
+    pp.row_off = pj.row_off;
+    pp.spade_C = pj.spade_C;
+    pp.spade_CT = pj.spade_CT;
+    pp.bias_accumulate = pj.bias_acc ? 1 : 0;
+    rc = launch_pack_weight(pp, stream);
+    if (rc) return fail(rc);
+  }
+  // instance-norm affine parameters stay in the caller's fp32 tensors
+  {
+    int err = 0;
+    auto reg = [&](const std::string& prefix, int ch) {
+      G->in_affine[prefix + ".weight"] = src.get(prefix + ".weight", ch, &err);
+      G->in_affine[prefix + ".bias"] = src.get(prefix + ".bias", ch, &err);
+    };
+    for (int br = 0; br < 2; ++br) {
+      const std::string bn = br == 0 ? "down_lbl" : "down_img";
+      for (int i = 0; i <= c.mask_down; ++i) reg(f + bn + "." + std::to_string(i) + ".layers.norm", mask_nfilt(c, i));
+    }
+    for (int i = 0; i < c.mask_res; ++i) {
+      reg(f + "res_flow." + std::to_string(i) + ".conv_block_0.layers.norm", mch);
+      reg(f + "res_flow." + std::to_string(i) + ".conv_block_1.layers.norm", mch);
+      if (i == 0) reg(f + "res_flow.0.conv_block_s.layers.norm", mch);
+    }
+    for (int k = 0; k < c.mask_down; ++k)
+      reg(f + "up_flow." + std::to_string(2 * k + 1) + ".layers.norm", mask_nfilt(c, c.mask_down - 1 - k));
+    if (err) return fail(err);
+  }
+  ce = cudaStreamSynchronize(stream);
+  if (ce != cudaSuccess) {
+    set_error(std::string("generator_create: ") + cudaGetErrorString(ce));
+    return fail(-2);
+  }
+  *out = G;
+  return 0;
+}
+
+void generator_destroy(Generator* G) {
+  if (!G) return;
+  if (G->arena) cudaFree(G->arena);
+  delete G;
+}
+
+// ---- plan construction ----------------------------------------------------------------------
+namespace {
+
+struct PlanBuilder {
+  Generator* G;
+  Bump ws;
+  int B;
+  bool real;  // false: size query only
+  std::vector<Op> ops;
+  std::map<std::string, View> views;
+  std::vector<std::pair<double*, size_t>> stats_bufs;
+  int rc = 0;
+
+  PlanBuilder(Generator* g, void* base, int b) : G(g), ws(base), B(b), real(base != nullptr) {}
+
+  View alloc(const std::string& name, int H, int W, int C) {
+    View v;
+    v.B = B;
+    v.H = H;
+    v.W = W;
+    v.C = C;
+    v.ld = C;
+    v.p = static_cast<act_t*>(ws.take((size_t)B * H * W * C * sizeof(act_t)));
+    views[name] = v;
+    return v;
+  }
+  static View slice(const View& v, int c_off, int C) {
+    View s = v;
+    s.p = v.p ? v.p + c_off : nullptr;
+    s.C = C;
+    return s;
+  }
+  double* alloc_stats(int C) {  // carved from one arena that is zeroed by a single memset
+    double* p = static_cast<double*>(ws.take((size_t)B * C * 2 * sizeof(double)));
+    stats_bufs.push_back({p, (size_t)B * C * 2 * sizeof(double)});
+    return p;
+  }
+
+  // Fills the geometry / tensor maps of one implicit-GEMM launch.
+  ConvGemmParams gemm_common(const GemmLayer& L, const View& in0, const View* in1, int stride, int Hout, int Wout,
+                             int BN) {
+    ConvGemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = B;
+    p.H = Hout;
+    p.W = Wout;
+    choose_tile(Hout, Wout, &p.TW, &p.TH);
+    p.tiles_x = ceil_div(Wout, p.TW);
+    p.tiles_y = ceil_div(Hout, p.TH);
+    int bk = std::min(64, in0.C);
+    if (in1) bk = std::min(bk, in1->C);
+    p.BK = bk;
+    p.BN = BN;
+    p.n_tiles = L.n_pad / BN;
+    p.ntaps = L.taps;
+    p.stride = stride;
+    p.cchunks0 = in0.C / bk;
+    p.cchunks1 = in1 ? in1->C / bk : 0;
+    const int ksteps = p.ntaps * p.cchunks0 + p.cchunks1;
+    const size_t stage_bytes = (size_t)128 * bk * 2 + (size_t)BN * bk * 2;
+    int stages = (int)((size_t)96 * 1024 / stage_bytes);
+    stages = std::max(2, std::min(stages, 8));
+    p.stages = std::min(stages, std::max(ksteps, 1));
+    p.idesc = make_idesc_f16(128, BN);
+    p.debug_simt = g_debug_simt;
+    p.src0 = in0.p;
+    p.ld0 = in0.ld;
+    p.Hin = in0.H;
+    p.Win = in0.W;
+    p.src1 = in1 ? in1->p : nullptr;
+    p.ld1 = in1 ? in1->ld : 0;
+    p.wpk = L.w;
+    p.ktotal = L.ktotal;
+    p.bias = L.bias;
+    p.n_valid = L.n_valid;
+    p.eps = 1e-5f;
+    if (in0.C != L.cin0 || (in1 ? in1->C : 0) != L.cin1 || L.n_pad % BN != 0 || in0.C % bk != 0 ||
+        (in1 && in1->C % bk != 0)) {
+      set_error("plan: layer/view channel mismatch in " + L.name);
+      rc = -4;
+      return p;
+    }
+    if (real && rc == 0) {
+      const size_t es = sizeof(act_t);
+      if (stride == 1) {
+        rc = make_tmap_act(&p.amap[0], in0.p, in0.C, in0.W, in0.H, B, (size_t)in0.ld * es, (size_t)in0.W * in0.ld * es,
+                           (size_t)in0.H * in0.W * in0.ld * es, bk, p.TW, p.TH);
+        if (!rc && in1)
+          rc = make_tmap_act(&p.amap[1], in1->p, in1->C, in1->W, in1->H, B, (size_t)in1->ld * es,
+                             (size_t)in1->W * in1->ld * es, (size_t)in1->H * in1->W * in1->ld * es, bk, p.TW, p.TH);
+      } else {
+        for (int py = 0; py < 2 && !rc; ++py)
+          for (int px = 0; px < 2 && !rc; ++px)
+            rc = make_tmap_act(&p.amap[py * 2 + px], in0.p + ((size_t)py * in0.W + px) * in0.ld, in0.C, in0.W / 2,
+                               in0.H / 2, B, (size_t)2 * in0.ld * es, (size_t)2 * in0.W * in0.ld * es,
+                               (size_t)in0.H * in0.W * in0.ld * es, bk, p.TW, p.TH);
+      }
+      if (!rc) rc = make_tmap_w(&p.bmap, L.w, L.ktotal, L.n_pad, bk, BN);
+    }
+    return p;
+  }
+
+  void push_gemm(const ConvGemmParams& p, int mode) {
+    Op op;
+    op.kind = OP_GEMM;
+    op.g = p;
+    op.mode = mode;
+    ops.push_back(op);
+  }
+
+  // conv (+bias, optional residual/second source) -> 16-bit NHWC store, optional statistics
+  void conv_store(const std::string& lname, const View& in0, const View* in1, int stride, const View& out,
+                  double* stats, int act, const View* res) {
+    const GemmLayer& L = G->layers.at(lname);
+    ConvGemmParams p = gemm_common(L, in0, in1, stride, out.H, out.W, std::min(L.n_pad, 128));
+    p.out = out.p;
+    p.ldo = out.ld;
+    p.stats = stats;
+    p.act = act;
+    p.res = res ? res->p : nullptr;
+    p.ldr = res ? res->ld : 0;
+    push_gemm(p, EPI_STORE);
+  }
+
+  // [gamma|beta] = conv1x1(cond); out_q = act_q((x - mean) * rstd * (1 + gamma) + beta)
+  void spade(const std::string& lname, const View& cond, const View& x, const double* xstats, bool ups, int nq,
+             const View* outs, const int* acts) {
+    const GemmLayer& L = G->layers.at(lname);
+    const int CT = spade_ct(x.C);
+    ConvGemmParams p = gemm_common(L, cond, nullptr, 1, cond.H, cond.W, 2 * CT);
+    p.x = x.p;
+    p.ldx = x.ld;
+    p.Hx = x.H;
+    p.Wx = x.W;
+    p.ups = ups ? 1 : 0;
+    p.xstats = xstats;
+    p.C = x.C;
+    p.CT = CT;
+    for (int q = 0; q < nq; ++q) {
+      p.outq[q] = outs[q].p;
+      p.ldq[q] = outs[q].ld;
+      p.actq[q] = acts[q];
+    }
+    push_gemm(p, EPI_SPADE);
+  }
+
+  void conv_final(const std::string& lname, const View& in0, int act, int ext, const View* copy) {
+    const GemmLayer& L = G->layers.at(lname);
+    ConvGemmParams p = gemm_common(L, in0, nullptr, 1, in0.H, in0.W, 16);
+    p.act = act;
+    p.out_act = copy ? copy->p : nullptr;
+    p.ld_act = copy ? copy->ld : 0;
+    Op op;
+    op.kind = OP_GEMM;
+    op.g = p;
+    op.mode = EPI_FINAL;
+    op.ext = ext;
+    ops.push_back(op);
+  }
+
+  void in_apply(const View& a, const double* astats, const std::string& aprefix, const View* b, const double* bstats,
+                const std::string& bprefix, const View& out, int act, bool ups) {
+    Op op;
+    op.kind = OP_IN_APPLY;
+    InApplyParams& p = op.ia;
+    memset(&p, 0, sizeof(p));
+    p.a = a.p;
+    p.lda = a.ld;
+    p.astats = astats;
+    p.aw = G->in_affine.at(aprefix + ".weight");
+    p.ab = G->in_affine.at(aprefix + ".bias");
+    if (b) {
+      p.b = b->p;
+      p.ldb = b->ld;
+      p.bstats = bstats;
+      if (bstats) {
+        p.bw = G->in_affine.at(bprefix + ".weight");
+        p.bb = G->in_affine.at(bprefix + ".bias");
+      }
+    }
+    p.out = out.p;
+    p.ldo = out.ld;
+    p.B = B;
+    p.H = a.H;
+    p.W = a.W;
+    p.C = a.C;
+    p.act = act;
+    p.ups = ups ? 1 : 0;
+    p.eps = 1e-5f;
+    ops.push_back(op);
+  }
+
+  void pool(const View& src, const View& dst, double* stats) {
+    Op op;
+    op.kind = OP_POOL;
+    op.pl_src = src.p;
+    op.pl_lds = src.ld;
+    op.pl_dst = dst.p;
+    op.pl_ldd = dst.ld;
+    op.pl_stats = stats;
+    op.pl_H = src.H;
+    op.pl_W = src.W;
+    op.pl_C = src.C;
+    ops.push_back(op);
+  }
+
+  void pack(int ext, int C, const View& dst, int c_off) {
+    Op op;
+    op.kind = OP_PACK;
+    op.ext = ext;
+    op.pk_C = C;
+    op.pk_dst = dst.p;
+    op.pk_ld = dst.ld;
+    op.pk_coff = c_off;
+    ops.push_back(op);
+  }
+};
+
+}  // namespace
+
+static int build_plan(Generator* G, int B, int H, int W, void* wsbase, size_t* bytes_out, cudaStream_t stream) {
+  const rib_gen_config& c = G->cfg;
+  RIB_REQUIRE(B >= 1 && H >= 16 && W >= 16, "forward: bad batch or image size");
+  const int max_down = std::max(std::max(c.n_down, c.emb_down), c.mask_down);
+  RIB_REQUIRE(H % (1 << max_down) == 0 && W % (1 << max_down) == 0,
+              "forward: H and W must be multiples of " + std::to_string(1 << max_down));
+  PlanBuilder pb(G, wsbase, B);
+  const std::string f = "flow_network_temp.";
+
+  // statistics arena first (zeroed by one memset per forward)
+  Op ms;
+  ms.kind = OP_MEMSET;
+  pb.ops.push_back(ms);
+  const size_t stats_begin = align_up(pb.ws.off, 1024);
+
+  // -- statistics buffers are allocated lazily below; remember the arena start --
+  std::vector<BlockDef> blocks = res_blocks(c);
+
+  // Input staging (padding channels are zeroed once, when the plan is built)
+  View lab = pb.alloc("label", H, W, 32);
+  View emb_in = pb.alloc("emb_in", H, W, 16);
+  View mask_in = pb.alloc("mask_in", H, W, 16);
+  // All statistics live in one contiguous region.
+  const size_t stats_region_begin = align_up(pb.ws.off, 1024);
+  (void)stats_begin;
+  std::vector<double*> blk_xstats;
+  // main-branch statistics: x0, per block: hidden, out (or pooled)
+  double* st_x0 = pb.alloc_stats(c.nf);
+  struct BlkStats {
+    double* hid;
+    double* out;
+    double* pooled;
+  };
+  std::vector<BlkStats> bst(blocks.size());
+  for (size_t i = 0; i < blocks.size(); ++i) {
+    bst[i].hid = pb.alloc_stats(blocks[i].hid);
+    bst[i].out = pb.alloc_stats(blocks[i].cout);
+    bst[i].pooled = pb.alloc_stats(blocks[i].cout);
+  }
+  // mask-network statistics
+  std::map<std::string, double*> mst;
+  for (int br = 0; br < 2; ++br) {
+    const std::string bn = br == 0 ? "down_lbl" : "down_img";
+    for (int i = 0; i <= c.mask_down; ++i) mst[bn + std::to_string(i)] = pb.alloc_stats(mask_nfilt(c, i));
+  }
+  const int mch = mask_nfilt(c, c.mask_down);
+  for (int i = 0; i < c.mask_res; ++i) {
+    mst["res" + std::to_string(i) + "c0"] = pb.alloc_stats(mch);
+    mst["res" + std::to_string(i) + "c1"] = pb.alloc_stats(mch);
+    if (i == 0) mst["res0cs"] = pb.alloc_stats(mch);
+  }
+  for (int k = 0; k < c.mask_down; ++k) mst["up" + std::to_string(k)] = pb.alloc_stats(mask_nfilt(c, c.mask_down - 1 - k));
+  const size_t stats_region_end = pb.ws.off;
+  pb.ops[0].ms_ptr = wsbase ? static_cast<uint8_t*>(wsbase) + stats_region_begin : nullptr;
+  pb.ops[0].ms_bytes = stats_region_end - stats_region_begin;
+
+  // -- inputs --
+  pb.pack(EXT_LABEL, c.label_nc, lab, 0);
+  pb.pack(EXT_FAKE, 3, emb_in, 0);   // cat([img_fake, img_prev])            generator.py:197
+  pb.pack(EXT_PREV, 3, emb_in, 3);
+  pb.pack(EXT_PREV, 3, mask_in, 0);  // cat([img_prev, img_fake, img_final])  generator.py:232
+  pb.pack(EXT_FAKE, 3, mask_in, 3);
+
+  // -- ref_embedding: 5 convs + LeakyReLU (generator.py:360-377) --
+  std::vector<View> cond;
+  {
+    View prev = emb_in;
+    for (int i = 0; i <= c.emb_down; ++i) {
+      const int h = H >> i, w = W >> i;
+      View o = pb.alloc("cond_" + std::to_string(i), h, w, emb_ch(c, i));
+      pb.conv_store("emb_" + std::to_string(i), prev, nullptr, i == 0 ? 1 : 2, o, nullptr, ACT_LRELU, nullptr);
+      cond.push_back(o);
+      prev = o;
+    }
+  }
+  // -- main branch --
+  View x = pb.alloc("down_first", H, W, c.nf);
+  pb.conv_store("down_first", lab, nullptr, 1, x, st_x0, ACT_NONE, nullptr);
+  const double* xst = st_x0;
+  bool x_ups = false;
+  int lvl_h = H, lvl_w = W;  // resolution at which the current block runs
+  for (size_t bi = 0; bi < blocks.size(); ++bi) {
+    const BlockDef& b = blocks[bi];
+    const bool is_down = b.name.compare(0, 5, "down_") == 0;
+    const bool is_up = b.name.compare(0, 3, "up_") == 0;
+    const int idx = std::stoi(b.name.substr(b.name.find('_') + 1));
+    const View& cd = cond[b.lvl];
+    if (cd.H != lvl_h || cd.W != lvl_w) {
+      set_error("plan: cond map resolution mismatch at " + b.name);
+      return -4;
+    }
+    View a0 = pb.alloc(b.name + ".a0", lvl_h, lvl_w, b.cin);
+    View as;
+    View outsA[2] = {a0, a0};
+    int actsA[2] = {ACT_LRELU, ACT_NONE};
+    if (b.shortcut) {
+      as = pb.alloc(b.name + ".as", lvl_h, lvl_w, b.cin);
+      outsA[1] = as;
+    }
+    pb.spade(b.name + ".spadeA", cd, x, xst, x_ups, b.shortcut ? 2 : 1, outsA, actsA);
+    View hbuf = pb.alloc(b.name + ".h", lvl_h, lvl_w, b.hid);
+    pb.conv_store(b.name + ".conv0", a0, nullptr, 1, hbuf, bst[bi].hid, ACT_NONE, nullptr);
+    View a1 = pb.alloc(b.name + ".a1", lvl_h, lvl_w, b.hid);
+    View outsB[1] = {a1};
+    int actsB[1] = {ACT_LRELU};
+    pb.spade(b.name + ".spadeB", cd, hbuf, bst[bi].hid, false, 1, outsB, actsB);
+    View o = pb.alloc(b.name, lvl_h, lvl_w, b.cout);
+    const bool last = (bi + 1 == blocks.size());
+    const bool pooled_next = is_down && idx != c.n_down;
+    double* ost = (last || pooled_next) ? nullptr : bst[bi].out;
+    // up_0 feeds conv_img through a LeakyReLU (conv_img order 'AC', generator.py:114-116)
+    pb.conv_store(b.name + ".conv1", a1, b.shortcut ? &as : nullptr, 1, o, ost, last ? ACT_LRELU : ACT_NONE,
+                  b.shortcut ? nullptr : &x);
+    if (pooled_next) {  // AvgPool2d(3, 2, 1)  generator.py:207-208
+      lvl_h /= 2;
+      lvl_w /= 2;
+      View pl = pb.alloc(b.name + ".pool", lvl_h, lvl_w, b.cout);
+      pb.pool(o, pl, bst[bi].pooled);
+      x = pl;
+      xst = bst[bi].pooled;
+      x_ups = false;
+    } else {
+      x = o;
+      xst = bst[bi].out;
+      x_ups = false;
+      if (is_up && idx != 0) {  // nearest x2 (generator.py:248-249): gathered by the next block's SPADE epilogue
+        x_ups = true;
+        lvl_h *= 2;
+        lvl_w *= 2;
+      }
+    }
+  }
+  // -- final image: tanh(conv_img(lrelu(x)))  generator.py:228 --
+  View img_slot = PlanBuilder::slice(mask_in, 6, 3);
+  pb.conv_final("conv_img", x, ACT_TANH, EXT_OUT_IMG, &img_slot);
+
+  // -- mask network (generator.py:493-510) --
+  View cat = pb.alloc("mask.cat", H >> c.mask_down, W >> c.mask_down, 2 * mch);
+  for (int br = 0; br < 2; ++br) {
+    const std::string bn = br == 0 ? "down_lbl" : "down_img";
+    View cur = br == 0 ? lab : mask_in;
+    for (int i = 0; i <= c.mask_down; ++i) {
+      const int h = H >> i, w = W >> i, ch = mask_nfilt(c, i);
+      const std::string nm = "mask." + bn + "." + std::to_string(i);
+      View raw = pb.alloc(nm + ".raw", h, w, ch);
+      double* st = mst[bn + std::to_string(i)];
+      pb.conv_store(nm, cur, nullptr, i == 0 ? 1 : 2, raw, st, ACT_NONE, nullptr);
+      View o = (i == c.mask_down) ? PlanBuilder::slice(cat, br * mch, mch) : pb.alloc(nm, h, w, ch);
+      pb.in_apply(raw, st, f + bn + "." + std::to_string(i) + ".layers.norm", nullptr, nullptr, "", o, 1, false);
+      cur = o;
+    }
+  }
+  View r = cat;
+  const int rh = H >> c.mask_down, rw = W >> c.mask_down;
+  for (int i = 0; i < c.mask_res; ++i) {
+    const std::string rn = "mask.res." + std::to_string(i), rp = f + "res_flow." + std::to_string(i);
+    View raw0 = pb.alloc(rn + ".raw0", rh, rw, mch);
+    pb.conv_store(rn + ".conv0", r, nullptr, 1, raw0, mst["res" + std::to_string(i) + "c0"], ACT_NONE, nullptr);
+    View t0 = pb.alloc(rn + ".t0", rh, rw, mch);
+    pb.in_apply(raw0, mst["res" + std::to_string(i) + "c0"], rp + ".conv_block_0.layers.norm", nullptr, nullptr, "", t0, 1, false);
+    View raw1 = pb.alloc(rn + ".raw1", rh, rw, mch);
+    pb.conv_store(rn + ".conv1", t0, nullptr, 1, raw1, mst["res" + std::to_string(i) + "c1"], ACT_NONE, nullptr);
+    const bool last = (i + 1 == c.mask_res);
+    // the last block's output is only consumed through nn.Upsample(2): store it up-sampled
+    View o = last ? pb.alloc(rn, 2 * rh, 2 * rw, mch) : pb.alloc(rn, rh, rw, mch);
+    if (i == 0) {
+      View raws = pb.alloc(rn + ".raws", rh, rw, mch);
+      pb.conv_store(rn + ".convs", r, nullptr, 1, raws, mst["res0cs"], ACT_NONE, nullptr);
+      pb.in_apply(raw1, mst["res0c1"], rp + ".conv_block_1.layers.norm", &raws, mst["res0cs"],
+                  rp + ".conv_block_s.layers.norm", o, 0, last);
+    } else {
+      pb.in_apply(raw1, mst["res" + std::to_string(i) + "c1"], rp + ".conv_block_1.layers.norm", &r, nullptr, "", o, 0, last);
+    }
+    r = o;
+  }
+  for (int k = 0; k < c.mask_down; ++k) {
+    const int i = c.mask_down - 1 - k;
+    const int h = H >> i, w = W >> i, ch = mask_nfilt(c, i);
+    const std::string nm = "mask.up." + std::to_string(k);
+    View raw = pb.alloc(nm + ".raw", h, w, ch);
+    pb.conv_store(nm, r, nullptr, 1, raw, mst["up" + std::to_string(k)], ACT_NONE, nullptr);
+    const bool ups = (k + 1 != c.mask_down);
+    View o = pb.alloc(nm, ups ? 2 * h : h, ups ? 2 * w : w, ch);
+    pb.in_apply(raw, mst["up" + std::to_string(k)], f + "up_flow." + std::to_string(2 * k + 1) + ".layers.norm", nullptr, nullptr,
+                "", o, 1, ups);
+    r = o;
+  }
+  pb.conv_final("mask.conv_mask", r, ACT_SIGMOID, EXT_OUT_MASK, nullptr);
+
+  if (pb.rc) return pb.rc;
+  *bytes_out = align_up(pb.ws.off, 1024);
+  if (wsbase) {
+    // zero the staging buffers once so that their padding channels read as 0
+    RIB_CHECK_CUDA(cudaMemsetAsync(lab.p, 0, (size_t)B * H * W * 32 * sizeof(act_t), stream));
+    RIB_CHECK_CUDA(cudaMemsetAsync(emb_in.p, 0, (size_t)B * H * W * 16 * sizeof(act_t), stream));
+    RIB_CHECK_CUDA(cudaMemsetAsync(mask_in.p, 0, (size_t)B * H * W * 16 * sizeof(act_t), stream));
+    G->ops.swap(pb.ops);
+    G->debug_views.swap(pb.views);
+    G->pB = B;
+    G->pH = H;
+    G->pW = W;
+    G->pws = wsbase;
+    G->ws_bytes_needed = *bytes_out;
+    G->plan_simt = g_debug_simt != 0;
+  }
+  return 0;
+}
+
+long long generator_workspace_bytes(Generator* G, int B, int H, int W) {
+  size_t bytes = 0;
+  int rc = build_plan(G, B, H, W, nullptr, &bytes, nullptr);
+  if (rc) return rc;
+  return (long long)bytes;
+}
+
+static std::atomic<long long> g_misc_launches{0};
+long long misc_launch_count() { return g_misc_launches.load(); }
+void count_misc_launch(int n) { g_misc_launches.fetch_add(n); }
+
+int generator_forward(Generator* G, int B, int H, int W, const float* label, const float* img_fake,
+                      const float* img_prev, float* out_img, float* out_mask, void* ws, long long ws_bytes,
+                      cudaStream_t stream) {
+  RIB_REQUIRE(G && label && img_fake && img_prev && out_img && out_mask && ws, "forward: null argument");
+  RIB_REQUIRE(((uintptr_t)ws & 1023) == 0, "forward: workspace must be 1024-byte aligned");
+  if (G->pB != B || G->pH != H || G->pW != W || G->pws != ws || G->plan_simt != (g_debug_simt != 0)) {
+    size_t need = 0;
+    int rc = build_plan(G, B, H, W, nullptr, &need, nullptr);
+    if (rc) return rc;
+    RIB_REQUIRE((long long)need <= ws_bytes, "forward: workspace too small");
+    rc = build_plan(G, B, H, W, ws, &need, stream);
+    if (rc) return rc;
+  }
+  RIB_REQUIRE((long long)G->ws_bytes_needed <= ws_bytes, "forward: workspace too small");
+  for (const Op& op : G->ops) {
+    int rc = 0;
+    switch (op.kind) {
+      case OP_MEMSET:
+        RIB_CHECK_CUDA(cudaMemsetAsync(op.ms_ptr, 0, op.ms_bytes, stream));
+        break;
+      case OP_PACK: {
+        const float* src = op.ext == EXT_LABEL ? label : (op.ext == EXT_FAKE ? img_fake : img_prev);
+        rc = launch_pack_nchw(src, op.pk_C, op.pk_dst, op.pk_ld, op.pk_coff, B, H, W, stream);
+        count_misc_launch(1);
+        break;
+      }
+      case OP_GEMM: {
+        if (op.mode == EPI_FINAL) {
+          ConvGemmParams p = op.g;
+          p.out_f32 = op.ext == EXT_OUT_IMG ? out_img : out_mask;
+          rc = launch_conv_gemm(p, op.mode, stream);
+        } else {
+          rc = launch_conv_gemm(op.g, op.mode, stream);
+        }
+        break;
+      }
+      case OP_IN_APPLY:
+        rc = launch_in_apply(op.ia, stream);
+        count_misc_launch(1);
+        break;
+      case OP_POOL:
+        rc = launch_avgpool3s2(op.pl_src, op.pl_lds, op.pl_dst, op.pl_ldd, op.pl_stats, B, op.pl_H, op.pl_W, op.pl_C,
+                               stream);
+        count_misc_launch(1);
+        break;
+    }
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int generator_debug_tensor(Generator* G, const char* name, const void** ptr, int* B, int* H, int* W, int* C,
+                           int* ld) {
+  auto it = G->debug_views.find(name);
+  if (it == G->debug_views.end()) {
+    set_error(std::string("no such plan tensor: ") + name);
+    return -1;
+  }
+  *ptr = it->second.p;
+  *B = it->second.B;
+  *H = it->second.H;
+  *W = it->second.W;
+  *C = it->second.C;
+  *ld = it->second.ld;
+  return 0;
+}
+
+// ---- stand-alone conv for unit tests ----------------------------------------------------------
+long long conv_test_scratch_bytes(int Cin, int Cout, int k) {
+  return (long long)(align_up((size_t)Cout * Cin * k * k * sizeof(act_t), 256) + align_up((size_t)Cout * 4, 256) + 1024);
+}
+
+int conv_test(const void* x, const float* w, const float* bias, void* out, double* stats, int B, int Hin, int Win,
+              int Cin, int Cout, int k, int stride, int act, void* scratch, cudaStream_t stream) {
+  RIB_REQUIRE(Cin % 16 == 0 && Cout % 16 == 0, "conv_test: channels must be multiples of 16");
+  RIB_REQUIRE((k == 1 || k == 3) && (stride == 1 || stride == 2), "conv_test: unsupported kernel/stride");
+  RIB_REQUIRE(Cin <= 64 || Cin % 64 == 0, "conv_test: Cin must be 16, 32, 64 or a multiple of 64");
+  Generator G;  // a throw-away holder for one layer
+  GemmLayer L;
+  L.name = "test";
+  L.n_valid = L.n_pad = Cout;
+  L.cin0 = Cin;
+  L.taps = k * k;
+  L.cin1 = 0;
+  L.ktotal = Cin * k * k;
+  uint8_t* sp = static_cast<uint8_t*>(scratch);
+  sp = reinterpret_cast<uint8_t*>(align_up((size_t)(uintptr_t)sp, 256));
+  L.w = reinterpret_cast<act_t*>(sp);
+  L.bias = reinterpret_cast<float*>(sp + align_up((size_t)Cout * L.ktotal * sizeof(act_t), 256));
+  G.layers["test"] = L;
+  RIB_CHECK_CUDA(cudaMemsetAsync(L.bias, 0, (size_t)Cout * 4, stream));
+  PackWeightParams pp;
+  memset(&pp, 0, sizeof(pp));
+  pp.w = w;
+  pp.bias = bias;
+  pp.Cout = Cout;
+  pp.Cin = Cin;
+  pp.taps = k * k;
+  pp.dst = L.w;
+  pp.bias_dst = L.bias;
+  pp.ktotal = L.ktotal;
+  pp.cin_pad = Cin;
+  int rc = launch_pack_weight(pp, stream);
+  if (rc) return rc;
+  PlanBuilder pb(&G, scratch, B);  // non-null base => builds real tensor maps; no allocation is made
+  View in;
+  in.p = static_cast<act_t*>(const_cast<void*>(x));
+  in.B = B;
+  in.H = Hin;
+  in.W = Win;
+  in.C = in.ld = Cin;
+  View o;
+  o.p = static_cast<act_t*>(out);
+  o.B = B;
+  o.H = Hin / stride;
+  o.W = Win / stride;
+  o.C = o.ld = Cout;
+  pb.conv_store("test", in, nullptr, stride, o, stats, act, nullptr);
+  if (pb.rc) return pb.rc;
+  return launch_conv_gemm(pb.ops[0].g, EPI_STORE, stream);
+}
+
+}  // namespace rib

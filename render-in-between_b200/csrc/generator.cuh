@@ -1,0 +1,24 @@
+// Generator plan / forward (declarations).  See generator.cu.
+#pragma once
+#include "common.cuh"
+#include "../../include/rib_b200.h"
+
+namespace rib {
+
+struct Generator;
+extern int g_debug_simt;
+
+int generator_create(const rib_gen_config* cfg, const rib_tensor* tensors, int n, cudaStream_t stream, Generator** out);
+void generator_destroy(Generator* g);
+long long generator_workspace_bytes(Generator* g, int B, int H, int W);
+int generator_forward(Generator* g, int B, int H, int W, const float* label, const float* img_fake,
+                      const float* img_prev, float* out_img, float* out_mask, void* ws, long long ws_bytes,
+                      cudaStream_t stream);
+int generator_debug_tensor(Generator* g, const char* name, const void** ptr, int* B, int* H, int* W, int* C, int* ld);
+long long conv_test_scratch_bytes(int Cin, int Cout, int k);
+int conv_test(const void* x, const float* w, const float* bias, void* out, double* stats, int B, int Hin, int Win,
+              int Cin, int Cout, int k, int stride, int act, void* scratch, cudaStream_t stream);
+long long misc_launch_count();
+void count_misc_launch(int n);
+
+}  // namespace rib

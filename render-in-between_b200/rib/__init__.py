@@ -1,0 +1,28 @@
+"""rib — B200-native hot path of Render-In-Between's pose-guided renderer.
+
+Public surface (mirrors the reference's names for this path):
+    Generator(gen_cfg).forward(label, label_prev, img_fake, img_prev)   models/generator.py
+    rasterize / warp / composite                                        evaluator.py, HSM_auto_dataset.py
+    ClipRenderer                                                        evaluator.py:238-266 (AR loop)
+    get_config / default_gen_cfg                                        utils/utils.py:77-79
+"""
+from .config import AttrDict, default_gen_cfg, get_config  # noqa: F401
+from .arch import Arch  # noqa: F401
+
+
+def __getattr__(name):
+    # CUDA-backed symbols load the shared library on first use, so that pure-host helpers
+    # (config, arch, synth) stay importable without it; using them without the library raises.
+    if name in ('Generator',):
+        from .generator import Generator
+        return Generator
+    if name in ('rasterize', 'warp', 'composite', 'gaussian_taps'):
+        from . import ops
+        return getattr(ops, name)
+    if name in ('ClipRenderer',):
+        from .clip import ClipRenderer
+        return ClipRenderer
+    if name == 'lib':
+        from ._lib import lib
+        return lib
+    raise AttributeError(name)

@@ -1,0 +1,76 @@
+"""ctypes binding of librib_b200.so (C ABI declared in include/rib_b200.h).
+
+The extension is the product: there is no Python/PyTorch fallback.  If the shared library is
+missing or fails to load, importing this module raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'librib_b200.so')
+
+# every symbol include/rib_b200.h declares
+SYMBOLS = [
+    'rib_last_error', 'rib_abi_version', 'rib_kernel_launch_count', 'rib_rasterize', 'rib_warp', 'rib_composite',
+    'rib_generator_create', 'rib_generator_destroy', 'rib_generator_workspace_bytes', 'rib_generator_forward',
+    'rib_debug_set_simt', 'rib_debug_get_simt', 'rib_generator_debug_tensor', 'rib_act_is_fp16',
+    'rib_conv_test_scratch_bytes', 'rib_conv_test',
+]
+
+
+class GenConfig(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        'label_nc', 'img_nc', 'nf', 'maxf', 'n_down', 'n_res', 'emb_nf', 'emb_max', 'emb_down',
+        'mask_nf', 'mask_max', 'mask_down', 'mask_res')]
+
+
+class Tensor(C.Structure):
+    _fields_ = [('name', C.c_char_p), ('data', C.c_void_p), ('numel', C.c_longlong)]
+
+
+def _load():
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(
+            'rib: %s not found - build it with `python -c "import __graft_entry__ as g; g.build()"` '
+            '(there is no fallback path)' % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, f64 = C.c_void_p, C.c_int, C.c_longlong, C.c_double
+    lib.rib_last_error.restype = C.c_char_p
+    lib.rib_last_error.argtypes = []
+    lib.rib_abi_version.restype = i32
+    lib.rib_kernel_launch_count.restype = i64
+    lib.rib_rasterize.restype = i32
+    lib.rib_rasterize.argtypes = [vp, i32, i32, i32, C.POINTER(f64), f64, f64, vp, vp]
+    lib.rib_warp.restype = i32
+    lib.rib_warp.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
+    lib.rib_composite.restype = i32
+    lib.rib_composite.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp]
+    lib.rib_generator_create.restype = i32
+    lib.rib_generator_create.argtypes = [C.POINTER(GenConfig), C.POINTER(Tensor), i32, vp, C.POINTER(vp)]
+    lib.rib_generator_destroy.restype = None
+    lib.rib_generator_destroy.argtypes = [vp]
+    lib.rib_generator_workspace_bytes.restype = i64
+    lib.rib_generator_workspace_bytes.argtypes = [vp, i32, i32, i32]
+    lib.rib_generator_forward.restype = i32
+    lib.rib_generator_forward.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, i64, vp]
+    lib.rib_debug_set_simt.restype = None
+    lib.rib_debug_set_simt.argtypes = [i32]
+    lib.rib_debug_get_simt.restype = i32
+    lib.rib_generator_debug_tensor.restype = i32
+    lib.rib_generator_debug_tensor.argtypes = [vp, C.c_char_p, C.POINTER(vp)] + [C.POINTER(i32)] * 5
+    lib.rib_act_is_fp16.restype = i32
+    lib.rib_conv_test_scratch_bytes.restype = i64
+    lib.rib_conv_test_scratch_bytes.argtypes = [i32, i32, i32]
+    lib.rib_conv_test.restype = i32
+    lib.rib_conv_test.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]
+    return lib
+
+
+lib = _load()
+
+
+def check(rc, what):
+    """Non-zero C return codes become RuntimeError (the reference raises Python exceptions)."""
+    if rc != 0:
+        msg = lib.rib_last_error()
+        raise RuntimeError('%s failed (%d): %s' % (what, rc, msg.decode() if msg else ''))

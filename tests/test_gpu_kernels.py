@@ -1,0 +1,174 @@
+"""GPU parity tests of the individual kernels, through the C ABI, against the CPU oracle."""
+import ctypes as C
+import glob
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import generator_oracle as go
+from oracle import raster_oracle as ro
+from rib.synth import synth_flow, synth_image, synth_joints
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+    return torch.device('cuda:0')
+
+
+# ---------------------------------------------------------------- A1 rasteriser (bit-exact)
+def test_rasterize_golden_bit_exact(dev, golden_dir):
+    import rib
+    for f in sorted(glob.glob(os.path.join(golden_dir, 'raster_[0-9].npz'))):
+        z = np.load(f)
+        h, w = int(z['height']), int(z['width'])
+        j = torch.from_numpy(z['joints'])[None].to(dev)
+        lab = rib.rasterize(j, h, w).cpu().numpy()[0]
+        ref = z['label']
+        bad = np.argwhere(lab != ref)
+        assert bad.shape[0] == 0, '%s: %d mismatching elements, first %s got %r want %r' % (
+            os.path.basename(f), bad.shape[0], bad[:1], lab[tuple(bad[0])] if len(bad) else None,
+            ref[tuple(bad[0])] if len(bad) else None)
+
+
+def test_rasterize_fullsize_hash_and_oracle(dev, golden_dir):
+    import rib
+    spec = json.load(open(os.path.join(golden_dir, 'raster_fullsize_sha256.json')))
+    for s in spec:
+        h, w = s['height'], s['width']
+        j = synth_joints(s['n_frames'], h, w, seed=s['seed'])
+        lab = rib.rasterize(torch.from_numpy(j).to(dev), h, w).cpu().numpy()
+        for t in range(s['n_frames']):
+            got = hashlib.sha256(np.ascontiguousarray(lab[t]).tobytes()).hexdigest()
+            if got != s['sha256'][t]:   # locate the damage with the oracle before failing
+                ref = ro.label([(a[0], a[1]) for a in j[t]], [a[2] for a in j[t]], h, w)
+                bad = np.argwhere(lab[t] != ref)
+                pytest.fail('%dx%d frame %d: hash mismatch, %d elements differ from the oracle, channels %s' % (
+                    h, w, t, bad.shape[0], sorted(set(bad[:, 0].tolist()))))
+
+
+def test_rasterize_batch_edge_cases(dev):
+    import rib
+    h, w = 64, 80
+    j = np.zeros((3, 19, 3))
+    j[0, :, 2] = 0.0                                   # nothing valid -> skeleton all -1, heat-maps 0
+    j[1] = synth_joints(1, h, w, seed=11)[0]
+    j[1, :, 2] = 1.0
+    j[2] = j[1]
+    j[2, :, 0] += 0.25                                 # same pose shifted by a sub-pixel amount
+    lab = rib.rasterize(torch.from_numpy(j).to(dev), h, w).cpu().numpy()
+    assert (lab[0, :3] == -1.0).all() and (lab[0, 3:] == 0.0).all()
+    for t in (1, 2):
+        ref = ro.label([(a[0], a[1]) for a in j[t]], [a[2] for a in j[t]], h, w)
+        assert np.array_equal(lab[t], ref)
+
+
+# ---------------------------------------------------------------- A4 composite
+def test_composite_matches_oracle(dev):
+    import rib
+    g = torch.Generator().manual_seed(0)
+    b, h, w = 3, 64, 96
+    img = torch.rand(b, 3, h, w, generator=g) * 2 - 1
+    dain = torch.rand(b, 3, h, w, generator=g) * 2.4 - 1.2
+    mask = torch.rand(b, 1, h, w, generator=g)
+    ref = go.composite(img, mask, dain)
+    out, u8 = rib.composite(img.to(dev), mask.to(dev), dain.to(dev), want_u8=True)
+    assert (out.cpu() - ref).abs().max().item() <= 1e-6       # tolerance stated in SURVEY.md §8c
+    assert torch.equal(out.cpu(), ref)                         # and in fact bit-exact (same roundings)
+    assert torch.equal(u8.cpu(), go.to_uint8(ref))
+
+
+# ---------------------------------------------------------------- A3 warp
+def test_warp_matches_grid_sample(dev):
+    import rib
+    b, h, w = 2, 64, 96
+    src = synth_image(b, h, w, seed=5)
+    flow = synth_flow(b, h, w, seed=5, max_px=8.0)
+    flow[0, :, :4, :4] = 50.0          # far out of range -> border clamp
+    flow[1, :, -4:, -4:] = -50.0
+    ref = go.warp(src, flow)
+    out = rib.warp(src.to(dev), flow.to(dev)).cpu()
+    assert (out - ref).abs().max().item() <= 1e-5
+    zero = rib.warp(src.to(dev), torch.zeros_like(flow).to(dev)).cpu()
+    assert (zero - src).abs().max().item() <= 1e-6            # identity flow
+
+
+# ---------------------------------------------------------------- implicit-GEMM convolution
+def _act_dtype():
+    from rib._lib import lib
+    return torch.float16 if lib.rib_act_is_fp16() else torch.bfloat16
+
+
+def _run_conv(dev, x_nchw, w, bias, k, stride, act, want_stats, simt):
+    from rib._lib import check, lib
+    dt = _act_dtype()
+    b, cin, h, wd = x_nchw.shape
+    cout = w.shape[0]
+    x = x_nchw.permute(0, 2, 3, 1).contiguous().to(dt).to(dev)
+    out = torch.zeros(b, h // stride, wd // stride, cout, dtype=dt, device=dev)
+    stats = torch.zeros(b, cout, 2, dtype=torch.float64, device=dev) if want_stats else None
+    scratch = torch.empty(lib.rib_conv_test_scratch_bytes(cin, cout, k) + 1024, dtype=torch.uint8, device=dev)
+    wd_, bd_ = w.contiguous().to(dev), bias.contiguous().to(dev)
+    lib.rib_debug_set_simt(1 if simt else 0)
+    try:
+        check(lib.rib_conv_test(x.data_ptr(), wd_.data_ptr(), bd_.data_ptr(), out.data_ptr(),
+                                stats.data_ptr() if want_stats else None, b, h, wd, cin, cout, k, stride, act,
+                                scratch.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream)), 'rib_conv_test')
+        torch.cuda.synchronize()
+    finally:
+        lib.rib_debug_set_simt(0)
+    return out.float().cpu().permute(0, 3, 1, 2), (stats.cpu() if want_stats else None)
+
+
+CONV_CASES = [
+    # (B, Cin, Cout, H, W, k, stride)
+    (1, 16, 16, 16, 16, 3, 1),     # one tile, BK=16 (SW32), BN=16
+    (2, 32, 32, 16, 32, 3, 1),     # BK=32 (SW64)
+    (1, 64, 64, 32, 32, 3, 1),     # BK=64 (SW128)
+    (1, 128, 256, 16, 16, 3, 1),   # two K chunks per tap, two N tiles
+    (2, 64, 128, 32, 32, 3, 2),    # stride 2 through the four parity views
+    (1, 512, 64, 16, 16, 1, 1),    # 1x1 (SPADE-shaped K)
+    (1, 32, 16, 20, 30, 3, 1),     # ragged: H, W not multiples of the tile (HSM.yaml's 320x480 / 16)
+    (1, 16, 32, 64, 96, 3, 2),     # stride 2, BK=16
+]
+
+
+@pytest.mark.parametrize('simt', [True, False], ids=['simt', 'tcgen05'])
+@pytest.mark.parametrize('case', CONV_CASES, ids=lambda c: 'B%d_%dto%d_%dx%d_k%ds%d' % c)
+def test_conv_gemm_matches_conv2d(dev, case, simt):
+    b, cin, cout, h, w, k, stride = case
+    dt = _act_dtype()
+    g = torch.Generator().manual_seed(cin * 1000 + cout + h)
+    x = torch.randn(b, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    # reference on the same 16-bit-rounded operands, fp32 math (the kernel accumulates in fp32)
+    xr, wr = x.to(dt).float(), wt.to(dt).float()
+    ref = F.conv2d(xr, wr, bias, stride=stride, padding=k // 2)
+    out, stats = _run_conv(dev, x, wt, bias, k, stride, act=0, want_stats=True, simt=simt)
+    err = (out - ref).abs()
+    tol = 2.0 ** -7 * ref.abs() + 2e-3        # one 16-bit rounding of the output + accumulation order
+    assert bool((err <= tol).all()), 'max err %.4g at %s (ref %.4g)' % (
+        err.max().item(), np.unravel_index(err.argmax().item(), err.shape), ref.flatten()[err.argmax()].item())
+    # instance-norm statistics from the epilogue (computed on the un-rounded fp32 accumulators)
+    s_ref = torch.stack([ref.double().sum(dim=(2, 3)), (ref.double() ** 2).sum(dim=(2, 3))], dim=2)
+    assert torch.allclose(stats, s_ref, rtol=2e-3, atol=2e-2), (stats - s_ref).abs().max().item()
+
+
+def test_conv_gemm_lrelu_epilogue(dev):
+    b, cin, cout, h, w = 1, 32, 32, 16, 16
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(b, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
+    bias = torch.zeros(cout)
+    dt = _act_dtype()
+    ref = F.leaky_relu(F.conv2d(x.to(dt).float(), wt.to(dt).float(), bias, padding=1), 0.2)
+    out, _ = _run_conv(dev, x, wt, bias, 3, 1, act=1, want_stats=False, simt=False)
+    assert bool(((out - ref).abs() <= 2.0 ** -7 * ref.abs() + 2e-3).all())
