@@ -94,6 +94,13 @@ int rib_generator_forward(rib_generator* g, int B, int H, int W, const float* la
                           const float* img_prev, float* out_img, float* out_mask, void* workspace,
                           long long workspace_bytes, void* stream);
 
+/* ---- measurement hooks (bench.py's roofline pass) ---------------------------------------------
+ * While enabled, every launch of the implicit-GEMM convolution kernel is bracketed by CUDA events
+ * on its stream; rib_profile_collect() synchronises them and returns the summed device time and
+ * the number of launches since the last collect. */
+void rib_profile_enable(int enable);
+int rib_profile_collect(double* conv_ms, long long* conv_launches);
+
 /* ---- bring-up / test hooks (not part of the drop-in surface) ----------------------------------
  * rib_debug_set_simt(1) replaces the tcgen05 main loop by a plain-FMA loop (same tiles and
  * epilogues); used by the tests to bisect tensor-core problems.  Never set by bench.py. */

@@ -86,6 +86,14 @@ int rib_generator_forward(rib_generator* g, int B, int H, int W, const float* la
   RIB_GUARD_END
 }
 
+void rib_profile_enable(int enable) { conv_gemm_profile_enable(enable); }
+int rib_profile_collect(double* conv_ms, long long* conv_launches) {
+  RIB_GUARD_BEGIN
+  RIB_REQUIRE(conv_ms && conv_launches, "rib_profile_collect: null argument");
+  return conv_gemm_profile_collect(conv_ms, conv_launches);
+  RIB_GUARD_END
+}
+
 void rib_debug_set_simt(int enable) { rib::g_debug_simt = enable ? 1 : 0; }
 int rib_debug_get_simt(void) { return rib::g_debug_simt; }
 

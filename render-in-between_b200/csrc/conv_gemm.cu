@@ -7,6 +7,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <vector>
 
 namespace rib {
 
@@ -442,6 +443,31 @@ size_t conv_gemm_smem_bytes(const ConvGemmParams& p) {
 static std::atomic<long long> g_launches{0};
 long long conv_gemm_launch_count() { return g_launches.load(); }
 
+// Optional per-launch CUDA-event timing of the implicit-GEMM kernel (bench.py's roofline pass).
+static bool g_profile = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+static std::mutex g_prof_mutex;
+void conv_gemm_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mutex);
+  g_profile = on != 0;
+}
+int conv_gemm_profile_collect(double* total_ms, long long* launches) {
+  std::lock_guard<std::mutex> lk(g_prof_mutex);
+  double ms = 0.0;
+  for (auto& ev : g_prof_events) {
+    RIB_CHECK_CUDA(cudaEventSynchronize(ev.second));
+    float t = 0.f;
+    RIB_CHECK_CUDA(cudaEventElapsedTime(&t, ev.first, ev.second));
+    ms += t;
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
+  *total_ms = ms;
+  *launches = (long long)g_prof_events.size();
+  g_prof_events.clear();
+  return 0;
+}
+
 int launch_conv_gemm(const ConvGemmParams& p, int mode, cudaStream_t stream) {
   RIB_REQUIRE(p.TW * p.TH == kTileM, "conv_gemm: spatial tile must hold 128 pixels");
   RIB_REQUIRE(p.BK == 16 || p.BK == 32 || p.BK == 64, "conv_gemm: BK must be 16/32/64");
@@ -468,10 +494,21 @@ int launch_conv_gemm(const ConvGemmParams& p, int mode, cudaStream_t stream) {
   RIB_CHECK_CUDA(attr_err);
   dim3 grid((unsigned)p.n_tiles, (unsigned)(p.tiles_x * p.tiles_y), (unsigned)p.B);
   dim3 block(kThreads);
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (g_profile) {
+    RIB_CHECK_CUDA(cudaEventCreate(&ev0));
+    RIB_CHECK_CUDA(cudaEventCreate(&ev1));
+    RIB_CHECK_CUDA(cudaEventRecord(ev0, stream));
+  }
   if (mode == EPI_STORE) conv_gemm_kernel<EPI_STORE><<<grid, block, smem, stream>>>(p);
   else if (mode == EPI_SPADE) conv_gemm_kernel<EPI_SPADE><<<grid, block, smem, stream>>>(p);
   else conv_gemm_kernel<EPI_FINAL><<<grid, block, smem, stream>>>(p);
   RIB_CHECK_CUDA(cudaGetLastError());
+  if (g_profile) {
+    RIB_CHECK_CUDA(cudaEventRecord(ev1, stream));
+    std::lock_guard<std::mutex> lk(g_prof_mutex);
+    g_prof_events.push_back({ev0, ev1});
+  }
   g_launches.fetch_add(1);
   return 0;
 }

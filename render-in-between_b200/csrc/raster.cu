@@ -105,10 +105,6 @@ __constant__ unsigned char c_colors[18][3] = {{153, 0, 51}, {153, 0, 0}, {153, 5
                                               {0, 153, 153}, {0, 102, 153}, {0, 51, 153}, {0, 0, 153}, {208, 208, 0},
                                               {0, 208, 0}, {0, 208, 208}, {0, 0, 208}};
 
-struct SkelShared {
-  int npts;
-};
-
 __device__ __forceinline__ uint32_t avg_color(uint32_t old, uint32_t col) {
   // per channel (v + c) >> 1 on packed 0x00BBGGRR; channels are <= 255 so (v + c) fits in 9 bits
   const uint32_t r = (((old & 0xffu) + (col & 0xffu)) >> 1);
@@ -131,7 +127,6 @@ __global__ void __launch_bounds__(256) skeleton_kernel(const double* __restrict_
   int* s_py = s_px + max(H, W);
   __shared__ double s_pts[19][2];
   __shared__ float s_lut[256];
-  __shared__ int s_n;
 
   for (int i = threadIdx.x; i < nwords; i += blockDim.x) s_bits[i] = 0u;
   for (int i = threadIdx.x; i < rows * W; i += blockDim.x) s_val[i] = 0u;
@@ -266,10 +261,10 @@ int launch_rasterize(const double* joints_dev, int B, int H, int W, const double
   const int bands = ceil_div(H, band_rows);
   band_rows = ceil_div(H, bands);
   const size_t smem = fixed + (size_t)band_rows * W * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
-    RIB_CHECK_CUDA(cudaFuncSetAttribute(skeleton_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+  static size_t attr_smem = 0;  // the kernel also has ~1.4 KB of static shared memory
+  if (smem > attr_smem) {
+    RIB_CHECK_CUDA(cudaFuncSetAttribute(skeleton_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
   }
   skeleton_kernel<<<dim3(bands, B), 256, smem, stream>>>(joints_dev, skeleton_thres, foot_thres, label, H, W, njoints,
                                                          band_rows);

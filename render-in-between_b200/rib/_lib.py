@@ -14,7 +14,7 @@ SYMBOLS = [
     'rib_last_error', 'rib_abi_version', 'rib_kernel_launch_count', 'rib_rasterize', 'rib_warp', 'rib_composite',
     'rib_generator_create', 'rib_generator_destroy', 'rib_generator_workspace_bytes', 'rib_generator_forward',
     'rib_debug_set_simt', 'rib_debug_get_simt', 'rib_generator_debug_tensor', 'rib_act_is_fp16',
-    'rib_conv_test_scratch_bytes', 'rib_conv_test',
+    'rib_conv_test_scratch_bytes', 'rib_conv_test', 'rib_profile_enable', 'rib_profile_collect',
 ]
 
 
@@ -59,6 +59,10 @@ def _load():
     lib.rib_generator_debug_tensor.restype = i32
     lib.rib_generator_debug_tensor.argtypes = [vp, C.c_char_p, C.POINTER(vp)] + [C.POINTER(i32)] * 5
     lib.rib_act_is_fp16.restype = i32
+    lib.rib_profile_enable.restype = None
+    lib.rib_profile_enable.argtypes = [i32]
+    lib.rib_profile_collect.restype = i32
+    lib.rib_profile_collect.argtypes = [C.POINTER(f64), C.POINTER(i64)]
     lib.rib_conv_test_scratch_bytes.restype = i64
     lib.rib_conv_test_scratch_bytes.argtypes = [i32, i32, i32]
     lib.rib_conv_test.restype = i32

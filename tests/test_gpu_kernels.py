@@ -97,7 +97,7 @@ def test_warp_matches_grid_sample(dev):
     out = rib.warp(src.to(dev), flow.to(dev)).cpu()
     assert (out - ref).abs().max().item() <= 1e-5
     zero = rib.warp(src.to(dev), torch.zeros_like(flow).to(dev)).cpu()
-    assert (zero - src).abs().max().item() <= 1e-6            # identity flow
+    assert (zero - src).abs().max().item() <= 1e-5            # identity flow (grid round-trip in fp32)
 
 
 # ---------------------------------------------------------------- implicit-GEMM convolution
