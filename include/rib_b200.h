@@ -106,16 +106,17 @@ int rib_profile_collect(double* conv_ms, long long* conv_launches);
  * epilogues); used by the tests to bisect tensor-core problems.  Never set by bench.py. */
 void rib_debug_set_simt(int enable);
 int rib_debug_get_simt(void);
-/* Looks up an intermediate activation of the last forward plan by name.  16-bit NHWC storage:
- * element (n, y, x, c) at ptr[((n*H + y)*W + x)*ld + c].  Returns 0 if found. */
+/* Looks up an intermediate activation of the last forward plan by name.  16-bit chunk-planar storage
+ * [B][ld/8][H][W][8] (ld = channels of the whole buffer the view is a slice of): element (n, c, y, x) at
+ * ptr[n*ld*H*W + (c/8)*H*W*8 + (y*W + x)*8 + c%8].  Returns 0 if found. */
 int rib_generator_debug_tensor(rib_generator* g, const char* name, const void** ptr, int* B, int* H, int* W, int* C,
                                int* ld);
 /* 1 if activations are stored as IEEE fp16, 0 for bf16. */
 int rib_act_is_fp16(void);
 /* Stand-alone launch of the implicit-GEMM convolution for unit tests:
- *   x    16-bit NHWC [B][Hin][Win][Cin]   (Cin multiple of 16)
+ *   x    16-bit chunk-planar [B][Cin/8][Hin][Win][8]   (Cin 16, 32 or a multiple of 64)
  *   w    f32 [Cout][Cin][k][k], bias f32 [Cout] (may be NULL), k in {1,3}, stride in {1,2}, pad k/2
- *   out  16-bit NHWC [B][Hout][Wout][Cout] (Cout multiple of 16), act: 0 none, 1 leaky-relu 0.2
+ *   out  16-bit chunk-planar [B][Cout/8][Hout][Wout][8] (Cout 16/32/64 or a multiple of 128), act: 0 none, 1 leaky-relu 0.2
  *   stats f64 [B][Cout][2] (may be NULL; accumulated into)
  *   scratch: device buffer of at least rib_conv_test_scratch_bytes() bytes */
 long long rib_conv_test_scratch_bytes(int Cin, int Cout, int k);

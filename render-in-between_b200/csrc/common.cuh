@@ -83,6 +83,9 @@ __device__ __forceinline__ void fence_barrier_init() {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -113,6 +116,19 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2,
@@ -180,6 +196,20 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_
   d |= (uint64_t)(((8u * row_bytes) >> 4) & 0x3fffu) << 32;
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)layout << 61;
+  return d;
+}
+
+// UMMA shared-memory descriptor for a K-major operand in the un-swizzled "interleave" layout:
+// a row is one 16-byte piece (8 elements of K); the 8 rows of a core matrix are contiguous (16-byte
+// pitch); `sbo` = byte stride between consecutive 8-row groups; `lbo` = byte stride between the two
+// 8-element K pieces of one K=16 MMA.  Only 16-byte alignment of the start address is required, which
+// is what lets the 3x3 taps be nine start addresses into one halo tile.
+__device__ __forceinline__ uint64_t make_nosw_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
+  d |= (uint64_t)((lbo >> 4) & 0x3fffu) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3fffu) << 32;
+  d |= (uint64_t)1 << 46;
   return d;
 }
 

@@ -1,18 +1,29 @@
 // Implicit-GEMM convolution on tcgen05 / TMEM fed by TMA (sm_100a) — declarations.
 //
-// One launch computes, for a batch of NHWC 16-bit activation maps,
-//     D[pixel, n] = sum_{tap, c} X0[pixel + tap, c] * Wp[n, (tap, c)]  (+ sum_c X1[pixel, c] * Wp[n, K0 + c])
-// with M = 128 output pixels (a TH x TW spatial tile of one image) per CTA, N = BN output columns,
-// K stepped as (tap, BK-channel chunk).  Zero padding of the 3x3 window comes from TMA
-// out-of-bounds fill; stride-2 convolutions read four parity views of the input.
+// Activations live in HBM as 16-bit "chunk-planar" maps  [B][C/8][H][W][8]  (8 channels = 16 bytes per
+// pixel per plane).  One launch computes, for a batch of such maps,
+//     D[pixel, n] = sum_{tap, c} X0[pixel + tap, c] * Wp[n, (c-group, tap, c)]  (+ sum_c X1[pixel, c] * Wp[n, K0 + c])
+// A CTA is persistent: it walks super-tiles of MT x (16 rows x 8 columns) = MT x 128 output pixels
+// (one tcgen05.mma M=128 per sub-tile), N = BN output columns.
+//
+// A operand: ONE halo tile per channel group, (8+2) x (16*MT+2) pixels x BKc channels, is brought into
+// shared memory by TMA as [BKc/8][halo pixel][8] (no swizzle).  In the K-major "interleave" UMMA layout
+// a row (pixel) is 16 bytes and an 8-row group is one image row of the tile, so the stride between
+// 8-row groups (SBO) is the halo row pitch and the 3x3 taps are nine descriptors that differ only in
+// their start address: every input byte crosses L2 -> SM once instead of nine times.  Zero padding is
+// TMA out-of-bounds fill.  Stride-2 convolutions load four parity views of the input the same way.
+// B operand: packed weights [Npad][Ktotal] (K-major, 32/64/128-byte swizzle); kept resident in shared
+// memory for the life of the CTA when they fit, streamed through the ring otherwise.
+// Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the loads and MMAs of
+// tile i+1.
 //
 // Epilogues (reference semantics each one replaces):
-//   EPI_STORE  bias (+identity residual) -> instance-norm statistics -> activation -> 16-bit NHWC store
+//   EPI_STORE  bias (+identity residual) -> instance-norm statistics -> activation -> 16-bit planar store
 //              conv.py:56-69 (conv [+ nonlinearity]) and residual.py:146-151 (shortcut add)
 //   EPI_SPADE  the GEMM produces [gamma|beta] = conv1x1(cond); the epilogue applies
 //              lrelu?((x - mean) * rstd * (1 + gamma) + beta)   activation_norm.py:211-234
 //              (x may be read through a nearest x2 up-sampling, generator.py:249)
-//   EPI_FINAL  bias -> tanh / sigmoid -> fp32 NCHW (+ optional 16-bit NHWC copy)  generator.py:228, :484-485
+//   EPI_FINAL  bias -> tanh / sigmoid -> fp32 NCHW (+ optional 16-bit planar copy)  generator.py:228, :484-485
 #pragma once
 #include "common.cuh"
 
@@ -21,46 +32,74 @@ namespace rib {
 enum { EPI_STORE = 0, EPI_SPADE = 1, EPI_FINAL = 2 };
 enum { ACT_NONE = 0, ACT_LRELU = 1, ACT_TANH = 2, ACT_SIGMOID = 3 };
 
+static constexpr int kTileW = 8;    // output pixels per tile row  (= one 8-row UMMA core-matrix group)
+static constexpr int kTileH = 16;   // tile rows per M=128 sub-tile
+
+// A chunk-planar activation map (or a channel slice of one): element (n, c, y, x) is at
+//   p[n * bstride + (c / 8) * H * W * 8 + (y * W + x) * 8 + c % 8].
+struct PlanarRef {
+  act_t* p;
+  long long bstride;  // elements between images = (channels of the whole buffer / 8) * H * W * 8
+};
+
 struct alignas(64) ConvGemmParams {
-  CUtensorMap amap[4];  // stride 1: [0] = X0, [1] = X1 (optional); stride 2: parity views (py*2+px) of X0
-  CUtensorMap bmap;     // packed weights [Npad][Ktotal], K-major
+  CUtensorMap amap[4];  // stride 1: [0] = X0, [1] = X1 (optional 1x1 source); stride 2: parity views (py*2+px) of X0
+  CUtensorMap bmap;     // packed weights, 3-D view (BKc, Npad, Ktotal/BKc)
   int B, H, W;          // output spatial size
-  int TW, TH, tiles_x, tiles_y;
-  int BK, BN, stages, n_tiles;
-  int ntaps, stride, cchunks0, cchunks1;
+  int tiles_x, tiles_y; // super-tiles per image
+  int MT;               // M=128 sub-tiles per super-tile (stacked vertically): 1 or 2
+  int BN, n_tiles;
+  int BKc;              // channels per pipeline stage (16/32/64)
+  int stages0, stages1; // channel groups of source 0 / source 1
+  int ntaps, stride, halo;
+  int ring;             // shared-memory ring slots
+  int b_resident;       // 1: all weight stages of this CTA's N tile stay in shared memory
+  int halo_w;           // pixels per halo-tile row
+  uint32_t a_tile_bytes;  // one halo tile (one parity view for stride 2), padded to 128 bytes
+  uint32_t a_slot_bytes;  // A bytes per ring slot (1 or 4 tiles), padded to 1024
+  uint32_t b_tap_bytes;   // BN * BKc * 2
+  uint32_t b_stage_bytes; // ntaps * b_tap_bytes (source-1 stages use one tap of it)
+  uint32_t a_tx_bytes;    // bytes TMA delivers per stage for A
+  uint32_t lbo, sbo;      // UMMA no-swizzle K-major descriptor strides (bytes)
   uint32_t idesc;
   int debug_simt;
   // raw views (bring-up mainloop) ------------------------------------------------------------
-  const act_t* src0; int ld0; int Hin, Win;
-  const act_t* src1; int ld1;
+  PlanarRef src0; int Hin, Win;
+  PlanarRef src1;
   const act_t* wpk; int ktotal;
   // epilogue ---------------------------------------------------------------------------------
   const float* bias;   // [Npad]
   int n_valid;         // real output columns (<= Npad)
   int act;
   // EPI_STORE
-  act_t* out; int ldo;
-  const act_t* res; int ldr;
+  PlanarRef out;
+  PlanarRef res; int has_res;
   double* stats;       // [B][n_valid][2] (sum, sum of squares) or null
   // EPI_SPADE
-  const act_t* x; int ldx, Hx, Wx, ups;
+  PlanarRef x; int Hx, Wx, ups;
   const double* xstats;  // [B][C][2]
   int C, CT;
-  act_t* outq[2]; int ldq[2]; int actq[2];
+  PlanarRef outq[2]; int actq[2];
   float eps;
   // EPI_FINAL
   float* out_f32;      // [B][n_valid][H][W]
-  act_t* out_act; int ld_act;
+  PlanarRef out_act; int out_act_coff; int has_out_act;
 };
 
 // Host helpers -------------------------------------------------------------------------------------
-// 4-D activation view (C, W, H, B) with explicit byte strides; box = (boxC, boxW, boxH, 1).
-int make_tmap_act(CUtensorMap* m, const act_t* base, int C, int W, int H, int B, size_t strideW, size_t strideH,
-                  size_t strideB, int boxC, int boxW, int boxH);
-// 2-D weight view (K, N); box = (boxK, boxN).
-int make_tmap_w(CUtensorMap* m, const act_t* w, int K, int N, int boxK, int boxN);
-// Chooses the spatial tile (TW x TH = 128) that wastes the fewest pixels.
-void choose_tile(int H, int W, int* TW, int* TH);
+// Stride-1 view of a planar map: dims (W*8, H, C/8, B); box = (box_w*8, box_h, box_c/8, 1).
+int make_tmap_act_s1(CUtensorMap* m, const act_t* base, int C, int W, int H, int B, long long bstride, int box_c,
+                     int box_w, int box_h);
+// Parity view (py, px) of a planar map for stride-2 convolutions: dims (8, W/2, H/2, C/8, B).
+int make_tmap_act_s2(CUtensorMap* m, const act_t* base, int C, int W, int H, int B, long long bstride, int py, int px,
+                     int box_c, int box_w, int box_h);
+// Weight view (BKc, Npad, Ktotal/BKc); box = (BKc, BN, taps).
+int make_tmap_w(CUtensorMap* m, const act_t* w, int K, int N, int bkc, int boxN, int taps);
+// Channels per pipeline stage for a layer (also fixes the K ordering of the packed weights).
+int choose_bkc(int cin0, int cin1, int taps, int BN);
+// Fills the tiling / pipeline fields of p (everything except tensor maps and epilogue pointers).
+int conv_gemm_configure(ConvGemmParams* p, int B, int Hout, int Wout, int cin0, int cin1, int taps, int stride,
+                        int BN, int n_pad);
 size_t conv_gemm_smem_bytes(const ConvGemmParams& p);
 int launch_conv_gemm(const ConvGemmParams& p, int mode, cudaStream_t stream);
 long long conv_gemm_launch_count();

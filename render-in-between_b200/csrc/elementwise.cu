@@ -5,23 +5,48 @@
 namespace rib {
 
 // ---------------------------------------------------------------------------------------------
-// NCHW fp32 -> NHWC 16-bit
+// NCHW fp32 -> chunk-planar 16-bit.  One thread builds one 16-byte vector (8 channels of one pixel):
+// reads are coalesced along x in every source plane, the store is one coalesced 16-byte piece.
+// Up to three NCHW sources are concatenated along channels (torch.cat never materialises); channels
+// of the destination planes outside [c_off, c_off + sum C) are written as zero.
 // ---------------------------------------------------------------------------------------------
-__global__ void pack_nchw_kernel(const float* __restrict__ src, int C, act_t* __restrict__ dst, int ld, int c_off,
-                                 int HW, size_t total) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // pixel index over B*H*W
+__global__ void pack_nchw_kernel(const PackSrc s0, const PackSrc s1, const PackSrc s2, act_t* __restrict__ dst,
+                                 long long dst_bs, int c_off, int plane0, int nplanes, int HW, size_t total) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over B * nplanes * HW
   if (i >= total) return;
-  const size_t n = i / HW, hw = i - n * HW;
-  const float* s = src + n * (size_t)C * HW + hw;
-  act_t* d = dst + i * ld + c_off;
-  for (int c = 0; c < C; ++c) d[c] = f2act(__ldg(s + (size_t)c * HW));
+  const int hw = (int)(i % HW);
+  const size_t r = i / HW;
+  const int pl = plane0 + (int)(r % nplanes);
+  const size_t n = r / nplanes;
+  uint32_t o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float v[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      int c = pl * 8 + 2 * k + h - c_off;
+      float x = 0.f;
+      if (c >= 0) {
+        if (c < s0.C) x = __ldg(s0.p + (n * s0.C + c) * (size_t)HW + hw);
+        else if ((c -= s0.C) < s1.C) x = __ldg(s1.p + (n * s1.C + c) * (size_t)HW + hw);
+        else if ((c -= s1.C) < s2.C) x = __ldg(s2.p + (n * s2.C + c) * (size_t)HW + hw);
+      }
+      v[h] = x;
+    }
+    o[k] = pack2(v[0], v[1]);
+  }
+  *reinterpret_cast<uint4*>(dst + n * dst_bs + ((size_t)pl * HW + hw) * 8) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
-int launch_pack_nchw(const float* src, int C, act_t* dst, int ld, int c_off, int B, int H, int W, cudaStream_t s) {
-  const size_t total = (size_t)B * H * W;
+int launch_pack_nchw(const PackSrc* srcs, int nsrc, act_t* dst, long long dst_bstride, int c_off, int plane0,
+                     int nplanes, int B, int H, int W, cudaStream_t s) {
+  RIB_REQUIRE(nsrc >= 1 && nsrc <= 3, "pack: 1..3 sources");
+  PackSrc z = {nullptr, 0};
+  const PackSrc s0 = srcs[0], s1 = nsrc > 1 ? srcs[1] : z, s2 = nsrc > 2 ? srcs[2] : z;
+  const size_t total = (size_t)B * nplanes * H * W;
   const int threads = 256;
-  pack_nchw_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(src, C, dst, ld, c_off, H * W,
-                                                                                   total);
+  pack_nchw_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(s0, s1, s2, dst, dst_bstride, c_off,
+                                                                                   plane0, nplanes, H * W, total);
   RIB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -51,13 +76,12 @@ __global__ void in_apply_kernel(const InApplyParams p) {
       in_coeffs(p.bstats, p.bw, p.bb, n, p.C, c, cnt, p.eps, &s_coef[2 * p.C + c], &s_coef[3 * p.C + c]);
   }
   __syncthreads();
-  const int vec_per_pix = p.C / 8;
-  const size_t nvec = (size_t)p.H * p.W * vec_per_pix;
+  const size_t HW = (size_t)p.H * p.W;
+  const size_t nvec = HW * (p.C / 8);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t pix = i / vec_per_pix;
-    const int c0 = (int)(i - pix * vec_per_pix) * 8;
-    const size_t gp = (size_t)n * p.H * p.W + pix;
-    const uint4 av = *reinterpret_cast<const uint4*>(p.a + gp * p.lda + c0);
+    const size_t pl = i / HW, pix = i - pl * HW;
+    const int c0 = (int)pl * 8;
+    const uint4 av = *reinterpret_cast<const uint4*>(p.a + (size_t)n * p.a_bs + i * 8);
     const uint32_t au[4] = {av.x, av.y, av.z, av.w};
     float v[8];
 #pragma unroll
@@ -68,7 +92,7 @@ __global__ void in_apply_kernel(const InApplyParams p) {
       if (p.act) v[k] = lrelu02(v[k]);
     }
     if (p.b != nullptr) {
-      const uint4 bv = *reinterpret_cast<const uint4*>(p.b + gp * p.ldb + c0);
+      const uint4 bv = *reinterpret_cast<const uint4*>(p.b + (size_t)n * p.b_bs + i * 8);
       const uint32_t bu[4] = {bv.x, bv.y, bv.z, bv.w};
       float w[8];
 #pragma unroll
@@ -79,21 +103,21 @@ __global__ void in_apply_kernel(const InApplyParams p) {
     }
     const uint4 o = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
     if (!p.ups) {
-      *reinterpret_cast<uint4*>(p.out + gp * p.ldo + c0) = o;
+      *reinterpret_cast<uint4*>(p.out + (size_t)n * p.o_bs + i * 8) = o;
     } else {
       const int y = (int)(pix / p.W), x = (int)(pix - (size_t)y * p.W);
       const int W2 = 2 * p.W;
-      const size_t base = ((size_t)n * 2 * p.H + 2 * y) * W2 + 2 * x;
-      *reinterpret_cast<uint4*>(p.out + base * p.ldo + c0) = o;
-      *reinterpret_cast<uint4*>(p.out + (base + 1) * p.ldo + c0) = o;
-      *reinterpret_cast<uint4*>(p.out + (base + W2) * p.ldo + c0) = o;
-      *reinterpret_cast<uint4*>(p.out + (base + W2 + 1) * p.ldo + c0) = o;
+      act_t* ob = p.out + (size_t)n * p.o_bs + (pl * 4 * HW + (size_t)(2 * y) * W2 + 2 * x) * 8;
+      *reinterpret_cast<uint4*>(ob) = o;
+      *reinterpret_cast<uint4*>(ob + 8) = o;
+      *reinterpret_cast<uint4*>(ob + (size_t)W2 * 8) = o;
+      *reinterpret_cast<uint4*>(ob + (size_t)W2 * 8 + 8) = o;
     }
   }
 }
 
 int launch_in_apply(const InApplyParams& p, cudaStream_t s) {
-  RIB_REQUIRE(p.C % 8 == 0 && p.lda % 8 == 0 && p.ldo % 8 == 0, "in_apply: channels must be a multiple of 8");
+  RIB_REQUIRE(p.C % 8 == 0, "in_apply: channels must be a multiple of 8");
   const size_t nvec = (size_t)p.H * p.W * (p.C / 8);
   const int threads = 256;
   unsigned gx = (unsigned)((nvec + threads - 1) / threads);
@@ -105,22 +129,24 @@ int launch_in_apply(const InApplyParams& p, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// AvgPool 3x3 s2 p1 + statistics
+// AvgPool 3x3 s2 p1 + statistics.  Grid = (x-blocks, channel plane, image): every thread of a block
+// works on the same 8 channels, so the statistics reduce with warp shuffles.
 // ---------------------------------------------------------------------------------------------
-__global__ void avgpool3s2_kernel(const act_t* __restrict__ src, int lds, act_t* __restrict__ dst, int ldd,
-                                  double* __restrict__ stats, int H, int W, int C) {
-  extern __shared__ float s_red[];  // [2][C]
-  const int n = blockIdx.y;
+__global__ void avgpool3s2_kernel(const act_t* __restrict__ src, long long src_bs, act_t* __restrict__ dst,
+                                  long long dst_bs, double* __restrict__ stats, int H, int W, int C) {
+  __shared__ float s_red[16];
+  const int pl = blockIdx.y, n = blockIdx.z;
   const int Ho = H / 2, Wo = W / 2;
-  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) s_red[c] = 0.f;
+  if (threadIdx.x < 16) s_red[threadIdx.x] = 0.f;
   __syncthreads();
-  const int vec_per_pix = C / 8;
-  const size_t nvec = (size_t)Ho * Wo * vec_per_pix;
-  // consecutive threads of a block share the channel group pattern: blockDim % vec_per_pix == 0 or vice versa
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t pix = i / vec_per_pix;
-    const int c0 = (int)(i - pix * vec_per_pix) * 8;
-    const int oy = (int)(pix / Wo), ox = (int)(pix - (size_t)oy * Wo);
+  const act_t* sp = src + (size_t)n * src_bs + (size_t)pl * H * W * 8;
+  act_t* dp = dst + (size_t)n * dst_bs + (size_t)pl * Ho * Wo * 8;
+  float t1[8], t2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) t1[k] = t2[k] = 0.f;
+  const int npix = Ho * Wo;
+  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += gridDim.x * blockDim.x) {
+    const int oy = pix / Wo, ox = pix - oy * Wo;
     float acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0.f;
@@ -132,7 +158,7 @@ __global__ void avgpool3s2_kernel(const act_t* __restrict__ src, int lds, act_t*
       for (int dx = -1; dx <= 1; ++dx) {
         const int ix = 2 * ox + dx;
         if (ix < 0 || ix >= W) continue;
-        const uint4 v = *reinterpret_cast<const uint4*>(src + (((size_t)n * H + iy) * W + ix) * lds + c0);
+        const uint4 v = *reinterpret_cast<const uint4*>(sp + ((size_t)iy * W + ix) * 8);
         const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -144,35 +170,48 @@ __global__ void avgpool3s2_kernel(const act_t* __restrict__ src, int lds, act_t*
       }
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = acc[k] / 9.0f;
-    *reinterpret_cast<uint4*>(dst + (((size_t)n * Ho + oy) * Wo + ox) * ldd + c0) =
-        make_uint4(pack2(acc[0], acc[1]), pack2(acc[2], acc[3]), pack2(acc[4], acc[5]), pack2(acc[6], acc[7]));
-    if (stats != nullptr) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        atomicAdd(&s_red[c0 + k], acc[k]);
-        atomicAdd(&s_red[C + c0 + k], acc[k] * acc[k]);
-      }
+    for (int k = 0; k < 8; ++k) {
+      acc[k] = acc[k] / 9.0f;
+      t1[k] += acc[k];
+      t2[k] += acc[k] * acc[k];
     }
+    *reinterpret_cast<uint4*>(dp + (size_t)pix * 8) =
+        make_uint4(pack2(acc[0], acc[1]), pack2(acc[2], acc[3]), pack2(acc[4], acc[5]), pack2(acc[6], acc[7]));
   }
   if (stats != nullptr) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        t1[k] += __shfl_xor_sync(0xffffffffu, t1[k], off);
+        t2[k] += __shfl_xor_sync(0xffffffffu, t2[k], off);
+      }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        atomicAdd(&s_red[k], t1[k]);
+        atomicAdd(&s_red[8 + k], t2[k]);
+      }
+    }
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      atomicAdd(&stats[((size_t)n * C + c) * 2 + 0], (double)s_red[c]);
-      atomicAdd(&stats[((size_t)n * C + c) * 2 + 1], (double)s_red[C + c]);
+    if (threadIdx.x < 8) {
+      const int c = pl * 8 + threadIdx.x;
+      atomicAdd(&stats[((size_t)n * C + c) * 2 + 0], (double)s_red[threadIdx.x]);
+      atomicAdd(&stats[((size_t)n * C + c) * 2 + 1], (double)s_red[8 + threadIdx.x]);
     }
   }
 }
 
-int launch_avgpool3s2(const act_t* src, int lds, act_t* dst, int ldd, double* stats, int B, int H, int W, int C,
-                      cudaStream_t s) {
+int launch_avgpool3s2(const act_t* src, long long src_bs, act_t* dst, long long dst_bs, double* stats, int B, int H,
+                      int W, int C, cudaStream_t s) {
   RIB_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "avgpool: bad shape");
-  const size_t nvec = (size_t)(H / 2) * (W / 2) * (C / 8);
+  const int npix = (H / 2) * (W / 2);
   const int threads = 256;
-  unsigned gx = (unsigned)((nvec + threads - 1) / threads);
-  if (gx > 148u * 8u) gx = 148u * 8u;
-  dim3 grid(gx, (unsigned)B);
-  avgpool3s2_kernel<<<grid, threads, 2 * C * sizeof(float), s>>>(src, lds, dst, ldd, stats, H, W, C);
+  unsigned gx = (unsigned)((npix + threads * 4 - 1) / (threads * 4));
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, (unsigned)(C / 8), (unsigned)B);
+  avgpool3s2_kernel<<<grid, threads, 0, s>>>(src, src_bs, dst, dst_bs, stats, H, W, C);
   RIB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -317,7 +356,7 @@ __global__ void pack_weight_kernel(const PackWeightParams p) {
     const int ci = (int)(r % p.Cin), co = (int)(r / p.Cin);
     // the reference divides the fp32 weight by sigma (W / sigma), then the conv runs on that weight
     const float wv = p.sigma_inv ? p.w[i] * scale : p.w[i];
-    p.dst[(size_t)pack_row(p, co) * p.ktotal + p.koff + tap * p.cin_pad + ci] = f2act(wv);
+    p.dst[(size_t)pack_row(p, co) * p.ktotal + p.koff + ((ci / p.bkc) * p.taps + tap) * p.bkc + ci % p.bkc] = f2act(wv);
   }
   if (p.bias_dst != nullptr) {
     for (int co = blockIdx.x * blockDim.x + threadIdx.x; co < p.Cout; co += gridDim.x * blockDim.x) {

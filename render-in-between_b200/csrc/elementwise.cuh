@@ -4,16 +4,27 @@
 
 namespace rib {
 
-// NCHW fp32 -> NHWC 16-bit, channels [c_off, c_off + C) of a buffer with `ld` channels per pixel.
-int launch_pack_nchw(const float* src, int C, act_t* dst, int ld, int c_off, int B, int H, int W, cudaStream_t s);
+// All 16-bit activation maps are chunk-planar: [B][Ctot/8][H][W][8] (see conv_gemm.cuh).  A map (or a
+// channel slice of one that starts on a multiple of 8) is passed as the pointer to its first plane
+// plus `bstride`, the element distance between images (= Ctot/8 * H * W * 8).
+
+// NCHW fp32 -> planar 16-bit.  Up to three sources are concatenated along channels and land in channels
+// [c_off, c_off + sum C) of the destination; planes [plane0, plane0 + nplanes) are fully written
+// (zero where no source channel maps), so padding channels need no separate memset.
+struct PackSrc {
+  const float* p;
+  int C;
+};
+int launch_pack_nchw(const PackSrc* srcs, int nsrc, act_t* dst, long long dst_bstride, int c_off, int plane0,
+                     int nplanes, int B, int H, int W, cudaStream_t s);
 
 // Instance-norm (affine) application for the C-N-A blocks of the mask network
 // (conv.py:56-69 with order 'CNA'; residual.py:146-151 for the two-term form):
 //   out = act(IN_a(a)) [+ IN_b(b) | + b]   with optional nearest x2 up-sampling on the store
 struct InApplyParams {
-  const act_t* a; int lda; const double* astats; const float* aw; const float* ab;
-  const act_t* b; int ldb; const double* bstats; const float* bw; const float* bb;  // b optional
-  act_t* out; int ldo;
+  const act_t* a; long long a_bs; const double* astats; const float* aw; const float* ab;
+  const act_t* b; long long b_bs; const double* bstats; const float* bw; const float* bb;  // b optional
+  act_t* out; long long o_bs;
   int B, H, W, C;  // input spatial size
   int act;         // 0 none, 1 leaky-relu(0.2) on the first term
   int ups;         // 1: write each pixel to the 2x2 block of a (2H, 2W) output
@@ -23,8 +34,8 @@ int launch_in_apply(const InApplyParams& p, cudaStream_t s);
 
 // AvgPool2d(3, stride 2, pad 1, count_include_pad) (generator.py:127,208) + instance-norm statistics
 // of the pooled map (sum, sum of squares per (n, c), fp64 atomics).
-int launch_avgpool3s2(const act_t* src, int lds, act_t* dst, int ldd, double* stats, int B, int H, int W, int C,
-                      cudaStream_t s);
+int launch_avgpool3s2(const act_t* src, long long src_bs, act_t* dst, long long dst_bs, double* stats, int B, int H,
+                      int W, int C, cudaStream_t s);
 
 // fuse = img * mask + dain * (1 - mask)   (evaluator.py:256-258); optional uint8 HWC frame
 // (utils.py:137-142: clip(x*0.5+0.5, 0, 1)*255 truncated, float64 arithmetic).
@@ -39,7 +50,8 @@ int launch_sn_sigma_inv(const float* w, const float* u, const float* v, int Cout
                         cudaStream_t s);
 
 // Repack a conv weight [Cout][Cin][taps] fp32 into the K-major 16-bit GEMM operand:
-//   dst[row(co) * ktotal + koff + tap * cin_pad + ci] = w[co][ci][tap] * (sigma_inv ? *sigma_inv : 1)
+//   dst[row(co) * ktotal + koff + ((ci / bkc) * taps + tap) * bkc + ci % bkc] = w[co][ci][tap] * (sigma_inv ? *sigma_inv : 1)
+// (bkc = channels per pipeline stage of the layer: all taps of one channel group are contiguous in K)
 //   bias_dst[row(co)] (+)= bias[co] (+ 1 for SPADE gamma rows)
 // row(co) = row_off + co for plain convs; for SPADE ([gamma(C) | beta(C)] -> per-tile [gamma(CT) | beta(CT)]):
 //   c = co % C, half = co / C, row = row_off + (c / CT) * 2 * CT + half * CT + c % CT.
@@ -47,7 +59,7 @@ struct PackWeightParams {
   const float* w; const float* bias; const float* sigma_inv;
   int Cout, Cin, taps;
   act_t* dst; float* bias_dst;
-  int ktotal, koff, cin_pad, row_off;
+  int ktotal, koff, bkc, row_off;
   int spade_C, spade_CT;  // 0 for plain convs
   int bias_accumulate;    // add into bias_dst instead of overwriting (fused shortcut)
 };

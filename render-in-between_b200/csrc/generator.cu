@@ -10,6 +10,8 @@
 //   * instance-norm statistics come out of the producing conv's epilogue (fp64 atomics)
 //   * nearest x2 up-sampling is a gather in the consumer (main branch) or the producer's store (mask net)
 //   * torch.cat never materialises: producers write channel slices
+//   * activations are chunk-planar 16-bit maps [B][C/8][H][W][8] (conv_gemm.cuh) so that a 3x3 conv reads one
+//     halo tile per channel group instead of nine shifted tiles
 #include "generator.cuh"
 
 #include <algorithm>
@@ -28,15 +30,18 @@ int g_debug_simt = 0;
 
 namespace {
 
-struct View {  // NHWC 16-bit activation (or a channel slice of one)
-  act_t* p = nullptr;
-  int B = 0, H = 0, W = 0, C = 0, ld = 0;
+struct View {  // chunk-planar 16-bit activation [B][Ctot/8][H][W][8] (or a channel slice of one)
+  act_t* p = nullptr;  // first plane of the slice, image 0
+  int B = 0, H = 0, W = 0, C = 0, Ctot = 0;
+  long long bstride() const { return (long long)Ctot * H * W; }
+  PlanarRef ref() const { return PlanarRef{p, bstride()}; }
 };
 
 struct GemmLayer {
   std::string name;
   int n_pad = 0, n_valid = 0, ktotal = 0;
   int cin0 = 0, taps = 0, cin1 = 0;  // padded input channels of source 0, its taps, source 1 (1x1) channels
+  int BN = 0, bkc = 0;               // N tile and channels per pipeline stage (fixes the packed K order)
   act_t* w = nullptr;
   float* bias = nullptr;
   size_t w_off = 0, b_off = 0;
@@ -52,7 +57,8 @@ struct Op {
   size_t ms_bytes = 0;
   // pack
   int ext = EXT_NONE;
-  int pk_C = 0, pk_ld = 0, pk_coff = 0;
+  int pk_nsrc = 0, pk_ext[3] = {0, 0, 0}, pk_C[3] = {0, 0, 0}, pk_nplanes = 0;
+  long long pk_bs = 0;
   act_t* pk_dst = nullptr;
   // gemm
   ConvGemmParams g;
@@ -63,7 +69,8 @@ struct Op {
   const act_t* pl_src = nullptr;
   act_t* pl_dst = nullptr;
   double* pl_stats = nullptr;
-  int pl_lds = 0, pl_ldd = 0, pl_H = 0, pl_W = 0, pl_C = 0;
+  long long pl_sbs = 0, pl_dbs = 0;
+  int pl_H = 0, pl_W = 0, pl_C = 0;
 };
 
 struct Bump {
@@ -100,7 +107,6 @@ namespace {
 int nfilt(const rib_gen_config& c, int i) { return std::min(c.maxf, c.nf << i); }
 int mask_nfilt(const rib_gen_config& c, int i) { return std::min(c.mask_max, c.mask_nf << i); }
 int emb_ch(const rib_gen_config& c, int i) { return std::min(c.emb_max, c.emb_nf << i); }
-int pad16(int c) { return (c + 15) / 16 * 16; }
 
 struct BlockDef {
   std::string name;
@@ -146,12 +152,18 @@ struct Source {
 struct PackJob {  // one reference conv placed inside a GEMM layer
   std::string layer, prefix;
   bool sn;
-  int cout, cin, taps, koff, cin_pad, row_off, spade_C, spade_CT;
+  int cout, cin, taps, koff, cin_pad /* padded input channels (informational) */, row_off, spade_C, spade_CT;
   bool bias_acc;
 };
 
-void add_layer(Generator* G, const std::string& name, int n_valid, int n_pad, int cin0_pad, int taps, int cin1) {
+int spade_ct(int C) { return std::min(C, 64); }
+
+// BN = 0 selects the plain-store default min(n_pad, 128).
+void add_layer(Generator* G, const std::string& name, int n_valid, int n_pad, int cin0_pad, int taps, int cin1,
+               int BN = 0) {
   GemmLayer L;
+  L.BN = BN ? BN : std::min(n_pad, 128);
+  L.bkc = choose_bkc(cin0_pad, cin1, taps, L.BN);
   L.name = name;
   L.n_valid = n_valid;
   L.n_pad = n_pad;
@@ -161,8 +173,6 @@ void add_layer(Generator* G, const std::string& name, int n_valid, int n_pad, in
   L.ktotal = cin0_pad * taps + cin1;
   G->layers[name] = L;
 }
-
-int spade_ct(int C) { return std::min(C, 64); }
 
 }  // namespace
 
@@ -195,13 +205,13 @@ int generator_create(const rib_gen_config* cfg, const rib_tensor* tensors, int n
   for (const BlockDef& b : res_blocks(c)) {
     const int cond = emb_ch(c, b.lvl);
     const int nq = b.shortcut ? 2 : 1;
-    add_layer(G, b.name + ".spadeA", nq * 2 * b.cin, nq * 2 * b.cin, cond, 1, 0);
+    add_layer(G, b.name + ".spadeA", nq * 2 * b.cin, nq * 2 * b.cin, cond, 1, 0, 2 * spade_ct(b.cin));
     jobs.push_back({b.name + ".spadeA", b.name + ".conv_block_0.layers.norm.mlps.0.0.layers.conv", false, 2 * b.cin, cond, 1, 0, cond, 0, b.cin, spade_ct(b.cin), false});
     if (b.shortcut)
       jobs.push_back({b.name + ".spadeA", b.name + ".conv_block_s.layers.norm.mlps.0.0.layers.conv", false, 2 * b.cin, cond, 1, 0, cond, 2 * b.cin, b.cin, spade_ct(b.cin), false});
     add_layer(G, b.name + ".conv0", b.hid, b.hid, b.cin, 9, 0);
     jobs.push_back({b.name + ".conv0", b.name + ".conv_block_0.layers.conv", true, b.hid, b.cin, 9, 0, b.cin, 0, 0, 0, false});
-    add_layer(G, b.name + ".spadeB", 2 * b.hid, 2 * b.hid, cond, 1, 0);
+    add_layer(G, b.name + ".spadeB", 2 * b.hid, 2 * b.hid, cond, 1, 0, 2 * spade_ct(b.hid));
     jobs.push_back({b.name + ".spadeB", b.name + ".conv_block_1.layers.norm.mlps.0.0.layers.conv", false, 2 * b.hid, cond, 1, 0, cond, 0, b.hid, spade_ct(b.hid), false});
     add_layer(G, b.name + ".conv1", b.cout, b.cout, b.hid, 9, b.shortcut ? b.cin : 0);
     jobs.push_back({b.name + ".conv1", b.name + ".conv_block_1.layers.conv", true, b.cout, b.hid, 9, 0, b.hid, 0, 0, 0, false});
@@ -307,7 +317,7 @@ int generator_create(const rib_gen_config* cfg, const rib_tensor* tensors, int n
     pp.bias_dst = L.bias;
     pp.ktotal = L.ktotal;
     pp.koff = pj.koff;
-    pp.cin_pad = pj.cin_pad;
+    pp.bkc = L.bkc;
     pp.row_off = pj.row_off;
     pp.spade_C = pj.spade_C;
     pp.spade_CT = pj.spade_CT;
@@ -371,14 +381,14 @@ struct PlanBuilder {
     v.H = H;
     v.W = W;
     v.C = C;
-    v.ld = C;
+    v.Ctot = C;
     v.p = static_cast<act_t*>(ws.take((size_t)B * H * W * C * sizeof(act_t)));
     views[name] = v;
     return v;
   }
   static View slice(const View& v, int c_off, int C) {
     View s = v;
-    s.p = v.p ? v.p + c_off : nullptr;
+    s.p = v.p ? v.p + (size_t)(c_off / 8) * v.H * v.W * 8 : nullptr;  // c_off is a multiple of 8
     s.C = C;
     return s;
   }
@@ -393,61 +403,41 @@ struct PlanBuilder {
                              int BN) {
     ConvGemmParams p;
     memset(&p, 0, sizeof(p));
-    p.B = B;
-    p.H = Hout;
-    p.W = Wout;
-    choose_tile(Hout, Wout, &p.TW, &p.TH);
-    p.tiles_x = ceil_div(Wout, p.TW);
-    p.tiles_y = ceil_div(Hout, p.TH);
-    int bk = std::min(64, in0.C);
-    if (in1) bk = std::min(bk, in1->C);
-    p.BK = bk;
-    p.BN = BN;
-    p.n_tiles = L.n_pad / BN;
-    p.ntaps = L.taps;
-    p.stride = stride;
-    p.cchunks0 = in0.C / bk;
-    p.cchunks1 = in1 ? in1->C / bk : 0;
-    const int ksteps = p.ntaps * p.cchunks0 + p.cchunks1;
-    const size_t stage_bytes = (size_t)128 * bk * 2 + (size_t)BN * bk * 2;
-    int stages = (int)((size_t)96 * 1024 / stage_bytes);
-    stages = std::max(2, std::min(stages, 8));
-    p.stages = std::min(stages, std::max(ksteps, 1));
-    p.idesc = make_idesc_f16(128, BN);
+    if (in0.C != L.cin0 || (in1 ? in1->C : 0) != L.cin1 || BN != L.BN || in0.C != in0.Ctot ||
+        (in1 && in1->C != in1->Ctot)) {
+      set_error("plan: layer/view channel mismatch in " + L.name);
+      rc = -4;
+      return p;
+    }
+    int r = conv_gemm_configure(&p, B, Hout, Wout, L.cin0, L.cin1, L.taps, stride, BN, L.n_pad);
+    if (r || p.BKc != L.bkc) {
+      if (!r) set_error("plan: K ordering mismatch in " + L.name);
+      rc = r ? r : -4;
+      return p;
+    }
     p.debug_simt = g_debug_simt;
-    p.src0 = in0.p;
-    p.ld0 = in0.ld;
+    p.src0 = in0.ref();
     p.Hin = in0.H;
     p.Win = in0.W;
-    p.src1 = in1 ? in1->p : nullptr;
-    p.ld1 = in1 ? in1->ld : 0;
+    if (in1) p.src1 = in1->ref();
     p.wpk = L.w;
     p.ktotal = L.ktotal;
     p.bias = L.bias;
     p.n_valid = L.n_valid;
     p.eps = 1e-5f;
-    if (in0.C != L.cin0 || (in1 ? in1->C : 0) != L.cin1 || L.n_pad % BN != 0 || in0.C % bk != 0 ||
-        (in1 && in1->C % bk != 0)) {
-      set_error("plan: layer/view channel mismatch in " + L.name);
-      rc = -4;
-      return p;
-    }
     if (real && rc == 0) {
-      const size_t es = sizeof(act_t);
+      const int halo_h = (int)(p.lbo / 16u) / p.halo_w;
       if (stride == 1) {
-        rc = make_tmap_act(&p.amap[0], in0.p, in0.C, in0.W, in0.H, B, (size_t)in0.ld * es, (size_t)in0.W * in0.ld * es,
-                           (size_t)in0.H * in0.W * in0.ld * es, bk, p.TW, p.TH);
+        rc = make_tmap_act_s1(&p.amap[0], in0.p, in0.C, in0.W, in0.H, B, in0.bstride(), p.BKc, p.halo_w, halo_h);
         if (!rc && in1)
-          rc = make_tmap_act(&p.amap[1], in1->p, in1->C, in1->W, in1->H, B, (size_t)in1->ld * es,
-                             (size_t)in1->W * in1->ld * es, (size_t)in1->H * in1->W * in1->ld * es, bk, p.TW, p.TH);
+          rc = make_tmap_act_s1(&p.amap[1], in1->p, in1->C, in1->W, in1->H, B, in1->bstride(), p.BKc, p.halo_w, halo_h);
       } else {
         for (int py = 0; py < 2 && !rc; ++py)
           for (int px = 0; px < 2 && !rc; ++px)
-            rc = make_tmap_act(&p.amap[py * 2 + px], in0.p + ((size_t)py * in0.W + px) * in0.ld, in0.C, in0.W / 2,
-                               in0.H / 2, B, (size_t)2 * in0.ld * es, (size_t)2 * in0.W * in0.ld * es,
-                               (size_t)in0.H * in0.W * in0.ld * es, bk, p.TW, p.TH);
+            rc = make_tmap_act_s2(&p.amap[py * 2 + px], in0.p, in0.C, in0.W, in0.H, B, in0.bstride(), py, px, p.BKc,
+                                  p.halo_w, halo_h);
       }
-      if (!rc) rc = make_tmap_w(&p.bmap, L.w, L.ktotal, L.n_pad, bk, BN);
+      if (!rc) rc = make_tmap_w(&p.bmap, L.w, L.ktotal, L.n_pad, p.BKc, BN, L.taps);
     }
     return p;
   }
@@ -464,13 +454,12 @@ struct PlanBuilder {
   void conv_store(const std::string& lname, const View& in0, const View* in1, int stride, const View& out,
                   double* stats, int act, const View* res) {
     const GemmLayer& L = G->layers.at(lname);
-    ConvGemmParams p = gemm_common(L, in0, in1, stride, out.H, out.W, std::min(L.n_pad, 128));
-    p.out = out.p;
-    p.ldo = out.ld;
+    ConvGemmParams p = gemm_common(L, in0, in1, stride, out.H, out.W, L.BN);
+    p.out = out.ref();
     p.stats = stats;
     p.act = act;
-    p.res = res ? res->p : nullptr;
-    p.ldr = res ? res->ld : 0;
+    p.has_res = res ? 1 : 0;
+    if (res) p.res = res->ref();
     push_gemm(p, EPI_STORE);
   }
 
@@ -480,8 +469,7 @@ struct PlanBuilder {
     const GemmLayer& L = G->layers.at(lname);
     const int CT = spade_ct(x.C);
     ConvGemmParams p = gemm_common(L, cond, nullptr, 1, cond.H, cond.W, 2 * CT);
-    p.x = x.p;
-    p.ldx = x.ld;
+    p.x = x.ref();
     p.Hx = x.H;
     p.Wx = x.W;
     p.ups = ups ? 1 : 0;
@@ -489,19 +477,19 @@ struct PlanBuilder {
     p.C = x.C;
     p.CT = CT;
     for (int q = 0; q < nq; ++q) {
-      p.outq[q] = outs[q].p;
-      p.ldq[q] = outs[q].ld;
+      p.outq[q] = outs[q].ref();
       p.actq[q] = acts[q];
     }
     push_gemm(p, EPI_SPADE);
   }
 
-  void conv_final(const std::string& lname, const View& in0, int act, int ext, const View* copy) {
+  void conv_final(const std::string& lname, const View& in0, int act, int ext, const View* copy, int copy_coff) {
     const GemmLayer& L = G->layers.at(lname);
     ConvGemmParams p = gemm_common(L, in0, nullptr, 1, in0.H, in0.W, 16);
     p.act = act;
-    p.out_act = copy ? copy->p : nullptr;
-    p.ld_act = copy ? copy->ld : 0;
+    p.has_out_act = copy ? 1 : 0;
+    if (copy) p.out_act = copy->ref();
+    p.out_act_coff = copy_coff;
     Op op;
     op.kind = OP_GEMM;
     op.g = p;
@@ -517,13 +505,13 @@ struct PlanBuilder {
     InApplyParams& p = op.ia;
     memset(&p, 0, sizeof(p));
     p.a = a.p;
-    p.lda = a.ld;
+    p.a_bs = a.bstride();
     p.astats = astats;
     p.aw = G->in_affine.at(aprefix + ".weight");
     p.ab = G->in_affine.at(aprefix + ".bias");
     if (b) {
       p.b = b->p;
-      p.ldb = b->ld;
+      p.b_bs = b->bstride();
       p.bstats = bstats;
       if (bstats) {
         p.bw = G->in_affine.at(bprefix + ".weight");
@@ -531,7 +519,7 @@ struct PlanBuilder {
       }
     }
     p.out = out.p;
-    p.ldo = out.ld;
+    p.o_bs = out.bstride();
     p.B = B;
     p.H = a.H;
     p.W = a.W;
@@ -546,9 +534,9 @@ struct PlanBuilder {
     Op op;
     op.kind = OP_POOL;
     op.pl_src = src.p;
-    op.pl_lds = src.ld;
+    op.pl_sbs = src.bstride();
     op.pl_dst = dst.p;
-    op.pl_ldd = dst.ld;
+    op.pl_dbs = dst.bstride();
     op.pl_stats = stats;
     op.pl_H = src.H;
     op.pl_W = src.W;
@@ -556,14 +544,18 @@ struct PlanBuilder {
     ops.push_back(op);
   }
 
-  void pack(int ext, int C, const View& dst, int c_off) {
+  // dst channels [0, sum C) <- cat(sources); every plane of dst is written (zero padding included)
+  void pack(int nsrc, const int* exts, const int* Cs, const View& dst) {
     Op op;
     op.kind = OP_PACK;
-    op.ext = ext;
-    op.pk_C = C;
+    op.pk_nsrc = nsrc;
+    for (int i = 0; i < nsrc; ++i) {
+      op.pk_ext[i] = exts[i];
+      op.pk_C[i] = Cs[i];
+    }
     op.pk_dst = dst.p;
-    op.pk_ld = dst.ld;
-    op.pk_coff = c_off;
+    op.pk_bs = dst.bstride();
+    op.pk_nplanes = dst.Ctot / 8;
     ops.push_back(op);
   }
 };
@@ -627,11 +619,14 @@ static int build_plan(Generator* G, int B, int H, int W, void* wsbase, size_t* b
   pb.ops[0].ms_bytes = stats_region_end - stats_region_begin;
 
   // -- inputs --
-  pb.pack(EXT_LABEL, c.label_nc, lab, 0);
-  pb.pack(EXT_FAKE, 3, emb_in, 0);   // cat([img_fake, img_prev])            generator.py:197
-  pb.pack(EXT_PREV, 3, emb_in, 3);
-  pb.pack(EXT_PREV, 3, mask_in, 0);  // cat([img_prev, img_fake, img_final])  generator.py:232
-  pb.pack(EXT_FAKE, 3, mask_in, 3);
+  {
+    const int e_lab[1] = {EXT_LABEL}, c_lab[1] = {c.label_nc};
+    pb.pack(1, e_lab, c_lab, lab);
+    const int e_emb[2] = {EXT_FAKE, EXT_PREV}, c_img[2] = {c.img_nc, c.img_nc};
+    pb.pack(2, e_emb, c_img, emb_in);   // cat([img_fake, img_prev])            generator.py:197
+    const int e_msk[2] = {EXT_PREV, EXT_FAKE};
+    pb.pack(2, e_msk, c_img, mask_in);  // cat([img_prev, img_fake, img_final])  generator.py:232 (img_final: conv_img)
+  }
 
   // -- ref_embedding: 5 convs + LeakyReLU (generator.py:360-377) --
   std::vector<View> cond;
@@ -703,8 +698,7 @@ static int build_plan(Generator* G, int B, int H, int W, void* wsbase, size_t* b
     }
   }
   // -- final image: tanh(conv_img(lrelu(x)))  generator.py:228 --
-  View img_slot = PlanBuilder::slice(mask_in, 6, 3);
-  pb.conv_final("conv_img", x, ACT_TANH, EXT_OUT_IMG, &img_slot);
+  pb.conv_final("conv_img", x, ACT_TANH, EXT_OUT_IMG, &mask_in, 2 * c.img_nc);
 
   // -- mask network (generator.py:493-510) --
   View cat = pb.alloc("mask.cat", H >> c.mask_down, W >> c.mask_down, 2 * mch);
@@ -757,15 +751,12 @@ static int build_plan(Generator* G, int B, int H, int W, void* wsbase, size_t* b
                 "", o, 1, ups);
     r = o;
   }
-  pb.conv_final("mask.conv_mask", r, ACT_SIGMOID, EXT_OUT_MASK, nullptr);
+  pb.conv_final("mask.conv_mask", r, ACT_SIGMOID, EXT_OUT_MASK, nullptr, 0);
 
   if (pb.rc) return pb.rc;
   *bytes_out = align_up(pb.ws.off, 1024);
   if (wsbase) {
-    // zero the staging buffers once so that their padding channels read as 0
-    RIB_CHECK_CUDA(cudaMemsetAsync(lab.p, 0, (size_t)B * H * W * 32 * sizeof(act_t), stream));
-    RIB_CHECK_CUDA(cudaMemsetAsync(emb_in.p, 0, (size_t)B * H * W * 16 * sizeof(act_t), stream));
-    RIB_CHECK_CUDA(cudaMemsetAsync(mask_in.p, 0, (size_t)B * H * W * 16 * sizeof(act_t), stream));
+    (void)stream;  // padding channels of the staging buffers are written by the pack kernels
     G->ops.swap(pb.ops);
     G->debug_views.swap(pb.views);
     G->pB = B;
@@ -810,8 +801,12 @@ int generator_forward(Generator* G, int B, int H, int W, const float* label, con
         RIB_CHECK_CUDA(cudaMemsetAsync(op.ms_ptr, 0, op.ms_bytes, stream));
         break;
       case OP_PACK: {
-        const float* src = op.ext == EXT_LABEL ? label : (op.ext == EXT_FAKE ? img_fake : img_prev);
-        rc = launch_pack_nchw(src, op.pk_C, op.pk_dst, op.pk_ld, op.pk_coff, B, H, W, stream);
+        PackSrc srcs[3];
+        for (int i = 0; i < op.pk_nsrc; ++i) {
+          srcs[i].p = op.pk_ext[i] == EXT_LABEL ? label : (op.pk_ext[i] == EXT_FAKE ? img_fake : img_prev);
+          srcs[i].C = op.pk_C[i];
+        }
+        rc = launch_pack_nchw(srcs, op.pk_nsrc, op.pk_dst, op.pk_bs, 0, 0, op.pk_nplanes, B, H, W, stream);
         count_misc_launch(1);
         break;
       }
@@ -830,7 +825,7 @@ int generator_forward(Generator* G, int B, int H, int W, const float* label, con
         count_misc_launch(1);
         break;
       case OP_POOL:
-        rc = launch_avgpool3s2(op.pl_src, op.pl_lds, op.pl_dst, op.pl_ldd, op.pl_stats, B, op.pl_H, op.pl_W, op.pl_C,
+        rc = launch_avgpool3s2(op.pl_src, op.pl_sbs, op.pl_dst, op.pl_dbs, op.pl_stats, B, op.pl_H, op.pl_W, op.pl_C,
                                stream);
         count_misc_launch(1);
         break;
@@ -852,7 +847,7 @@ int generator_debug_tensor(Generator* G, const char* name, const void** ptr, int
   *H = it->second.H;
   *W = it->second.W;
   *C = it->second.C;
-  *ld = it->second.ld;
+  *ld = it->second.Ctot;
   return 0;
 }
 
@@ -874,6 +869,8 @@ int conv_test(const void* x, const float* w, const float* bias, void* out, doubl
   L.taps = k * k;
   L.cin1 = 0;
   L.ktotal = Cin * k * k;
+  L.BN = std::min(Cout, 128);
+  L.bkc = choose_bkc(Cin, 0, k * k, L.BN);
   uint8_t* sp = static_cast<uint8_t*>(scratch);
   sp = reinterpret_cast<uint8_t*>(align_up((size_t)(uintptr_t)sp, 256));
   L.w = reinterpret_cast<act_t*>(sp);
@@ -890,7 +887,7 @@ int conv_test(const void* x, const float* w, const float* bias, void* out, doubl
   pp.dst = L.w;
   pp.bias_dst = L.bias;
   pp.ktotal = L.ktotal;
-  pp.cin_pad = Cin;
+  pp.bkc = L.bkc;
   int rc = launch_pack_weight(pp, stream);
   if (rc) return rc;
   PlanBuilder pb(&G, scratch, B);  // non-null base => builds real tensor maps; no allocation is made
@@ -899,13 +896,13 @@ int conv_test(const void* x, const float* w, const float* bias, void* out, doubl
   in.B = B;
   in.H = Hin;
   in.W = Win;
-  in.C = in.ld = Cin;
+  in.C = in.Ctot = Cin;
   View o;
   o.p = static_cast<act_t*>(out);
   o.B = B;
   o.H = Hin / stride;
   o.W = Win / stride;
-  o.C = o.ld = Cout;
+  o.C = o.Ctot = Cout;
   pb.conv_store("test", in, nullptr, stride, o, stats, act, nullptr);
   if (pb.rc) return pb.rc;
   return launch_conv_gemm(pb.ops[0].g, EPI_STORE, stream);

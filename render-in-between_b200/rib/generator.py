@@ -138,8 +138,9 @@ class Generator(nn.Module):
         buf, _, _ = next(iter(self._workspaces.values()))
         off = ptr.value - buf.data_ptr()
         dt = torch.float16 if lib.rib_act_is_fp16() else torch.bfloat16
-        b, h, w, c, ld = b.value, h.value, w.value, c.value, ld.value
-        n = (b * h * w - 1) * ld + c          # the view may be a channel slice of a wider buffer
+        b, h, w, c, ctot = b.value, h.value, w.value, c.value, ld.value
+        # chunk-planar [B][ctot/8][H][W][8]; the view may be a channel slice (whole planes) of a wider buffer
+        n = (b - 1) * ctot * h * w + c * h * w
         flat = buf[off:off + 2 * n].view(dt)
-        t = torch.as_strided(flat, (b, h, w, c), (h * w * ld, w * ld, ld, 1))
-        return t.permute(0, 3, 1, 2).float().contiguous()
+        t = torch.as_strided(flat, (b, c // 8, h, w, 8), (ctot * h * w, h * w * 8, w * 8, 8, 1))
+        return t.permute(0, 1, 4, 2, 3).reshape(b, c, h, w).float().contiguous()

@@ -12,6 +12,7 @@ import torch.nn.functional as F
 
 from oracle import generator_oracle as go
 from oracle import raster_oracle as ro
+from rib.layout import from_planar, to_planar
 from rib.synth import synth_flow, synth_image, synth_joints
 
 pytestmark = pytest.mark.gpu
@@ -111,8 +112,8 @@ def _run_conv(dev, x_nchw, w, bias, k, stride, act, want_stats, simt):
     dt = _act_dtype()
     b, cin, h, wd = x_nchw.shape
     cout = w.shape[0]
-    x = x_nchw.permute(0, 2, 3, 1).contiguous().to(dt).to(dev)
-    out = torch.zeros(b, h // stride, wd // stride, cout, dtype=dt, device=dev)
+    x = to_planar(x_nchw, dt).to(dev)
+    out = torch.zeros(b, cout // 8, h // stride, wd // stride, 8, dtype=dt, device=dev)
     stats = torch.zeros(b, cout, 2, dtype=torch.float64, device=dev) if want_stats else None
     scratch = torch.empty(lib.rib_conv_test_scratch_bytes(cin, cout, k) + 1024, dtype=torch.uint8, device=dev)
     wd_, bd_ = w.contiguous().to(dev), bias.contiguous().to(dev)
@@ -124,19 +125,23 @@ def _run_conv(dev, x_nchw, w, bias, k, stride, act, want_stats, simt):
         torch.cuda.synchronize()
     finally:
         lib.rib_debug_set_simt(0)
-    return out.float().cpu().permute(0, 3, 1, 2), (stats.cpu() if want_stats else None)
+    return from_planar(out.float().cpu()), (stats.cpu() if want_stats else None)
 
 
 CONV_CASES = [
     # (B, Cin, Cout, H, W, k, stride)
-    (1, 16, 16, 16, 16, 3, 1),     # one tile, BK=16 (SW32), BN=16
-    (2, 32, 32, 16, 32, 3, 1),     # BK=32 (SW64)
-    (1, 64, 64, 32, 32, 3, 1),     # BK=64 (SW128)
-    (1, 128, 256, 16, 16, 3, 1),   # two K chunks per tap, two N tiles
+    (1, 16, 16, 16, 8, 3, 1),      # one tile, one stage of 16 channels (weights SW32), BN=16
+    (1, 16, 16, 16, 16, 3, 1),     # two tiles side by side (halo columns come from the neighbour)
+    (2, 32, 32, 16, 32, 3, 1),     # 32-channel stage (SW64)
+    (1, 64, 64, 32, 32, 3, 1),     # 64-channel stage, 32-channel K groups
+    (1, 128, 256, 16, 16, 3, 1),   # streamed weights, several stages, two N tiles
+    (1, 256, 256, 32, 32, 3, 1),   # streamed weights with two M sub-tiles per super-tile (MT=2)
     (2, 64, 128, 32, 32, 3, 2),    # stride 2 through the four parity views
-    (1, 512, 64, 16, 16, 1, 1),    # 1x1 (SPADE-shaped K)
+    (1, 512, 64, 16, 16, 1, 1),    # 1x1 (SPADE-shaped K), resident weights
+    (2, 512, 128, 64, 16, 1, 1),   # 1x1, streamed weights, MT=2
     (1, 32, 16, 20, 30, 3, 1),     # ragged: H, W not multiples of the tile (HSM.yaml's 320x480 / 16)
-    (1, 16, 32, 64, 96, 3, 2),     # stride 2, BK=16
+    (1, 16, 32, 64, 96, 3, 2),     # stride 2, 16-channel stage
+    (3, 16, 64, 128, 128, 3, 1),   # more tiles than persistent CTAs: tile loop, TMEM double buffering, stats per image
 ]
 
 

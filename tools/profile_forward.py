@@ -1,0 +1,44 @@
+#!/usr/bin/env python
+"""Runs N generator forwards (B, H, W) on cuda:0 — the command ncu wraps for the per-kernel captures
+under profiles/ (B200_PROFILING.md recipe).  No timing is reported from here."""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, 'render-in-between_b200')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--batch', type=int, default=32)
+    ap.add_argument('--size', type=int, default=512)
+    ap.add_argument('--iters', type=int, default=2)
+    a = ap.parse_args()
+    from rib.arch import Arch
+    from rib.config import default_gen_cfg
+    from rib.generator import Generator
+    from rib.synth import synth_image, synth_joints, synth_state_dict
+    import rib
+    dev = torch.device('cuda:0')
+    cfg = default_gen_cfg()
+    gen = Generator(cfg)
+    gen.load_state_dict(synth_state_dict(Arch(cfg), seed=0, power_iters=5), strict=True)
+    gen = gen.to(dev).eval()
+    b, h, w = a.batch, a.size, a.size
+    label = rib.rasterize(torch.from_numpy(synth_joints(b, h, w, seed=3)).to(dev), h, w)
+    fake, prev = synth_image(b, h, w, seed=1).to(dev), synth_image(b, h, w, seed=2).to(dev)
+    with torch.no_grad():
+        for _ in range(a.iters):
+            img, mask = gen(label, None, fake, prev)
+            rib.composite(img, mask, fake)
+    torch.cuda.synchronize()
+    print('ok', float(img.abs().mean()), float(mask.mean()))
+
+
+if __name__ == '__main__':
+    main()
