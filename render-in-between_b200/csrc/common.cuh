@@ -29,14 +29,24 @@ __device__ __forceinline__ act_t f2act(float v) { return __float2bfloat16_rn(v);
 __device__ __forceinline__ float act2f(act_t v) { return __bfloat162float(v); }
 #endif
 
+// two floats -> one packed 16-bit pair (a in the low half), one F2FP instruction
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
-  act_t x = f2act(a), y = f2act(b);
-  return (uint32_t)(*reinterpret_cast<uint16_t*>(&x)) | ((uint32_t)(*reinterpret_cast<uint16_t*>(&y)) << 16);
+#ifdef RIB_ACT_FP16
+  __half2 h = __floats2half2_rn(a, b);
+#else
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+#endif
+  return *reinterpret_cast<uint32_t*>(&h);
 }
 __device__ __forceinline__ void unpack2(uint32_t u, float& a, float& b) {
-  uint16_t lo = (uint16_t)(u & 0xffffu), hi = (uint16_t)(u >> 16);
-  a = act2f(*reinterpret_cast<act_t*>(&lo));
-  b = act2f(*reinterpret_cast<act_t*>(&hi));
+#ifdef RIB_ACT_FP16
+  const float2 f = __half22float2(*reinterpret_cast<__half2*>(&u));
+  a = f.x;
+  b = f.y;
+#else
+  a = __uint_as_float(u << 16);          // bf16 -> fp32 is a 16-bit shift
+  b = __uint_as_float(u & 0xffff0000u);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -182,6 +192,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Split form of tmem_ld16: issue the load, and later wait for it.  The wait names the destination
+// registers as in/out operands so that no use of them can be scheduled above it.
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
 }
 
 // UMMA shared-memory descriptor for a K-major tile whose rows are `row_bytes` (32/64/128) wide and

@@ -109,97 +109,111 @@ __device__ void simt_chunk(const ConvGemmParams& p, int n, int oy, int ox, int c
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-template <int MODE>
+// Per-warp staging buffer for the instance-norm statistics: 32 rows (pixels) x 16 columns fp32 with a
+// 20-float row pitch (conflict-free 16-byte row writes and scalar column reads).
+static constexpr int kStatPitch = 20;
+static constexpr int kStatWarpFloats = 32 * kStatPitch;
+
+template <int MODE, int BN, bool SIMT>
 __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
-  const int S = p.stages0 + p.stages1;  // pipeline stages per tile
+  constexpr int NCH = BN / 16;                         // 16-column chunks of the N tile
+  constexpr int CT = BN / 2;                           // EPI_SPADE: channels per tile ([gamma | beta])
+  const int G = p.stages0 + p.stages1;                 // channel groups (halo tiles) per output tile
+  const int n_bt = p.stages0 * p.ntaps + p.stages1;    // weight sub-tiles per output tile
   uint8_t* sA = smem;
-  uint8_t* sB = sA + (size_t)p.ring * p.a_slot_bytes;
-  const size_t b_bytes = (size_t)(p.b_resident ? S : p.ring) * p.b_stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + b_bytes);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + p.ring;
-  uint64_t* tmem_full_bar = bars + 2 * p.ring;       // [2]
-  uint64_t* tmem_empty_bar = bars + 2 * p.ring + 2;  // [2]
-  uint64_t* bres_bar = bars + 2 * p.ring + 4;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * p.ring + 5);
-  float* s_bias = reinterpret_cast<float*>(tmem_ptr + 4);  // [BN]
-  float* s_aux = s_bias + p.BN;                            // STORE: [2*BN] stats; SPADE: [2*CT] mean, rstd
+  uint8_t* sB = sA + (size_t)p.a_ring * p.a_slot_bytes;
+  uint8_t* sStat = sB + (size_t)(p.b_resident ? n_bt : p.b_ring) * p.b_tap_bytes;
+  const bool want_stats = MODE == EPI_STORE && p.stats != nullptr;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + (want_stats ? 4 * kStatWarpFloats * 4 : 0));
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + p.a_ring;
+  uint64_t* b_full = a_empty + p.a_ring;
+  uint64_t* b_empty = b_full + p.b_ring;
+  uint64_t* tmem_full_bar = b_empty + p.b_ring;  // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [2]
+  uint64_t* bres_bar = tmem_empty_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bres_bar + 1);
+  float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr + 4) + 15) & ~(uintptr_t)15);  // [BN], 16-byte aligned
+  float* s_aux = s_bias + BN;                              // STORE: [2*BN] stats; SPADE: [2*CT] rstd, -mean*rstd
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int ntile = blockIdx.x % p.n_tiles;
   const int cta_m = blockIdx.x / p.n_tiles;
-  const int cta_m_stride = gridDim.x / p.n_tiles;
+  const int cta_groups = gridDim.x / p.n_tiles;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
-  const int total_tiles = tiles_per_img * p.B;
-  const int acc_cols = p.MT * p.BN;  // TMEM columns of one accumulator buffer
+  const long long total_tiles = (long long)tiles_per_img * p.B;
+  // contiguous range of super-tiles: neighbouring tiles share halo rows in L2 and an image's statistics
+  // are flushed by few CTAs
+  const int t_begin = (int)(total_tiles * cta_m / cta_groups);
+  const int t_end = (int)(total_tiles * (cta_m + 1) / cta_groups);
+  const int acc_cols = p.MT * BN;  // TMEM columns of one accumulator buffer
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < 2 * acc_cols) tmem_cols <<= 1;
-  const bool tc = !p.debug_simt;
 
-  if (warp == 0 && lane == 0 && tc) {
-    prefetch_tmap(&p.amap[0]);
-    prefetch_tmap(&p.bmap);
-    for (int i = 0; i < p.ring; ++i) {
-      mbar_init(smem_u32(&full_bar[i]), 1);
-      mbar_init(smem_u32(&empty_bar[i]), 1);
+  if (!SIMT) {
+    if (warp == 0 && lane == 0) {
+      prefetch_tmap(&p.amap[0]);
+      prefetch_tmap(&p.bmap);
+      for (int i = 0; i < p.a_ring; ++i) {
+        mbar_init(smem_u32(&a_full[i]), 1);
+        mbar_init(smem_u32(&a_empty[i]), 1);
+      }
+      for (int i = 0; i < p.b_ring; ++i) {
+        mbar_init(smem_u32(&b_full[i]), 1);
+        mbar_init(smem_u32(&b_empty[i]), 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(smem_u32(&tmem_full_bar[i]), 1);
+        mbar_init(smem_u32(&tmem_empty_bar[i]), 4);
+      }
+      mbar_init(smem_u32(bres_bar), 1);
+      fence_barrier_init();
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&tmem_full_bar[i]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[i]), 4);
+    if (warp == 1) {
+      tmem_alloc(smem_u32(tmem_ptr), tmem_cols);
+      tmem_relinquish();
     }
-    mbar_init(smem_u32(bres_bar), 1);
-    fence_barrier_init();
-  }
-  if (warp == 1 && tc) {
-    tmem_alloc(smem_u32(tmem_ptr), tmem_cols);
-    tmem_relinquish();
   }
   if (warp >= 2) {
     const int e = threadIdx.x - 64;
-    for (int c = e; c < p.BN; c += 128) s_bias[c] = p.bias[ntile * p.BN + c];
+    for (int c = e; c < BN; c += 128) s_bias[c] = p.bias[ntile * BN + c];
     if (MODE == EPI_STORE) {
-      for (int c = e; c < 2 * p.BN; c += 128) s_aux[c] = 0.f;
+      for (int c = e; c < 2 * BN; c += 128) s_aux[c] = 0.f;
     }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = tc ? *tmem_ptr : 0u;
+  const uint32_t tmem_base = SIMT ? 0u : *tmem_ptr;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0 && tc) {
-      if (p.b_resident) {  // all weight stages of this N tile, once
+    if (!SIMT && lane == 0) {
+      if (p.b_resident) {  // all weight sub-tiles of this N tile, once
         const uint32_t bb = smem_u32(bres_bar);
-        mbar_arrive_expect_tx(bb, (uint32_t)((p.stages0 * p.ntaps + p.stages1) * p.b_tap_bytes));
-        for (int s = 0; s < S; ++s) {
-          const int nt = s < p.stages0 ? p.ntaps : 1;
-          const int k0 = s < p.stages0 ? s * p.ntaps * p.BKc : (p.stages0 * p.ntaps + (s - p.stages0)) * p.BKc;
-          for (int t = 0; t < nt; ++t)
-            tma_load_2d(smem_u32(sB + (size_t)s * p.b_stage_bytes + (size_t)t * p.b_tap_bytes), &p.bmap, bb,
-                        k0 + t * p.BKc, ntile * p.BN);
-        }
+        mbar_arrive_expect_tx(bb, (uint32_t)n_bt * p.b_tap_bytes);
+        for (int i = 0; i < n_bt; ++i)
+          tma_load_2d(smem_u32(sB + (size_t)i * p.b_tap_bytes), &p.bmap, bb, i * p.BKc, ntile * BN);
       }
-      int slot = 0;
-      uint32_t phase = 0;
-      for (int mt = cta_m; mt < total_tiles; mt += cta_m_stride) {
+      int a_slot = 0, b_slot = 0;
+      uint32_t a_phase = 0, b_phase = 0;
+      for (int mt = t_begin; mt < t_end; ++mt) {
         const int n = mt / tiles_per_img;
         const int rem = mt - n * tiles_per_img;
         const int tile_y = rem / p.tiles_x, tile_x = rem - tile_y * p.tiles_x;
         const int oy0 = tile_y * kTileH * p.MT, ox0 = tile_x * kTileW;
-        for (int s = 0; s < S; ++s) {
-          mbar_wait(smem_u32(&empty_bar[slot]), phase ^ 1u);
-          const uint32_t fb = smem_u32(&full_bar[slot]);
-          const bool src1 = s >= p.stages0;
-          const int nt = src1 ? 1 : p.ntaps;
-          mbar_arrive_expect_tx(fb, p.a_tx_bytes + (p.b_resident ? 0u : (uint32_t)nt * p.b_tap_bytes));
-          const uint32_t a_dst = smem_u32(sA + (size_t)slot * p.a_slot_bytes);
-          const int cg = (src1 ? s - p.stages0 : s) * (p.BKc >> 3);  // first 8-channel plane of the group
+        for (int g = 0; g < G; ++g) {
+          mbar_wait(smem_u32(&a_empty[a_slot]), a_phase ^ 1u);
+          const uint32_t fb = smem_u32(&a_full[a_slot]);
+          const bool src1 = g >= p.stages0;
+          mbar_arrive_expect_tx(fb, p.a_tx_bytes);
+          const uint32_t a_dst = smem_u32(sA + (size_t)a_slot * p.a_slot_bytes);
+          const int cg = (src1 ? g - p.stages0 : g) * (p.BKc >> 3);  // first 8-channel plane of the group
           if (p.stride == 1) {
             tma_load_4d(a_dst, &p.amap[src1 ? 1 : 0], fb, (ox0 - p.halo) * 8, oy0 - p.halo, cg, n);
           } else {
@@ -207,24 +221,32 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
             for (int q = 0; q < 4; ++q)
               tma_load_5d(a_dst + q * p.a_tile_bytes, &p.amap[q], fb, 0, ox0 - 1, oy0 - 1, cg, n);
           }
-          if (!p.b_resident) {
-            const int k0 = src1 ? (p.stages0 * p.ntaps + (s - p.stages0)) * p.BKc : s * p.ntaps * p.BKc;
-            for (int t = 0; t < nt; ++t)
-              tma_load_2d(smem_u32(sB + (size_t)slot * p.b_stage_bytes + (size_t)t * p.b_tap_bytes), &p.bmap, fb,
-                          k0 + t * p.BKc, ntile * p.BN);
+          if (++a_slot == p.a_ring) {
+            a_slot = 0;
+            a_phase ^= 1u;
           }
-          if (++slot == p.ring) {
-            slot = 0;
-            phase ^= 1u;
+          if (!p.b_resident) {
+            const int nt = src1 ? 1 : p.ntaps;
+            const int i0 = src1 ? p.stages0 * p.ntaps + (g - p.stages0) : g * p.ntaps;
+            for (int t = 0; t < nt; ++t) {
+              mbar_wait(smem_u32(&b_empty[b_slot]), b_phase ^ 1u);
+              const uint32_t bf = smem_u32(&b_full[b_slot]);
+              mbar_arrive_expect_tx(bf, p.b_tap_bytes);
+              tma_load_2d(smem_u32(sB + (size_t)b_slot * p.b_tap_bytes), &p.bmap, bf, (i0 + t) * p.BKc, ntile * BN);
+              if (++b_slot == p.b_ring) {
+                b_slot = 0;
+                b_phase ^= 1u;
+              }
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && tc) {
-      int slot = 0;
-      uint32_t phase = 0;
+    if (!SIMT && lane == 0) {
+      int a_slot = 0, b_slot = 0;
+      uint32_t a_phase = 0, b_phase = 0;
       const uint32_t b_row_bytes = (uint32_t)p.BKc * 2u;
       const int kk_steps = p.BKc >> 4;
       if (p.b_resident) {
@@ -232,36 +254,51 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
         tc_fence_after();
       }
       int it = 0;
-      for (int mt = cta_m; mt < total_tiles; mt += cta_m_stride, ++it) {
+      for (int mt = t_begin; mt < t_end; ++mt, ++it) {
         const int buf = it & 1;
         const uint32_t use = (uint32_t)(it >> 1);
         mbar_wait(smem_u32(&tmem_empty_bar[buf]), (use & 1u) ^ 1u);  // epilogue has drained this buffer
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)(buf * acc_cols);
-        for (int s = 0; s < S; ++s) {
-          mbar_wait(smem_u32(&full_bar[slot]), phase);
+        for (int g = 0; g < G; ++g) {
+          mbar_wait(smem_u32(&a_full[a_slot]), a_phase);
           tc_fence_after();
-          const bool src1 = s >= p.stages0;
+          const bool src1 = g >= p.stages0;
           const int nt = src1 ? 1 : p.ntaps;
-          const uint32_t a_base = smem_u32(sA + (size_t)slot * p.a_slot_bytes);
-          const uint32_t b_base = smem_u32(sB + (size_t)(p.b_resident ? s : slot) * p.b_stage_bytes);
+          const int i0 = src1 ? p.stages0 * p.ntaps + (g - p.stages0) : g * p.ntaps;
+          const uint32_t a_base = smem_u32(sA + (size_t)a_slot * p.a_slot_bytes);
           for (int t = 0; t < nt; ++t) {
-            const TapGeom g = tap_geom(p, src1, t);
-            const uint64_t bdesc = make_kmajor_desc(b_base + (uint32_t)t * p.b_tap_bytes, b_row_bytes);
+            uint32_t b_addr;
+            if (p.b_resident) {
+              b_addr = smem_u32(sB + (size_t)(i0 + t) * p.b_tap_bytes);
+            } else {
+              mbar_wait(smem_u32(&b_full[b_slot]), b_phase);
+              tc_fence_after();
+              b_addr = smem_u32(sB + (size_t)b_slot * p.b_tap_bytes);
+            }
+            const TapGeom tg = tap_geom(p, src1, t);
+            const uint64_t bdesc = make_kmajor_desc(b_addr, b_row_bytes);
             for (int m = 0; m < p.MT; ++m) {
               const uint32_t a_addr =
-                  a_base + (uint32_t)g.tile * p.a_tile_bytes + (uint32_t)(g.poff + m * kTileH * p.halo_w) * 16u;
+                  a_base + (uint32_t)tg.tile * p.a_tile_bytes + (uint32_t)(tg.poff + m * kTileH * p.halo_w) * 16u;
               for (int kk = 0; kk < kk_steps; ++kk) {
                 const uint64_t adesc = make_nosw_desc(a_addr + (uint32_t)(2 * kk) * p.lbo, p.lbo, p.sbo);
-                umma_f16(d0 + (uint32_t)(m * p.BN), adesc, bdesc + (uint64_t)(2 * kk), p.idesc,
-                         (uint32_t)((s | t | kk) != 0));
+                umma_f16(d0 + (uint32_t)(m * BN), adesc, bdesc + (uint64_t)(2 * kk), p.idesc,
+                         (uint32_t)((g | t | kk) != 0));
+              }
+            }
+            if (!p.b_resident) {
+              umma_commit(smem_u32(&b_empty[b_slot]));  // frees the weight slot once the MMAs have read it
+              if (++b_slot == p.b_ring) {
+                b_slot = 0;
+                b_phase ^= 1u;
               }
             }
           }
-          umma_commit(smem_u32(&empty_bar[slot]));  // frees this ring slot once the MMAs have read it
-          if (++slot == p.ring) {
-            slot = 0;
-            phase ^= 1u;
+          umma_commit(smem_u32(&a_empty[a_slot]));  // frees the halo-tile slot
+          if (++a_slot == p.a_ring) {
+            a_slot = 0;
+            a_phase ^= 1u;
           }
         }
         umma_commit(smem_u32(&tmem_full_bar[buf]));
@@ -271,12 +308,44 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
     // ===================== Epilogue =====================
     const int q = warp & 3;
     const int e = threadIdx.x - 64;
-    const int prow = q * 32 + lane;             // row of the M=128 sub-tile = TMEM lane
-    const int ty = prow >> 3, tx = prow & 7;    // 16 x 8 pixel tile
+    const int prow = q * 32 + lane;           // row of the M=128 sub-tile = TMEM lane
+    const int ty = prow >> 3, tx = prow & 7;  // 16 x 8 pixel tile
     const size_t HW8 = (size_t)p.H * p.W * 8;
+    const float slope = p.act == ACT_LRELU ? 0.2f : 1.0f;  // lrelu(v) = max(v, 0.2 v); identity = max(v, v)
+    float* sbuf = reinterpret_cast<float*>(sStat) + (warp - 2) * kStatWarpFloats;
+    // column sums: lane l owns column (l & 15) of every chunk for half of the 32 rows
+    const int st_col = lane & 15, st_half = lane >> 4;
+    float acc1[NCH], acc2[NCH];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) acc1[j] = acc2[j] = 0.f;
     int cur_n = -1;
     int it = 0;
-    for (int mt = cta_m; mt < total_tiles; mt += cta_m_stride, ++it) {
+
+    auto flush_stats = [&](int n_img) {
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        const float t1 = acc1[j] + __shfl_xor_sync(0xffffffffu, acc1[j], 16);
+        const float t2 = acc2[j] + __shfl_xor_sync(0xffffffffu, acc2[j], 16);
+        if (lane < 16) {
+          atomicAdd(&s_aux[j * 16 + lane], t1);
+          atomicAdd(&s_aux[BN + j * 16 + lane], t2);
+        }
+        acc1[j] = acc2[j] = 0.f;
+      }
+      epi_bar();
+      for (int c = e; c < BN; c += 128) {
+        const int col = ntile * BN + c;
+        if (col < p.n_valid) {
+          atomicAdd(&p.stats[((size_t)n_img * p.n_valid + col) * 2 + 0], (double)s_aux[c]);
+          atomicAdd(&p.stats[((size_t)n_img * p.n_valid + col) * 2 + 1], (double)s_aux[BN + c]);
+        }
+        s_aux[c] = 0.f;
+        s_aux[BN + c] = 0.f;
+      }
+      epi_bar();
+    };
+
+    for (int mt = t_begin; mt < t_end; ++mt, ++it) {
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
       const int n = mt / tiles_per_img;
@@ -285,39 +354,28 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
       const int oy0 = tile_y * kTileH * p.MT, ox0 = tile_x * kTileW;
 
       if (n != cur_n) {  // uniform over the 128 epilogue threads
-        if (MODE == EPI_STORE && p.stats != nullptr && cur_n >= 0) {
-          epi_bar();
-          for (int c = e; c < p.BN; c += 128) {
-            const int col = ntile * p.BN + c;
-            if (col < p.n_valid) {
-              atomicAdd(&p.stats[((size_t)cur_n * p.n_valid + col) * 2 + 0], (double)s_aux[c]);
-              atomicAdd(&p.stats[((size_t)cur_n * p.n_valid + col) * 2 + 1], (double)s_aux[p.BN + c]);
-            }
-            s_aux[c] = 0.f;
-            s_aux[p.BN + c] = 0.f;
-          }
-          epi_bar();
-        }
+        if (MODE == EPI_STORE && want_stats && cur_n >= 0) flush_stats(cur_n);
         if (MODE == EPI_SPADE) {
-          const int tiles_per_q = p.C / p.CT;
-          const int c0 = (ntile % tiles_per_q) * p.CT;
+          const int tiles_per_q = p.C / CT;
+          const int c0 = (ntile % tiles_per_q) * CT;
           const double cnt = (double)p.Hx * (double)p.Wx;
           epi_bar();
-          for (int c = e; c < p.CT; c += 128) {
+          for (int c = e; c < CT; c += 128) {
             const double s = p.xstats[((size_t)n * p.C + c0 + c) * 2 + 0];
             const double ss = p.xstats[((size_t)n * p.C + c0 + c) * 2 + 1];
             const double mean = s / cnt;
             double var = ss / cnt - mean * mean;
             var = var < 0.0 ? 0.0 : var;
-            s_aux[c] = (float)mean;
-            s_aux[p.CT + c] = (float)(1.0 / sqrt(var + (double)p.eps));
+            const double rstd = 1.0 / sqrt(var + (double)p.eps);
+            s_aux[c] = (float)rstd;
+            s_aux[CT + c] = (float)(-mean * rstd);
           }
           epi_bar();
         }
         cur_n = n;
       }
 
-      if (tc) {
+      if (!SIMT) {
         mbar_wait(smem_u32(&tmem_full_bar[buf]), use & 1u);
         tc_fence_after();
       }
@@ -325,23 +383,38 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
         const int oy = oy0 + m * kTileH + ty, ox = ox0 + tx;
         const bool valid = (oy < p.H) && (ox < p.W);
         const size_t pix8 = ((size_t)oy * p.W + ox) * 8;
-        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols + m * p.BN);
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols + m * BN);
 
         if (MODE == EPI_STORE) {
-          const int nchunks = p.BN / 16;
-          for (int j = 0; j < nchunks; ++j) {
-            float v[16];
-            const int col0 = ntile * p.BN + j * 16;
+          act_t* obase = p.out.p + (size_t)n * p.out.bstride + (size_t)((ntile * BN) >> 3) * HW8 + pix8;
+          const act_t* rbase = p.has_res ? p.res.p + (size_t)n * p.res.bstride + (size_t)((ntile * BN) >> 3) * HW8 + pix8
+                                         : nullptr;
+          uint32_t r[2][16];
+          if (!SIMT) tmem_ld16_issue(trow, r[0]);
+#pragma unroll
+          for (int j = 0; j < NCH; ++j) {
             uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
             if (p.has_res && valid) {
-              const act_t* rp = p.res.p + (size_t)n * p.res.bstride + (size_t)(col0 >> 3) * HW8 + pix8;
-              r0 = *reinterpret_cast<const uint4*>(rp);
-              r1 = *reinterpret_cast<const uint4*>(rp + HW8);
+              r0 = *reinterpret_cast<const uint4*>(rbase + (size_t)(2 * j) * HW8);
+              r1 = *reinterpret_cast<const uint4*>(rbase + (size_t)(2 * j + 1) * HW8);
             }
-            if (!tc) simt_chunk(p, n, oy, ox, col0, v);
-            else tmem_ld16(trow + (uint32_t)(j * 16), v);
+            float v[16];
+            if (SIMT) {
+              simt_chunk(p, n, oy, ox, ntile * BN + j * 16, v);
+            } else {
+              tmem_ld16_wait(r[j & 1]);
+              if (j + 1 < NCH) tmem_ld16_issue(trow + (uint32_t)((j + 1) * 16), r[(j + 1) & 1]);
 #pragma unroll
-            for (int c = 0; c < 16; ++c) v[c] += s_bias[j * 16 + c];
+              for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(r[j & 1][c]);
+            }
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(s_bias + j * 16 + c4 * 4);
+              v[c4 * 4 + 0] += b4.x;
+              v[c4 * 4 + 1] += b4.y;
+              v[c4 * 4 + 2] += b4.z;
+              v[c4 * 4 + 3] += b4.w;
+            }
             if (p.has_res) {
               const uint32_t ru[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
@@ -352,78 +425,96 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
                 v[2 * c + 1] += b;
               }
             }
-            if (p.stats != nullptr) {
-              float s1[16], s2[16];
+            if (want_stats) {
+              // transpose through shared memory: rows = pixels of this warp, then per-lane column sums
+              float4* srow = reinterpret_cast<float4*>(sbuf + lane * kStatPitch);
 #pragma unroll
-              for (int c = 0; c < 16; ++c) {
-                s1[c] = valid ? v[c] : 0.f;
-                s2[c] = valid ? v[c] * v[c] : 0.f;
+              for (int c4 = 0; c4 < 4; ++c4)
+                srow[c4] = valid ? make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3])
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+              __syncwarp();
+              float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int row = (i >> 2) * 8 + st_half * 4 + (i & 3);
+                const float xv = sbuf[row * kStatPitch + st_col];
+                s1 += xv;
+                s2 = fmaf(xv, xv, s2);
               }
-              const float t1 = warp_colsum16(s1, lane);
-              const float t2 = warp_colsum16(s2, lane);
-              if ((lane & 1) == 0) {
-                const int c = (lane >> 1) & 15;
-                atomicAdd(&s_aux[j * 16 + c], t1);
-                atomicAdd(&s_aux[p.BN + j * 16 + c], t2);
-              }
+              acc1[j] += s1;
+              acc2[j] += s2;
+              __syncwarp();
             }
-            if (valid && col0 < p.n_valid) {
+            if (valid) {
               uint32_t o[8];
 #pragma unroll
-              for (int c = 0; c < 8; ++c) o[c] = pack2(apply_act(v[2 * c], p.act), apply_act(v[2 * c + 1], p.act));
-              act_t* op = p.out.p + (size_t)n * p.out.bstride + (size_t)(col0 >> 3) * HW8 + pix8;
-              *reinterpret_cast<uint4*>(op) = make_uint4(o[0], o[1], o[2], o[3]);
-              *reinterpret_cast<uint4*>(op + HW8) = make_uint4(o[4], o[5], o[6], o[7]);
+              for (int c = 0; c < 8; ++c)
+                o[c] = pack2(fmaxf(v[2 * c], slope * v[2 * c]), fmaxf(v[2 * c + 1], slope * v[2 * c + 1]));
+              *reinterpret_cast<uint4*>(obase + (size_t)(2 * j) * HW8) = make_uint4(o[0], o[1], o[2], o[3]);
+              *reinterpret_cast<uint4*>(obase + (size_t)(2 * j + 1) * HW8) = make_uint4(o[4], o[5], o[6], o[7]);
             }
           }
         } else if (MODE == EPI_SPADE) {
-          const int tiles_per_q = p.C / p.CT;
+          constexpr int NCS = CT / 16;
+          const int tiles_per_q = p.C / CT;
           const int qq = ntile / tiles_per_q;
-          const int c0 = (ntile - qq * tiles_per_q) * p.CT;
+          const int c0 = (ntile - qq * tiles_per_q) * CT;
           const int sy = p.ups ? (oy >> 1) : oy, sx = p.ups ? (ox >> 1) : ox;
           const size_t xHW8 = (size_t)p.Hx * p.Wx * 8;
           const act_t* xrow = p.x.p + (size_t)n * p.x.bstride + (size_t)(c0 >> 3) * xHW8 + ((size_t)sy * p.Wx + sx) * 8;
           act_t* orow = p.outq[qq].p + (size_t)n * p.outq[qq].bstride + (size_t)(c0 >> 3) * HW8 + pix8;
-          const int actq = p.actq[qq];
-          const int nchunks = p.CT / 16;
-          for (int j = 0; j < nchunks; ++j) {
-            float g[16], b[16];
+          const float sl = p.actq[qq] == ACT_LRELU ? 0.2f : 1.0f;
+          uint32_t rg[16], rb[16];
+#pragma unroll
+          for (int j = 0; j < NCS; ++j) {
             uint4 x0 = make_uint4(0, 0, 0, 0), x1 = x0;
             if (valid) {
               x0 = *reinterpret_cast<const uint4*>(xrow + (size_t)(2 * j) * xHW8);
               x1 = *reinterpret_cast<const uint4*>(xrow + (size_t)(2 * j + 1) * xHW8);
             }
-            if (!tc) {
-              simt_chunk(p, n, oy, ox, ntile * p.BN + j * 16, g);
-              simt_chunk(p, n, oy, ox, ntile * p.BN + p.CT + j * 16, b);
+            float g[16], b[16];
+            if (SIMT) {
+              simt_chunk(p, n, oy, ox, ntile * BN + j * 16, g);
+              simt_chunk(p, n, oy, ox, ntile * BN + CT + j * 16, b);
             } else {
-              tmem_ld16(trow + (uint32_t)(j * 16), g);
-              tmem_ld16(trow + (uint32_t)(p.CT + j * 16), b);
+              tmem_ld16_issue(trow + (uint32_t)(j * 16), rg);
+              tmem_ld16_issue(trow + (uint32_t)(CT + j * 16), rb);
+              tmem_ld16_wait(rg);
+              tmem_ld16_wait(rb);
+#pragma unroll
+              for (int c = 0; c < 16; ++c) {
+                g[c] = __uint_as_float(rg[c]);
+                b[c] = __uint_as_float(rb[c]);
+              }
             }
             if (valid) {
               const uint32_t xu[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+              float y[16];
+#pragma unroll
+              for (int c4 = 0; c4 < 4; ++c4) {
+                const int cb = j * 16 + c4 * 4;
+                const float4 rs = *reinterpret_cast<const float4*>(s_aux + cb);        // rstd
+                const float4 ms = *reinterpret_cast<const float4*>(s_aux + CT + cb);   // -mean * rstd
+                const float4 bg = *reinterpret_cast<const float4*>(s_bias + cb);       // gamma bias + 1
+                const float4 bb = *reinterpret_cast<const float4*>(s_bias + CT + cb);  // beta bias
+                float xa, xb, xc, xd;
+                unpack2(xu[c4 * 2], xa, xb);
+                unpack2(xu[c4 * 2 + 1], xc, xd);
+                y[c4 * 4 + 0] = fmaf(fmaf(xa, rs.x, ms.x), g[c4 * 4 + 0] + bg.x, b[c4 * 4 + 0] + bb.x);
+                y[c4 * 4 + 1] = fmaf(fmaf(xb, rs.y, ms.y), g[c4 * 4 + 1] + bg.y, b[c4 * 4 + 1] + bb.y);
+                y[c4 * 4 + 2] = fmaf(fmaf(xc, rs.z, ms.z), g[c4 * 4 + 2] + bg.z, b[c4 * 4 + 2] + bb.z);
+                y[c4 * 4 + 3] = fmaf(fmaf(xd, rs.w, ms.w), g[c4 * 4 + 3] + bg.w, b[c4 * 4 + 3] + bb.w);
+              }
               uint32_t o[8];
 #pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                float xa, xb;
-                unpack2(xu[c], xa, xb);
-                const int ca = j * 16 + 2 * c, cb = ca + 1;
-                // s_bias of the gamma half already holds (bias + 1)
-                float ya = (xa - s_aux[ca]) * s_aux[p.CT + ca] * (g[2 * c] + s_bias[ca]) + (b[2 * c] + s_bias[p.CT + ca]);
-                float yb = (xb - s_aux[cb]) * s_aux[p.CT + cb] * (g[2 * c + 1] + s_bias[cb]) + (b[2 * c + 1] + s_bias[p.CT + cb]);
-                if (actq == ACT_LRELU) {
-                  ya = lrelu02(ya);
-                  yb = lrelu02(yb);
-                }
-                o[c] = pack2(ya, yb);
-              }
+              for (int c = 0; c < 8; ++c) o[c] = pack2(fmaxf(y[2 * c], sl * y[2 * c]), fmaxf(y[2 * c + 1], sl * y[2 * c + 1]));
               *reinterpret_cast<uint4*>(orow + (size_t)(2 * j) * HW8) = make_uint4(o[0], o[1], o[2], o[3]);
               *reinterpret_cast<uint4*>(orow + (size_t)(2 * j + 1) * HW8) = make_uint4(o[4], o[5], o[6], o[7]);
             }
           }
         } else {  // EPI_FINAL (BN == 16)
           float v[16];
-          if (!tc) simt_chunk(p, n, oy, ox, 0, v);
+          if (SIMT) simt_chunk(p, n, oy, ox, 0, v);
           else tmem_ld16(trow, v);
           if (valid) {
 #pragma unroll
@@ -440,27 +531,18 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
           }
         }
       }
-      if (tc) {  // hand the accumulator buffer back to the MMA issuer
+      if (!SIMT) {  // hand the accumulator buffer back to the MMA issuer
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[buf]));
       }
     }
-    if (MODE == EPI_STORE && p.stats != nullptr && cur_n >= 0) {
-      epi_bar();
-      for (int c = e; c < p.BN; c += 128) {
-        const int col = ntile * p.BN + c;
-        if (col < p.n_valid) {
-          atomicAdd(&p.stats[((size_t)cur_n * p.n_valid + col) * 2 + 0], (double)s_aux[c]);
-          atomicAdd(&p.stats[((size_t)cur_n * p.n_valid + col) * 2 + 1], (double)s_aux[p.BN + c]);
-        }
-      }
-    }
+    if (MODE == EPI_STORE && want_stats && cur_n >= 0) flush_stats(cur_n);
     tc_fence_before();
   }
 
   __syncthreads();
-  if (warp == 1 && tc) {
+  if (!SIMT && warp == 1) {
     __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
@@ -541,19 +623,23 @@ int make_tmap_w(CUtensorMap* m, const act_t* w, int K, int N, int bkc, int boxN,
   return 0;
 }
 
-int choose_bkc(int cin0, int cin1, int taps, int BN) {
-  int bk = cin0 < 64 ? cin0 : 64;
+int choose_bkc(int cin0, int cin1, int taps, int BN, int stride) {
+  (void)taps;
+  (void)BN;
+  const int cap = stride == 2 ? 32 : 64;  // stride 2 keeps four parity tiles per group in a ring slot
+  int bk = cin0 < cap ? cin0 : cap;
   if (cin1 > 0 && cin1 < bk) bk = cin1;
-  while (bk > 16 && (size_t)taps * BN * bk * 2 > 40 * 1024) bk /= 2;
   return bk;
 }
+
+static constexpr size_t kStatStageBytes = 4 * kStatWarpFloats * 4;
 
 int conv_gemm_configure(ConvGemmParams* p, int B, int Hout, int Wout, int cin0, int cin1, int taps, int stride,
                         int BN, int n_pad) {
   RIB_REQUIRE(taps == 1 || taps == 9, "conv_gemm: 1x1 or 3x3 only");
   RIB_REQUIRE(stride == 1 || (stride == 2 && taps == 9 && cin1 == 0), "conv_gemm: stride 2 needs a plain 3x3");
   RIB_REQUIRE(BN >= 16 && BN <= 128 && (BN & (BN - 1)) == 0 && n_pad % BN == 0, "conv_gemm: bad BN");
-  const int bkc = choose_bkc(cin0, cin1, taps, BN);
+  const int bkc = choose_bkc(cin0, cin1, taps, BN, stride);
   RIB_REQUIRE((bkc == 16 || bkc == 32 || bkc == 64) && cin0 % bkc == 0 && cin1 % bkc == 0,
               "conv_gemm: channel counts must be 16, 32 or multiples of 64");
   p->B = B;
@@ -568,11 +654,10 @@ int conv_gemm_configure(ConvGemmParams* p, int B, int Hout, int Wout, int cin0, 
   p->stride = stride;
   p->halo = taps == 9 ? 1 : 0;
   p->b_tap_bytes = (uint32_t)(BN * bkc * 2);
-  p->b_stage_bytes = (uint32_t)taps * p->b_tap_bytes;
-  const int S = p->stages0 + p->stages1;
-  const size_t b_all = (size_t)S * p->b_stage_bytes;
+  const int n_bt = p->stages0 * taps + p->stages1;
+  const size_t b_all = (size_t)n_bt * p->b_tap_bytes;
   p->b_resident = b_all <= 72 * 1024 ? 1 : 0;
-  p->MT = (!p->b_resident && Hout >= 2 * kTileH) ? 2 : 1;
+  p->MT = (!p->b_resident && stride == 1 && Hout >= 2 * kTileH) ? 2 : 1;
   const int hw = stride == 1 ? kTileW + 2 * p->halo : kTileW + 1;
   const int hh = stride == 1 ? kTileH * p->MT + 2 * p->halo : kTileH * p->MT + 1;
   p->halo_w = hw;
@@ -585,25 +670,36 @@ int conv_gemm_configure(ConvGemmParams* p, int B, int Hout, int Wout, int cin0, 
   p->a_tx_bytes = (uint32_t)ntile_a * tile_raw;
   p->tiles_x = ceil_div(Wout, kTileW);
   p->tiles_y = ceil_div(Hout, kTileH * p->MT);
-  // ring depth: resident-weight (bandwidth-bound) layers keep the CTA small so that two fit on an SM
-  const size_t per_slot = p->a_slot_bytes + (p->b_resident ? 0 : p->b_stage_bytes);
-  const size_t budget = p->b_resident ? (size_t)100 * 1024 - b_all : (size_t)200 * 1024;
-  int ring = (int)(budget / per_slot);
-  const int want = p->b_resident ? (S <= 2 ? 4 : 2 * S) : 8;
-  if (ring > want) ring = want;
-  if (ring > 8) ring = 8;
-  if (ring < 2) ring = 2;
-  p->ring = ring;
+  const int G = p->stages0 + p->stages1;
+  if (p->b_resident) {
+    // bandwidth-bound layers: keep the CTA near 100 KB so that two (or more) fit on an SM
+    const size_t budget = (size_t)100 * 1024 - b_all - kStatStageBytes;
+    int ring = (int)(budget / p->a_slot_bytes);
+    const int want = G <= 2 ? 4 : 2 * G;
+    if (ring > want) ring = want;
+    if (ring > 8) ring = 8;
+    if (ring < 2) ring = 2;
+    p->a_ring = ring;
+    p->b_ring = 1;  // unused
+  } else {
+    p->a_ring = 2;
+    const size_t budget = (size_t)205 * 1024 - kStatStageBytes - (size_t)2 * p->a_slot_bytes;
+    int ring = (int)(budget / p->b_tap_bytes);
+    if (ring > 12) ring = 12;
+    if (ring < 2) ring = 2;
+    p->b_ring = ring;
+  }
   p->idesc = make_idesc_f16(128, BN);
   return 0;
 }
 
 size_t conv_gemm_smem_bytes(const ConvGemmParams& p) {
-  const int S = p.stages0 + p.stages1;
-  size_t tiles = (size_t)p.ring * p.a_slot_bytes + (size_t)(p.b_resident ? S : p.ring) * p.b_stage_bytes;
-  size_t bars = (size_t)(2 * p.ring + 5) * 8 + 16;
-  size_t scratch = (size_t)p.BN * 4 * 3 + (size_t)(p.CT > 0 ? p.CT : 0) * 8 + 64;
-  return 1024 + tiles + bars + scratch;
+  const int n_bt = p.stages0 * p.ntaps + p.stages1;
+  size_t tiles = (size_t)p.a_ring * p.a_slot_bytes + (size_t)(p.b_resident ? n_bt : p.b_ring) * p.b_tap_bytes;
+  size_t stat = p.stats != nullptr ? kStatStageBytes : 0;
+  size_t bars = (size_t)(2 * p.a_ring + 2 * p.b_ring + 5) * 8 + 32;
+  size_t scratch = (size_t)p.BN * 4 * 3 + 64;
+  return 1024 + tiles + stat + bars + scratch;
 }
 
 static std::atomic<long long> g_launches{0};
@@ -634,48 +730,73 @@ int conv_gemm_profile_collect(double* total_ms, long long* launches) {
   return 0;
 }
 
-template <int MODE>
-static int occupancy_for(size_t smem, int* occ) {
-  int n = 0;
-  RIB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, conv_gemm_kernel<MODE>, kThreads, smem));
-  *occ = n;
+// Resident CTAs per SM for a given dynamic shared-memory size: limited by shared memory (227 KB usable,
+// 1 KB reserved per CTA), registers (64 K per SM) and TMEM columns (512 per SM).
+static int ctas_per_sm(const void* fn, size_t smem, int tmem_cols, int* occ) {
+  cudaFuncAttributes fa;
+  RIB_CHECK_CUDA(cudaFuncGetAttributes(&fa, fn));
+  const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * kThreads;
+  int o = (int)((size_t)227 * 1024 / (smem + 1024));
+  if (regs_per_cta > 0 && o > 65536 / regs_per_cta) o = 65536 / regs_per_cta;
+  if (o > 512 / tmem_cols) o = 512 / tmem_cols;
+  if (o > 4) o = 4;
+  if (o < 1) o = 1;
+  *occ = o;
   return 0;
+}
+
+typedef void (*ConvKernel)(const ConvGemmParams);
+
+template <bool SIMT>
+static ConvKernel pick_kernel(int mode, int BN) {
+  if (mode == EPI_STORE) {
+    switch (BN) {
+      case 16: return conv_gemm_kernel<EPI_STORE, 16, SIMT>;
+      case 32: return conv_gemm_kernel<EPI_STORE, 32, SIMT>;
+      case 64: return conv_gemm_kernel<EPI_STORE, 64, SIMT>;
+      case 128: return conv_gemm_kernel<EPI_STORE, 128, SIMT>;
+    }
+  } else if (mode == EPI_SPADE) {
+    switch (BN) {
+      case 32: return conv_gemm_kernel<EPI_SPADE, 32, SIMT>;
+      case 64: return conv_gemm_kernel<EPI_SPADE, 64, SIMT>;
+      case 128: return conv_gemm_kernel<EPI_SPADE, 128, SIMT>;
+    }
+  } else if (mode == EPI_FINAL && BN == 16) {
+    return conv_gemm_kernel<EPI_FINAL, 16, SIMT>;
+  }
+  return nullptr;
 }
 
 int launch_conv_gemm(const ConvGemmParams& p, int mode, cudaStream_t stream) {
   RIB_REQUIRE(p.BKc == 16 || p.BKc == 32 || p.BKc == 64, "conv_gemm: BKc must be 16/32/64");
-  RIB_REQUIRE(p.BN >= 16 && p.BN <= 128 && (p.BN & (p.BN - 1)) == 0, "conv_gemm: BN must be a power of two in [16,128]");
-  RIB_REQUIRE(p.ring >= 2 && p.ring <= 8, "conv_gemm: bad ring depth");
+  RIB_REQUIRE(p.a_ring >= 2 && p.a_ring <= 8 && p.b_ring >= 1 && p.b_ring <= 12, "conv_gemm: bad ring depth");
   RIB_REQUIRE(p.MT == 1 || p.MT == 2, "conv_gemm: MT must be 1 or 2");
   RIB_REQUIRE(2 * p.MT * p.BN <= 512, "conv_gemm: accumulators exceed TMEM");
   RIB_REQUIRE(p.n_tiles >= 1, "conv_gemm: no N tiles");
-  RIB_REQUIRE(mode != EPI_FINAL || p.BN == 16, "conv_gemm: EPI_FINAL needs BN == 16");
   RIB_REQUIRE(mode != EPI_SPADE || (p.BN == 2 * p.CT && p.CT % 16 == 0 && p.C % p.CT == 0),
               "conv_gemm: EPI_SPADE needs BN == 2*CT");
+  ConvKernel fn = p.debug_simt ? pick_kernel<true>(mode, p.BN) : pick_kernel<false>(mode, p.BN);
+  RIB_REQUIRE(fn != nullptr, "conv_gemm: no kernel for this (epilogue, BN)");
   const size_t smem = conv_gemm_smem_bytes(p);
   RIB_REQUIRE(smem <= 227 * 1024, "conv_gemm: shared memory budget exceeded");
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    cudaError_t e;
-    e = cudaFuncSetAttribute(conv_gemm_kernel<EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) attr_err = e;
-    e = cudaFuncSetAttribute(conv_gemm_kernel<EPI_SPADE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) attr_err = e;
-    e = cudaFuncSetAttribute(conv_gemm_kernel<EPI_FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) attr_err = e;
-  });
-  RIB_CHECK_CUDA(attr_err);
-  // persistent grid: as many CTAs as fit on the chip (shared memory and TMEM columns), a multiple of n_tiles
-  int occ = 1;
-  int rc = mode == EPI_STORE ? occupancy_for<EPI_STORE>(smem, &occ)
-                             : (mode == EPI_SPADE ? occupancy_for<EPI_SPADE>(smem, &occ) : occupancy_for<EPI_FINAL>(smem, &occ));
-  if (rc) return rc;
+  {
+    static std::mutex mu;
+    static std::vector<const void*> done;
+    std::lock_guard<std::mutex> lk(mu);
+    bool seen = false;
+    for (const void* f : done) seen = seen || f == (const void*)fn;
+    if (!seen) {
+      RIB_CHECK_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      done.push_back((const void*)fn);
+    }
+  }
+  // persistent grid: as many CTAs as fit on the chip, a multiple of n_tiles
   int tmem_cols = 32;
   while (tmem_cols < 2 * p.MT * p.BN) tmem_cols <<= 1;
-  if (occ > 512 / tmem_cols) occ = 512 / tmem_cols;
-  if (occ > 4) occ = 4;
-  if (occ < 1) occ = 1;
+  int occ = 1;
+  int rc = ctas_per_sm((const void*)fn, smem, tmem_cols, &occ);
+  if (rc) return rc;
   const long long m_tiles = (long long)p.tiles_x * p.tiles_y * p.B;
   long long groups = ((long long)kNumSms * occ) / p.n_tiles;
   if (groups < 1) groups = 1;
@@ -688,9 +809,7 @@ int launch_conv_gemm(const ConvGemmParams& p, int mode, cudaStream_t stream) {
     RIB_CHECK_CUDA(cudaEventCreate(&ev1));
     RIB_CHECK_CUDA(cudaEventRecord(ev0, stream));
   }
-  if (mode == EPI_STORE) conv_gemm_kernel<EPI_STORE><<<grid, block, smem, stream>>>(p);
-  else if (mode == EPI_SPADE) conv_gemm_kernel<EPI_SPADE><<<grid, block, smem, stream>>>(p);
-  else conv_gemm_kernel<EPI_FINAL><<<grid, block, smem, stream>>>(p);
+  fn<<<grid, block, smem, stream>>>(p);
   RIB_CHECK_CUDA(cudaGetLastError());
   if (g_profile) {
     RIB_CHECK_CUDA(cudaEventRecord(ev1, stream));

@@ -12,8 +12,9 @@
 // 8-row groups (SBO) is the halo row pitch and the 3x3 taps are nine descriptors that differ only in
 // their start address: every input byte crosses L2 -> SM once instead of nine times.  Zero padding is
 // TMA out-of-bounds fill.  Stride-2 convolutions load four parity views of the input the same way.
-// B operand: packed weights [Npad][Ktotal] (K-major, 32/64/128-byte swizzle); kept resident in shared
-// memory for the life of the CTA when they fit, streamed through the ring otherwise.
+// B operand: packed weights [Npad][Ktotal] (K-major, 32/64/128-byte swizzle), one [BN][BKc] sub-tile per
+// (channel group, tap); kept resident in shared memory for the life of the CTA when they fit, streamed
+// through their own ring (decoupled from the A ring: nine weight sub-tiles per halo tile) otherwise.
 // Accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the loads and MMAs of
 // tile i+1.
 //
@@ -49,17 +50,16 @@ struct alignas(64) ConvGemmParams {
   int tiles_x, tiles_y; // super-tiles per image
   int MT;               // M=128 sub-tiles per super-tile (stacked vertically): 1 or 2
   int BN, n_tiles;
-  int BKc;              // channels per pipeline stage (16/32/64)
+  int BKc;              // channels per group = per halo tile (16/32/64)
   int stages0, stages1; // channel groups of source 0 / source 1
   int ntaps, stride, halo;
-  int ring;             // shared-memory ring slots
-  int b_resident;       // 1: all weight stages of this CTA's N tile stay in shared memory
+  int a_ring, b_ring;   // shared-memory ring slots for halo tiles / streamed weight sub-tiles
+  int b_resident;       // 1: all weight sub-tiles of this CTA's N tile stay in shared memory
   int halo_w;           // pixels per halo-tile row
   uint32_t a_tile_bytes;  // one halo tile (one parity view for stride 2), padded to 128 bytes
   uint32_t a_slot_bytes;  // A bytes per ring slot (1 or 4 tiles), padded to 1024
-  uint32_t b_tap_bytes;   // BN * BKc * 2
-  uint32_t b_stage_bytes; // ntaps * b_tap_bytes (source-1 stages use one tap of it)
-  uint32_t a_tx_bytes;    // bytes TMA delivers per stage for A
+  uint32_t b_tap_bytes;   // BN * BKc * 2: one weight sub-tile
+  uint32_t a_tx_bytes;    // bytes TMA delivers per halo-tile slot
   uint32_t lbo, sbo;      // UMMA no-swizzle K-major descriptor strides (bytes)
   uint32_t idesc;
   int debug_simt;
@@ -96,7 +96,7 @@ int make_tmap_act_s2(CUtensorMap* m, const act_t* base, int C, int W, int H, int
 // Weight view (BKc, Npad, Ktotal/BKc); box = (BKc, BN, taps).
 int make_tmap_w(CUtensorMap* m, const act_t* w, int K, int N, int bkc, int boxN, int taps);
 // Channels per pipeline stage for a layer (also fixes the K ordering of the packed weights).
-int choose_bkc(int cin0, int cin1, int taps, int BN);
+int choose_bkc(int cin0, int cin1, int taps, int BN, int stride);
 // Fills the tiling / pipeline fields of p (everything except tensor maps and epilogue pointers).
 int conv_gemm_configure(ConvGemmParams* p, int B, int Hout, int Wout, int cin0, int cin1, int taps, int stride,
                         int BN, int n_pad);

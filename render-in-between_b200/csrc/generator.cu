@@ -41,7 +41,7 @@ struct GemmLayer {
   std::string name;
   int n_pad = 0, n_valid = 0, ktotal = 0;
   int cin0 = 0, taps = 0, cin1 = 0;  // padded input channels of source 0, its taps, source 1 (1x1) channels
-  int BN = 0, bkc = 0;               // N tile and channels per pipeline stage (fixes the packed K order)
+  int BN = 0, bkc = 0, stride = 1;   // N tile, channels per group (fixes the packed K order), conv stride
   act_t* w = nullptr;
   float* bias = nullptr;
   size_t w_off = 0, b_off = 0;
@@ -160,10 +160,11 @@ int spade_ct(int C) { return std::min(C, 64); }
 
 // BN = 0 selects the plain-store default min(n_pad, 128).
 void add_layer(Generator* G, const std::string& name, int n_valid, int n_pad, int cin0_pad, int taps, int cin1,
-               int BN = 0) {
+               int BN = 0, int stride = 1) {
   GemmLayer L;
   L.BN = BN ? BN : std::min(n_pad, 128);
-  L.bkc = choose_bkc(cin0_pad, cin1, taps, L.BN);
+  L.stride = stride;
+  L.bkc = choose_bkc(cin0_pad, cin1, taps, L.BN, stride);
   L.name = name;
   L.n_valid = n_valid;
   L.n_pad = n_pad;
@@ -195,7 +196,7 @@ int generator_create(const rib_gen_config* cfg, const rib_tensor* tensors, int n
   jobs.push_back({"emb_0", "ref_embedding.conv_first.layers.conv", true, emb_ch(c, 0), 2 * c.img_nc, 9, 0, emb_in_pad, 0, 0, 0, false});
   for (int i = 0; i < c.emb_down; ++i) {
     std::string ln = "emb_" + std::to_string(i + 1);
-    add_layer(G, ln, emb_ch(c, i + 1), emb_ch(c, i + 1), emb_ch(c, i), 9, 0);
+    add_layer(G, ln, emb_ch(c, i + 1), emb_ch(c, i + 1), emb_ch(c, i), 9, 0, 0, 2);
     jobs.push_back({ln, "ref_embedding.down_" + std::to_string(i) + ".layers.conv", true, emb_ch(c, i + 1), emb_ch(c, i), 9, 0, emb_ch(c, i), 0, 0, 0, false});
   }
   // down_first
@@ -229,7 +230,7 @@ int generator_create(const rib_gen_config* cfg, const rib_tensor* tensors, int n
     jobs.push_back({"mask." + bn + ".0", f + bn + ".0.layers.conv", true, c.mask_nf, cin, 9, 0, cpad, 0, 0, 0, false});
     for (int i = 0; i < c.mask_down; ++i) {
       std::string ln = "mask." + bn + "." + std::to_string(i + 1);
-      add_layer(G, ln, mask_nfilt(c, i + 1), mask_nfilt(c, i + 1), mask_nfilt(c, i), 9, 0);
+      add_layer(G, ln, mask_nfilt(c, i + 1), mask_nfilt(c, i + 1), mask_nfilt(c, i), 9, 0, 0, 2);
       jobs.push_back({ln, f + bn + "." + std::to_string(i + 1) + ".layers.conv", true, mask_nfilt(c, i + 1), mask_nfilt(c, i), 9, 0, mask_nfilt(c, i), 0, 0, 0, false});
     }
   }
@@ -403,7 +404,7 @@ struct PlanBuilder {
                              int BN) {
     ConvGemmParams p;
     memset(&p, 0, sizeof(p));
-    if (in0.C != L.cin0 || (in1 ? in1->C : 0) != L.cin1 || BN != L.BN || in0.C != in0.Ctot ||
+    if (in0.C != L.cin0 || (in1 ? in1->C : 0) != L.cin1 || BN != L.BN || stride != L.stride || in0.C != in0.Ctot ||
         (in1 && in1->C != in1->Ctot)) {
       set_error("plan: layer/view channel mismatch in " + L.name);
       rc = -4;
@@ -870,7 +871,8 @@ int conv_test(const void* x, const float* w, const float* bias, void* out, doubl
   L.cin1 = 0;
   L.ktotal = Cin * k * k;
   L.BN = std::min(Cout, 128);
-  L.bkc = choose_bkc(Cin, 0, k * k, L.BN);
+  L.stride = stride;
+  L.bkc = choose_bkc(Cin, 0, k * k, L.BN, stride);
   uint8_t* sp = static_cast<uint8_t*>(scratch);
   sp = reinterpret_cast<uint8_t*>(align_up((size_t)(uintptr_t)sp, 256));
   L.w = reinterpret_cast<act_t*>(sp);
