@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define RIB_ABI_VERSION 1
+#define RIB_ABI_VERSION 2
 
 /* Message of the last failing call on this host thread ("" if none). */
 const char* rib_last_error(void);
@@ -31,28 +31,39 @@ long long rib_kernel_launch_count(void);
  * Replaces HSMAutoDataset._generate_skeleton + _generate_pose_map + to_tensor_norm and the label
  * concatenation (datasets/HSM_auto_dataset.py:205-251, :73-75; utils/keypoint2img.py:36-173;
  * models/evaluator.py:222-229, :250).  Bit-exact.
- *   joints      device  f64 [B][19][3]  (x, y, confidence), model-pixel coordinates
- *   gauss_taps  HOST    f64 [41]        normalised Gaussian taps (sigma 5, radius 20)
- *   label       device  f32 [B][22][H][W]  = [skeleton RGB normalised to [-1,1] | 19 heat-maps]
+ *   joints        device  f64 [B][19][3]  (x, y, confidence), model-pixel coordinates
+ *   gauss_taps    HOST    f64 [41]        normalised Gaussian taps (sigma 5, radius 20)
+ *   label         device  f32 [B][22][H][W]  = [skeleton RGB normalised to [-1,1] | 19 heat-maps]; may be NULL
+ *   label_planar  device  16-bit [B][4][H][W][8]: the same label rounded to the generator's activation type
+ *                 in its input layout (32 channels, 22..31 zero) (see rib_generator_bind); may be NULL
+ *   workspace     device scratch of rib_rasterize_workspace_bytes(B) bytes, 16-byte aligned
  */
+long long rib_rasterize_workspace_bytes(int B);
 int rib_rasterize(const double* joints, int B, int H, int W, const double* gauss_taps, double skeleton_thres,
-                  double foot_thres, float* label, void* stream);
+                  double foot_thres, float* label, void* label_planar, void* workspace, long long workspace_bytes,
+                  void* stream);
 
 /* ---- A3: flow-based bilinear resampling ------------------------------------------------------
  * No call site in the reference tree; semantics of imaginaire's resample():
  * out = grid_sample(src, identity + flow, bilinear, padding_mode='border', align_corners=True).
  *   src f32 [B][C][H][W], flow f32 [B][2][H][W] (pixels; channel 0 = x), out f32 [B][C][H][W]
+ *   *_bstride: elements between consecutive frames (0 = dense), so that every r-th frame of a clip can be
+ *   addressed without a gather copy.
  */
-int rib_warp(const float* src, const float* flow, float* out, int B, int C, int H, int W, void* stream);
+int rib_warp(const float* src, const float* flow, float* out, int B, int C, int H, int W, long long src_bstride,
+             long long flow_bstride, long long out_bstride, void* stream);
 
 /* ---- A4: mask-blend composite ----------------------------------------------------------------
  * Replaces models/evaluator.py:256-258 (fuse = pred*mask + dain*(1-mask)) and, when out_u8 is not
  * NULL, utils/utils.py:122-147 tensor2images (uint8 HWC frame, truncating).
  *   img, dain f32 [B][3][H][W]; mask f32 [B][1][H][W]; out_f32 f32 [B][3][H][W] (may be NULL);
- *   out_u8 u8 [B][H][W][3] (may be NULL)
+ *   out_u8 u8 [B][H][W][3] (may be NULL).  mask == NULL: out = img (key frames pass through,
+ *   evaluator.py:240-244; dain is ignored).  img / out_f32 / out_u8 take a frame stride in elements
+ *   (0 = dense): the batch of AR step s is written to frames s, s + r, s + 2r, ... of the clip.
  */
 int rib_composite(const float* img, const float* mask, const float* dain, float* out_f32, uint8_t* out_u8, int B,
-                  int H, int W, void* stream);
+                  int H, int W, long long img_bstride, long long out_f32_bstride, long long out_u8_bstride,
+                  void* stream);
 
 /* ---- A2: generator ---------------------------------------------------------------------------
  * Replaces models.generator.Generator (models/generator.py:35-302), LabelEmbedder (:306-410) and
@@ -85,9 +96,17 @@ void rib_generator_destroy(rib_generator* g);
 /* Bytes of caller-provided scratch needed by rib_generator_forward for a (B, H, W) batch. */
 long long rib_generator_workspace_bytes(rib_generator* g, int B, int H, int W);
 
+/* Builds the launch plan of a (B, H, W) batch on `workspace` (no kernel is launched) and returns the address,
+ * inside the workspace, of the generator's label input in its native layout (16-bit [B][4][H][W][8]).  A caller
+ * that rasterises on the GPU lets rib_rasterize write `label_planar` there and then passes label = NULL to
+ * rib_generator_forward, which skips the fp32 -> 16-bit repack of the label (same values, one pass less). */
+int rib_generator_bind(rib_generator* g, int B, int H, int W, void* workspace, long long workspace_bytes,
+                       void** label_planar);
+
 /* Generator.forward(label, label_prev, img_fake, img_prev) -> (img_final, mask)
  * (models/generator.py:181-234; label_prev is dead in the reference and is not taken).
- *   label f32 [B][22][H][W]; img_fake, img_prev f32 [B][3][H][W]; H, W multiples of 16
+ *   label f32 [B][22][H][W] (or NULL after rib_generator_bind, see above); img_fake, img_prev f32 [B][3][H][W];
+ *   H, W multiples of 16
  *   out_img f32 [B][3][H][W] in (-1,1); out_mask f32 [B][1][H][W] in (0,1)
  * The workspace must stay bound to this generator between calls with the same (B, H, W). */
 int rib_generator_forward(rib_generator* g, int B, int H, int W, const float* label, const float* img_fake,
@@ -111,6 +130,9 @@ int rib_debug_get_simt(void);
  * ptr[n*ld*H*W + (c/8)*H*W*8 + (y*W + x)*8 + c%8].  Returns 0 if found. */
 int rib_generator_debug_tensor(rib_generator* g, const char* name, const void** ptr, int* B, int* H, int* W, int* C,
                                int* ld);
+/* Text description (one line per planned kernel launch, in launch order) of the plan built by the last
+ * rib_generator_forward: layer name, tiling, algorithmic FLOPs.  Joined with ncu launch lists by tools/. */
+int rib_generator_plan_text(rib_generator* g, char* buf, long long cap);
 /* 1 if activations are stored as IEEE fp16, 0 for bf16. */
 int rib_act_is_fp16(void);
 /* Stand-alone launch of the implicit-GEMM convolution for unit tests:

@@ -32,30 +32,38 @@ const char* rib_last_error(void) { return rib::last_error(); }
 int rib_abi_version(void) { return RIB_ABI_VERSION; }
 long long rib_kernel_launch_count(void) { return conv_gemm_launch_count() + misc_launch_count(); }
 
+long long rib_rasterize_workspace_bytes(int B) { return B > 0 ? raster_workspace_bytes(B) : -1; }
+
 int rib_rasterize(const double* joints, int B, int H, int W, const double* gauss_taps, double skeleton_thres,
-                  double foot_thres, float* label, void* stream) {
+                  double foot_thres, float* label, void* label_planar, void* workspace, long long workspace_bytes,
+                  void* stream) {
   RIB_GUARD_BEGIN
-  RIB_REQUIRE(joints && gauss_taps && label, "rib_rasterize: null argument");
-  int rc = launch_rasterize(joints, B, H, W, gauss_taps, skeleton_thres, foot_thres, label, (cudaStream_t)stream);
-  if (!rc) count_misc_launch(2);
+  RIB_REQUIRE(joints && gauss_taps && (label || label_planar) && workspace, "rib_rasterize: null argument");
+  int rc = launch_rasterize(joints, B, H, W, gauss_taps, skeleton_thres, foot_thres, label,
+                            static_cast<act_t*>(label_planar), workspace, workspace_bytes, (cudaStream_t)stream);
+  if (!rc) count_misc_launch(3);
   return rc;
   RIB_GUARD_END
 }
 
-int rib_warp(const float* src, const float* flow, float* out, int B, int C, int H, int W, void* stream) {
+int rib_warp(const float* src, const float* flow, float* out, int B, int C, int H, int W, long long src_bstride,
+             long long flow_bstride, long long out_bstride, void* stream) {
   RIB_GUARD_BEGIN
   RIB_REQUIRE(src && flow && out && B > 0 && C > 0 && H > 0 && W > 0, "rib_warp: bad argument");
-  int rc = launch_warp(src, flow, out, B, C, H, W, (cudaStream_t)stream);
+  int rc = launch_warp(src, flow, out, B, C, H, W, src_bstride, flow_bstride, out_bstride, (cudaStream_t)stream);
   if (!rc) count_misc_launch(1);
   return rc;
   RIB_GUARD_END
 }
 
 int rib_composite(const float* img, const float* mask, const float* dain, float* out_f32, uint8_t* out_u8, int B,
-                  int H, int W, void* stream) {
+                  int H, int W, long long img_bstride, long long out_f32_bstride, long long out_u8_bstride,
+                  void* stream) {
   RIB_GUARD_BEGIN
-  RIB_REQUIRE(img && mask && dain && (out_f32 || out_u8) && B > 0 && H > 0 && W > 0, "rib_composite: bad argument");
-  int rc = launch_composite(img, mask, dain, out_f32, out_u8, B, H, W, (cudaStream_t)stream);
+  RIB_REQUIRE(img && (mask == nullptr || dain != nullptr) && (out_f32 || out_u8) && B > 0 && H > 0 && W > 0,
+              "rib_composite: bad argument");
+  int rc = launch_composite(img, mask, dain, out_f32, out_u8, B, H, W, img_bstride, out_f32_bstride, out_u8_bstride,
+                            (cudaStream_t)stream);
   if (!rc) count_misc_launch(1);
   return rc;
   RIB_GUARD_END
@@ -74,6 +82,14 @@ long long rib_generator_workspace_bytes(rib_generator* g, int B, int H, int W) {
   RIB_GUARD_BEGIN
   RIB_REQUIRE(g, "rib_generator_workspace_bytes: null generator");
   return generator_workspace_bytes(reinterpret_cast<Generator*>(g), B, H, W);
+  RIB_GUARD_END
+}
+
+int rib_generator_bind(rib_generator* g, int B, int H, int W, void* workspace, long long workspace_bytes,
+                       void** label_planar) {
+  RIB_GUARD_BEGIN
+  RIB_REQUIRE(g && workspace, "rib_generator_bind: null argument");
+  return generator_bind(reinterpret_cast<Generator*>(g), B, H, W, workspace, workspace_bytes, label_planar);
   RIB_GUARD_END
 }
 
@@ -102,6 +118,13 @@ int rib_generator_debug_tensor(rib_generator* g, const char* name, const void** 
   RIB_GUARD_BEGIN
   RIB_REQUIRE(g && name && ptr && B && H && W && C && ld, "rib_generator_debug_tensor: null argument");
   return generator_debug_tensor(reinterpret_cast<Generator*>(g), name, ptr, B, H, W, C, ld);
+  RIB_GUARD_END
+}
+
+int rib_generator_plan_text(rib_generator* g, char* buf, long long cap) {
+  RIB_GUARD_BEGIN
+  RIB_REQUIRE(g && buf && cap > 0, "rib_generator_plan_text: bad argument");
+  return generator_plan_text(reinterpret_cast<Generator*>(g), buf, cap);
   RIB_GUARD_END
 }
 

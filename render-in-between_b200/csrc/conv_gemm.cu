@@ -114,6 +114,63 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: 
 static constexpr int kStatPitch = 20;
 static constexpr int kStatWarpFloats = 32 * kStatPitch;
 
+// State of the MMA issuer that does not change during a launch.
+struct IssueCtx {
+  uint32_t a_hi, b_hi, idesc;
+  uint32_t b_lo_base;        // b_lo_c + sB16
+  uint32_t b_tap16;
+  uint32_t b_full0, b_empty0;
+  int b_ring;
+  bool b_resident;
+  uint32_t bn;               // TMEM columns per sub-tile
+};
+
+// All tcgen05.mma of one channel group (NT taps x MT sub-tiles x KK k-steps), fully unrolled: per MMA the
+// issuing lane executes two adds and the instruction itself.
+//   a_lo      low descriptor word of the halo tile in this ring slot (tap offset not yet added)
+//   tap       per-tap A offsets (16-byte units);  mk[m * KK + kk] = m * m_step + kk * a_kk_step
+template <int NT, int KK, int MT>
+__device__ __forceinline__ void issue_group(const IssueCtx& c, uint32_t a_lo, const uint32_t* tap, const uint32_t* mk,
+                                            uint32_t b_res_lo, uint32_t d0, uint32_t acc_first, int& b_slot,
+                                            uint32_t& b_phase) {
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    uint32_t b_lo;
+    if (c.b_resident) {
+      b_lo = b_res_lo + (uint32_t)t * c.b_tap16;
+    } else {
+      mbar_wait(c.b_full0 + 8u * b_slot, b_phase);
+      tc_fence_after();
+      b_lo = c.b_lo_base + (uint32_t)b_slot * c.b_tap16;
+    }
+    const uint32_t a_t = a_lo + tap[t];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+#pragma unroll
+      for (int kk = 0; kk < KK; ++kk) {
+        const uint32_t acc = (t == 0 && kk == 0) ? acc_first : 1u;
+        umma_f16(d0 + (uint32_t)m * c.bn, ((uint64_t)c.a_hi << 32) | (uint64_t)(a_t + mk[m * KK + kk]),
+                 ((uint64_t)c.b_hi << 32) | (uint64_t)(b_lo + 2u * (uint32_t)kk), c.idesc, acc);
+      }
+    }
+    if (!c.b_resident) {
+      umma_commit(c.b_empty0 + 8u * b_slot);  // frees the weight slot once the MMAs have read it
+      if (++b_slot == c.b_ring) {
+        b_slot = 0;
+        b_phase ^= 1u;
+      }
+    }
+  }
+}
+
+template <int KK, int MT>
+__device__ __forceinline__ void issue_group_nt(int nt, const IssueCtx& c, uint32_t a_lo, const uint32_t* tap,
+                                               const uint32_t* mk, uint32_t b_res_lo, uint32_t d0, uint32_t acc_first,
+                                               int& b_slot, uint32_t& b_phase) {
+  if (nt == 9) issue_group<9, KK, MT>(c, a_lo, tap, mk, b_res_lo, d0, acc_first, b_slot, b_phase);
+  else issue_group<1, KK, MT>(c, a_lo, tap, mk, b_res_lo, d0, acc_first, b_slot, b_phase);
+}
+
 template <int MODE, int BN, bool SIMT>
 __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -139,6 +196,7 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bres_bar + 1);
   float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr + 4) + 15) & ~(uintptr_t)15);  // [BN], 16-byte aligned
   float* s_aux = s_bias + BN;                              // STORE: [2*BN] stats; SPADE: [2*CT] rstd, -mean*rstd
+  uint32_t* s_tapoff = reinterpret_cast<uint32_t*>(s_aux + 2 * BN);  // [10] A start offset (16-byte units) of tap t; [9]: 1x1 second source
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -181,6 +239,10 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
   }
   if (warp >= 2) {
     const int e = threadIdx.x - 64;
+    if (e < 10) {
+      const TapGeom tg = tap_geom(p, e == 9, e == 9 ? 0 : e);
+      s_tapoff[e] = (uint32_t)tg.tile * (p.a_tile_bytes >> 4) + (uint32_t)tg.poff;
+    }
     for (int c = e; c < BN; c += 128) s_bias[c] = p.bias[ntile * BN + c];
     if (MODE == EPI_STORE) {
       for (int c = e; c < 2 * BN; c += 128) s_aux[c] = 0.f;
@@ -193,117 +255,152 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (!SIMT && lane == 0) {
-      if (p.b_resident) {  // all weight sub-tiles of this N tile, once
+    // One elected lane runs the whole role: inside `if (elect_one())` the compiler knows that a single lane is
+    // active, so addresses and coordinates move to uniform registers without per-lane loops.
+    if (!SIMT && elect_one()) {
+      const int ntaps = p.ntaps, stages0 = p.stages0, a_ring = p.a_ring, b_ring = p.b_ring, BKc = p.BKc;
+      const int halo = p.halo, stride = p.stride, MT = p.MT, tiles_x = p.tiles_x;
+      const bool b_resident = p.b_resident != 0;
+      const uint32_t a_slot_bytes = p.a_slot_bytes, a_tile_bytes = p.a_tile_bytes, a_tx_bytes = p.a_tx_bytes;
+      const uint32_t b_tap_bytes = p.b_tap_bytes;
+      const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+      const uint32_t a_full0 = smem_u32(a_full), a_empty0 = smem_u32(a_empty);
+      const uint32_t b_full0 = smem_u32(b_full), b_empty0 = smem_u32(b_empty);
+      const int planes_per_group = BKc >> 3;
+      const int n_col0 = ntile * BN;
+      if (b_resident) {  // all weight sub-tiles of this N tile, once
         const uint32_t bb = smem_u32(bres_bar);
-        mbar_arrive_expect_tx(bb, (uint32_t)n_bt * p.b_tap_bytes);
-        for (int i = 0; i < n_bt; ++i)
-          tma_load_2d(smem_u32(sB + (size_t)i * p.b_tap_bytes), &p.bmap, bb, i * p.BKc, ntile * BN);
+        mbar_arrive_expect_tx(bb, (uint32_t)n_bt * b_tap_bytes);
+        for (int i = 0; i < n_bt; ++i) tma_load_2d(sB_addr + (uint32_t)i * b_tap_bytes, &p.bmap, bb, i * BKc, n_col0);
       }
       int a_slot = 0, b_slot = 0;
       uint32_t a_phase = 0, b_phase = 0;
+      // tile coordinates are advanced incrementally (no divisions in the loop)
+      int n = t_begin / tiles_per_img;
+      int rem0 = t_begin - n * tiles_per_img;
+      int tile_y = rem0 / tiles_x, tile_x = rem0 - tile_y * tiles_x;
+      const int tiles_y = p.tiles_y;
       for (int mt = t_begin; mt < t_end; ++mt) {
-        const int n = mt / tiles_per_img;
-        const int rem = mt - n * tiles_per_img;
-        const int tile_y = rem / p.tiles_x, tile_x = rem - tile_y * p.tiles_x;
-        const int oy0 = tile_y * kTileH * p.MT, ox0 = tile_x * kTileW;
+        const int oy0 = tile_y * kTileH * MT, ox0 = tile_x * kTileW;
         for (int g = 0; g < G; ++g) {
-          mbar_wait(smem_u32(&a_empty[a_slot]), a_phase ^ 1u);
-          const uint32_t fb = smem_u32(&a_full[a_slot]);
-          const bool src1 = g >= p.stages0;
-          mbar_arrive_expect_tx(fb, p.a_tx_bytes);
-          const uint32_t a_dst = smem_u32(sA + (size_t)a_slot * p.a_slot_bytes);
-          const int cg = (src1 ? g - p.stages0 : g) * (p.BKc >> 3);  // first 8-channel plane of the group
-          if (p.stride == 1) {
-            tma_load_4d(a_dst, &p.amap[src1 ? 1 : 0], fb, (ox0 - p.halo) * 8, oy0 - p.halo, cg, n);
+          mbar_wait(a_empty0 + 8u * a_slot, a_phase ^ 1u);
+          const uint32_t fb = a_full0 + 8u * a_slot;
+          const bool src1 = g >= stages0;
+          const uint32_t a_dst = sA_addr + (uint32_t)a_slot * a_slot_bytes;
+          const int cg = (src1 ? g - stages0 : g) * planes_per_group;  // first 8-channel plane of the group
+          mbar_arrive_expect_tx(fb, a_tx_bytes);
+          if (stride == 1) {
+            tma_load_4d(a_dst, &p.amap[src1 ? 1 : 0], fb, (ox0 - halo) * 8, oy0 - halo, cg, n);
           } else {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              tma_load_5d(a_dst + q * p.a_tile_bytes, &p.amap[q], fb, 0, ox0 - 1, oy0 - 1, cg, n);
+            for (int q = 0; q < 4; ++q) tma_load_5d(a_dst + q * a_tile_bytes, &p.amap[q], fb, 0, ox0 - 1, oy0 - 1, cg, n);
           }
-          if (++a_slot == p.a_ring) {
+          if (++a_slot == a_ring) {
             a_slot = 0;
             a_phase ^= 1u;
           }
-          if (!p.b_resident) {
-            const int nt = src1 ? 1 : p.ntaps;
-            const int i0 = src1 ? p.stages0 * p.ntaps + (g - p.stages0) : g * p.ntaps;
+          if (!b_resident) {
+            const int nt = src1 ? 1 : ntaps;
+            const int i0 = src1 ? stages0 * ntaps + (g - stages0) : g * ntaps;
+#pragma unroll 1
             for (int t = 0; t < nt; ++t) {
-              mbar_wait(smem_u32(&b_empty[b_slot]), b_phase ^ 1u);
-              const uint32_t bf = smem_u32(&b_full[b_slot]);
-              mbar_arrive_expect_tx(bf, p.b_tap_bytes);
-              tma_load_2d(smem_u32(sB + (size_t)b_slot * p.b_tap_bytes), &p.bmap, bf, (i0 + t) * p.BKc, ntile * BN);
-              if (++b_slot == p.b_ring) {
+              mbar_wait(b_empty0 + 8u * b_slot, b_phase ^ 1u);
+              const uint32_t bf = b_full0 + 8u * b_slot;
+              mbar_arrive_expect_tx(bf, b_tap_bytes);
+              tma_load_2d(sB_addr + (uint32_t)b_slot * b_tap_bytes, &p.bmap, bf, (i0 + t) * BKc, n_col0);
+              if (++b_slot == b_ring) {
                 b_slot = 0;
                 b_phase ^= 1u;
               }
             }
           }
         }
+        if (++tile_x == tiles_x) {
+          tile_x = 0;
+          if (++tile_y == tiles_y) {
+            tile_y = 0;
+            ++n;
+          }
+        }
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (!SIMT && lane == 0) {
-      int a_slot = 0, b_slot = 0;
-      uint32_t a_phase = 0, b_phase = 0;
+    // One elected lane; the MMAs of a channel group are fully unrolled (issue_group).
+    if (!SIMT && elect_one()) {
+      const int ntaps = p.ntaps, stages0 = p.stages0, a_ring = p.a_ring, MT = p.MT;
+      const uint32_t a_slot16 = p.a_slot_bytes >> 4;
+      const uint32_t sA16 = smem_u32(sA) >> 4, sB16 = smem_u32(sB) >> 4;
+      const uint32_t a_full0 = smem_u32(a_full), a_empty0 = smem_u32(a_empty);
+      const uint32_t tfull0 = smem_u32(tmem_full_bar), tempty0 = smem_u32(tmem_empty_bar);
       const uint32_t b_row_bytes = (uint32_t)p.BKc * 2u;
       const int kk_steps = p.BKc >> 4;
-      if (p.b_resident) {
+      // descriptor halves that never change (see make_nosw_desc / make_kmajor_desc); start addresses (>> 4) are
+      // below 2^14, so they are simply added to the low word
+      const uint32_t a_lo_c = ((p.lbo >> 4) & 0x3fffu) << 16;
+      const uint32_t b_layout = b_row_bytes == 128 ? 2u : (b_row_bytes == 64 ? 4u : 6u);
+      IssueCtx c;
+      c.a_hi = ((p.sbo >> 4) & 0x3fffu) | (1u << 14);
+      c.b_hi = (((8u * b_row_bytes) >> 4) & 0x3fffu) | (1u << 14) | (b_layout << 29);
+      c.idesc = p.idesc;
+      c.b_lo_base = (1u << 16) + sB16;
+      c.b_tap16 = p.b_tap_bytes >> 4;
+      c.b_full0 = smem_u32(b_full);
+      c.b_empty0 = smem_u32(b_empty);
+      c.b_ring = p.b_ring;
+      c.b_resident = p.b_resident != 0;
+      c.bn = BN;
+      const uint32_t a_kk_step = (2u * p.lbo) >> 4;             // K = 16 is two 8-channel planes
+      const uint32_t m_step = (uint32_t)(kTileH * p.halo_w);    // 16-byte pixels between stacked sub-tiles
+      uint32_t tap[9], mk[8];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) tap[t] = s_tapoff[t];
+      const uint32_t tap1 = s_tapoff[9];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mk[i] = (uint32_t)(i / kk_steps) * m_step + (uint32_t)(i % kk_steps) * a_kk_step;
+      if (c.b_resident) {
         mbar_wait(smem_u32(bres_bar), 0u);
         tc_fence_after();
       }
+      int a_slot = 0, b_slot = 0;
+      uint32_t a_phase = 0, b_phase = 0;
       int it = 0;
       for (int mt = t_begin; mt < t_end; ++mt, ++it) {
         const int buf = it & 1;
         const uint32_t use = (uint32_t)(it >> 1);
-        mbar_wait(smem_u32(&tmem_empty_bar[buf]), (use & 1u) ^ 1u);  // epilogue has drained this buffer
+        mbar_wait(tempty0 + 8u * buf, (use & 1u) ^ 1u);  // epilogue has drained this buffer
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)(buf * acc_cols);
         for (int g = 0; g < G; ++g) {
-          mbar_wait(smem_u32(&a_full[a_slot]), a_phase);
+          mbar_wait(a_full0 + 8u * a_slot, a_phase);
           tc_fence_after();
-          const bool src1 = g >= p.stages0;
-          const int nt = src1 ? 1 : p.ntaps;
-          const int i0 = src1 ? p.stages0 * p.ntaps + (g - p.stages0) : g * p.ntaps;
-          const uint32_t a_base = smem_u32(sA + (size_t)a_slot * p.a_slot_bytes);
-          for (int t = 0; t < nt; ++t) {
-            uint32_t b_addr;
-            if (p.b_resident) {
-              b_addr = smem_u32(sB + (size_t)(i0 + t) * p.b_tap_bytes);
-            } else {
-              mbar_wait(smem_u32(&b_full[b_slot]), b_phase);
-              tc_fence_after();
-              b_addr = smem_u32(sB + (size_t)b_slot * p.b_tap_bytes);
-            }
-            const TapGeom tg = tap_geom(p, src1, t);
-            const uint64_t bdesc = make_kmajor_desc(b_addr, b_row_bytes);
-            for (int m = 0; m < p.MT; ++m) {
-              const uint32_t a_addr =
-                  a_base + (uint32_t)tg.tile * p.a_tile_bytes + (uint32_t)(tg.poff + m * kTileH * p.halo_w) * 16u;
-              for (int kk = 0; kk < kk_steps; ++kk) {
-                const uint64_t adesc = make_nosw_desc(a_addr + (uint32_t)(2 * kk) * p.lbo, p.lbo, p.sbo);
-                umma_f16(d0 + (uint32_t)(m * BN), adesc, bdesc + (uint64_t)(2 * kk), p.idesc,
-                         (uint32_t)((g | t | kk) != 0));
-              }
-            }
-            if (!p.b_resident) {
-              umma_commit(smem_u32(&b_empty[b_slot]));  // frees the weight slot once the MMAs have read it
-              if (++b_slot == p.b_ring) {
-                b_slot = 0;
-                b_phase ^= 1u;
-              }
-            }
+          const bool src1 = g >= stages0;
+          const int nt = src1 ? 1 : ntaps;
+          const int i0 = src1 ? stages0 * ntaps + (g - stages0) : g * ntaps;
+          const uint32_t a_lo = a_lo_c + sA16 + (uint32_t)a_slot * a_slot16;
+          const uint32_t b_res_lo = c.b_lo_base + (uint32_t)i0 * c.b_tap16;
+          const uint32_t acc_first = g != 0 ? 1u : 0u;
+          const uint32_t* tp = src1 ? &tap1 : tap;
+          if (MT == 1) {
+            if (kk_steps == 1) issue_group_nt<1, 1>(nt, c, a_lo, tp, mk, b_res_lo, d0, acc_first, b_slot, b_phase);
+            else if (kk_steps == 2) issue_group_nt<2, 1>(nt, c, a_lo, tp, mk, b_res_lo, d0, acc_first, b_slot, b_phase);
+            else issue_group_nt<4, 1>(nt, c, a_lo, tp, mk, b_res_lo, d0, acc_first, b_slot, b_phase);
+          } else {
+            if (kk_steps == 1) issue_group_nt<1, 2>(nt, c, a_lo, tp, mk, b_res_lo, d0, acc_first, b_slot, b_phase);
+            else if (kk_steps == 2) issue_group_nt<2, 2>(nt, c, a_lo, tp, mk, b_res_lo, d0, acc_first, b_slot, b_phase);
+            else issue_group_nt<4, 2>(nt, c, a_lo, tp, mk, b_res_lo, d0, acc_first, b_slot, b_phase);
           }
-          umma_commit(smem_u32(&a_empty[a_slot]));  // frees the halo-tile slot
-          if (++a_slot == p.a_ring) {
+          umma_commit(a_empty0 + 8u * a_slot);  // frees the halo-tile slot
+          if (++a_slot == a_ring) {
             a_slot = 0;
             a_phase ^= 1u;
           }
         }
-        umma_commit(smem_u32(&tmem_full_bar[buf]));
+        umma_commit(tfull0 + 8u * buf);
       }
     }
+    __syncwarp();
   } else {
     // ===================== Epilogue =====================
     const int q = warp & 3;
@@ -698,7 +795,7 @@ size_t conv_gemm_smem_bytes(const ConvGemmParams& p) {
   size_t tiles = (size_t)p.a_ring * p.a_slot_bytes + (size_t)(p.b_resident ? n_bt : p.b_ring) * p.b_tap_bytes;
   size_t stat = p.stats != nullptr ? kStatStageBytes : 0;
   size_t bars = (size_t)(2 * p.a_ring + 2 * p.b_ring + 5) * 8 + 32;
-  size_t scratch = (size_t)p.BN * 4 * 3 + 64;
+  size_t scratch = (size_t)p.BN * 4 * 3 + 64 + 64;
   return 1024 + tiles + stat + bars + scratch;
 }
 

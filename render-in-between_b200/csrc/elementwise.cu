@@ -227,24 +227,35 @@ __device__ __forceinline__ uint8_t to_u8(float x) {
 
 __global__ void composite_kernel(const float* __restrict__ img, const float* __restrict__ mask,
                                  const float* __restrict__ dain, float* __restrict__ out_f32,
-                                 uint8_t* __restrict__ out_u8, int HW4, int HW, size_t total) {
+                                 uint8_t* __restrict__ out_u8, int HW4, int HW, size_t total, long long img_bs,
+                                 long long f32_bs, long long u8_bs) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over B * HW/4
   if (i >= total) return;
   const size_t n = i / HW4, q = i - n * HW4;
-  const float4 m = __ldg(reinterpret_cast<const float4*>(mask + n * HW) + q);
-  const float mm[4] = {m.x, m.y, m.z, m.w};
+  float mm[4] = {1.f, 1.f, 1.f, 1.f};
+  if (mask != nullptr) {
+    const float4 m = __ldg(reinterpret_cast<const float4*>(mask + n * HW) + q);
+    mm[0] = m.x, mm[1] = m.y, mm[2] = m.z, mm[3] = m.w;
+  }
   float res[3][4];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     const size_t off = (n * 3 + c) * (size_t)HW;
-    const float4 a = __ldg(reinterpret_cast<const float4*>(img + off) + q);
-    const float4 d = __ldg(reinterpret_cast<const float4*>(dain + off) + q);
-    const float aa[4] = {a.x, a.y, a.z, a.w}, dd[4] = {d.x, d.y, d.z, d.w};
+    const float4 a = __ldg(reinterpret_cast<const float4*>(img + n * img_bs + (size_t)c * HW) + q);
+    const float aa[4] = {a.x, a.y, a.z, a.w};
+    if (mask != nullptr) {
+      const float4 d = __ldg(reinterpret_cast<const float4*>(dain + off) + q);
+      const float dd[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
-    for (int k = 0; k < 4; ++k)  // separate roundings, as the reference's three elementwise ops
-      res[c][k] = __fadd_rn(__fmul_rn(aa[k], mm[k]), __fmul_rn(dd[k], __fsub_rn(1.0f, mm[k])));
+      for (int k = 0; k < 4; ++k)  // separate roundings, as the reference's three elementwise ops
+        res[c][k] = __fadd_rn(__fmul_rn(aa[k], mm[k]), __fmul_rn(dd[k], __fsub_rn(1.0f, mm[k])));
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) res[c][k] = aa[k];
+    }
     if (out_f32 != nullptr)
-      reinterpret_cast<float4*>(out_f32 + off)[q] = make_float4(res[c][0], res[c][1], res[c][2], res[c][3]);
+      reinterpret_cast<float4*>(out_f32 + n * f32_bs + (size_t)c * HW)[q] =
+          make_float4(res[c][0], res[c][1], res[c][2], res[c][3]);
   }
   if (out_u8 != nullptr) {
     uint8_t px[12];
@@ -252,7 +263,7 @@ __global__ void composite_kernel(const float* __restrict__ img, const float* __r
     for (int k = 0; k < 4; ++k)
 #pragma unroll
       for (int c = 0; c < 3; ++c) px[3 * k + c] = to_u8(res[c][k]);
-    uint32_t* o = reinterpret_cast<uint32_t*>(out_u8 + (n * (size_t)HW + q * 4) * 3);
+    uint32_t* o = reinterpret_cast<uint32_t*>(out_u8 + n * u8_bs + q * 12);
     o[0] = px[0] | (px[1] << 8) | (px[2] << 16) | ((uint32_t)px[3] << 24);
     o[1] = px[4] | (px[5] << 8) | (px[6] << 16) | ((uint32_t)px[7] << 24);
     o[2] = px[8] | (px[9] << 8) | (px[10] << 16) | ((uint32_t)px[11] << 24);
@@ -260,13 +271,17 @@ __global__ void composite_kernel(const float* __restrict__ img, const float* __r
 }
 
 int launch_composite(const float* img, const float* mask, const float* dain, float* out_f32, uint8_t* out_u8, int B,
-                     int H, int W, cudaStream_t s) {
+                     int H, int W, long long img_bstride, long long f32_bstride, long long u8_bstride, cudaStream_t s) {
   RIB_REQUIRE((H * W) % 4 == 0, "composite: H*W must be a multiple of 4");
   const int HW = H * W;
+  if (img_bstride == 0) img_bstride = 3LL * HW;
+  if (f32_bstride == 0) f32_bstride = 3LL * HW;
+  if (u8_bstride == 0) u8_bstride = 3LL * HW;
+  RIB_REQUIRE(img_bstride % 4 == 0 && f32_bstride % 4 == 0 && u8_bstride % 4 == 0, "composite: strides must be multiples of 4");
   const size_t total = (size_t)B * (HW / 4);
   const int threads = 256;
-  composite_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(img, mask, dain, out_f32, out_u8,
-                                                                                   HW / 4, HW, total);
+  composite_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(
+      img, mask, dain, out_f32, out_u8, HW / 4, HW, total, img_bstride, f32_bstride, u8_bstride);
   RIB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -275,15 +290,16 @@ int launch_composite(const float* img, const float* mask, const float* dain, flo
 // Flow warp (bilinear, border, align_corners=True)
 // ---------------------------------------------------------------------------------------------
 __global__ void warp_kernel(const float* __restrict__ src, const float* __restrict__ flow, float* __restrict__ out,
-                            int C, int H, int W, float sx, float sy, size_t total) {
+                            int C, int H, int W, float sx, float sy, size_t total, long long src_bs, long long flow_bs,
+                            long long out_bs) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over B*H*W
   if (i >= total) return;
   const int HW = H * W;
   const size_t n = i / HW;
   const int hw = (int)(i - n * HW);
   const int y = hw / W, x = hw - y * W;
-  const float fx = __ldg(flow + (n * 2 + 0) * (size_t)HW + hw);
-  const float fy = __ldg(flow + (n * 2 + 1) * (size_t)HW + hw);
+  const float fx = __ldg(flow + n * flow_bs + hw);
+  const float fy = __ldg(flow + n * flow_bs + (size_t)HW + hw);
   // same float sequence as building the normalised grid and un-normalising it in grid_sample
   const float gx = __fsub_rn(__fmul_rn(__fadd_rn((float)x, fx), sx), 1.0f);
   const float gy = __fsub_rn(__fmul_rn(__fadd_rn((float)y, fy), sy), 1.0f);
@@ -296,20 +312,25 @@ __global__ void warp_kernel(const float* __restrict__ src, const float* __restri
   const float tx = ix - x0f, ty = iy - y0f;
   const float wnw = (1.f - tx) * (1.f - ty), wne = tx * (1.f - ty), wsw = (1.f - tx) * ty, wse = tx * ty;
   for (int c = 0; c < C; ++c) {
-    const float* s = src + (n * C + c) * (size_t)HW;
+    const float* s = src + n * src_bs + (size_t)c * HW;
     float acc = __ldg(s + y0 * W + x0) * wnw;
     if (x1 < W) acc += __ldg(s + y0 * W + x1) * wne;
     if (y1 < H) acc += __ldg(s + y1 * W + x0) * wsw;
     if (x1 < W && y1 < H) acc += __ldg(s + y1 * W + x1) * wse;
-    out[(n * C + c) * (size_t)HW + hw] = acc;
+    out[n * out_bs + (size_t)c * HW + hw] = acc;
   }
 }
 
-int launch_warp(const float* src, const float* flow, float* out, int B, int C, int H, int W, cudaStream_t s) {
+int launch_warp(const float* src, const float* flow, float* out, int B, int C, int H, int W, long long src_bstride,
+                long long flow_bstride, long long out_bstride, cudaStream_t s) {
   const size_t total = (size_t)B * H * W;
+  if (src_bstride == 0) src_bstride = (long long)C * H * W;
+  if (flow_bstride == 0) flow_bstride = 2LL * H * W;
+  if (out_bstride == 0) out_bstride = (long long)C * H * W;
   const int threads = 256;
   const float sx = (float)(2.0 / (double)(W > 1 ? W - 1 : 1)), sy = (float)(2.0 / (double)(H > 1 ? H - 1 : 1));
-  warp_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(src, flow, out, C, H, W, sx, sy, total);
+  warp_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(src, flow, out, C, H, W, sx, sy, total,
+                                                                              src_bstride, flow_bstride, out_bstride);
   RIB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -39,11 +39,14 @@ int launch_avgpool3s2(const act_t* src, long long src_bs, act_t* dst, long long 
 
 // fuse = img * mask + dain * (1 - mask)   (evaluator.py:256-258); optional uint8 HWC frame
 // (utils.py:137-142: clip(x*0.5+0.5, 0, 1)*255 truncated, float64 arithmetic).
+// mask == nullptr: out = img (pure conversion of key frames).  *_bstride: elements between consecutive frames of
+// img / out_f32 / out_u8 (0 = dense), so a batch can be read from / written into every r-th frame of a clip.
 int launch_composite(const float* img, const float* mask, const float* dain, float* out_f32, uint8_t* out_u8, int B,
-                     int H, int W, cudaStream_t s);
+                     int H, int W, long long img_bstride, long long f32_bstride, long long u8_bstride, cudaStream_t s);
 
 // out = bilinear sample of src at (x + flow_x, y + flow_y), border padding, align_corners=True.
-int launch_warp(const float* src, const float* flow, float* out, int B, int C, int H, int W, cudaStream_t s);
+int launch_warp(const float* src, const float* flow, float* out, int B, int C, int H, int W, long long src_bstride,
+                long long flow_bstride, long long out_bstride, cudaStream_t s);
 
 // sigma_inv[0] = 1 / (u . (W v)),  W = [Cout, K] fp32 (torch.nn.utils.spectral_norm, eval mode).
 int launch_sn_sigma_inv(const float* w, const float* u, const float* v, int Cout, int K, float* sigma_inv,

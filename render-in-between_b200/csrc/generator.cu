@@ -52,6 +52,7 @@ enum ExtPtr { EXT_NONE = 0, EXT_LABEL, EXT_FAKE, EXT_PREV, EXT_OUT_IMG, EXT_OUT_
 
 struct Op {
   OpKind kind;
+  std::string name;
   // memset
   void* ms_ptr = nullptr;
   size_t ms_bytes = 0;
@@ -443,9 +444,10 @@ struct PlanBuilder {
     return p;
   }
 
-  void push_gemm(const ConvGemmParams& p, int mode) {
+  void push_gemm(const ConvGemmParams& p, int mode, const std::string& name) {
     Op op;
     op.kind = OP_GEMM;
+    op.name = name;
     op.g = p;
     op.mode = mode;
     ops.push_back(op);
@@ -461,7 +463,7 @@ struct PlanBuilder {
     p.act = act;
     p.has_res = res ? 1 : 0;
     if (res) p.res = res->ref();
-    push_gemm(p, EPI_STORE);
+    push_gemm(p, EPI_STORE, lname);
   }
 
   // [gamma|beta] = conv1x1(cond); out_q = act_q((x - mean) * rstd * (1 + gamma) + beta)
@@ -481,7 +483,7 @@ struct PlanBuilder {
       p.outq[q] = outs[q].ref();
       p.actq[q] = acts[q];
     }
-    push_gemm(p, EPI_SPADE);
+    push_gemm(p, EPI_SPADE, lname);
   }
 
   void conv_final(const std::string& lname, const View& in0, int act, int ext, const View* copy, int copy_coff) {
@@ -493,6 +495,7 @@ struct PlanBuilder {
     p.out_act_coff = copy_coff;
     Op op;
     op.kind = OP_GEMM;
+    op.name = lname;
     op.g = p;
     op.mode = EPI_FINAL;
     op.ext = ext;
@@ -781,10 +784,9 @@ static std::atomic<long long> g_misc_launches{0};
 long long misc_launch_count() { return g_misc_launches.load(); }
 void count_misc_launch(int n) { g_misc_launches.fetch_add(n); }
 
-int generator_forward(Generator* G, int B, int H, int W, const float* label, const float* img_fake,
-                      const float* img_prev, float* out_img, float* out_mask, void* ws, long long ws_bytes,
-                      cudaStream_t stream) {
-  RIB_REQUIRE(G && label && img_fake && img_prev && out_img && out_mask && ws, "forward: null argument");
+// Builds (or re-uses) the launch plan for (B, H, W) on this workspace.
+static int ensure_plan(Generator* G, int B, int H, int W, void* ws, long long ws_bytes, cudaStream_t stream) {
+  RIB_REQUIRE(G && ws, "forward: null argument");
   RIB_REQUIRE(((uintptr_t)ws & 1023) == 0, "forward: workspace must be 1024-byte aligned");
   if (G->pB != B || G->pH != H || G->pW != W || G->pws != ws || G->plan_simt != (g_debug_simt != 0)) {
     size_t need = 0;
@@ -795,6 +797,22 @@ int generator_forward(Generator* G, int B, int H, int W, const float* label, con
     if (rc) return rc;
   }
   RIB_REQUIRE((long long)G->ws_bytes_needed <= ws_bytes, "forward: workspace too small");
+  return 0;
+}
+
+int generator_bind(Generator* G, int B, int H, int W, void* ws, long long ws_bytes, void** label_planar) {
+  int rc = ensure_plan(G, B, H, W, ws, ws_bytes, nullptr);
+  if (rc) return rc;
+  if (label_planar) *label_planar = G->debug_views.at("label").p;
+  return 0;
+}
+
+int generator_forward(Generator* G, int B, int H, int W, const float* label, const float* img_fake,
+                      const float* img_prev, float* out_img, float* out_mask, void* ws, long long ws_bytes,
+                      cudaStream_t stream) {
+  RIB_REQUIRE(G && img_fake && img_prev && out_img && out_mask && ws, "forward: null argument");
+  int prc = ensure_plan(G, B, H, W, ws, ws_bytes, stream);
+  if (prc) return prc;
   for (const Op& op : G->ops) {
     int rc = 0;
     switch (op.kind) {
@@ -802,6 +820,7 @@ int generator_forward(Generator* G, int B, int H, int W, const float* label, con
         RIB_CHECK_CUDA(cudaMemsetAsync(op.ms_ptr, 0, op.ms_bytes, stream));
         break;
       case OP_PACK: {
+        if (op.pk_ext[0] == EXT_LABEL && label == nullptr) break;  // the caller filled the planar label buffer
         PackSrc srcs[3];
         for (int i = 0; i < op.pk_nsrc; ++i) {
           srcs[i].p = op.pk_ext[i] == EXT_LABEL ? label : (op.pk_ext[i] == EXT_FAKE ? img_fake : img_prev);
@@ -833,6 +852,49 @@ int generator_forward(Generator* G, int B, int H, int W, const float* label, con
     }
     if (rc) return rc;
   }
+  return 0;
+}
+
+// One text line per planned launch: kind, layer, tiling and the algorithmic work, in launch order.
+int generator_plan_text(Generator* G, char* buf, long long cap) {
+  std::string out;
+  char line[512];
+  for (const Op& op : G->ops) {
+    switch (op.kind) {
+      case OP_MEMSET:
+        snprintf(line, sizeof(line), "memset bytes=%zu\n", op.ms_bytes);
+        break;
+      case OP_PACK:
+        snprintf(line, sizeof(line), "pack planes=%d\n", op.pk_nplanes);
+        break;
+      case OP_GEMM: {
+        const ConvGemmParams& p = op.g;
+        const long long K = (long long)p.stages0 * p.BKc * p.ntaps + (long long)p.stages1 * p.BKc;
+        const long long N = (long long)p.n_tiles * p.BN;
+        const long long M = (long long)p.B * p.H * p.W;
+        snprintf(line, sizeof(line),
+                 "gemm %s mode=%d B=%d H=%d W=%d N=%lld nvalid=%d K=%lld BN=%d BKc=%d MT=%d taps=%d stride=%d "
+                 "cin0=%d cin1=%d bres=%d aring=%d bring=%d smem=%zu flops=%.6g\n",
+                 op.name.c_str(), op.mode, p.B, p.H, p.W, N, p.n_valid, K, p.BN, p.BKc, p.MT, p.ntaps, p.stride,
+                 p.stages0 * p.BKc, p.stages1 * p.BKc, p.b_resident, p.a_ring, p.b_ring, conv_gemm_smem_bytes(p),
+                 2.0 * (double)M * (double)N * (double)K);
+        break;
+      }
+      case OP_IN_APPLY:
+        snprintf(line, sizeof(line), "in_apply B=%d H=%d W=%d C=%d ups=%d two=%d\n", op.ia.B, op.ia.H, op.ia.W, op.ia.C,
+                 op.ia.ups, op.ia.b != nullptr);
+        break;
+      case OP_POOL:
+        snprintf(line, sizeof(line), "pool H=%d W=%d C=%d\n", op.pl_H, op.pl_W, op.pl_C);
+        break;
+    }
+    out += line;
+  }
+  if ((long long)out.size() + 1 > cap) {
+    set_error("plan text does not fit the buffer");
+    return -1;
+  }
+  memcpy(buf, out.c_str(), out.size() + 1);
   return 0;
 }
 

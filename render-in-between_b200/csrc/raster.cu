@@ -6,19 +6,63 @@
 //              connect_keypoints / interpPoints / drawEdge / setColor  PGNR/utils/keypoint2img.py:36-148
 //   to-tensor  ToTensor + Normalize(0.5, 0.5)      PGNR/datasets/HSM_auto_dataset.py:73-75
 //
-// Output: fp32 label [B, 22, H, W] = [skeleton(3) | heat-maps(19)] (models/evaluator.py:250).
+// Output: fp32 label [B, 22, H, W] = [skeleton(3) | heat-maps(19)] (models/evaluator.py:250) and / or the
+// same label as the generator's 16-bit chunk-planar input [B][32/8][H][W][8] (channels 22..31 zero).
 // All fp64 arithmetic uses explicit round-to-nearest intrinsics so that no FMA contraction can
 // change a rounding with respect to numpy / scipy's C loops.
+//
+// Skeleton algorithm.  The reference draws 18 limbs in order; each limb is 64 shifted copies ("stamps") of
+// an integer curve followed by 193 two-point end-cap stamps.  setColor paints a stamp's pixels with the
+// colour if NONE of them was touched before, otherwise every pixel of the stamp becomes (v + c) >> 1.
+// Because a touched pixel stays touched, a pixel's final value is a function of the ORDERED list of stamps
+// that touch it and of one global bit per stamp ("did this stamp hit anything older?"), which only matters
+// for the pixel's first stamp.  So instead of replaying stamps serially, three data-parallel passes:
+//   prep   per frame: the integer curve of every limb as a lookup table f_e[major coord] -> minor coord
+//   mark   per pixel: enumerate the stamps touching it in order; every stamp after the first one is, by
+//          definition, a stamp that hit an older pixel -> set its flag
+//   paint  per pixel: enumerate again, first stamp -> colour (or colour >> 1 if its flag is set), then average
+// A stamp (i, j) of a limb touches pixel (y, x) iff f[x - j] == y - i (roles of x / y swapped for steep limbs):
+// 8 table look-ups per limb give the 64-bit set of body stamps, whose bit order is the stamp order.
 #include "raster.cuh"
 
 namespace rib {
 
 static constexpr int kRadius = 20;  // int(4.0 * 5 + 0.5)
 static constexpr int kTaps = 41;
+static constexpr int kJoints = 19;
+static constexpr int kEdges = 18;
+static constexpr int kWin = kTaps * kTaps;
+static constexpr int kBodyKeys = 64;            // (i + 4) * 8 + (j + 4)
+static constexpr int kCapKeys = 24 * 24;        // 64 + (i + 12) * 24 + (j + 12)
+static constexpr int kKeys = kBodyKeys + kCapKeys;
+static constexpr int kMaxDim = 1024;
 
 struct GaussTable {
   double w[kTaps];
 };
+
+struct EdgeMeta {
+  int valid, swap;      // swap: the major axis is y (keypoint2img.py:67-70)
+  int mlo, mhi;         // first / last major coordinate of the curve
+  int ex0, ey0, ex1, ey1;
+  int bx0, bx1, by0, by1;  // bounding box of everything the limb can touch (curve +- 12, clipped later)
+  float a, b;           // minor ~= a * major + b (culling only)
+};
+
+struct JointMeta {
+  int valid, ix, iy, pad;
+};
+
+// Per-frame scratch (device): everything `paint` needs.
+struct FrameScratch {
+  short f[kEdges][kMaxDim];
+  EdgeMeta edge[kEdges];
+  JointMeta joint[kJoints];
+  unsigned char flag[kEdges][kKeys];
+  float win[kJoints][kWin];
+};
+
+long long raster_workspace_bytes(int B) { return (long long)B * (long long)sizeof(FrameScratch); }
 
 __device__ __forceinline__ int reflect_idx(int i, int n) {  // ndimage 'reflect': d c b a | a b c d | d c b a
   const int period = 2 * n;
@@ -27,13 +71,30 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {  // ndimage 'reflect'
   return m >= n ? period - 1 - m : m;
 }
 
-// One block per (joint, frame): the response of a unit impulse is non-zero only in the 41x41 window.
-__global__ void __launch_bounds__(256) heatmap_kernel(const double* __restrict__ joints, GaussTable tab, double thres,
-                                                      float* __restrict__ label, int H, int W, int njoints) {
-  const int j = blockIdx.x, b = blockIdx.y;
-  const double* jp = joints + ((size_t)b * njoints + j) * 3;
+__constant__ int c_edges[kEdges][2] = {{0, 1}, {1, 8}, {1, 2}, {2, 3}, {3, 4}, {1, 5}, {5, 6}, {6, 7}, {8, 9},
+                                       {9, 10}, {10, 11}, {8, 12}, {12, 13}, {13, 14}, {4, 18}, {7, 17}, {11, 16}, {14, 15}};
+__constant__ unsigned char c_colors[kEdges][3] = {{153, 0, 51}, {153, 0, 0}, {153, 51, 0}, {153, 102, 0}, {153, 153, 0},
+                                                  {102, 153, 0}, {51, 153, 0}, {0, 153, 0}, {0, 153, 51}, {0, 153, 102},
+                                                  {0, 153, 153}, {0, 102, 153}, {0, 51, 153}, {0, 0, 153}, {208, 208, 0},
+                                                  {0, 208, 0}, {0, 208, 208}, {0, 0, 208}};
+
+// ---------------------------------------------------------------------------------------------
+// prep: grid (20, B).  blockIdx.x < 19: the 41x41 response window of joint blockIdx.x (already divided
+// by its maximum); blockIdx.x == 19: limb tables.
+// ---------------------------------------------------------------------------------------------
+__device__ void heat_window(const double* __restrict__ jp, const GaussTable& tab, double thres, FrameScratch* fs, int j,
+                            int H, int W) {
   const double x = jp[0], y = jp[1], c = jp[2];
-  if (!(x >= 0.0 && y >= 0.0 && c > thres && x < (double)W && y < (double)H)) return;  // map stays all-zero
+  const bool ok = x >= 0.0 && y >= 0.0 && c > thres && x < (double)W && y < (double)H;
+  if (threadIdx.x == 0) {
+    JointMeta m;
+    m.valid = ok ? 1 : 0;
+    m.ix = ok ? (int)x : 0;
+    m.iy = ok ? (int)y : 0;
+    m.pad = 0;
+    fs->joint[j] = m;
+  }
+  if (!ok) return;  // map stays all-zero
   const int iy = (int)y, ix = (int)x;
   __shared__ double s_ky[kTaps];
   __shared__ double s_max[8];
@@ -59,7 +120,7 @@ __global__ void __launch_bounds__(256) heatmap_kernel(const double* __restrict__
   for (int k = 0; k < 7; ++k) {
     g[k] = -1.0;
     const int idx = threadIdx.x + k * 256;
-    if (idx >= kTaps * kTaps) continue;
+    if (idx >= kWin) continue;
     const int wy = idx / kTaps, wx = idx - wy * kTaps;
     const int oy = iy - kRadius + wy, ox = ix - kRadius + wx;
     if (oy < 0 || oy >= H || ox < 0 || ox >= W) continue;
@@ -80,30 +141,201 @@ __global__ void __launch_bounds__(256) heatmap_kernel(const double* __restrict__
   double gmax = s_max[0];
 #pragma unroll
   for (int k = 1; k < 8; ++k) gmax = fmax(gmax, s_max[k]);
-  float* out = label + ((size_t)b * (3 + njoints) + 3 + j) * (size_t)H * W;
 #pragma unroll
   for (int k = 0; k < 7; ++k) {
     if (g[k] < 0.0) continue;
-    const int idx = threadIdx.x + k * 256;
-    const int wy = idx / kTaps, wx = idx - wy * kTaps;
-    const int oy = iy - kRadius + wy, ox = ix - kRadius + wx;
-    out[(size_t)oy * W + ox] = __double2float_rn(__ddiv_rn(g[k], gmax));
+    fs->win[j][threadIdx.x + k * 256] = __double2float_rn(__ddiv_rn(g[k], gmax));
   }
 }
 
+__device__ void limb_tables(const double* __restrict__ joints, double thres, double foot_thres, FrameScratch* fs, int H,
+                            int W) {
+  __shared__ double s_pts[kJoints][2];
+  for (int i = threadIdx.x; i < kEdges * kKeys; i += blockDim.x) (&fs->flag[0][0])[i] = 0;
+  if (threadIdx.x < kJoints) {  // extract_valid_keypoints (keypoint2img.py:114-130)
+    const double* jp = joints + threadIdx.x * 3;
+    const int i = threadIdx.x;
+    const double thr = (i >= 8 && i <= 16) ? foot_thres : thres;
+    const double x = jp[0], y = jp[1], c = jp[2];
+    const bool ok = x >= 0.0 && y >= 0.0 && c > thr && x < (double)W && y < (double)H;
+    s_pts[i][0] = ok ? x : 0.0;
+    s_pts[i][1] = ok ? y : 0.0;
+  }
+  __syncthreads();
+  for (int e = 0; e < kEdges; ++e) {
+    EdgeMeta m;
+    memset(&m, 0, sizeof(m));
+    const double xa = s_pts[c_edges[e][0]][0], ya = s_pts[c_edges[e][0]][1];
+    const double xb = s_pts[c_edges[e][1]][0], yb = s_pts[c_edges[e][1]][1];
+    bool draw = !(xa == 0.0 || xb == 0.0);  // `0 not in x` (keypoint2img.py:144); uniform across the block
+    // interpPoints: major axis = the one with the larger extent (keypoint2img.py:67-70)
+    const bool swap = fabs(xa - xb) < fabs(ya - yb);
+    double m0 = swap ? ya : xa, m1 = swap ? yb : xb;
+    const double n0 = swap ? xa : ya, n1 = swap ? xb : yb;
+    if (m0 == m1) draw = false;  // zero-length: int(x1 - x0) == 0 -> empty curve
+    double slope = 0.0, icpt = 0.0;
+    int npts = 0;
+    double start = 0.0, stop = 0.0, step = 0.0;
+    if (draw) {
+      slope = __ddiv_rn(__dsub_rn(n1, n0), __dsub_rn(m1, m0));
+      icpt = __dsub_rn(n0, __dmul_rn(slope, m0));
+      if (m0 > m1) {
+        const double t = m0;
+        m0 = m1;
+        m1 = t;
+      }
+      npts = (int)__dsub_rn(m1, m0);
+      if (npts <= 0) draw = false;
+      start = (double)(int)m0;
+      stop = (double)(int)m1;
+      step = npts > 1 ? __ddiv_rn(__dsub_rn(stop, start), (double)(npts - 1)) : 0.0;
+    }
+    if (!draw) {
+      if (threadIdx.x == 0) fs->edge[e] = m;
+      continue;
+    }
+    const int dim = swap ? H : W;
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) fs->f[e][i] = -1;
+    __syncthreads();
+    for (int k = threadIdx.x; k < npts; k += blockDim.x) {  // numpy.linspace: k * step + start, last = stop
+      double cm = __dadd_rn(__dmul_rn((double)k, step), start);
+      if (npts > 1 && k == npts - 1) cm = stop;
+      const double cn = __dadd_rn(__dmul_rn(slope, cm), icpt);
+      const int im = (int)cm, in_ = (int)cn;  // astype(int): truncation toward zero
+      if (im >= 0 && im < dim) fs->f[e][im] = (short)in_;
+    }
+    if (threadIdx.x == 0) {
+      const int mlo = (int)start, mhi = (int)stop;
+      const int nlo = (int)__dadd_rn(__dmul_rn(slope, start), icpt);
+      double cl = stop;
+      if (npts == 1) cl = start;
+      const int nhi = (int)__dadd_rn(__dmul_rn(slope, cl), icpt);
+      const int mlast = npts == 1 ? mlo : mhi;
+      m.valid = 1;
+      m.swap = swap ? 1 : 0;
+      m.mlo = mlo;
+      m.mhi = mlast;
+      m.ex0 = swap ? nlo : mlo;
+      m.ey0 = swap ? mlo : nlo;
+      m.ex1 = swap ? nhi : mlast;
+      m.ey1 = swap ? mlast : nhi;
+      const int nmin = min(nlo, nhi), nmax = max(nlo, nhi);
+      m.bx0 = (swap ? nmin : mlo) - 12;
+      m.bx1 = (swap ? nmax : mlast) + 12;
+      m.by0 = (swap ? mlo : nmin) - 12;
+      m.by1 = (swap ? mlast : nmax) + 12;
+      m.a = (float)slope;
+      m.b = (float)icpt;
+      fs->edge[e] = m;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) raster_prep_kernel(const double* __restrict__ joints, GaussTable tab, double thres,
+                                                          double foot_thres, FrameScratch* __restrict__ scratch, int H,
+                                                          int W) {
+  const int b = blockIdx.y;
+  FrameScratch* fs = scratch + b;
+  const double* jf = joints + (size_t)b * kJoints * 3;
+  if (blockIdx.x < kJoints) heat_window(jf + blockIdx.x * 3, tab, thres, fs, blockIdx.x, H, W);
+  else limb_tables(jf, thres, foot_thres, fs, H, W);
+}
+
 // ---------------------------------------------------------------------------------------------
-// Skeleton.  The reference draws 18 limbs in order; each limb is 64 shifted copies of an integer
-// curve followed by 193 two-point end-cap stamps.  A stamp either paints its pixels (if none of
-// them was ever touched) or averages all of them with the colour, so stamps must be replayed in
-// order.  One CTA replays the whole frame with a visited bitmap of the full image in shared
-// memory and keeps the pixel values of its own band of rows; several CTAs (bands) per frame.
+// Stamp enumeration for one pixel and one limb, in the reference's drawing order.
 // ---------------------------------------------------------------------------------------------
-__constant__ int c_edges[18][2] = {{0, 1}, {1, 8}, {1, 2}, {2, 3}, {3, 4}, {1, 5}, {5, 6}, {6, 7}, {8, 9},
-                                   {9, 10}, {10, 11}, {8, 12}, {12, 13}, {13, 14}, {4, 18}, {7, 17}, {11, 16}, {14, 15}};
-__constant__ unsigned char c_colors[18][3] = {{153, 0, 51}, {153, 0, 0}, {153, 51, 0}, {153, 102, 0}, {153, 153, 0},
-                                              {102, 153, 0}, {51, 153, 0}, {0, 153, 0}, {0, 153, 51}, {0, 153, 102},
-                                              {0, 153, 153}, {0, 102, 153}, {0, 51, 153}, {0, 0, 153}, {208, 208, 0},
-                                              {0, 208, 0}, {0, 208, 208}, {0, 0, 208}};
+// Source coordinates s with clamp(s + shift, 0, n - 1) == v (np.clip in drawEdge, keypoint2img.py:52-53).
+__device__ __forceinline__ void src_range(int v, int shift, int n, int* lo, int* hi) {
+  if (v > 0 && v < n - 1) {
+    *lo = *hi = v - shift;
+  } else if (v == 0) {
+    *lo = -(1 << 20);
+    *hi = -shift;
+  } else {
+    *lo = n - 1 - shift;
+    *hi = 1 << 20;
+  }
+}
+
+template <typename Visit>
+__device__ __forceinline__ void visit_limb(const EdgeMeta& m, const short* __restrict__ f, int y, int x, int H, int W,
+                                           Visit&& visit) {
+  const bool interior = x > 0 && x < W - 1 && y > 0 && y < H - 1;
+  unsigned long long mask = 0ull;
+  if (interior) {
+    const int pm = m.swap ? y : x, pn = m.swap ? x : y;
+    const bool near_body = pm >= m.mlo - 4 && pm <= m.mhi + 3 && fabsf((float)pn - (m.a * (float)pm + m.b)) <= 11.0f;
+    if (near_body) {
+#pragma unroll
+      for (int s = -4; s < 4; ++s) {  // shift along the major axis
+        const int mm = pm - s;
+        if (mm < m.mlo || mm > m.mhi) continue;
+        const int nn = f[mm];
+        if (nn < 0) continue;
+        const int t = pn - nn;  // shift along the minor axis
+        if ((unsigned)(t + 4) < 8u) {
+          const int i = m.swap ? s : t, j = m.swap ? t : s;
+          mask |= 1ull << ((i + 4) * 8 + (j + 4));
+        }
+      }
+    }
+  } else {
+    for (int i = -4; i < 4; ++i) {
+      int ylo, yhi;
+      src_range(y, i, H, &ylo, &yhi);
+      for (int j = -4; j < 4; ++j) {
+        int xlo, xhi;
+        src_range(x, j, W, &xlo, &xhi);
+        const int mlo = max(m.swap ? ylo : xlo, m.mlo), mhi = min(m.swap ? yhi : xhi, m.mhi);
+        const int nlo = m.swap ? xlo : ylo, nhi = m.swap ? xhi : yhi;
+        bool hit = false;
+        for (int mm = mlo; mm <= mhi && !hit; ++mm) {
+          const int nn = f[mm];
+          hit = nn >= 0 && nn >= nlo && nn <= nhi;
+        }
+        if (hit) mask |= 1ull << ((i + 4) * 8 + (j + 4));
+      }
+    }
+  }
+  while (mask) {
+    const int bit = __ffsll((long long)mask) - 1;
+    mask &= mask - 1;
+    visit(bit);
+  }
+  // end caps (keypoint2img.py:59-64): stamps (i, j), i outer, both end points in one stamp
+  if (interior) {
+    int k0 = -1, k1 = -1;
+    {
+      const int i = y - m.ey0, j = x - m.ex0;
+      if (i >= -12 && i < 12 && j >= -12 && j < 12 && i * i + j * j < 64) k0 = kBodyKeys + (i + 12) * 24 + (j + 12);
+    }
+    {
+      const int i = y - m.ey1, j = x - m.ex1;
+      if (i >= -12 && i < 12 && j >= -12 && j < 12 && i * i + j * j < 64) k1 = kBodyKeys + (i + 12) * 24 + (j + 12);
+    }
+    if (k0 >= 0 && k1 >= 0) {
+      if (k0 == k1) {
+        visit(k0);
+      } else {
+        visit(min(k0, k1));
+        visit(max(k0, k1));
+      }
+    } else if (k0 >= 0) {
+      visit(k0);
+    } else if (k1 >= 0) {
+      visit(k1);
+    }
+  } else {
+    for (int i = -12; i < 12; ++i)
+      for (int j = -12; j < 12; ++j) {
+        if (i * i + j * j >= 64) continue;
+        const bool h0 = min(max(m.ey0 + i, 0), H - 1) == y && min(max(m.ex0 + j, 0), W - 1) == x;
+        const bool h1 = min(max(m.ey1 + i, 0), H - 1) == y && min(max(m.ex1 + j, 0), W - 1) == x;
+        if (h0 || h1) visit(kBodyKeys + (i + 12) * 24 + (j + 12));
+      }
+  }
+}
 
 __device__ __forceinline__ uint32_t avg_color(uint32_t old, uint32_t col) {
   // per channel (v + c) >> 1 on packed 0x00BBGGRR; channels are <= 255 so (v + c) fits in 9 bits
@@ -113,161 +345,159 @@ __device__ __forceinline__ uint32_t avg_color(uint32_t old, uint32_t col) {
   return r | (g << 8) | (b << 16);
 }
 
-__global__ void __launch_bounds__(256) skeleton_kernel(const double* __restrict__ joints, double thres,
-                                                       double foot_thres, float* __restrict__ label, int H, int W,
-                                                       int njoints, int band_rows) {
-  extern __shared__ uint32_t s_mem[];
-  const int b = blockIdx.y;
-  const int row0 = blockIdx.x * band_rows;
-  const int rows = min(band_rows, H - row0);
-  const int nwords = (H * W + 31) / 32;
-  uint32_t* s_bits = s_mem;                   // visited bitmap, whole image
-  uint32_t* s_val = s_bits + nwords;          // packed RGB of rows [row0, row0+rows)
-  int* s_px = reinterpret_cast<int*>(s_val + (size_t)band_rows * W);
-  int* s_py = s_px + max(H, W);
-  __shared__ double s_pts[19][2];
-  __shared__ float s_lut[256];
+// Tile of 8 rows x 128 columns per CTA (256 threads x 4 consecutive pixels).
+static constexpr int kTileRows = 8, kTileCols = 128, kPxPerThread = 4;
 
-  for (int i = threadIdx.x; i < nwords; i += blockDim.x) s_bits[i] = 0u;
-  for (int i = threadIdx.x; i < rows * W; i += blockDim.x) s_val[i] = 0u;
-  // ToTensor: float32(v) / 255, Normalize: (t - 0.5) / 0.5, both in fp32
-  for (int i = threadIdx.x; i < 256; i += blockDim.x)
-    s_lut[i] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)i, 255.0f), 0.5f), 0.5f);
-  if (threadIdx.x < njoints) {  // extract_valid_keypoints (keypoint2img.py:114-130)
-    const double* jp = joints + ((size_t)b * njoints + threadIdx.x) * 3;
-    const int i = threadIdx.x;
-    const double thr = (i >= 8 && i <= 16) ? foot_thres : thres;
-    const double x = jp[0], y = jp[1], c = jp[2];
-    const bool ok = x >= 0.0 && y >= 0.0 && c > thr && x < (double)W && y < (double)H;
-    s_pts[i][0] = ok ? x : 0.0;
-    s_pts[i][1] = ok ? y : 0.0;
+struct TileEdges {
+  int n;
+  int idx[kEdges];
+};
+
+__device__ __forceinline__ void tile_edges(const FrameScratch* fs, int y0, int x0, int H, int W, TileEdges* te,
+                                           EdgeMeta* s_meta) {
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int e = 0; e < kEdges; ++e) {
+      const EdgeMeta m = fs->edge[e];
+      if (!m.valid) continue;
+      // everything a limb touches lies in its bounding box clipped to the image
+      const int bx0 = max(m.bx0, 0), bx1 = min(m.bx1, W - 1), by0 = max(m.by0, 0), by1 = min(m.by1, H - 1);
+      if (bx1 < x0 || bx0 >= x0 + kTileCols || by1 < y0 || by0 >= y0 + kTileRows) continue;
+      s_meta[n] = m;
+      te->idx[n++] = e;
+    }
+    te->n = n;
   }
   __syncthreads();
+}
 
-  for (int e = 0; e < 18; ++e) {
-    const double xa = s_pts[c_edges[e][0]][0], ya = s_pts[c_edges[e][0]][1];
-    const double xb = s_pts[c_edges[e][1]][0], yb = s_pts[c_edges[e][1]][1];
-    if (xa == 0.0 || xb == 0.0) continue;  // `0 not in x` (keypoint2img.py:144); uniform across the block
-    // interpPoints: major axis = the one with the larger extent (keypoint2img.py:67-70)
-    const bool swap = fabs(xa - xb) < fabs(ya - yb);
-    double m0 = swap ? ya : xa, m1 = swap ? yb : xb;
-    const double n0 = swap ? xa : ya, n1 = swap ? xb : yb;
-    if (m0 == m1) continue;                       // zero-length: int(x1 - x0) == 0 -> empty curve
-    const double slope = __ddiv_rn(__dsub_rn(n1, n0), __dsub_rn(m1, m0));
-    const double icpt = __dsub_rn(n0, __dmul_rn(slope, m0));
-    if (m0 > m1) {
-      const double t = m0;
-      m0 = m1;
-      m1 = t;
+// mark: every stamp that is not the first one of some pixel hit an older pixel.
+__global__ void __launch_bounds__(256) raster_mark_kernel(FrameScratch* __restrict__ scratch, int H, int W) {
+  __shared__ TileEdges te;
+  __shared__ EdgeMeta s_meta[kEdges];
+  FrameScratch* fs = scratch + blockIdx.z;
+  const int y0 = blockIdx.y * kTileRows, x0 = blockIdx.x * kTileCols;
+  tile_edges(fs, y0, x0, H, W, &te, s_meta);
+  if (te.n == 0) return;
+  const int y = y0 + (threadIdx.x >> 5);
+  const int xb = x0 + (threadIdx.x & 31) * kPxPerThread;
+  if (y >= H) return;
+  for (int p = 0; p < kPxPerThread; ++p) {
+    const int x = xb + p;
+    if (x >= W) break;
+    int count = 0;
+    for (int k = 0; k < te.n; ++k) {
+      const EdgeMeta& m = s_meta[k];
+      if (x < m.bx0 || x > m.bx1 || y < m.by0 || y > m.by1) continue;
+      const int e = te.idx[k];
+      visit_limb(m, fs->f[e], y, x, H, W, [&](int key) {
+        if (count++ > 0) fs->flag[e][key] = 1;
+      });
     }
-    const int npts = (int)__dsub_rn(m1, m0);
-    if (npts <= 0) continue;
-    const double start = (double)(int)m0, stop = (double)(int)m1;
-    const double step = npts > 1 ? __ddiv_rn(__dsub_rn(stop, start), (double)(npts - 1)) : 0.0;
-    for (int k = threadIdx.x; k < npts; k += blockDim.x) {  // numpy.linspace: k * step + start, last = stop
-      double cm = __dadd_rn(__dmul_rn((double)k, step), start);
-      if (npts > 1 && k == npts - 1) cm = stop;
-      const double cn = __dadd_rn(__dmul_rn(slope, cm), icpt);
-      const int im = (int)cm, in_ = (int)cn;  // astype(int): truncation toward zero
-      s_px[k] = swap ? in_ : im;
-      s_py[k] = swap ? im : in_;
-    }
-    const uint32_t col = (uint32_t)c_colors[e][0] | ((uint32_t)c_colors[e][1] << 8) | ((uint32_t)c_colors[e][2] << 16);
-    __syncthreads();
-    // ---- body: 64 shifted copies of the curve (drawEdge, keypoint2img.py:51-55) ----
-    for (int i = -4; i < 4; ++i) {
-      for (int j = -4; j < 4; ++j) {
-        uint32_t old[4];
-        int touched = 0;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const int k = threadIdx.x + r * 256;
-          old[r] = 0u;
-          if (k < npts) {
-            const int yy = min(max(s_py[k] + i, 0), H - 1), xx = min(max(s_px[k] + j, 0), W - 1);
-            const int p = yy * W + xx;
-            touched |= (s_bits[p >> 5] >> (p & 31)) & 1u;
-            if (yy >= row0 && yy < row0 + rows) old[r] = s_val[(yy - row0) * W + xx];
-          }
-        }
-        const int any = __syncthreads_or(touched);  // setColor's `(im[yy, xx] == 0).all()` over the whole stamp
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const int k = threadIdx.x + r * 256;
-          if (k < npts) {
-            const int yy = min(max(s_py[k] + i, 0), H - 1), xx = min(max(s_px[k] + j, 0), W - 1);
-            const int p = yy * W + xx;
-            atomicOr(&s_bits[p >> 5], 1u << (p & 31));
-            if (yy >= row0 && yy < row0 + rows) s_val[(yy - row0) * W + xx] = any ? avg_color(old[r], col) : col;
-          }
-        }
-        __syncthreads();
-      }
-    }
-    // ---- end caps: 193 two-point stamps (keypoint2img.py:59-64), replayed by one thread ----
-    if (threadIdx.x == 0) {
-      const int ex[2] = {s_px[0], s_px[npts - 1]}, ey[2] = {s_py[0], s_py[npts - 1]};
-      for (int i = -12; i < 12; ++i) {
-        for (int j = -12; j < 12; ++j) {
-          if (i * i + j * j >= 64) continue;
-          int p[2], yy[2], xx[2];
-          uint32_t old[2];
-          int any = 0;
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            yy[t] = min(max(ey[t] + i, 0), H - 1);
-            xx[t] = min(max(ex[t] + j, 0), W - 1);
-            p[t] = yy[t] * W + xx[t];
-            any |= (s_bits[p[t] >> 5] >> (p[t] & 31)) & 1u;
-            old[t] = (yy[t] >= row0 && yy[t] < row0 + rows) ? s_val[(yy[t] - row0) * W + xx[t]] : 0u;
-          }
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            s_bits[p[t] >> 5] |= 1u << (p[t] & 31);
-            if (yy[t] >= row0 && yy[t] < row0 + rows)
-              s_val[(yy[t] - row0) * W + xx[t]] = any ? avg_color(old[t], col) : col;
-          }
-        }
-      }
-    }
-    __syncthreads();
   }
-  // ---- write the band: uint8 -> normalised fp32, channels 0..2 of the label ----
-  float* out = label + (size_t)b * (3 + njoints) * (size_t)H * W;
-  for (int c = 0; c < 3; ++c) {
-    float* oc = out + (size_t)c * H * W + (size_t)row0 * W;
-    for (int i = threadIdx.x; i < rows * W; i += blockDim.x) oc[i] = s_lut[(s_val[i] >> (8 * c)) & 0xffu];
+}
+
+// paint: all 22 channels of every pixel, as fp32 NCHW and / or the generator's 16-bit planar input.
+__global__ void __launch_bounds__(256) raster_paint_kernel(const FrameScratch* __restrict__ scratch,
+                                                           float* __restrict__ label, act_t* __restrict__ planar,
+                                                           int H, int W) {
+  __shared__ TileEdges te;
+  __shared__ EdgeMeta s_meta[kEdges];
+  __shared__ JointMeta s_joint[kJoints];
+  __shared__ float s_lut[256];
+  const int b = blockIdx.z;
+  const FrameScratch* fs = scratch + b;
+  const int y0 = blockIdx.y * kTileRows, x0 = blockIdx.x * kTileCols;
+  // ToTensor: float32(v) / 255, Normalize: (t - 0.5) / 0.5, both in fp32
+  s_lut[threadIdx.x] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)threadIdx.x, 255.0f), 0.5f), 0.5f);
+  if (threadIdx.x < kJoints) s_joint[threadIdx.x] = fs->joint[threadIdx.x];
+  tile_edges(const_cast<FrameScratch*>(fs), y0, x0, H, W, &te, s_meta);
+  const int y = y0 + (threadIdx.x >> 5);
+  const int xb = x0 + (threadIdx.x & 31) * kPxPerThread;
+  if (y >= H || xb >= W) return;
+  float v[22][kPxPerThread];
+#pragma unroll
+  for (int p = 0; p < kPxPerThread; ++p) {
+    const int x = xb + p;
+    uint32_t rgb = 0u;
+    if (x < W) {
+      int count = 0;
+      for (int k = 0; k < te.n; ++k) {
+        const EdgeMeta& m = s_meta[k];
+        if (x < m.bx0 || x > m.bx1 || y < m.by0 || y > m.by1) continue;
+        const int e = te.idx[k];
+        const uint32_t col =
+            (uint32_t)c_colors[e][0] | ((uint32_t)c_colors[e][1] << 8) | ((uint32_t)c_colors[e][2] << 16);
+        visit_limb(m, fs->f[e], y, x, H, W, [&](int key) {
+          if (count++ == 0) rgb = fs->flag[e][key] ? avg_color(0u, col) : col;
+          else rgb = avg_color(rgb, col);
+        });
+      }
+    }
+    v[0][p] = s_lut[rgb & 0xffu];
+    v[1][p] = s_lut[(rgb >> 8) & 0xffu];
+    v[2][p] = s_lut[(rgb >> 16) & 0xffu];
+#pragma unroll
+    for (int j = 0; j < kJoints; ++j) {
+      const JointMeta jm = s_joint[j];
+      const int wy = y - jm.iy + kRadius, wx = x - jm.ix + kRadius;
+      float h = 0.f;
+      if (jm.valid && (unsigned)wy < (unsigned)kTaps && (unsigned)wx < (unsigned)kTaps) h = fs->win[j][wy * kTaps + wx];
+      v[3 + j][p] = h;
+    }
+  }
+  const size_t HW = (size_t)H * W;
+  const size_t pix = (size_t)y * W + xb;
+  const bool full = xb + kPxPerThread <= W && (W & 3) == 0;
+  if (label != nullptr) {
+    float* out = label + (size_t)b * 22 * HW + pix;
+#pragma unroll
+    for (int c = 0; c < 22; ++c) {
+      if (full) {
+        *reinterpret_cast<float4*>(out + (size_t)c * HW) = make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
+      } else {
+        for (int p = 0; p < kPxPerThread && xb + p < W; ++p) out[(size_t)c * HW + p] = v[c][p];
+      }
+    }
+  }
+  if (planar != nullptr) {  // [B][4][H][W][8], channels 22..31 zero
+    act_t* out = planar + (size_t)b * 32 * HW + pix * 8;
+#pragma unroll
+    for (int pl = 0; pl < 4; ++pl) {
+#pragma unroll
+      for (int p = 0; p < kPxPerThread; ++p) {
+        if (xb + p >= W) break;
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c0 = pl * 8 + 2 * k;
+          const float a = c0 < 22 ? v[c0 < 22 ? c0 : 0][p] : 0.f;
+          const float bb = c0 + 1 < 22 ? v[c0 + 1 < 22 ? c0 + 1 : 0][p] : 0.f;
+          o[k] = pack2(a, bb);
+        }
+        *reinterpret_cast<uint4*>(out + (size_t)pl * HW * 8 + (size_t)p * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
   }
 }
 
 int launch_rasterize(const double* joints_dev, int B, int H, int W, const double* wtab41_host, double skeleton_thres,
-                     double foot_thres, float* label, cudaStream_t stream) {
-  const int njoints = 19;
-  RIB_REQUIRE(H >= 1 && W >= 1 && B >= 1, "rasterize: bad shape");
-  RIB_REQUIRE(H <= 1024 && W <= 1024, "rasterize: images larger than 1024 px are not supported");
+                     double foot_thres, float* label, act_t* label_planar, void* workspace, long long workspace_bytes,
+                     cudaStream_t stream) {
+  RIB_REQUIRE(H >= 2 && W >= 2 && B >= 1, "rasterize: bad shape");
+  RIB_REQUIRE(H <= kMaxDim && W <= kMaxDim, "rasterize: images larger than 1024 px are not supported");
+  RIB_REQUIRE(label != nullptr || label_planar != nullptr, "rasterize: no output requested");
+  RIB_REQUIRE(workspace != nullptr && workspace_bytes >= raster_workspace_bytes(B), "rasterize: workspace too small");
+  RIB_REQUIRE(((uintptr_t)workspace & 15) == 0, "rasterize: workspace must be 16-byte aligned");
   GaussTable tab;
   for (int i = 0; i < kTaps; ++i) tab.w[i] = wtab41_host[i];
-  // heat-map channels are zero outside the 41x41 windows
-  RIB_CHECK_CUDA(cudaMemsetAsync(label, 0, (size_t)B * (3 + njoints) * H * W * sizeof(float), stream));
-  heatmap_kernel<<<dim3(njoints, B), 256, 0, stream>>>(joints_dev, tab, skeleton_thres, label, H, W, njoints);
+  FrameScratch* fs = static_cast<FrameScratch*>(workspace);
+  raster_prep_kernel<<<dim3(kJoints + 1, B), 256, 0, stream>>>(joints_dev, tab, skeleton_thres, foot_thres, fs, H, W);
   RIB_CHECK_CUDA(cudaGetLastError());
-
-  const size_t bitmap_bytes = (size_t)((H * W + 31) / 32) * 4;
-  const size_t fixed = bitmap_bytes + (size_t)2 * (H > W ? H : W) * 4;
-  const size_t budget = 200 * 1024;
-  RIB_REQUIRE(fixed + (size_t)W * 4 <= budget, "rasterize: image does not fit the shared-memory plan");
-  int band_rows = (int)((budget - fixed) / ((size_t)W * 4));
-  if (band_rows > H) band_rows = H;
-  const int bands = ceil_div(H, band_rows);
-  band_rows = ceil_div(H, bands);
-  const size_t smem = fixed + (size_t)band_rows * W * 4;
-  static size_t attr_smem = 0;  // the kernel also has ~1.4 KB of static shared memory
-  if (smem > attr_smem) {
-    RIB_CHECK_CUDA(cudaFuncSetAttribute(skeleton_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
-  }
-  skeleton_kernel<<<dim3(bands, B), 256, smem, stream>>>(joints_dev, skeleton_thres, foot_thres, label, H, W, njoints,
-                                                         band_rows);
+  const dim3 grid(ceil_div(W, kTileCols), ceil_div(H, kTileRows), B);
+  raster_mark_kernel<<<grid, 256, 0, stream>>>(fs, H, W);
+  RIB_CHECK_CUDA(cudaGetLastError());
+  raster_paint_kernel<<<grid, 256, 0, stream>>>(fs, label, label_planar, H, W);
   RIB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

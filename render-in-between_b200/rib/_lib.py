@@ -11,9 +11,9 @@ LIB_PATH = os.path.join(_HERE, 'librib_b200.so')
 
 # every symbol include/rib_b200.h declares
 SYMBOLS = [
-    'rib_last_error', 'rib_abi_version', 'rib_kernel_launch_count', 'rib_rasterize', 'rib_warp', 'rib_composite',
-    'rib_generator_create', 'rib_generator_destroy', 'rib_generator_workspace_bytes', 'rib_generator_forward',
-    'rib_debug_set_simt', 'rib_debug_get_simt', 'rib_generator_debug_tensor', 'rib_act_is_fp16',
+    'rib_last_error', 'rib_abi_version', 'rib_kernel_launch_count', 'rib_rasterize_workspace_bytes', 'rib_rasterize', 'rib_warp', 'rib_composite',
+    'rib_generator_create', 'rib_generator_destroy', 'rib_generator_workspace_bytes', 'rib_generator_bind', 'rib_generator_forward',
+    'rib_debug_set_simt', 'rib_debug_get_simt', 'rib_generator_debug_tensor', 'rib_generator_plan_text', 'rib_act_is_fp16',
     'rib_conv_test_scratch_bytes', 'rib_conv_test', 'rib_profile_enable', 'rib_profile_collect',
 ]
 
@@ -40,17 +40,21 @@ def _load():
     lib.rib_abi_version.restype = i32
     lib.rib_kernel_launch_count.restype = i64
     lib.rib_rasterize.restype = i32
-    lib.rib_rasterize.argtypes = [vp, i32, i32, i32, C.POINTER(f64), f64, f64, vp, vp]
+    lib.rib_rasterize.argtypes = [vp, i32, i32, i32, C.POINTER(f64), f64, f64, vp, vp, vp, i64, vp]
+    lib.rib_rasterize_workspace_bytes.restype = i64
+    lib.rib_rasterize_workspace_bytes.argtypes = [i32]
     lib.rib_warp.restype = i32
-    lib.rib_warp.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
+    lib.rib_warp.argtypes = [vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, vp]
     lib.rib_composite.restype = i32
-    lib.rib_composite.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp]
+    lib.rib_composite.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i64, i64, i64, vp]
     lib.rib_generator_create.restype = i32
     lib.rib_generator_create.argtypes = [C.POINTER(GenConfig), C.POINTER(Tensor), i32, vp, C.POINTER(vp)]
     lib.rib_generator_destroy.restype = None
     lib.rib_generator_destroy.argtypes = [vp]
     lib.rib_generator_workspace_bytes.restype = i64
     lib.rib_generator_workspace_bytes.argtypes = [vp, i32, i32, i32]
+    lib.rib_generator_bind.restype = i32
+    lib.rib_generator_bind.argtypes = [vp, i32, i32, i32, vp, i64, C.POINTER(vp)]
     lib.rib_generator_forward.restype = i32
     lib.rib_generator_forward.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, i64, vp]
     lib.rib_debug_set_simt.restype = None
@@ -58,6 +62,8 @@ def _load():
     lib.rib_debug_get_simt.restype = i32
     lib.rib_generator_debug_tensor.restype = i32
     lib.rib_generator_debug_tensor.argtypes = [vp, C.c_char_p, C.POINTER(vp)] + [C.POINTER(i32)] * 5
+    lib.rib_generator_plan_text.restype = i32
+    lib.rib_generator_plan_text.argtypes = [vp, C.c_char_p, i64]
     lib.rib_act_is_fp16.restype = i32
     lib.rib_profile_enable.restype = None
     lib.rib_profile_enable.argtypes = [i32]

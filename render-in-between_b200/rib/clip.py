@@ -23,11 +23,16 @@ class ClipRenderer:
     def seq_len(num_keyframes, sample_rate):
         return (num_keyframes - 1) * sample_rate + 1            # evaluator.py:191
 
-    def render(self, key_frames, joints, backgrounds=None, flows=None, want_u8=True, want_mask=False):
+    def render(self, key_frames, joints, backgrounds=None, flows=None, want_u8=True, want_mask=False, want_fuse=True):
         """key_frames [K,3,H,W] f32, joints [T,19,3] f64, and either backgrounds [T,3,H,W] f32 (the
         pre-computed DAIN frames of the reference) or flows [T,2,H,W] f32 from which the background of
         frame i is resampled out of the preceding key frame (stage A3).  All CUDA tensors.
-        Returns dict(fuse [T,3,H,W] f32, u8 [T,H,W,3] uint8 | None, mask [T,1,H,W] | None)."""
+        Returns dict(fuse [T,3,H,W] f32 | None, u8 [T,H,W,3] uint8 | None, mask [T,1,H,W] | None).
+
+        Only the labels of generated frames are rasterised: a key frame's label is consumed by the reference
+        solely as `label_prev`, which Generator.forward never reads (generator.py:181-234).  Each AR step
+        rasterises straight into the generator's input buffer and blends straight into frames s, s+r, ... of
+        the clip, so no frame is gathered, scattered or converted twice."""
         r = self.rate
         k, _, h, w = key_frames.shape
         t = self.seq_len(k, r)
@@ -35,27 +40,33 @@ class ClipRenderer:
             raise ValueError('need %d joint sets for %d key frames at %dx' % (t, k, r))
         if (backgrounds is None) == (flows is None):
             raise ValueError('pass exactly one of backgrounds / flows')
+        if not (want_u8 or want_fuse):
+            raise ValueError('nothing to return')
         dev = key_frames.device
-        fuse = torch.empty(t, 3, h, w, dtype=torch.float32, device=dev)
+        key_frames = key_frames.contiguous()
+        fuse = torch.empty(t, 3, h, w, dtype=torch.float32, device=dev) if want_fuse else None
         u8 = torch.empty(t, h, w, 3, dtype=torch.uint8, device=dev) if want_u8 else None
         mask_out = torch.zeros(t, 1, h, w, dtype=torch.float32, device=dev) if want_mask else None
-        fuse[0::r] = key_frames                                   # key frames pass through (:240-244)
-        label = ops.rasterize(joints, h, w)                       # all frames at once (label-only work)
+        # key frames pass through (:240-244)
+        ops.composite(key_frames, None, None, out=fuse[0::r] if want_fuse else None, out_u8=u8[0::r] if want_u8 else None)
+        b = k - 1
+        prev = key_frames[:b]                                      # fuse[i-1] of step 1 is the key frame
         for s in range(1, r):
-            idx = torch.arange(s, t, r, device=dev)               # frames i = j*r + s of every interval j
-            lab = label[s::r]
+            lab_addr = self.gen.bind(b, h, w, dev)
+            ops.rasterize(joints[s::r].contiguous(), h, w, planar_out=lab_addr, want_label=False)
             if backgrounds is not None:
                 dain = backgrounds[s::r].contiguous()
             else:
-                dain = ops.warp(key_frames[:-1].contiguous(), flows[s::r].contiguous())
-            prev = fuse[s - 1::r][:k - 1].contiguous()            # fuse[i-1] (key frame when s == 1)
-            pred, m = self.gen(lab.contiguous(), None, dain, prev)
-            fused = ops.composite(pred, m, dain)
-            fuse[idx] = fused
+                dain = ops.warp(key_frames[:b], flows[s::r])
+            pred, m = self.gen.forward_bound(b, h, w, dain, prev)
+            need_f32 = want_fuse or s + 1 < r                      # the next AR step reads this step's frames
+            step_out = None
+            if want_fuse:
+                step_out = fuse[s::r]
+            elif need_f32:
+                step_out = torch.empty(b, 3, h, w, dtype=torch.float32, device=dev)
+            res = ops.composite(pred, m, dain, out=step_out, out_u8=u8[s::r] if want_u8 else None)
+            prev = (res[0] if isinstance(res, tuple) else res) if need_f32 else None
             if want_mask:
-                mask_out[idx] = m
-        if want_u8:
-            # tensor2images of every output frame (utils.py:122-147): composite with mask == 1 is a pure convert
-            ones = torch.ones(t, 1, h, w, dtype=torch.float32, device=dev)
-            _, u8 = ops.composite(fuse, ones, fuse, want_u8=True)
+                mask_out[s::r] = m
         return {'fuse': fuse, 'u8': u8, 'mask': mask_out}

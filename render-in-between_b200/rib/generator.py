@@ -107,29 +107,60 @@ class Generator(nn.Module):
     def forward(self, label, label_prev, img_fake, img_prev):
         """label [B,22,H,W], label_prev (ignored, as in the reference), img_fake / img_prev [B,3,H,W]
         -> (img_final [B,3,H,W], mask [B,1,H,W])   (PGNR/models/generator.py:181-234)"""
+        if not (label.is_cuda and label.dtype == torch.float32):
+            raise RuntimeError('rib.Generator: label must be a CUDA float32 tensor')
+        label = label.contiguous()
+        b, c, h, w = label.shape
+        if c != self.arch.label_nc:
+            raise ValueError('rib.Generator: input shape mismatch')
+        return self._run(label, b, h, w, img_fake, img_prev)
+
+    def bind(self, b, h, w, device):
+        """Builds the launch plan for a (b, h, w) batch and returns the device address of the generator's label
+        input (16-bit [b][4][h][w][8]) inside its workspace: `rib.rasterize(..., planar_out=addr)` writes the
+        label there, and `forward_bound` then runs without the fp32 label round trip."""
+        self._ensure_packed(device)
+        _, ws_ptr, ws_bytes = self._workspace(b, h, w, device)
+        out = C.c_void_p()
+        with torch.cuda.device(device):
+            check(lib.rib_generator_bind(self._handle, b, h, w, C.c_void_p(ws_ptr), ws_bytes, C.byref(out)),
+                  'rib_generator_bind')
+        return out.value
+
+    def forward_bound(self, b, h, w, img_fake, img_prev):
+        """forward() for a label that was rasterised straight into the buffer returned by bind()."""
+        return self._run(None, b, h, w, img_fake, img_prev)
+
+    def _run(self, label, b, h, w, img_fake, img_prev):
         if self.training:
             raise RuntimeError('rib.Generator implements the eval-mode forward only; call .eval() '
                                '(Evaluator does, PGNR/models/evaluator.py:170)')
-        for name, t in (('label', label), ('img_fake', img_fake), ('img_prev', img_prev)):
+        for name, t in (('img_fake', img_fake), ('img_prev', img_prev)):
             if not (t.is_cuda and t.dtype == torch.float32):
                 raise RuntimeError('rib.Generator: %s must be a CUDA float32 tensor' % name)
-        label, img_fake, img_prev = label.contiguous(), img_fake.contiguous(), img_prev.contiguous()
-        b, c, h, w = label.shape
-        if c != self.arch.label_nc or tuple(img_fake.shape) != (b, 3, h, w) or tuple(img_prev.shape) != (b, 3, h, w):
+        img_fake, img_prev = img_fake.contiguous(), img_prev.contiguous()
+        if tuple(img_fake.shape) != (b, 3, h, w) or tuple(img_prev.shape) != (b, 3, h, w):
             raise ValueError('rib.Generator: input shape mismatch')
-        self._ensure_packed(label.device)
-        out_img = torch.empty(b, 3, h, w, dtype=torch.float32, device=label.device)
-        out_mask = torch.empty(b, 1, h, w, dtype=torch.float32, device=label.device)
-        _, ws_ptr, ws_bytes = self._workspace(b, h, w, label.device)
-        with torch.cuda.device(label.device):
-            check(lib.rib_generator_forward(self._handle, b, h, w, label.data_ptr(), img_fake.data_ptr(),
-                                            img_prev.data_ptr(), out_img.data_ptr(), out_mask.data_ptr(),
-                                            C.c_void_p(ws_ptr), ws_bytes,
+        dev = img_fake.device
+        self._ensure_packed(dev)
+        out_img = torch.empty(b, 3, h, w, dtype=torch.float32, device=dev)
+        out_mask = torch.empty(b, 1, h, w, dtype=torch.float32, device=dev)
+        _, ws_ptr, ws_bytes = self._workspace(b, h, w, dev)
+        with torch.cuda.device(dev):
+            check(lib.rib_generator_forward(self._handle, b, h, w, label.data_ptr() if label is not None else None,
+                                            img_fake.data_ptr(), img_prev.data_ptr(), out_img.data_ptr(),
+                                            out_mask.data_ptr(), C.c_void_p(ws_ptr), ws_bytes,
                                             C.c_void_p(torch.cuda.current_stream().cuda_stream)),
                   'rib_generator_forward')
         return out_img, out_mask
 
-    # -- test hook ----------------------------------------------------------------------------
+    # -- test / profiling hooks ---------------------------------------------------------------
+    def plan_text(self):
+        """One line per planned kernel launch of the last forward (layer, tiling, FLOPs)."""
+        buf = C.create_string_buffer(1 << 16)
+        check(lib.rib_generator_plan_text(self._handle, buf, len(buf)), 'rib_generator_plan_text')
+        return buf.value.decode()
+
     def debug_tensor(self, name):
         """Intermediate activation of the last forward as an fp32 NCHW tensor (tests only)."""
         ptr, b, h, w, c, ld = C.c_void_p(), C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()

@@ -29,49 +29,111 @@ def gaussian_taps(sigma=HSM_RASTER['gauss_sigma'], truncate=4.0):
     return np.ascontiguousarray(phi / phi.sum(), dtype=np.float64)
 
 
+_raster_ws = {}
+
+
+def _raster_workspace(b, device):
+    """Per-device scratch for the rasteriser (limb tables, stamp flags, heat-map windows); grown on demand."""
+    key = (device.type, device.index)
+    need = int(lib.rib_rasterize_workspace_bytes(b))
+    ws = _raster_ws.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=device)
+        _raster_ws[key] = ws
+    return ws
+
+
 def rasterize(joints, height, width, skeleton_thres=HSM_RASTER['skeleton_thres'],
-              foot_thres=HSM_RASTER['foot_thres']):
+              foot_thres=HSM_RASTER['foot_thres'], planar_out=None, want_label=True):
     """joints [B,19,3] float64 (x, y, conf) CUDA -> label [B,22,H,W] float32 CUDA.
 
     Replaces dataset._generate_skeleton + _generate_pose_map + to_tensor_norm + cat
     (PGNR/models/evaluator.py:222-229, :250); bit-exact.
+
+    planar_out: optional device address of a 16-bit [B][4][H][W][8] buffer (Generator.bind) that receives the
+    same label in the generator's input layout; with want_label=False only that buffer is written.
     """
     _require_cuda(joints, 'joints', torch.float64)
     if joints.dim() != 3 or joints.shape[1] != 19 or joints.shape[2] != 3:
         raise ValueError('joints must be [B, 19, 3]')
+    if not want_label and planar_out is None:
+        raise ValueError('rasterize: nothing to write')
     b = joints.shape[0]
-    label = torch.empty(b, 22, height, width, dtype=torch.float32, device=joints.device)
+    label = torch.empty(b, 22, height, width, dtype=torch.float32, device=joints.device) if want_label else None
     taps = gaussian_taps()
     if taps.shape[0] != 41:
         raise ValueError('rasteriser supports sigma=5 (41 taps) only')
-    check(lib.rib_rasterize(joints.data_ptr(), b, height, width, taps.ctypes.data_as(C.POINTER(C.c_double)),
-                            float(skeleton_thres), float(foot_thres), label.data_ptr(), _stream()), 'rib_rasterize')
+    ws = _raster_workspace(b, joints.device)
+    with torch.cuda.device(joints.device):
+        check(lib.rib_rasterize(joints.data_ptr(), b, height, width, taps.ctypes.data_as(C.POINTER(C.c_double)),
+                                float(skeleton_thres), float(foot_thres), label.data_ptr() if want_label else None,
+                                C.c_void_p(planar_out) if planar_out is not None else None, ws.data_ptr(), ws.numel(),
+                                _stream()), 'rib_rasterize')
     return label
 
 
+def _frames(t, name, tail):
+    """A float32 CUDA tensor [B, *tail] whose frames are dense but may be strided along dim 0 (t[s::r] views)."""
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32):
+        raise ValueError('%s must be a CUDA float32 tensor' % name)
+    if tuple(t.shape[1:]) != tuple(tail):
+        raise ValueError('%s: shape mismatch' % name)
+    if t.shape[0] > 0 and not t[0].is_contiguous():
+        t = t.contiguous()
+    return t, (t.stride(0) if t.shape[0] > 1 else 0)
+
+
 def warp(src, flow):
-    """Bilinear resample of src [B,C,H,W] by flow [B,2,H,W] (pixels), border padding (stage A3)."""
-    _require_cuda(src, 'src', torch.float32)
-    _require_cuda(flow, 'flow', torch.float32)
+    """Bilinear resample of src [B,C,H,W] by flow [B,2,H,W] (pixels), border padding (stage A3).
+    Both inputs may be strided along the frame dimension (e.g. flows[s::r])."""
+    if src.dim() != 4:
+        raise ValueError('src must be [B, C, H, W]')
     b, c, h, w = src.shape
+    src, src_bs = _frames(src, 'src', (c, h, w))
     if tuple(flow.shape) != (b, 2, h, w):
         raise ValueError('flow must be [B, 2, H, W]')
-    out = torch.empty_like(src)
-    check(lib.rib_warp(src.data_ptr(), flow.data_ptr(), out.data_ptr(), b, c, h, w, _stream()), 'rib_warp')
+    flow, flow_bs = _frames(flow, 'flow', (2, h, w))
+    out = torch.empty(b, c, h, w, dtype=torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        check(lib.rib_warp(src.data_ptr(), flow.data_ptr(), out.data_ptr(), b, c, h, w, src_bs, flow_bs, 0, _stream()),
+              'rib_warp')
     return out
 
 
-def composite(pred_img, pred_mask, dain_img, want_u8=False):
+def composite(pred_img, pred_mask, dain_img, want_u8=False, out=None, out_u8=None):
     """fuse = pred*mask + dain*(1-mask) (PGNR/models/evaluator.py:256-258); optionally also the
-    uint8 HWC frame of tensor2images (PGNR/utils/utils.py:122-147)."""
-    _require_cuda(pred_img, 'pred_img', torch.float32)
-    _require_cuda(pred_mask, 'pred_mask', torch.float32)
-    _require_cuda(dain_img, 'dain_img', torch.float32)
+    uint8 HWC frame of tensor2images (PGNR/utils/utils.py:122-147).
+
+    pred_mask=None: frames pass through unchanged (key frames, evaluator.py:240-244; dain_img is ignored).
+    out / out_u8: optional destinations [B,3,H,W] f32 / [B,H,W,3] u8 that may be strided along the frame
+    dimension (e.g. clip[s::r]), so a batch lands in its frames of the clip without a scatter copy."""
     b, c, h, w = pred_img.shape
-    if c != 3 or tuple(pred_mask.shape) != (b, 1, h, w) or dain_img.shape != pred_img.shape:
-        raise ValueError('composite: shape mismatch')
-    out = torch.empty_like(pred_img)
-    u8 = torch.empty(b, h, w, 3, dtype=torch.uint8, device=pred_img.device) if want_u8 else None
-    check(lib.rib_composite(pred_img.data_ptr(), pred_mask.data_ptr(), dain_img.data_ptr(), out.data_ptr(),
-                            u8.data_ptr() if want_u8 else None, b, h, w, _stream()), 'rib_composite')
-    return (out, u8) if want_u8 else out
+    pred_img, img_bs = _frames(pred_img, 'pred_img', (3, h, w))
+    if pred_mask is not None:
+        _require_cuda(pred_mask, 'pred_mask', torch.float32)
+        _require_cuda(dain_img, 'dain_img', torch.float32)
+        if tuple(pred_mask.shape) != (b, 1, h, w) or dain_img.shape != pred_img.shape:
+            raise ValueError('composite: shape mismatch')
+    if out is None and out_u8 is None:                            # plain call: allocate the results
+        out = torch.empty(b, 3, h, w, dtype=torch.float32, device=pred_img.device)
+        if want_u8:
+            out_u8 = torch.empty(b, h, w, 3, dtype=torch.uint8, device=pred_img.device)
+    elif want_u8 and out_u8 is None:
+        out_u8 = torch.empty(b, h, w, 3, dtype=torch.uint8, device=pred_img.device)
+    f32_bs = u8_bs = 0
+    if out is not None:
+        if not (out.is_cuda and out.dtype == torch.float32 and tuple(out.shape) == (b, 3, h, w) and out[0].is_contiguous()):
+            raise ValueError('composite: bad out tensor')
+        f32_bs = out.stride(0) if b > 1 else 0
+    if out_u8 is not None:
+        if not (out_u8.is_cuda and out_u8.dtype == torch.uint8 and tuple(out_u8.shape) == (b, h, w, 3)
+                and out_u8[0].is_contiguous()):
+            raise ValueError('composite: bad out_u8 tensor')
+        u8_bs = out_u8.stride(0) if b > 1 else 0
+    with torch.cuda.device(pred_img.device):
+        check(lib.rib_composite(pred_img.data_ptr(), pred_mask.data_ptr() if pred_mask is not None else None,
+                                dain_img.data_ptr() if pred_mask is not None else None,
+                                out.data_ptr() if out is not None else None,
+                                out_u8.data_ptr() if out_u8 is not None else None, b, h, w, img_bs, f32_bs, u8_bs,
+                                _stream()), 'rib_composite')
+    return (out, out_u8) if (want_u8 or out_u8 is not None) else out

@@ -1,0 +1,125 @@
+"""GPU parity tests of the on-GPU clip scheduler (AR loop of evaluator.py:238-266) against a CPU restatement
+of that loop built from the oracle pieces, and of the fused label path (rasterise -> generator input)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import generator_oracle as go
+from oracle import raster_oracle as ro
+from rib.synth import synth_flow, synth_image, synth_joints
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+    return torch.device('cuda:0')
+
+
+@pytest.fixture(scope='module')
+def gen(dev, arch, synth_sd):
+    from rib.config import default_gen_cfg
+    from rib.generator import Generator
+    g = Generator(default_gen_cfg())
+    g.load_state_dict(synth_sd, strict=True)
+    return g.to(dev).eval()
+
+
+def oracle_clip(sd, arch, key, joints, dain, rate):
+    """evaluate_from_folder's phase-2 loop (evaluator.py:238-266), one frame at a time on the CPU."""
+    t = joints.shape[0]
+    h, w = key.shape[-2:]
+    fuse, masks = [], []
+    for i in range(t):
+        if i % rate == 0:
+            fuse.append(key[i // rate][None])
+            masks.append(torch.zeros(1, 1, h, w))
+            continue
+        lab = torch.from_numpy(ro.label([(a[0], a[1]) for a in joints[i]], [a[2] for a in joints[i]], h, w))[None]
+        with torch.no_grad():
+            img, m = go.generator_forward(sd, arch, lab, dain[i][None], fuse[-1])
+            fuse.append(go.composite(img, m, dain[i][None]))
+        masks.append(m)
+    return torch.cat(fuse), torch.cat(masks)
+
+
+@pytest.mark.parametrize('rate,nkey', [(2, 4), (4, 3)], ids=['2x', '4x'])
+def test_clip_renderer_matches_oracle_loop(dev, gen, arch, synth_sd, rate, nkey):
+    from rib.clip import ClipRenderer
+    h, w = 64, 96
+    t = (nkey - 1) * rate + 1
+    key = synth_image(nkey, h, w, seed=21)
+    joints = synth_joints(t, h, w, seed=22)
+    dain = synth_image(t, h, w, seed=23)
+    ref_fuse, ref_mask = oracle_clip(synth_sd, arch, key, joints, dain, rate)
+    r = ClipRenderer(gen, sample_rate=rate)
+    with torch.no_grad():
+        out = r.render(key.to(dev), torch.from_numpy(joints).to(dev), backgrounds=dain.to(dev), want_u8=True,
+                       want_mask=True, want_fuse=True)
+    fuse = out['fuse'].cpu()
+    assert torch.equal(fuse[0::rate], key)                       # key frames pass through untouched
+    assert (out['mask'].cpu()[0::rate] == 0).all()
+    p = go.psnr(fuse, ref_fuse)
+    assert p >= 45.0, 'clip PSNR %.2f dB over the AR chain (rate %d)' % (p, rate)
+    assert torch.equal(out['u8'].cpu(), go.to_uint8(fuse))       # uint8 frames == tensor2images(fuse)
+    # u8-only mode (what the benchmark uses) returns the same frames
+    with torch.no_grad():
+        out2 = r.render(key.to(dev), torch.from_numpy(joints).to(dev), backgrounds=dain.to(dev), want_u8=True,
+                        want_fuse=False)
+    # (instance-norm statistics are accumulated with atomics, so two runs may differ in the last 16-bit ulp)
+    d = (out2['u8'].int() - out['u8'].int()).abs()
+    assert out2['fuse'] is None and d.max().item() <= 2 and (d > 0).float().mean().item() < 0.02
+
+
+def test_clip_renderer_flow_backgrounds(dev, gen):
+    """backgrounds resampled from the preceding key frame (stage A3) == explicit backgrounds."""
+    import rib
+    from rib.clip import ClipRenderer
+    h, w, nkey, rate = 64, 96, 3, 2
+    t = (nkey - 1) * rate + 1
+    key = synth_image(nkey, h, w, seed=31).to(dev)
+    joints = torch.from_numpy(synth_joints(t, h, w, seed=32)).to(dev)
+    flows = synth_flow(t, h, w, seed=33).to(dev)
+    bg = torch.zeros(t, 3, h, w, device=dev)
+    bg[1::rate] = rib.warp(key[:-1], flows[1::rate])
+    r = ClipRenderer(gen, sample_rate=rate)
+    with torch.no_grad():
+        a = r.render(key, joints, flows=flows)
+        b = r.render(key, joints, backgrounds=bg)
+    assert torch.equal(a['fuse'], b['fuse']) and torch.equal(a['u8'], b['u8'])
+
+
+def test_bound_label_path_is_bit_identical(dev, gen):
+    """rasterise straight into the generator's input buffer == rasterise fp32 label -> forward(label)."""
+    import rib
+    b, h, w = 3, 64, 96
+    joints = torch.from_numpy(synth_joints(b, h, w, seed=41)).to(dev)
+    fake, prev = synth_image(b, h, w, seed=42).to(dev), synth_image(b, h, w, seed=43).to(dev)
+    with torch.no_grad():
+        label = rib.rasterize(joints, h, w)
+        img0, mask0 = gen(label, None, fake, prev)
+        addr = gen.bind(b, h, w, dev)
+        both = rib.rasterize(joints, h, w, planar_out=addr)
+        img1, mask1 = gen.forward_bound(b, h, w, fake, prev)
+    assert torch.equal(both, label)
+    assert torch.equal(img0, img1) and torch.equal(mask0, mask1)
+
+
+def test_strided_composite_and_warp(dev):
+    import rib
+    g = torch.Generator().manual_seed(5)
+    b, h, w, r = 3, 32, 48, 2
+    img = (torch.rand(b, 3, h, w, generator=g) * 2 - 1).to(dev)
+    dain = (torch.rand(b, 3, h, w, generator=g) * 2 - 1).to(dev)
+    mask = torch.rand(b, 1, h, w, generator=g).to(dev)
+    dense, dense_u8 = rib.composite(img, mask, dain, want_u8=True)
+    clip = torch.zeros(b * r, 3, h, w, device=dev)
+    clip_u8 = torch.zeros(b * r, h, w, 3, dtype=torch.uint8, device=dev)
+    rib.composite(img, mask, dain, out=clip[1::r], out_u8=clip_u8[1::r])
+    assert torch.equal(clip[1::r], dense) and torch.equal(clip_u8[1::r], dense_u8)
+    assert (clip[0::r] == 0).all() and (clip_u8[0::r] == 0).all()
+    rib.composite(img, None, None, out=clip[0::r], out_u8=clip_u8[0::r])       # pass-through (key frames)
+    assert torch.equal(clip[0::r], img) and torch.equal(clip_u8[0::r].cpu(), go.to_uint8(img.cpu()))
+    flows = synth_flow(b * r, h, w, seed=6).to(dev)
+    assert torch.equal(rib.warp(img, flows[1::r]), rib.warp(img, flows[1::r].contiguous()))

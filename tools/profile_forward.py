@@ -37,6 +37,9 @@ def main():
             img, mask = gen(label, None, fake, prev)
             rib.composite(img, mask, fake)
     torch.cuda.synchronize()
+    os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+    with open(os.path.join(ROOT, 'gpurun_out', 'plan_B%d_%d.txt' % (b, h)), 'w') as f:
+        f.write(gen.plan_text())
     print('ok', float(img.abs().mean()), float(mask.mean()))
 
 
