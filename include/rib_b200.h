@@ -119,6 +119,8 @@ int rib_generator_forward(rib_generator* g, int B, int H, int W, const float* la
  * the number of launches since the last collect. */
 void rib_profile_enable(int enable);
 int rib_profile_collect(double* conv_ms, long long* conv_launches);
+/* Same, and also copies the device time of each launch (in launch order) into per_launch_ms[0 .. cap). */
+int rib_profile_collect_launches(double* conv_ms, long long* conv_launches, float* per_launch_ms, long long cap);
 
 /* ---- bring-up / test hooks (not part of the drop-in surface) ----------------------------------
  * rib_debug_set_simt(1) replaces the tcgen05 main loop by a plain-FMA loop (same tiles and

@@ -106,7 +106,13 @@ void rib_profile_enable(int enable) { conv_gemm_profile_enable(enable); }
 int rib_profile_collect(double* conv_ms, long long* conv_launches) {
   RIB_GUARD_BEGIN
   RIB_REQUIRE(conv_ms && conv_launches, "rib_profile_collect: null argument");
-  return conv_gemm_profile_collect(conv_ms, conv_launches);
+  return conv_gemm_profile_collect(conv_ms, conv_launches, nullptr, 0);
+  RIB_GUARD_END
+}
+int rib_profile_collect_launches(double* conv_ms, long long* conv_launches, float* per_launch_ms, long long cap) {
+  RIB_GUARD_BEGIN
+  RIB_REQUIRE(conv_ms && conv_launches && per_launch_ms && cap > 0, "rib_profile_collect_launches: bad argument");
+  return conv_gemm_profile_collect(conv_ms, conv_launches, per_launch_ms, cap);
   RIB_GUARD_END
 }
 

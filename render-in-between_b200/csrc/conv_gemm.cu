@@ -172,7 +172,7 @@ __device__ __forceinline__ void issue_group_nt(int nt, const IssueCtx& c, uint32
 }
 
 template <int MODE, int BN, bool SIMT>
-__global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+__global__ void __launch_bounds__(kThreads, SIMT ? 1 : (BN <= 32 ? 3 : 2)) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -195,8 +195,8 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
   uint64_t* bres_bar = tmem_empty_bar + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bres_bar + 1);
   float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr + 4) + 15) & ~(uintptr_t)15);  // [BN], 16-byte aligned
-  float* s_aux = s_bias + BN;                              // STORE: [2*BN] stats; SPADE: [2*CT] rstd, -mean*rstd
-  uint32_t* s_tapoff = reinterpret_cast<uint32_t*>(s_aux + 2 * BN);  // [10] A start offset (16-byte units) of tap t; [9]: 1x1 second source
+  float* s_aux = s_bias + BN;                              // STORE: [4 warps][2*BN] stats; SPADE: [2*CT] rstd, -mean*rstd
+  uint32_t* s_tapoff = reinterpret_cast<uint32_t*>(s_aux + 8 * BN);  // [10] A start offset (16-byte units) of tap t; [9]: 1x1 second source
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -244,9 +244,6 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
       s_tapoff[e] = (uint32_t)tg.tile * (p.a_tile_bytes >> 4) + (uint32_t)tg.poff;
     }
     for (int c = e; c < BN; c += 128) s_bias[c] = p.bias[ntile * BN + c];
-    if (MODE == EPI_STORE) {
-      for (int c = e; c < 2 * BN; c += 128) s_aux[c] = 0.f;
-    }
   }
   tc_fence_before();
   __syncthreads();
@@ -415,39 +412,68 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
     float acc1[NCH], acc2[NCH];
 #pragma unroll
     for (int j = 0; j < NCH; ++j) acc1[j] = acc2[j] = 0.f;
+    // The narrowest tiles (BN = 16) are bound by the epilogue's instruction latency, not by the tensor pipe: there every
+    // thread keeps the running sums of its own pixel row in registers (two FMAs per value, no shuffle, no shared
+    // memory) and the 32 lanes are combined only when the image changes.
+    #ifndef RIB_REGSTATS_MAXBN
+#define RIB_REGSTATS_MAXBN 16
+#endif
+    constexpr bool kRegStats = MODE == EPI_STORE && BN <= RIB_REGSTATS_MAXBN;
+    constexpr int kRegN = kRegStats ? BN : 1;
+    float ps1[kRegN], ps2[kRegN];
+#pragma unroll
+    for (int c = 0; c < kRegN; ++c) ps1[c] = ps2[c] = 0.f;
     int cur_n = -1;
     int it = 0;
 
+    // Deterministic: every warp parks its column sums in its own slot, then one thread per column adds the
+    // four slots in a fixed order and issues the fp64 atomics (whose rounding is far below fp32 resolution).
     auto flush_stats = [&](int n_img) {
+      float* slot = s_aux + (warp - 2) * 2 * BN;
+      if (kRegStats) {
 #pragma unroll
-      for (int j = 0; j < NCH; ++j) {
-        const float t1 = acc1[j] + __shfl_xor_sync(0xffffffffu, acc1[j], 16);
-        const float t2 = acc2[j] + __shfl_xor_sync(0xffffffffu, acc2[j], 16);
-        if (lane < 16) {
-          atomicAdd(&s_aux[j * 16 + lane], t1);
-          atomicAdd(&s_aux[BN + j * 16 + lane], t2);
+        for (int j = 0; j < NCH; ++j) {
+          const float t1 = warp_colsum16(ps1 + (kRegStats ? j * 16 : 0), lane);  // lanes 2c, 2c+1 hold column c
+          const float t2 = warp_colsum16(ps2 + (kRegStats ? j * 16 : 0), lane);
+          if ((lane & 1) == 0) {
+            slot[j * 16 + (lane >> 1)] = t1;
+            slot[BN + j * 16 + (lane >> 1)] = t2;
+          }
         }
-        acc1[j] = acc2[j] = 0.f;
+#pragma unroll
+        for (int c = 0; c < kRegN; ++c) ps1[c] = ps2[c] = 0.f;
+      } else {
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+          const float t1 = acc1[j] + __shfl_xor_sync(0xffffffffu, acc1[j], 16);
+          const float t2 = acc2[j] + __shfl_xor_sync(0xffffffffu, acc2[j], 16);
+          if (lane < 16) {
+            slot[j * 16 + lane] = t1;
+            slot[BN + j * 16 + lane] = t2;
+          }
+          acc1[j] = acc2[j] = 0.f;
+        }
       }
       epi_bar();
       for (int c = e; c < BN; c += 128) {
         const int col = ntile * BN + c;
         if (col < p.n_valid) {
-          atomicAdd(&p.stats[((size_t)n_img * p.n_valid + col) * 2 + 0], (double)s_aux[c]);
-          atomicAdd(&p.stats[((size_t)n_img * p.n_valid + col) * 2 + 1], (double)s_aux[BN + c]);
+          const float t1 = ((s_aux[c] + s_aux[2 * BN + c]) + s_aux[4 * BN + c]) + s_aux[6 * BN + c];
+          const float t2 = ((s_aux[BN + c] + s_aux[3 * BN + c]) + s_aux[5 * BN + c]) + s_aux[7 * BN + c];
+          atomicAdd(&p.stats[((size_t)n_img * p.n_valid + col) * 2 + 0], (double)t1);
+          atomicAdd(&p.stats[((size_t)n_img * p.n_valid + col) * 2 + 1], (double)t2);
         }
-        s_aux[c] = 0.f;
-        s_aux[BN + c] = 0.f;
       }
       epi_bar();
     };
 
+    // tile coordinates advance incrementally (no divisions per tile)
+    int n = t_begin / tiles_per_img;
+    int tile_y = (t_begin - n * tiles_per_img) / p.tiles_x;
+    int tile_x = (t_begin - n * tiles_per_img) - tile_y * p.tiles_x;
     for (int mt = t_begin; mt < t_end; ++mt, ++it) {
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
-      const int n = mt / tiles_per_img;
-      const int rem = mt - n * tiles_per_img;
-      const int tile_y = rem / p.tiles_x, tile_x = rem - tile_y * p.tiles_x;
       const int oy0 = tile_y * kTileH * p.MT, ox0 = tile_x * kTileW;
 
       if (n != cur_n) {  // uniform over the 128 epilogue threads
@@ -472,6 +498,28 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
         cur_n = n;
       }
 
+      // EPI_SPADE: the x values of a sub-tile are fetched one sub-tile ahead (the first one before waiting for
+      // the accumulator), so that their DRAM latency overlaps the MMAs / the previous sub-tile's arithmetic
+      constexpr int NXC = MODE == EPI_SPADE ? CT / 16 : 1;
+      uint4 xcur[NXC][2], xnext[NXC][2];
+      auto load_x = [&](int m, uint4 (*dst)[2]) {
+        const int oy = oy0 + m * kTileH + ty, ox = ox0 + tx;
+        const bool valid = (oy < p.H) && (ox < p.W);
+        const int tiles_per_q = p.C / CT;
+        const int c0 = (ntile % tiles_per_q) * CT;
+        const int sy = p.ups ? (oy >> 1) : oy, sx = p.ups ? (ox >> 1) : ox;
+        const size_t xHW8 = (size_t)p.Hx * p.Wx * 8;
+        const act_t* xrow = p.x.p + (size_t)n * p.x.bstride + (size_t)(c0 >> 3) * xHW8 + ((size_t)sy * p.Wx + sx) * 8;
+#pragma unroll
+        for (int j = 0; j < NXC; ++j) {
+          dst[j][0] = dst[j][1] = make_uint4(0, 0, 0, 0);
+          if (valid) {
+            dst[j][0] = *reinterpret_cast<const uint4*>(xrow + (size_t)(2 * j) * xHW8);
+            dst[j][1] = *reinterpret_cast<const uint4*>(xrow + (size_t)(2 * j + 1) * xHW8);
+          }
+        }
+      };
+      if (MODE == EPI_SPADE) load_x(0, xcur);
       if (!SIMT) {
         mbar_wait(smem_u32(&tmem_full_bar[buf]), use & 1u);
         tc_fence_after();
@@ -522,7 +570,15 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
                 v[2 * c + 1] += b;
               }
             }
-            if (want_stats) {
+            if (want_stats && kRegStats) {
+              if (valid) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                  ps1[kRegStats ? j * 16 + c : 0] += v[c];
+                  ps2[kRegStats ? j * 16 + c : 0] = fmaf(v[c], v[c], ps2[kRegStats ? j * 16 + c : 0]);
+                }
+              }
+            } else if (want_stats) {
               // transpose through shared memory: rows = pixels of this warp, then per-lane column sums
               float4* srow = reinterpret_cast<float4*>(sbuf + lane * kStatPitch);
 #pragma unroll
@@ -544,9 +600,12 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
             }
             if (valid) {
               uint32_t o[8];
+              if (p.act == ACT_LRELU) {  // uniform branch
 #pragma unroll
-              for (int c = 0; c < 8; ++c)
-                o[c] = pack2(fmaxf(v[2 * c], slope * v[2 * c]), fmaxf(v[2 * c + 1], slope * v[2 * c + 1]));
+                for (int c = 0; c < 16; ++c) v[c] = fmaxf(v[c], slope * v[c]);
+              }
+#pragma unroll
+              for (int c = 0; c < 8; ++c) o[c] = pack2(v[2 * c], v[2 * c + 1]);
               *reinterpret_cast<uint4*>(obase + (size_t)(2 * j) * HW8) = make_uint4(o[0], o[1], o[2], o[3]);
               *reinterpret_cast<uint4*>(obase + (size_t)(2 * j + 1) * HW8) = make_uint4(o[4], o[5], o[6], o[7]);
             }
@@ -556,19 +615,13 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
           const int tiles_per_q = p.C / CT;
           const int qq = ntile / tiles_per_q;
           const int c0 = (ntile - qq * tiles_per_q) * CT;
-          const int sy = p.ups ? (oy >> 1) : oy, sx = p.ups ? (ox >> 1) : ox;
-          const size_t xHW8 = (size_t)p.Hx * p.Wx * 8;
-          const act_t* xrow = p.x.p + (size_t)n * p.x.bstride + (size_t)(c0 >> 3) * xHW8 + ((size_t)sy * p.Wx + sx) * 8;
           act_t* orow = p.outq[qq].p + (size_t)n * p.outq[qq].bstride + (size_t)(c0 >> 3) * HW8 + pix8;
           const float sl = p.actq[qq] == ACT_LRELU ? 0.2f : 1.0f;
           uint32_t rg[16], rb[16];
+          if (m + 1 < p.MT) load_x(m + 1, xnext);
 #pragma unroll
           for (int j = 0; j < NCS; ++j) {
-            uint4 x0 = make_uint4(0, 0, 0, 0), x1 = x0;
-            if (valid) {
-              x0 = *reinterpret_cast<const uint4*>(xrow + (size_t)(2 * j) * xHW8);
-              x1 = *reinterpret_cast<const uint4*>(xrow + (size_t)(2 * j + 1) * xHW8);
-            }
+            const uint4 x0 = xcur[j][0], x1 = xcur[j][1];
             float g[16], b[16];
             if (SIMT) {
               simt_chunk(p, n, oy, ox, ntile * BN + j * 16, g);
@@ -609,6 +662,11 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
               *reinterpret_cast<uint4*>(orow + (size_t)(2 * j + 1) * HW8) = make_uint4(o[4], o[5], o[6], o[7]);
             }
           }
+#pragma unroll
+          for (int j = 0; j < NCS; ++j) {
+            xcur[j][0] = xnext[j][0];
+            xcur[j][1] = xnext[j][1];
+          }
         } else {  // EPI_FINAL (BN == 16)
           float v[16];
           if (SIMT) simt_chunk(p, n, oy, ox, 0, v);
@@ -632,6 +690,13 @@ __global__ void __launch_bounds__(kThreads) conv_gemm_kernel(const __grid_consta
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[buf]));
+      }
+      if (++tile_x == p.tiles_x) {
+        tile_x = 0;
+        if (++tile_y == p.tiles_y) {
+          tile_y = 0;
+          ++n;
+        }
       }
     }
     if (MODE == EPI_STORE && want_stats && cur_n >= 0) flush_stats(cur_n);
@@ -795,7 +860,7 @@ size_t conv_gemm_smem_bytes(const ConvGemmParams& p) {
   size_t tiles = (size_t)p.a_ring * p.a_slot_bytes + (size_t)(p.b_resident ? n_bt : p.b_ring) * p.b_tap_bytes;
   size_t stat = p.stats != nullptr ? kStatStageBytes : 0;
   size_t bars = (size_t)(2 * p.a_ring + 2 * p.b_ring + 5) * 8 + 32;
-  size_t scratch = (size_t)p.BN * 4 * 3 + 64 + 64;
+  size_t scratch = (size_t)p.BN * 4 * 9 + 64 + 64;
   return 1024 + tiles + stat + bars + scratch;
 }
 
@@ -810,14 +875,17 @@ void conv_gemm_profile_enable(int on) {
   std::lock_guard<std::mutex> lk(g_prof_mutex);
   g_profile = on != 0;
 }
-int conv_gemm_profile_collect(double* total_ms, long long* launches) {
+int conv_gemm_profile_collect(double* total_ms, long long* launches, float* per_launch_ms, long long cap) {
   std::lock_guard<std::mutex> lk(g_prof_mutex);
   double ms = 0.0;
+  long long i = 0;
   for (auto& ev : g_prof_events) {
     RIB_CHECK_CUDA(cudaEventSynchronize(ev.second));
     float t = 0.f;
     RIB_CHECK_CUDA(cudaEventElapsedTime(&t, ev.first, ev.second));
     ms += t;
+    if (per_launch_ms != nullptr && i < cap) per_launch_ms[i] = t;
+    ++i;
     cudaEventDestroy(ev.first);
     cudaEventDestroy(ev.second);
   }

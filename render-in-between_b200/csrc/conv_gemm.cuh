@@ -104,6 +104,6 @@ size_t conv_gemm_smem_bytes(const ConvGemmParams& p);
 int launch_conv_gemm(const ConvGemmParams& p, int mode, cudaStream_t stream);
 long long conv_gemm_launch_count();
 void conv_gemm_profile_enable(int on);
-int conv_gemm_profile_collect(double* total_ms, long long* launches);
+int conv_gemm_profile_collect(double* total_ms, long long* launches, float* per_launch_ms, long long cap);
 
 }  // namespace rib

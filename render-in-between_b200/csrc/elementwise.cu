@@ -78,40 +78,54 @@ __global__ void in_apply_kernel(const InApplyParams p) {
   __syncthreads();
   const size_t HW = (size_t)p.H * p.W;
   const size_t nvec = HW * (p.C / 8);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t pl = i / HW, pix = i - pl * HW;
-    const int c0 = (int)pl * 8;
-    const uint4 av = *reinterpret_cast<const uint4*>(p.a + (size_t)n * p.a_bs + i * 8);
-    const uint32_t au[4] = {av.x, av.y, av.z, av.w};
-    float v[8];
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  constexpr int U = 4;  // independent 16-byte vectors in flight per thread
+  for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < nvec; i0 += U * step) {
+    uint4 av[U], bv[U];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) unpack2(au[k], v[2 * k], v[2 * k + 1]);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      v[k] = v[k] * s_coef[c0 + k] + s_coef[p.C + c0 + k];
-      if (p.act) v[k] = lrelu02(v[k]);
+    for (int u = 0; u < U; ++u) {
+      const size_t i = i0 + u * step;
+      if (i < nvec) {
+        av[u] = *reinterpret_cast<const uint4*>(p.a + (size_t)n * p.a_bs + i * 8);
+        if (p.b != nullptr) bv[u] = *reinterpret_cast<const uint4*>(p.b + (size_t)n * p.b_bs + i * 8);
+      }
     }
-    if (p.b != nullptr) {
-      const uint4 bv = *reinterpret_cast<const uint4*>(p.b + (size_t)n * p.b_bs + i * 8);
-      const uint32_t bu[4] = {bv.x, bv.y, bv.z, bv.w};
-      float w[8];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) unpack2(bu[k], w[2 * k], w[2 * k + 1]);
+    for (int u = 0; u < U; ++u) {
+      const size_t i = i0 + u * step;
+      if (i >= nvec) break;
+      const size_t pl = i / HW, pix = i - pl * HW;
+      const int c0 = (int)pl * 8;
+      const uint32_t au[4] = {av[u].x, av[u].y, av[u].z, av[u].w};
+      float v[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        v[k] += p.bstats ? (w[k] * s_coef[2 * p.C + c0 + k] + s_coef[3 * p.C + c0 + k]) : w[k];
-    }
-    const uint4 o = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
-    if (!p.ups) {
-      *reinterpret_cast<uint4*>(p.out + (size_t)n * p.o_bs + i * 8) = o;
-    } else {
-      const int y = (int)(pix / p.W), x = (int)(pix - (size_t)y * p.W);
-      const int W2 = 2 * p.W;
-      act_t* ob = p.out + (size_t)n * p.o_bs + (pl * 4 * HW + (size_t)(2 * y) * W2 + 2 * x) * 8;
-      *reinterpret_cast<uint4*>(ob) = o;
-      *reinterpret_cast<uint4*>(ob + 8) = o;
-      *reinterpret_cast<uint4*>(ob + (size_t)W2 * 8) = o;
-      *reinterpret_cast<uint4*>(ob + (size_t)W2 * 8 + 8) = o;
+      for (int k = 0; k < 4; ++k) unpack2(au[k], v[2 * k], v[2 * k + 1]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        v[k] = v[k] * s_coef[c0 + k] + s_coef[p.C + c0 + k];
+        if (p.act) v[k] = lrelu02(v[k]);
+      }
+      if (p.b != nullptr) {
+        const uint32_t bu[4] = {bv[u].x, bv[u].y, bv[u].z, bv[u].w};
+        float w[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) unpack2(bu[k], w[2 * k], w[2 * k + 1]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          v[k] += p.bstats ? (w[k] * s_coef[2 * p.C + c0 + k] + s_coef[3 * p.C + c0 + k]) : w[k];
+      }
+      const uint4 o = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+      if (!p.ups) {
+        *reinterpret_cast<uint4*>(p.out + (size_t)n * p.o_bs + i * 8) = o;
+      } else {
+        const int y = (int)(pix / p.W), x = (int)(pix - (size_t)y * p.W);
+        const int W2 = 2 * p.W;
+        act_t* ob = p.out + (size_t)n * p.o_bs + (pl * 4 * HW + (size_t)(2 * y) * W2 + 2 * x) * 8;
+        *reinterpret_cast<uint4*>(ob) = o;
+        *reinterpret_cast<uint4*>(ob + 8) = o;
+        *reinterpret_cast<uint4*>(ob + (size_t)W2 * 8) = o;
+        *reinterpret_cast<uint4*>(ob + (size_t)W2 * 8 + 8) = o;
+      }
     }
   }
 }
@@ -120,8 +134,12 @@ int launch_in_apply(const InApplyParams& p, cudaStream_t s) {
   RIB_REQUIRE(p.C % 8 == 0, "in_apply: channels must be a multiple of 8");
   const size_t nvec = (size_t)p.H * p.W * (p.C / 8);
   const int threads = 256;
+  // every block first derives the normalisation coefficients of its image (fp64 divide + sqrt per channel),
+  // so blocks are kept few and fat: about 8 resident blocks per SM over the whole batch
   unsigned gx = (unsigned)((nvec + threads - 1) / threads);
-  if (gx > 148u * 16u) gx = 148u * 16u;
+  unsigned want = (148u * 8u + (unsigned)p.B - 1u) / (unsigned)p.B;
+  if (want < 1u) want = 1u;
+  if (gx > want) gx = want;
   dim3 grid(gx, (unsigned)p.B);
   in_apply_kernel<<<grid, threads, 4 * p.C * sizeof(float), s>>>(p);
   RIB_CHECK_CUDA(cudaGetLastError());
@@ -134,11 +152,9 @@ int launch_in_apply(const InApplyParams& p, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------
 __global__ void avgpool3s2_kernel(const act_t* __restrict__ src, long long src_bs, act_t* __restrict__ dst,
                                   long long dst_bs, double* __restrict__ stats, int H, int W, int C) {
-  __shared__ float s_red[16];
+  __shared__ float s_red[8][16];  // one slot per warp: fixed-order (deterministic) block reduction
   const int pl = blockIdx.y, n = blockIdx.z;
   const int Ho = H / 2, Wo = W / 2;
-  if (threadIdx.x < 16) s_red[threadIdx.x] = 0.f;
-  __syncthreads();
   const act_t* sp = src + (size_t)n * src_bs + (size_t)pl * H * W * 8;
   act_t* dp = dst + (size_t)n * dst_bs + (size_t)pl * Ho * Wo * 8;
   float t1[8], t2[8];
@@ -190,15 +206,17 @@ __global__ void avgpool3s2_kernel(const act_t* __restrict__ src, long long src_b
     if ((threadIdx.x & 31) == 0) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        atomicAdd(&s_red[k], t1[k]);
-        atomicAdd(&s_red[8 + k], t2[k]);
+        s_red[threadIdx.x >> 5][k] = t1[k];
+        s_red[threadIdx.x >> 5][8 + k] = t2[k];
       }
     }
     __syncthreads();
-    if (threadIdx.x < 8) {
-      const int c = pl * 8 + threadIdx.x;
-      atomicAdd(&stats[((size_t)n * C + c) * 2 + 0], (double)s_red[threadIdx.x]);
-      atomicAdd(&stats[((size_t)n * C + c) * 2 + 1], (double)s_red[8 + threadIdx.x]);
+    if (threadIdx.x < 16) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += s_red[w][threadIdx.x];
+      const int c = pl * 8 + (threadIdx.x & 7);
+      atomicAdd(&stats[((size_t)n * C + c) * 2 + (threadIdx.x >> 3)], (double)t);
     }
   }
 }

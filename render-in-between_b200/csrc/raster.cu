@@ -298,10 +298,16 @@ __device__ __forceinline__ void visit_limb(const EdgeMeta& m, const short* __res
       }
     }
   }
-  while (mask) {
-    const int bit = __ffsll((long long)mask) - 1;
-    mask &= mask - 1;
+  uint32_t mlo32 = (uint32_t)mask, mhi32 = (uint32_t)(mask >> 32);
+  while (mlo32) {
+    const int bit = __ffs((int)mlo32) - 1;
+    mlo32 &= mlo32 - 1;
     visit(bit);
+  }
+  while (mhi32) {
+    const int bit = __ffs((int)mhi32) - 1;
+    mhi32 &= mhi32 - 1;
+    visit(32 + bit);
   }
   // end caps (keypoint2img.py:59-64): stamps (i, j), i outer, both end points in one stamp
   if (interior) {
@@ -327,11 +333,24 @@ __device__ __forceinline__ void visit_limb(const EdgeMeta& m, const short* __res
       visit(k1);
     }
   } else {
-    for (int i = -12; i < 12; ++i)
-      for (int j = -12; j < 12; ++j) {
+    // clamped pixel: the stamps (i, j) of end point t that land on (y, x) form a rectangle (a range where the
+    // coordinate is clamped, a single value otherwise); enumerate the hull of the two rectangles in stamp order
+    int ilo[2], ihi[2], jlo[2], jhi[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int ey = t ? m.ey1 : m.ey0, ex = t ? m.ex1 : m.ex0;
+      src_range(y, ey, H, &ilo[t], &ihi[t]);  // i with clamp(ey + i) == y
+      src_range(x, ex, W, &jlo[t], &jhi[t]);
+      ilo[t] = max(ilo[t], -12), ihi[t] = min(ihi[t], 11);
+      jlo[t] = max(jlo[t], -12), jhi[t] = min(jhi[t], 11);
+    }
+    const int i_beg = min(ilo[0], ilo[1]), i_end = max(ihi[0], ihi[1]);
+    const int j_beg = min(jlo[0], jlo[1]), j_end = max(jhi[0], jhi[1]);
+    for (int i = i_beg; i <= i_end; ++i)
+      for (int j = j_beg; j <= j_end; ++j) {
         if (i * i + j * j >= 64) continue;
-        const bool h0 = min(max(m.ey0 + i, 0), H - 1) == y && min(max(m.ex0 + j, 0), W - 1) == x;
-        const bool h1 = min(max(m.ey1 + i, 0), H - 1) == y && min(max(m.ex1 + j, 0), W - 1) == x;
+        const bool h0 = i >= ilo[0] && i <= ihi[0] && j >= jlo[0] && j <= jhi[0];
+        const bool h1 = i >= ilo[1] && i <= ihi[1] && j >= jlo[1] && j <= jhi[1];
         if (h0 || h1) visit(kBodyKeys + (i + 12) * 24 + (j + 12));
       }
   }
@@ -355,18 +374,25 @@ struct TileEdges {
 
 __device__ __forceinline__ void tile_edges(const FrameScratch* fs, int y0, int x0, int H, int W, TileEdges* te,
                                            EdgeMeta* s_meta) {
-  if (threadIdx.x == 0) {
-    int n = 0;
-    for (int e = 0; e < kEdges; ++e) {
-      const EdgeMeta m = fs->edge[e];
-      if (!m.valid) continue;
-      // everything a limb touches lies in its bounding box clipped to the image
-      const int bx0 = max(m.bx0, 0), bx1 = min(m.bx1, W - 1), by0 = max(m.by0, 0), by1 = min(m.by1, H - 1);
-      if (bx1 < x0 || bx0 >= x0 + kTileCols || by1 < y0 || by0 >= y0 + kTileRows) continue;
-      s_meta[n] = m;
-      te->idx[n++] = e;
+  if (threadIdx.x < 32) {  // one lane per limb, compacted with a ballot (limb order is preserved)
+    const int e = threadIdx.x;
+    bool keep = false;
+    EdgeMeta m;
+    if (e < kEdges) {
+      m = fs->edge[e];
+      if (m.valid) {
+        // everything a limb touches lies in its bounding box clipped to the image
+        const int bx0 = max(m.bx0, 0), bx1 = min(m.bx1, W - 1), by0 = max(m.by0, 0), by1 = min(m.by1, H - 1);
+        keep = !(bx1 < x0 || bx0 >= x0 + kTileCols || by1 < y0 || by0 >= y0 + kTileRows);
+      }
     }
-    te->n = n;
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (keep) {
+      const int pos = __popc(bal & ((1u << e) - 1u));
+      s_meta[pos] = m;
+      te->idx[pos] = e;
+    }
+    if (e == 0) te->n = __popc(bal);
   }
   __syncthreads();
 }
@@ -415,11 +441,11 @@ __global__ void __launch_bounds__(256) raster_paint_kernel(const FrameScratch* _
   const int y = y0 + (threadIdx.x >> 5);
   const int xb = x0 + (threadIdx.x & 31) * kPxPerThread;
   if (y >= H || xb >= W) return;
-  float v[22][kPxPerThread];
+  uint32_t rgb[kPxPerThread];
 #pragma unroll
   for (int p = 0; p < kPxPerThread; ++p) {
     const int x = xb + p;
-    uint32_t rgb = 0u;
+    rgb[p] = 0u;
     if (x < W) {
       int count = 0;
       for (int k = 0; k < te.n; ++k) {
@@ -429,53 +455,52 @@ __global__ void __launch_bounds__(256) raster_paint_kernel(const FrameScratch* _
         const uint32_t col =
             (uint32_t)c_colors[e][0] | ((uint32_t)c_colors[e][1] << 8) | ((uint32_t)c_colors[e][2] << 16);
         visit_limb(m, fs->f[e], y, x, H, W, [&](int key) {
-          if (count++ == 0) rgb = fs->flag[e][key] ? avg_color(0u, col) : col;
-          else rgb = avg_color(rgb, col);
+          if (count++ == 0) rgb[p] = fs->flag[e][key] ? avg_color(0u, col) : col;
+          else rgb[p] = avg_color(rgb[p], col);
         });
       }
-    }
-    v[0][p] = s_lut[rgb & 0xffu];
-    v[1][p] = s_lut[(rgb >> 8) & 0xffu];
-    v[2][p] = s_lut[(rgb >> 16) & 0xffu];
-#pragma unroll
-    for (int j = 0; j < kJoints; ++j) {
-      const JointMeta jm = s_joint[j];
-      const int wy = y - jm.iy + kRadius, wx = x - jm.ix + kRadius;
-      float h = 0.f;
-      if (jm.valid && (unsigned)wy < (unsigned)kTaps && (unsigned)wx < (unsigned)kTaps) h = fs->win[j][wy * kTaps + wx];
-      v[3 + j][p] = h;
     }
   }
   const size_t HW = (size_t)H * W;
   const size_t pix = (size_t)y * W + xb;
   const bool full = xb + kPxPerThread <= W && (W & 3) == 0;
-  if (label != nullptr) {
-    float* out = label + (size_t)b * 22 * HW + pix;
+  float* out = label != nullptr ? label + (size_t)b * 22 * HW + pix : nullptr;
+  act_t* pout = planar != nullptr ? planar + (size_t)b * 32 * HW + pix * 8 : nullptr;
+  // channel c of the label: 0..2 skeleton, 3..21 heat-maps, 22..31 zero padding of the planar copy;
+  // produced one 8-channel plane at a time to keep the register footprint small
 #pragma unroll
-    for (int c = 0; c < 22; ++c) {
-      if (full) {
-        *reinterpret_cast<float4*>(out + (size_t)c * HW) = make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
-      } else {
-        for (int p = 0; p < kPxPerThread && xb + p < W; ++p) out[(size_t)c * HW + p] = v[c][p];
+  for (int pl = 0; pl < 4; ++pl) {
+    float v[8][kPxPerThread];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = pl * 8 + k;
+#pragma unroll
+      for (int p = 0; p < kPxPerThread; ++p) {
+        float h = 0.f;
+        if (c < 3) {
+          h = s_lut[(rgb[p] >> (8 * c)) & 0xffu];
+        } else if (c < 22) {
+          const JointMeta jm = s_joint[c - 3];
+          const int wy = y - jm.iy + kRadius, wx = xb + p - jm.ix + kRadius;
+          if (jm.valid && (unsigned)wy < (unsigned)kTaps && (unsigned)wx < (unsigned)kTaps)
+            h = fs->win[c - 3][wy * kTaps + wx];
+        }
+        v[k][p] = h;
+      }
+      if (out != nullptr && c < 22) {
+        if (full) {
+          *reinterpret_cast<float4*>(out + (size_t)c * HW) = make_float4(v[k][0], v[k][1], v[k][2], v[k][3]);
+        } else {
+          for (int p = 0; p < kPxPerThread && xb + p < W; ++p) out[(size_t)c * HW + p] = v[k][p];
+        }
       }
     }
-  }
-  if (planar != nullptr) {  // [B][4][H][W][8], channels 22..31 zero
-    act_t* out = planar + (size_t)b * 32 * HW + pix * 8;
-#pragma unroll
-    for (int pl = 0; pl < 4; ++pl) {
+    if (pout != nullptr) {  // [B][4][H][W][8]
 #pragma unroll
       for (int p = 0; p < kPxPerThread; ++p) {
         if (xb + p >= W) break;
-        uint32_t o[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int c0 = pl * 8 + 2 * k;
-          const float a = c0 < 22 ? v[c0 < 22 ? c0 : 0][p] : 0.f;
-          const float bb = c0 + 1 < 22 ? v[c0 + 1 < 22 ? c0 + 1 : 0][p] : 0.f;
-          o[k] = pack2(a, bb);
-        }
-        *reinterpret_cast<uint4*>(out + (size_t)pl * HW * 8 + (size_t)p * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4*>(pout + (size_t)pl * HW * 8 + (size_t)p * 8) =
+            make_uint4(pack2(v[0][p], v[1][p]), pack2(v[2][p], v[3][p]), pack2(v[4][p], v[5][p]), pack2(v[6][p], v[7][p]));
       }
     }
   }

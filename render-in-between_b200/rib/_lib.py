@@ -7,14 +7,15 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'librib_b200.so')
+# RIB_LIB selects another build of the same library (kernel-variant experiments under tools/); never set in tests or bench
+LIB_PATH = os.environ.get('RIB_LIB') or os.path.join(_HERE, 'librib_b200.so')
 
 # every symbol include/rib_b200.h declares
 SYMBOLS = [
     'rib_last_error', 'rib_abi_version', 'rib_kernel_launch_count', 'rib_rasterize_workspace_bytes', 'rib_rasterize', 'rib_warp', 'rib_composite',
     'rib_generator_create', 'rib_generator_destroy', 'rib_generator_workspace_bytes', 'rib_generator_bind', 'rib_generator_forward',
     'rib_debug_set_simt', 'rib_debug_get_simt', 'rib_generator_debug_tensor', 'rib_generator_plan_text', 'rib_act_is_fp16',
-    'rib_conv_test_scratch_bytes', 'rib_conv_test', 'rib_profile_enable', 'rib_profile_collect',
+    'rib_conv_test_scratch_bytes', 'rib_conv_test', 'rib_profile_enable', 'rib_profile_collect', 'rib_profile_collect_launches',
 ]
 
 
@@ -69,6 +70,8 @@ def _load():
     lib.rib_profile_enable.argtypes = [i32]
     lib.rib_profile_collect.restype = i32
     lib.rib_profile_collect.argtypes = [C.POINTER(f64), C.POINTER(i64)]
+    lib.rib_profile_collect_launches.restype = i32
+    lib.rib_profile_collect_launches.argtypes = [C.POINTER(f64), C.POINTER(i64), C.POINTER(C.c_float), i64]
     lib.rib_conv_test_scratch_bytes.restype = i64
     lib.rib_conv_test_scratch_bytes.argtypes = [i32, i32, i32]
     lib.rib_conv_test.restype = i32

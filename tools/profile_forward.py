@@ -18,6 +18,7 @@ def main():
     ap.add_argument('--batch', type=int, default=32)
     ap.add_argument('--size', type=int, default=512)
     ap.add_argument('--iters', type=int, default=2)
+    ap.add_argument('--clip', action='store_true', help='render one bench clip (65 frames, 2x) instead of a bare forward')
     a = ap.parse_args()
     from rib.arch import Arch
     from rib.config import default_gen_cfg
@@ -30,6 +31,21 @@ def main():
     gen.load_state_dict(synth_state_dict(Arch(cfg), seed=0, power_iters=5), strict=True)
     gen = gen.to(dev).eval()
     b, h, w = a.batch, a.size, a.size
+    if a.clip:
+        from rib.clip import ClipRenderer
+        from rib.synth import synth_flow
+        nkey, rate = b + 1, 2
+        t = (nkey - 1) * rate + 1
+        key = synth_image(nkey, h, w, seed=0).to(dev)
+        joints = torch.from_numpy(synth_joints(t, h, w, seed=0)).to(dev)
+        flows = synth_flow(t, h, w, seed=0).to(dev)
+        r = ClipRenderer(gen, sample_rate=rate)
+        with torch.no_grad():
+            for _ in range(a.iters):
+                out = r.render(key, joints, flows=flows, want_u8=True, want_fuse=False)
+        torch.cuda.synchronize()
+        print('ok clip', int(out['u8'].sum()))
+        return
     label = rib.rasterize(torch.from_numpy(synth_joints(b, h, w, seed=3)).to(dev), h, w)
     fake, prev = synth_image(b, h, w, seed=1).to(dev), synth_image(b, h, w, seed=2).to(dev)
     with torch.no_grad():
