@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (BN <= 32 ? 3 : 2)) conv_
   const int G = p.stages0 + p.stages1;                 // channel groups (halo tiles) per output tile
   const int n_bt = p.stages0 * p.ntaps + p.stages1;    // weight sub-tiles per output tile
   uint8_t* sA = smem;
-  uint8_t* sB = sA + (size_t)p.a_ring * p.a_slot_bytes;
+  uint8_t* sB = sA + (((size_t)p.a_ring * p.a_slot_bytes + 1023) & ~(size_t)1023);  // swizzled weight tiles: 1024-byte aligned
   uint8_t* sStat = sB + (size_t)(p.b_resident ? n_bt : p.b_ring) * p.b_tap_bytes;
   const bool want_stats = MODE == EPI_STORE && p.stats != nullptr;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + (want_stats ? 4 * kStatWarpFloats * 4 : 0));
@@ -818,23 +818,31 @@ int conv_gemm_configure(ConvGemmParams* p, int B, int Hout, int Wout, int cin0, 
   p->b_tap_bytes = (uint32_t)(BN * bkc * 2);
   const int n_bt = p->stages0 * taps + p->stages1;
   const size_t b_all = (size_t)n_bt * p->b_tap_bytes;
-  p->b_resident = b_all <= 72 * 1024 ? 1 : 0;
-  p->MT = (!p->b_resident && stride == 1 && Hout >= 2 * kTileH) ? 2 : 1;
-  const int hw = stride == 1 ? kTileW + 2 * p->halo : kTileW + 1;
-  const int hh = stride == 1 ? kTileH * p->MT + 2 * p->halo : kTileH * p->MT + 1;
-  p->halo_w = hw;
-  p->lbo = (uint32_t)(hw * hh * 16);
-  p->sbo = (uint32_t)(hw * 16);
-  const uint32_t tile_raw = (uint32_t)(hw * hh * 16 * (bkc / 8));
-  p->a_tile_bytes = (tile_raw + 127u) & ~127u;
-  const int ntile_a = stride == 2 ? 4 : 1;
-  p->a_slot_bytes = ((uint32_t)ntile_a * p->a_tile_bytes + 1023u) & ~1023u;
-  p->a_tx_bytes = (uint32_t)ntile_a * tile_raw;
-  p->tiles_x = ceil_div(Wout, kTileW);
-  p->tiles_y = ceil_div(Hout, kTileH * p->MT);
   const int G = p->stages0 + p->stages1;
-  if (p->b_resident) {
-    // bandwidth-bound layers: keep the CTA near 100 KB so that two (or more) fit on an SM
+  const int ntile_a = stride == 2 ? 4 : 1;
+  // geometry of one halo-tile slot for a given number of stacked sub-tiles
+  auto set_geometry = [&](int MT) {
+    p->MT = MT;
+    const int hw = stride == 1 ? kTileW + 2 * p->halo : kTileW + 1;
+    const int hh = stride == 1 ? kTileH * MT + 2 * p->halo : kTileH * MT + 1;
+    p->halo_w = hw;
+    p->lbo = (uint32_t)(hw * hh * 16);
+    p->sbo = (uint32_t)(hw * 16);
+    const uint32_t tile_raw = (uint32_t)(hw * hh * 16 * (bkc / 8));
+    p->a_tile_bytes = (tile_raw + 127u) & ~127u;
+    p->a_slot_bytes = ((uint32_t)ntile_a * p->a_tile_bytes + 127u) & ~127u;
+    p->a_tx_bytes = (uint32_t)ntile_a * tile_raw;
+    p->tiles_x = ceil_div(Wout, kTileW);
+    p->tiles_y = ceil_div(Hout, kTileH * MT);
+  };
+  const size_t kSmemMax = (size_t)227 * 1024, kOverhead = 8 * 1024;  // barriers, bias, statistics slots, alignment
+  // (stride 2 is bound by its 16-byte parity gathers, not by weight traffic: stacking sub-tiles does not help it)
+  const bool can_mt2 = Hout >= 2 * kTileH && stride == 1;
+  p->b_ring = 1;
+  if (b_all <= 72 * 1024) {
+    // small weights stay resident; bandwidth-bound layers: keep the CTA near 100 KB so that several fit on an SM
+    p->b_resident = 1;
+    set_geometry(1);
     const size_t budget = (size_t)100 * 1024 - b_all - kStatStageBytes;
     int ring = (int)(budget / p->a_slot_bytes);
     const int want = G <= 2 ? 4 : 2 * G;
@@ -842,14 +850,29 @@ int conv_gemm_configure(ConvGemmParams* p, int B, int Hout, int Wout, int cin0, 
     if (ring > 8) ring = 8;
     if (ring < 2) ring = 2;
     p->a_ring = ring;
-    p->b_ring = 1;  // unused
   } else {
-    p->a_ring = 2;
-    const size_t budget = (size_t)205 * 1024 - kStatStageBytes - (size_t)2 * p->a_slot_bytes;
-    int ring = (int)(budget / p->b_tap_bytes);
-    if (ring > 12) ring = 12;
-    if (ring < 2) ring = 2;
-    p->b_ring = ring;
+    // medium weights: one CTA per SM keeps its whole N tile of weights in shared memory (no weight traffic per
+    // output tile at all) if at least two halo-tile slots still fit
+    p->b_resident = 0;
+    for (int MT = can_mt2 ? 2 : 1; MT >= 1 && !p->b_resident; --MT) {
+      set_geometry(MT);
+      const size_t fixed = b_all + kStatStageBytes + kOverhead;
+      if (fixed + 2 * (size_t)p->a_slot_bytes <= kSmemMax) {
+        p->b_resident = 1;
+        int ring = (int)((kSmemMax - fixed) / p->a_slot_bytes);
+        p->a_ring = ring > 4 ? 4 : ring;
+      }
+    }
+    if (!p->b_resident) {
+      // large weights are streamed through their own ring; two stacked sub-tiles halve that traffic per pixel
+      set_geometry(can_mt2 ? 2 : 1);
+      p->a_ring = 2;
+      const size_t budget = kSmemMax - kStatStageBytes - kOverhead - (size_t)2 * p->a_slot_bytes;
+      int ring = (int)(budget / p->b_tap_bytes);
+      if (ring > 12) ring = 12;
+      if (ring < 2) ring = 2;
+      p->b_ring = ring;
+    }
   }
   p->idesc = make_idesc_f16(128, BN);
   return 0;
@@ -857,7 +880,8 @@ int conv_gemm_configure(ConvGemmParams* p, int B, int Hout, int Wout, int cin0, 
 
 size_t conv_gemm_smem_bytes(const ConvGemmParams& p) {
   const int n_bt = p.stages0 * p.ntaps + p.stages1;
-  size_t tiles = (size_t)p.a_ring * p.a_slot_bytes + (size_t)(p.b_resident ? n_bt : p.b_ring) * p.b_tap_bytes;
+  size_t tiles = (((size_t)p.a_ring * p.a_slot_bytes + 1023) & ~(size_t)1023) +
+                 (size_t)(p.b_resident ? n_bt : p.b_ring) * p.b_tap_bytes;
   size_t stat = p.stats != nullptr ? kStatStageBytes : 0;
   size_t bars = (size_t)(2 * p.a_ring + 2 * p.b_ring + 5) * 8 + 32;
   size_t scratch = (size_t)p.BN * 4 * 9 + 64 + 64;
