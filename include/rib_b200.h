@@ -138,7 +138,8 @@ int rib_generator_plan_text(rib_generator* g, char* buf, long long cap);
 /* 1 if activations are stored as IEEE fp16, 0 for bf16. */
 int rib_act_is_fp16(void);
 /* Stand-alone launch of the implicit-GEMM convolution for unit tests:
- *   x    16-bit chunk-planar [B][Cin/8][Hin][Win][8]   (Cin 16, 32 or a multiple of 64)
+ *   x    16-bit chunk-planar [B][Cin/8][Hin][Win][8]   (Cin 16, 32 or a multiple of 64); for stride 2 the
+ *        parity-planar layout [B][Cin/8][py][px][Hin/2][Win/2][8] that a stride-2 layer's producer writes
  *   w    f32 [Cout][Cin][k][k], bias f32 [Cout] (may be NULL), k in {1,3}, stride in {1,2}, pad k/2
  *   out  16-bit chunk-planar [B][Cout/8][Hout][Wout][8] (Cout 16/32/64 or a multiple of 128), act: 0 none, 1 leaky-relu 0.2
  *   stats f64 [B][Cout][2] (may be NULL; accumulated into)

@@ -93,7 +93,13 @@ __device__ void simt_chunk(const ConvGemmParams& p, int n, int oy, int ox, int c
       const int r = p.ntaps == 9 ? t / 3 : 1, s = p.ntaps == 9 ? t - 3 * (t / 3) : 1;
       const int iy = oy * p.stride + r - 1, ix = ox * p.stride + s - 1;
       if (iy < 0 || ix < 0 || iy >= p.Hin || ix >= p.Win) continue;
-      const float av = act2f(*planar_at(p.src0, n, ci, p.Hin, p.Win, iy, ix));
+      // a stride-2 input is parity-planar: [plane][py][px][H/2][W/2][8]
+      const act_t* ap = (p.stride == 2 && p.s2_parity)
+                            ? p.src0.p + (size_t)n * p.src0.bstride +
+                                  ((size_t)(ci >> 3) * p.Hin * p.Win + (size_t)((iy & 1) * 2 + (ix & 1)) * (p.Hin / 2) * (p.Win / 2) +
+                                   (size_t)(iy >> 1) * (p.Win / 2) + (ix >> 1)) * 8 + (ci & 7)
+                            : planar_at(p.src0, n, ci, p.Hin, p.Win, iy, ix);
+      const float av = act2f(*ap);
       const int k = (grp * p.ntaps + t) * p.BKc + cc;
 #pragma unroll
       for (int c = 0; c < 16; ++c) acc[c] += av * act2f(p.wpk[(size_t)(col0 + c) * p.ktotal + k]);
@@ -117,47 +123,30 @@ static constexpr int kStatWarpFloats = 32 * kStatPitch;
 // State of the MMA issuer that does not change during a launch.
 struct IssueCtx {
   uint32_t a_hi, b_hi, idesc;
-  uint32_t b_lo_base;        // b_lo_c + sB16
-  uint32_t b_tap16;
-  uint32_t b_full0, b_empty0;
-  int b_ring;
-  bool b_resident;
+  uint32_t b_tap16;          // 16-byte units between consecutive weight sub-tiles (taps)
   uint32_t bn;               // TMEM columns per sub-tile
 };
 
-// All tcgen05.mma of one channel group (NT taps x MT sub-tiles x KK k-steps), fully unrolled: per MMA the
-// issuing lane executes two adds and the instruction itself.
+// All tcgen05.mma of one channel group (NT taps x MT sub-tiles x KK k-steps), fully unrolled and free of waits:
+// the halo tile and all weight sub-tiles of the group are covered by ONE full barrier.  Per MMA the issuing lane
+// executes two adds and the instruction itself.
 //   a_lo      low descriptor word of the halo tile in this ring slot (tap offset not yet added)
+//   b_lo      low descriptor word of the group's first weight sub-tile
 //   tap       per-tap A offsets (16-byte units);  mk[m * KK + kk] = m * m_step + kk * a_kk_step
 template <int NT, int KK, int MT>
 __device__ __forceinline__ void issue_group(const IssueCtx& c, uint32_t a_lo, const uint32_t* tap, const uint32_t* mk,
-                                            uint32_t b_res_lo, uint32_t d0, uint32_t acc_first, int& b_slot,
-                                            uint32_t& b_phase) {
+                                            uint32_t b_lo, uint32_t d0, uint32_t acc_first) {
 #pragma unroll
   for (int t = 0; t < NT; ++t) {
-    uint32_t b_lo;
-    if (c.b_resident) {
-      b_lo = b_res_lo + (uint32_t)t * c.b_tap16;
-    } else {
-      mbar_wait(c.b_full0 + 8u * b_slot, b_phase);
-      tc_fence_after();
-      b_lo = c.b_lo_base + (uint32_t)b_slot * c.b_tap16;
-    }
     const uint32_t a_t = a_lo + tap[t];
+    const uint32_t b_t = b_lo + (uint32_t)t * c.b_tap16;
 #pragma unroll
     for (int m = 0; m < MT; ++m) {
 #pragma unroll
       for (int kk = 0; kk < KK; ++kk) {
         const uint32_t acc = (t == 0 && kk == 0) ? acc_first : 1u;
         umma_f16(d0 + (uint32_t)m * c.bn, ((uint64_t)c.a_hi << 32) | (uint64_t)(a_t + mk[m * KK + kk]),
-                 ((uint64_t)c.b_hi << 32) | (uint64_t)(b_lo + 2u * (uint32_t)kk), c.idesc, acc);
-      }
-    }
-    if (!c.b_resident) {
-      umma_commit(c.b_empty0 + 8u * b_slot);  // frees the weight slot once the MMAs have read it
-      if (++b_slot == c.b_ring) {
-        b_slot = 0;
-        b_phase ^= 1u;
+                 ((uint64_t)c.b_hi << 32) | (uint64_t)(b_t + 2u * (uint32_t)kk), c.idesc, acc);
       }
     }
   }
@@ -165,10 +154,9 @@ __device__ __forceinline__ void issue_group(const IssueCtx& c, uint32_t a_lo, co
 
 template <int KK, int MT>
 __device__ __forceinline__ void issue_group_nt(int nt, const IssueCtx& c, uint32_t a_lo, const uint32_t* tap,
-                                               const uint32_t* mk, uint32_t b_res_lo, uint32_t d0, uint32_t acc_first,
-                                               int& b_slot, uint32_t& b_phase) {
-  if (nt == 9) issue_group<9, KK, MT>(c, a_lo, tap, mk, b_res_lo, d0, acc_first, b_slot, b_phase);
-  else issue_group<1, KK, MT>(c, a_lo, tap, mk, b_res_lo, d0, acc_first, b_slot, b_phase);
+                                               const uint32_t* mk, uint32_t b_lo, uint32_t d0, uint32_t acc_first) {
+  if (nt == 9) issue_group<9, KK, MT>(c, a_lo, tap, mk, b_lo, d0, acc_first);
+  else issue_group<1, KK, MT>(c, a_lo, tap, mk, b_lo, d0, acc_first);
 }
 
 template <int MODE, int BN, bool SIMT>
@@ -181,16 +169,15 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (BN <= 32 ? 3 : 2)) conv_
   constexpr int CT = BN / 2;                           // EPI_SPADE: channels per tile ([gamma | beta])
   const int G = p.stages0 + p.stages1;                 // channel groups (halo tiles) per output tile
   const int n_bt = p.stages0 * p.ntaps + p.stages1;    // weight sub-tiles per output tile
+  // ring of group slots: [halo tile(s) | (streamed mode) the group's weight sub-tiles]; then the resident weights
   uint8_t* sA = smem;
-  uint8_t* sB = sA + (((size_t)p.a_ring * p.a_slot_bytes + 1023) & ~(size_t)1023);  // swizzled weight tiles: 1024-byte aligned
-  uint8_t* sStat = sB + (size_t)(p.b_resident ? n_bt : p.b_ring) * p.b_tap_bytes;
+  uint8_t* sB = sA + (((size_t)p.a_ring * p.g_slot_bytes + 1023) & ~(size_t)1023);  // swizzled tiles: 1024-byte aligned
+  uint8_t* sStat = sB + (size_t)(p.b_resident ? n_bt : 0) * p.b_tap_bytes;
   const bool want_stats = MODE == EPI_STORE && p.stats != nullptr;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + (want_stats ? 4 * kStatWarpFloats * 4 : 0));
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + p.a_ring;
-  uint64_t* b_full = a_empty + p.a_ring;
-  uint64_t* b_empty = b_full + p.b_ring;
-  uint64_t* tmem_full_bar = b_empty + p.b_ring;  // [2]
+  uint64_t* tmem_full_bar = a_empty + p.a_ring;  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [2]
   uint64_t* bres_bar = tmem_empty_bar + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bres_bar + 1);
@@ -220,10 +207,6 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (BN <= 32 ? 3 : 2)) conv_
       for (int i = 0; i < p.a_ring; ++i) {
         mbar_init(smem_u32(&a_full[i]), 1);
         mbar_init(smem_u32(&a_empty[i]), 1);
-      }
-      for (int i = 0; i < p.b_ring; ++i) {
-        mbar_init(smem_u32(&b_full[i]), 1);
-        mbar_init(smem_u32(&b_empty[i]), 1);
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(smem_u32(&tmem_full_bar[i]), 1);
@@ -255,14 +238,13 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (BN <= 32 ? 3 : 2)) conv_
     // One elected lane runs the whole role: inside `if (elect_one())` the compiler knows that a single lane is
     // active, so addresses and coordinates move to uniform registers without per-lane loops.
     if (!SIMT && elect_one()) {
-      const int ntaps = p.ntaps, stages0 = p.stages0, a_ring = p.a_ring, b_ring = p.b_ring, BKc = p.BKc;
+      const int ntaps = p.ntaps, stages0 = p.stages0, a_ring = p.a_ring, BKc = p.BKc;
       const int halo = p.halo, stride = p.stride, MT = p.MT, tiles_x = p.tiles_x;
       const bool b_resident = p.b_resident != 0;
-      const uint32_t a_slot_bytes = p.a_slot_bytes, a_tile_bytes = p.a_tile_bytes, a_tx_bytes = p.a_tx_bytes;
-      const uint32_t b_tap_bytes = p.b_tap_bytes;
+      const uint32_t g_slot_bytes = p.g_slot_bytes, a_tile_bytes = p.a_tile_bytes, a_tx_bytes = p.a_tx_bytes;
+      const uint32_t b_tap_bytes = p.b_tap_bytes, b_off = p.b_off;
       const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
       const uint32_t a_full0 = smem_u32(a_full), a_empty0 = smem_u32(a_empty);
-      const uint32_t b_full0 = smem_u32(b_full), b_empty0 = smem_u32(b_empty);
       const int planes_per_group = BKc >> 3;
       const int n_col0 = ntile * BN;
       if (b_resident) {  // all weight sub-tiles of this N tile, once
@@ -270,8 +252,8 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (BN <= 32 ? 3 : 2)) conv_
         mbar_arrive_expect_tx(bb, (uint32_t)n_bt * b_tap_bytes);
         for (int i = 0; i < n_bt; ++i) tma_load_2d(sB_addr + (uint32_t)i * b_tap_bytes, &p.bmap, bb, i * BKc, n_col0);
       }
-      int a_slot = 0, b_slot = 0;
-      uint32_t a_phase = 0, b_phase = 0;
+      int a_slot = 0;
+      uint32_t a_phase = 0;
       // tile coordinates are advanced incrementally (no divisions in the loop)
       int n = t_begin / tiles_per_img;
       int rem0 = t_begin - n * tiles_per_img;
@@ -283,33 +265,31 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (BN <= 32 ? 3 : 2)) conv_
           mbar_wait(a_empty0 + 8u * a_slot, a_phase ^ 1u);
           const uint32_t fb = a_full0 + 8u * a_slot;
           const bool src1 = g >= stages0;
-          const uint32_t a_dst = sA_addr + (uint32_t)a_slot * a_slot_bytes;
+          const uint32_t a_dst = sA_addr + (uint32_t)a_slot * g_slot_bytes;
           const int cg = (src1 ? g - stages0 : g) * planes_per_group;  // first 8-channel plane of the group
-          mbar_arrive_expect_tx(fb, a_tx_bytes);
+          const int nt = src1 ? 1 : ntaps;
+          // one barrier covers the halo tile and (streamed mode) every weight sub-tile of the group
+          mbar_arrive_expect_tx(fb, a_tx_bytes + (b_resident ? 0u : (uint32_t)nt * b_tap_bytes));
           if (stride == 1) {
             tma_load_4d(a_dst, &p.amap[src1 ? 1 : 0], fb, (ox0 - halo) * 8, oy0 - halo, cg, n);
           } else {
+            if (p.s2_parity) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) tma_load_5d(a_dst + q * a_tile_bytes, &p.amap[q], fb, 0, ox0 - 1, oy0 - 1, cg, n);
+              for (int q = 0; q < 4; ++q) tma_load_4d(a_dst + q * a_tile_bytes, &p.amap[q], fb, (ox0 - 1) * 8, oy0 - 1, cg, n);
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) tma_load_5d(a_dst + q * a_tile_bytes, &p.amap[q], fb, 0, ox0 - 1, oy0 - 1, cg, n);
+            }
+          }
+          if (!b_resident) {
+            const int i0 = src1 ? stages0 * ntaps + (g - stages0) : g * ntaps;
+#pragma unroll 1
+            for (int t = 0; t < nt; ++t)
+              tma_load_2d(a_dst + b_off + (uint32_t)t * b_tap_bytes, &p.bmap, fb, (i0 + t) * BKc, n_col0);
           }
           if (++a_slot == a_ring) {
             a_slot = 0;
             a_phase ^= 1u;
-          }
-          if (!b_resident) {
-            const int nt = src1 ? 1 : ntaps;
-            const int i0 = src1 ? stages0 * ntaps + (g - stages0) : g * ntaps;
-#pragma unroll 1
-            for (int t = 0; t < nt; ++t) {
-              mbar_wait(b_empty0 + 8u * b_slot, b_phase ^ 1u);
-              const uint32_t bf = b_full0 + 8u * b_slot;
-              mbar_arrive_expect_tx(bf, b_tap_bytes);
-              tma_load_2d(sB_addr + (uint32_t)b_slot * b_tap_bytes, &p.bmap, bf, (i0 + t) * BKc, n_col0);
-              if (++b_slot == b_ring) {
-                b_slot = 0;
-                b_phase ^= 1u;
-              }
-            }
           }
         }
         if (++tile_x == tiles_x) {
@@ -327,7 +307,8 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (BN <= 32 ? 3 : 2)) conv_
     // One elected lane; the MMAs of a channel group are fully unrolled (issue_group).
     if (!SIMT && elect_one()) {
       const int ntaps = p.ntaps, stages0 = p.stages0, a_ring = p.a_ring, MT = p.MT;
-      const uint32_t a_slot16 = p.a_slot_bytes >> 4;
+      const bool b_resident = p.b_resident != 0;
+      const uint32_t g_slot16 = p.g_slot_bytes >> 4, b_off16 = p.b_off >> 4;
       const uint32_t sA16 = smem_u32(sA) >> 4, sB16 = smem_u32(sB) >> 4;
       const uint32_t a_full0 = smem_u32(a_full), a_empty0 = smem_u32(a_empty);
       const uint32_t tfull0 = smem_u32(tmem_full_bar), tempty0 = smem_u32(tmem_empty_bar);
@@ -336,17 +317,13 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (BN <= 32 ? 3 : 2)) conv_
       // descriptor halves that never change (see make_nosw_desc / make_kmajor_desc); start addresses (>> 4) are
       // below 2^14, so they are simply added to the low word
       const uint32_t a_lo_c = ((p.lbo >> 4) & 0x3fffu) << 16;
+      const uint32_t b_lo_c = 1u << 16;
       const uint32_t b_layout = b_row_bytes == 128 ? 2u : (b_row_bytes == 64 ? 4u : 6u);
       IssueCtx c;
       c.a_hi = ((p.sbo >> 4) & 0x3fffu) | (1u << 14);
       c.b_hi = (((8u * b_row_bytes) >> 4) & 0x3fffu) | (1u << 14) | (b_layout << 29);
       c.idesc = p.idesc;
-      c.b_lo_base = (1u << 16) + sB16;
       c.b_tap16 = p.b_tap_bytes >> 4;
-      c.b_full0 = smem_u32(b_full);
-      c.b_empty0 = smem_u32(b_empty);
-      c.b_ring = p.b_ring;
-      c.b_resident = p.b_resident != 0;
       c.bn = BN;
       const uint32_t a_kk_step = (2u * p.lbo) >> 4;             // K = 16 is two 8-channel planes
       const uint32_t m_step = (uint32_t)(kTileH * p.halo_w);    // 16-byte pixels between stacked sub-tiles
@@ -356,12 +333,12 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (BN <= 32 ? 3 : 2)) conv_
       const uint32_t tap1 = s_tapoff[9];
 #pragma unroll
       for (int i = 0; i < 8; ++i) mk[i] = (uint32_t)(i / kk_steps) * m_step + (uint32_t)(i % kk_steps) * a_kk_step;
-      if (c.b_resident) {
+      if (b_resident) {
         mbar_wait(smem_u32(bres_bar), 0u);
         tc_fence_after();
       }
-      int a_slot = 0, b_slot = 0;
-      uint32_t a_phase = 0, b_phase = 0;
+      int a_slot = 0;
+      uint32_t a_phase = 0;
       int it = 0;
       for (int mt = t_begin; mt < t_end; ++mt, ++it) {
         const int buf = it & 1;
@@ -375,20 +352,21 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (BN <= 32 ? 3 : 2)) conv_
           const bool src1 = g >= stages0;
           const int nt = src1 ? 1 : ntaps;
           const int i0 = src1 ? stages0 * ntaps + (g - stages0) : g * ntaps;
-          const uint32_t a_lo = a_lo_c + sA16 + (uint32_t)a_slot * a_slot16;
-          const uint32_t b_res_lo = c.b_lo_base + (uint32_t)i0 * c.b_tap16;
+          const uint32_t slot16 = sA16 + (uint32_t)a_slot * g_slot16;
+          const uint32_t a_lo = a_lo_c + slot16;
+          const uint32_t b_lo = b_lo_c + (b_resident ? sB16 + (uint32_t)i0 * c.b_tap16 : slot16 + b_off16);
           const uint32_t acc_first = g != 0 ? 1u : 0u;
           const uint32_t* tp = src1 ? &tap1 : tap;
           if (MT == 1) {
-            if (kk_steps == 1) issue_group_nt<1, 1>(nt, c, a_lo, tp, mk, b_res_lo, d0, acc_first, b_slot, b_phase);
-            else if (kk_steps == 2) issue_group_nt<2, 1>(nt, c, a_lo, tp, mk, b_res_lo, d0, acc_first, b_slot, b_phase);
-            else issue_group_nt<4, 1>(nt, c, a_lo, tp, mk, b_res_lo, d0, acc_first, b_slot, b_phase);
+            if (kk_steps == 1) issue_group_nt<1, 1>(nt, c, a_lo, tp, mk, b_lo, d0, acc_first);
+            else if (kk_steps == 2) issue_group_nt<2, 1>(nt, c, a_lo, tp, mk, b_lo, d0, acc_first);
+            else issue_group_nt<4, 1>(nt, c, a_lo, tp, mk, b_lo, d0, acc_first);
           } else {
-            if (kk_steps == 1) issue_group_nt<1, 2>(nt, c, a_lo, tp, mk, b_res_lo, d0, acc_first, b_slot, b_phase);
-            else if (kk_steps == 2) issue_group_nt<2, 2>(nt, c, a_lo, tp, mk, b_res_lo, d0, acc_first, b_slot, b_phase);
-            else issue_group_nt<4, 2>(nt, c, a_lo, tp, mk, b_res_lo, d0, acc_first, b_slot, b_phase);
+            if (kk_steps == 1) issue_group_nt<1, 2>(nt, c, a_lo, tp, mk, b_lo, d0, acc_first);
+            else if (kk_steps == 2) issue_group_nt<2, 2>(nt, c, a_lo, tp, mk, b_lo, d0, acc_first);
+            else issue_group_nt<4, 2>(nt, c, a_lo, tp, mk, b_lo, d0, acc_first);
           }
-          umma_commit(a_empty0 + 8u * a_slot);  // frees the halo-tile slot
+          umma_commit(a_empty0 + 8u * a_slot);  // frees the slot (halo tile + streamed weights) once the MMAs have read it
           if (++a_slot == a_ring) {
             a_slot = 0;
             a_phase ^= 1u;
@@ -532,6 +510,11 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (BN <= 32 ? 3 : 2)) conv_
 
         if (MODE == EPI_STORE) {
           act_t* obase = p.out.p + (size_t)n * p.out.bstride + (size_t)((ntile * BN) >> 3) * HW8 + pix8;
+          // parity-planar copy for a stride-2 consumer: [plane][py][px][H/2][W/2][8]
+          act_t* obase2 = nullptr;
+          if (p.has_out2)
+            obase2 = p.out2.p + (size_t)n * p.out2.bstride + (size_t)((ntile * BN) >> 3) * HW8 +
+                     (size_t)((oy & 1) * 2 + (ox & 1)) * (HW8 >> 2) + ((size_t)(oy >> 1) * (p.W >> 1) + (ox >> 1)) * 8;
           const act_t* rbase = p.has_res ? p.res.p + (size_t)n * p.res.bstride + (size_t)((ntile * BN) >> 3) * HW8 + pix8
                                          : nullptr;
           uint32_t r[2][16];
@@ -608,6 +591,10 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (BN <= 32 ? 3 : 2)) conv_
               for (int c = 0; c < 8; ++c) o[c] = pack2(v[2 * c], v[2 * c + 1]);
               *reinterpret_cast<uint4*>(obase + (size_t)(2 * j) * HW8) = make_uint4(o[0], o[1], o[2], o[3]);
               *reinterpret_cast<uint4*>(obase + (size_t)(2 * j + 1) * HW8) = make_uint4(o[4], o[5], o[6], o[7]);
+              if (p.has_out2) {
+                *reinterpret_cast<uint4*>(obase2 + (size_t)(2 * j) * HW8) = make_uint4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<uint4*>(obase2 + (size_t)(2 * j + 1) * HW8) = make_uint4(o[4], o[5], o[6], o[7]);
+              }
             }
           }
         } else if (MODE == EPI_SPADE) {
@@ -757,6 +744,29 @@ int make_tmap_act_s2(CUtensorMap* m, const act_t* base, int C, int W, int H, int
   EncodeTiledFn fn = get_encode_fn();
   RIB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   RIB_REQUIRE(C % 8 == 0 && box_c % 8 == 0 && W % 2 == 0 && H % 2 == 0, "bad stride-2 activation view");
+  RIB_REQUIRE(box_w * 8 <= 256 && box_h <= 256, "bad stride-2 activation box");
+  const cuuint64_t es = sizeof(act_t);
+  const int Hh = H / 2, Wh = W / 2;
+  const act_t* b0 = base + (size_t)(py * 2 + px) * Hh * Wh * 8;
+  RIB_REQUIRE(((uintptr_t)b0 & 15) == 0, "activation view must be 16-byte aligned");
+  cuuint64_t dims[4] = {(cuuint64_t)Wh * 8, (cuuint64_t)Hh, (cuuint64_t)(C / 8), (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)Wh * 8 * es, (cuuint64_t)H * W * 8 * es, (cuuint64_t)bstride * es};
+  cuuint32_t box[4] = {(cuuint32_t)(box_w * 8), (cuuint32_t)box_h, (cuuint32_t)(box_c / 8), 1u};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  CUresult r = fn(m, RIB_TMAP_DTYPE, 4, const_cast<act_t*>(b0), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RIB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(stride-2 activation) failed: " + std::to_string((int)r));
+  return 0;
+}
+
+// Parity view (py, px) of a NORMAL planar map (strided gather, 16-byte pieces): dims (8, W/2, H/2, C/8, B).  Used when
+// the producer also has stride-1 consumers and a second, parity-planar copy of its output would cost more than it saves.
+int make_tmap_act_s2_strided(CUtensorMap* m, const act_t* base, int C, int W, int H, int B, long long bstride, int py,
+                             int px, int box_c, int box_w, int box_h) {
+  EncodeTiledFn fn = get_encode_fn();
+  RIB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  RIB_REQUIRE(C % 8 == 0 && box_c % 8 == 0 && W % 2 == 0 && H % 2 == 0, "bad stride-2 activation view");
   const cuuint64_t es = sizeof(act_t);
   const act_t* b0 = base + ((size_t)py * W + px) * 8;
   cuuint64_t dims[5] = {8, (cuuint64_t)(W / 2), (cuuint64_t)(H / 2), (cuuint64_t)(C / 8), (cuuint64_t)B};
@@ -766,7 +776,7 @@ int make_tmap_act_s2(CUtensorMap* m, const act_t* base, int C, int W, int H, int
   CUresult r = fn(m, RIB_TMAP_DTYPE, 5, const_cast<act_t*>(b0), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  RIB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(stride-2 activation) failed: " + std::to_string((int)r));
+  RIB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(strided stride-2 activation) failed: " + std::to_string((int)r));
   return 0;
 }
 
@@ -785,16 +795,21 @@ int make_tmap_w(CUtensorMap* m, const act_t* w, int K, int N, int bkc, int boxN,
   return 0;
 }
 
+static constexpr size_t kStatStageBytes = 4 * kStatWarpFloats * 4;
+static constexpr size_t kSmallResident = (size_t)72 * 1024;   // weights of an N tile that leave room for several CTAs per SM
+static constexpr size_t kBigResident = (size_t)152 * 1024;    // ... that still fit beside two halo-tile slots (one CTA per SM)
+
+// Channels per group.  Also fixes the K order of the packed weights, so it may only depend on the layer shape.
 int choose_bkc(int cin0, int cin1, int taps, int BN, int stride) {
-  (void)taps;
-  (void)BN;
-  const int cap = stride == 2 ? 32 : 64;  // stride 2 keeps four parity tiles per group in a ring slot
+  const size_t b_all = ((size_t)cin0 * taps + cin1) * BN * 2;
+  int cap;
+  if (b_all <= kSmallResident) cap = stride == 2 ? 32 : 64;       // stride 2 keeps four parity tiles per slot
+  else if (b_all <= kBigResident) cap = stride == 2 ? 16 : 64;    // big resident weights: small halo slots
+  else cap = stride == 2 ? 16 : 32;                               // streamed: a slot holds the halo tile(s) AND 9 weight sub-tiles
   int bk = cin0 < cap ? cin0 : cap;
   if (cin1 > 0 && cin1 < bk) bk = cin1;
   return bk;
 }
-
-static constexpr size_t kStatStageBytes = 4 * kStatWarpFloats * 4;
 
 int conv_gemm_configure(ConvGemmParams* p, int B, int Hout, int Wout, int cin0, int cin1, int taps, int stride,
                         int BN, int n_pad) {
@@ -834,12 +849,14 @@ int conv_gemm_configure(ConvGemmParams* p, int B, int Hout, int Wout, int cin0, 
     p->a_tx_bytes = (uint32_t)ntile_a * tile_raw;
     p->tiles_x = ceil_div(Wout, kTileW);
     p->tiles_y = ceil_div(Hout, kTileH * MT);
+    p->b_off = 0;
+    p->g_slot_bytes = p->a_slot_bytes;
   };
   const size_t kSmemMax = (size_t)227 * 1024, kOverhead = 8 * 1024;  // barriers, bias, statistics slots, alignment
-  // (stride 2 is bound by its 16-byte parity gathers, not by weight traffic: stacking sub-tiles does not help it)
+  // (stride 2 is not bound by weight traffic: stacking sub-tiles does not help it)
   const bool can_mt2 = Hout >= 2 * kTileH && stride == 1;
-  p->b_ring = 1;
-  if (b_all <= 72 * 1024) {
+  p->b_ring = 1;  // unused
+  if (b_all <= kSmallResident) {
     // small weights stay resident; bandwidth-bound layers: keep the CTA near 100 KB so that several fit on an SM
     p->b_resident = 1;
     set_geometry(1);
@@ -850,29 +867,27 @@ int conv_gemm_configure(ConvGemmParams* p, int B, int Hout, int Wout, int cin0, 
     if (ring > 8) ring = 8;
     if (ring < 2) ring = 2;
     p->a_ring = ring;
-  } else {
+  } else if (b_all <= kBigResident) {
     // medium weights: one CTA per SM keeps its whole N tile of weights in shared memory (no weight traffic per
-    // output tile at all) if at least two halo-tile slots still fit
+    // output tile at all); the remaining space is the halo-tile ring
+    p->b_resident = 1;
+    const size_t fixed = b_all + kStatStageBytes + kOverhead;
+    set_geometry(can_mt2 ? 2 : 1);
+    if (fixed + 2 * (size_t)p->a_slot_bytes > kSmemMax) set_geometry(1);
+    RIB_REQUIRE(fixed + 2 * (size_t)p->a_slot_bytes <= kSmemMax, "conv_gemm: resident weights do not fit");
+    int ring = (int)((kSmemMax - fixed) / p->a_slot_bytes);
+    p->a_ring = ring > 4 ? 4 : ring;
+  } else {
+    // large weights are streamed: a ring slot holds the halo tile of a channel group AND that group's weight
+    // sub-tiles (one barrier round trip per group); two stacked sub-tiles halve the weight traffic per pixel
     p->b_resident = 0;
-    for (int MT = can_mt2 ? 2 : 1; MT >= 1 && !p->b_resident; --MT) {
-      set_geometry(MT);
-      const size_t fixed = b_all + kStatStageBytes + kOverhead;
-      if (fixed + 2 * (size_t)p->a_slot_bytes <= kSmemMax) {
-        p->b_resident = 1;
-        int ring = (int)((kSmemMax - fixed) / p->a_slot_bytes);
-        p->a_ring = ring > 4 ? 4 : ring;
-      }
-    }
-    if (!p->b_resident) {
-      // large weights are streamed through their own ring; two stacked sub-tiles halve that traffic per pixel
-      set_geometry(can_mt2 ? 2 : 1);
-      p->a_ring = 2;
-      const size_t budget = kSmemMax - kStatStageBytes - kOverhead - (size_t)2 * p->a_slot_bytes;
-      int ring = (int)(budget / p->b_tap_bytes);
-      if (ring > 12) ring = 12;
-      if (ring < 2) ring = 2;
-      p->b_ring = ring;
-    }
+    set_geometry(can_mt2 ? 2 : 1);
+    p->b_off = (p->a_slot_bytes + 1023u) & ~1023u;
+    p->g_slot_bytes = p->b_off + (uint32_t)taps * p->b_tap_bytes;
+    const size_t budget = kSmemMax - kStatStageBytes - kOverhead;
+    int ring = (int)(budget / p->g_slot_bytes);
+    RIB_REQUIRE(ring >= 2, "conv_gemm: streamed group slots do not fit");
+    p->a_ring = ring > 4 ? 4 : ring;
   }
   p->idesc = make_idesc_f16(128, BN);
   return 0;
@@ -880,10 +895,10 @@ int conv_gemm_configure(ConvGemmParams* p, int B, int Hout, int Wout, int cin0, 
 
 size_t conv_gemm_smem_bytes(const ConvGemmParams& p) {
   const int n_bt = p.stages0 * p.ntaps + p.stages1;
-  size_t tiles = (((size_t)p.a_ring * p.a_slot_bytes + 1023) & ~(size_t)1023) +
-                 (size_t)(p.b_resident ? n_bt : p.b_ring) * p.b_tap_bytes;
+  size_t tiles = (((size_t)p.a_ring * p.g_slot_bytes + 1023) & ~(size_t)1023) +
+                 (size_t)(p.b_resident ? n_bt : 0) * p.b_tap_bytes;
   size_t stat = p.stats != nullptr ? kStatStageBytes : 0;
-  size_t bars = (size_t)(2 * p.a_ring + 2 * p.b_ring + 5) * 8 + 32;
+  size_t bars = (size_t)(2 * p.a_ring + 5) * 8 + 32;
   size_t scratch = (size_t)p.BN * 4 * 9 + 64 + 64;
   return 1024 + tiles + stat + bars + scratch;
 }
@@ -959,7 +974,7 @@ static ConvKernel pick_kernel(int mode, int BN) {
 
 int launch_conv_gemm(const ConvGemmParams& p, int mode, cudaStream_t stream) {
   RIB_REQUIRE(p.BKc == 16 || p.BKc == 32 || p.BKc == 64, "conv_gemm: BKc must be 16/32/64");
-  RIB_REQUIRE(p.a_ring >= 2 && p.a_ring <= 8 && p.b_ring >= 1 && p.b_ring <= 12, "conv_gemm: bad ring depth");
+  RIB_REQUIRE(p.a_ring >= 2 && p.a_ring <= 8, "conv_gemm: bad ring depth");
   RIB_REQUIRE(p.MT == 1 || p.MT == 2, "conv_gemm: MT must be 1 or 2");
   RIB_REQUIRE(2 * p.MT * p.BN <= 512, "conv_gemm: accumulators exceed TMEM");
   RIB_REQUIRE(p.n_tiles >= 1, "conv_gemm: no N tiles");

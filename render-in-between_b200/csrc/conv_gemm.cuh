@@ -11,7 +11,8 @@
 // a row (pixel) is 16 bytes and an 8-row group is one image row of the tile, so the stride between
 // 8-row groups (SBO) is the halo row pitch and the 3x3 taps are nine descriptors that differ only in
 // their start address: every input byte crosses L2 -> SM once instead of nine times.  Zero padding is
-// TMA out-of-bounds fill.  Stride-2 convolutions load four parity views of the input the same way.
+// TMA out-of-bounds fill.  Stride-2 convolutions load four parity tiles (even/odd rows x even/odd columns) the same
+// way from a parity-planar copy of their input.
 // B operand: packed weights [Npad][Ktotal] (K-major, 32/64/128-byte swizzle), one [BN][BKc] sub-tile per
 // (channel group, tap); kept resident in shared memory for the life of the CTA when they fit, streamed
 // through their own ring (decoupled from the A ring: nine weight sub-tiles per halo tile) otherwise.
@@ -53,11 +54,14 @@ struct alignas(64) ConvGemmParams {
   int BKc;              // channels per group = per halo tile (16/32/64)
   int stages0, stages1; // channel groups of source 0 / source 1
   int ntaps, stride, halo;
-  int a_ring, b_ring;   // shared-memory ring slots for halo tiles / streamed weight sub-tiles
+  int s2_parity;        // stride 2: 1 = the input is a parity-planar map, 0 = strided parity views of a normal map
+  int a_ring, b_ring;   // ring slots (one channel group each); b_ring is unused
   int b_resident;       // 1: all weight sub-tiles of this CTA's N tile stay in shared memory
   int halo_w;           // pixels per halo-tile row
   uint32_t a_tile_bytes;  // one halo tile (one parity view for stride 2), padded to 128 bytes
-  uint32_t a_slot_bytes;  // A bytes per ring slot (1 or 4 tiles), padded to 1024
+  uint32_t a_slot_bytes;  // A bytes per ring slot (1 or 4 tiles)
+  uint32_t g_slot_bytes;  // bytes per ring slot: halo tile(s) [+ the group's weight sub-tiles at b_off when streamed]
+  uint32_t b_off;         // offset of the streamed weight sub-tiles inside a slot (1024-byte aligned)
   uint32_t b_tap_bytes;   // BN * BKc * 2: one weight sub-tile
   uint32_t a_tx_bytes;    // bytes TMA delivers per halo-tile slot
   uint32_t lbo, sbo;      // UMMA no-swizzle K-major descriptor strides (bytes)
@@ -74,6 +78,7 @@ struct alignas(64) ConvGemmParams {
   // EPI_STORE
   PlanarRef out;
   PlanarRef res; int has_res;
+  PlanarRef out2; int has_out2;  // optional second copy of the output in parity-planar layout (feeds a stride-2 conv)
   double* stats;       // [B][n_valid][2] (sum, sum of squares) or null
   // EPI_SPADE
   PlanarRef x; int Hx, Wx, ups;
@@ -90,10 +95,15 @@ struct alignas(64) ConvGemmParams {
 // Stride-1 view of a planar map: dims (W*8, H, C/8, B); box = (box_w*8, box_h, box_c/8, 1).
 int make_tmap_act_s1(CUtensorMap* m, const act_t* base, int C, int W, int H, int B, long long bstride, int box_c,
                      int box_w, int box_h);
-// Parity view (py, px) of a planar map for stride-2 convolutions: dims (8, W/2, H/2, C/8, B).
+// Parity view (py, px) of a PARITY-PLANAR map for stride-2 convolutions.  A stride-2 consumer reads its input
+// from the layout [B][C/8][py][px][H/2][W/2][8] (written by its producer, see ConvGemmParams::out2 and
+// InApplyParams::out_parity), so that each of the four parity tiles is a dense box with long rows:
+// dims (W/2*8, H/2, C/8, B), base = plane + (py*2+px) * (H/2*W/2*8).
 int make_tmap_act_s2(CUtensorMap* m, const act_t* base, int C, int W, int H, int B, long long bstride, int py, int px,
                      int box_c, int box_w, int box_h);
 // Weight view (BKc, Npad, Ktotal/BKc); box = (BKc, BN, taps).
+int make_tmap_act_s2_strided(CUtensorMap* m, const act_t* base, int C, int W, int H, int B, long long bstride, int py,
+                             int px, int box_c, int box_w, int box_h);
 int make_tmap_w(CUtensorMap* m, const act_t* w, int K, int N, int bkc, int boxN, int taps);
 // Channels per pipeline stage for a layer (also fixes the K ordering of the packed weights).
 int choose_bkc(int cin0, int cin1, int taps, int BN, int stride);

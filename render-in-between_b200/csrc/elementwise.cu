@@ -115,7 +115,11 @@ __global__ void in_apply_kernel(const InApplyParams p) {
           v[k] += p.bstats ? (w[k] * s_coef[2 * p.C + c0 + k] + s_coef[3 * p.C + c0 + k]) : w[k];
       }
       const uint4 o = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
-      if (!p.ups) {
+      if (p.out_parity) {
+        const int y = (int)(pix / p.W), x = (int)(pix - (size_t)y * p.W);
+        const size_t q = (size_t)((y & 1) * 2 + (x & 1)) * (HW >> 2) + (size_t)(y >> 1) * (p.W >> 1) + (x >> 1);
+        *reinterpret_cast<uint4*>(p.out + (size_t)n * p.o_bs + (pl * HW + q) * 8) = o;
+      } else if (!p.ups) {
         *reinterpret_cast<uint4*>(p.out + (size_t)n * p.o_bs + i * 8) = o;
       } else {
         const int y = (int)(pix / p.W), x = (int)(pix - (size_t)y * p.W);

@@ -28,6 +28,7 @@ struct InApplyParams {
   int B, H, W, C;  // input spatial size
   int act;         // 0 none, 1 leaky-relu(0.2) on the first term
   int ups;         // 1: write each pixel to the 2x2 block of a (2H, 2W) output
+  int out_parity;  // 1: write the output in parity-planar layout [plane][py][px][H/2][W/2][8] (feeds a stride-2 conv)
   float eps;
 };
 int launch_in_apply(const InApplyParams& p, cudaStream_t s);

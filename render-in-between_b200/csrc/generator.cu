@@ -33,6 +33,7 @@ namespace {
 struct View {  // chunk-planar 16-bit activation [B][Ctot/8][H][W][8] (or a channel slice of one)
   act_t* p = nullptr;  // first plane of the slice, image 0
   int B = 0, H = 0, W = 0, C = 0, Ctot = 0;
+  bool parity = false;  // parity-planar layout [plane][py][px][H/2][W/2][8] (input of a stride-2 conv)
   long long bstride() const { return (long long)Ctot * H * W; }
   PlanarRef ref() const { return PlanarRef{p, bstride()}; }
 };
@@ -406,7 +407,7 @@ struct PlanBuilder {
     ConvGemmParams p;
     memset(&p, 0, sizeof(p));
     if (in0.C != L.cin0 || (in1 ? in1->C : 0) != L.cin1 || BN != L.BN || stride != L.stride || in0.C != in0.Ctot ||
-        (in1 && in1->C != in1->Ctot)) {
+        (in1 && in1->C != in1->Ctot) || (in0.parity && stride != 2) || (in1 && in1->parity)) {
       set_error("plan: layer/view channel mismatch in " + L.name);
       rc = -4;
       return p;
@@ -418,6 +419,7 @@ struct PlanBuilder {
       return p;
     }
     p.debug_simt = g_debug_simt;
+    p.s2_parity = in0.parity ? 1 : 0;
     p.src0 = in0.ref();
     p.Hin = in0.H;
     p.Win = in0.W;
@@ -436,8 +438,10 @@ struct PlanBuilder {
       } else {
         for (int py = 0; py < 2 && !rc; ++py)
           for (int px = 0; px < 2 && !rc; ++px)
-            rc = make_tmap_act_s2(&p.amap[py * 2 + px], in0.p, in0.C, in0.W, in0.H, B, in0.bstride(), py, px, p.BKc,
-                                  p.halo_w, halo_h);
+            rc = in0.parity ? make_tmap_act_s2(&p.amap[py * 2 + px], in0.p, in0.C, in0.W, in0.H, B, in0.bstride(), py, px,
+                                               p.BKc, p.halo_w, halo_h)
+                            : make_tmap_act_s2_strided(&p.amap[py * 2 + px], in0.p, in0.C, in0.W, in0.H, B,
+                                                       in0.bstride(), py, px, p.BKc, p.halo_w, halo_h);
       }
       if (!rc) rc = make_tmap_w(&p.bmap, L.w, L.ktotal, L.n_pad, p.BKc, BN, L.taps);
     }
@@ -455,10 +459,12 @@ struct PlanBuilder {
 
   // conv (+bias, optional residual/second source) -> 16-bit NHWC store, optional statistics
   void conv_store(const std::string& lname, const View& in0, const View* in1, int stride, const View& out,
-                  double* stats, int act, const View* res) {
+                  double* stats, int act, const View* res, const View* out2 = nullptr) {
     const GemmLayer& L = G->layers.at(lname);
     ConvGemmParams p = gemm_common(L, in0, in1, stride, out.H, out.W, L.BN);
     p.out = out.ref();
+    p.has_out2 = out2 ? 1 : 0;
+    if (out2) p.out2 = out2->ref();
     p.stats = stats;
     p.act = act;
     p.has_res = res ? 1 : 0;
@@ -504,6 +510,10 @@ struct PlanBuilder {
 
   void in_apply(const View& a, const double* astats, const std::string& aprefix, const View* b, const double* bstats,
                 const std::string& bprefix, const View& out, int act, bool ups) {
+    if (out.parity && ups) {
+      set_error("plan: in_apply cannot up-sample into a parity-planar map");
+      rc = -4;
+    }
     Op op;
     op.kind = OP_IN_APPLY;
     InApplyParams& p = op.ia;
@@ -530,6 +540,7 @@ struct PlanBuilder {
     p.C = a.C;
     p.act = act;
     p.ups = ups ? 1 : 0;
+    p.out_parity = out.parity ? 1 : 0;
     p.eps = 1e-5f;
     ops.push_back(op);
   }
@@ -639,9 +650,19 @@ static int build_plan(Generator* G, int B, int H, int W, void* wsbase, size_t* b
     for (int i = 0; i <= c.emb_down; ++i) {
       const int h = H >> i, w = W >> i;
       View o = pb.alloc("cond_" + std::to_string(i), h, w, emb_ch(c, i));
-      pb.conv_store("emb_" + std::to_string(i), prev, nullptr, i == 0 ? 1 : 2, o, nullptr, ACT_LRELU, nullptr);
+      // cond_1..3 are also written as a parity-planar copy for the next (stride-2) embedder conv: its four parity
+      // tiles become dense TMA boxes.  cond_0 is not: emb_0 is bound by its epilogue and the copy would add 1 GB of
+      // stores, more than emb_1 saves (measured), so emb_1 gathers strided parity views of cond_0.
+      View o2;
+      const bool dual = i >= 1 && i < c.emb_down;
+      if (dual) {
+        o2 = pb.alloc("cond_" + std::to_string(i) + ".s2", h, w, emb_ch(c, i));
+        o2.parity = true;
+      }
+      pb.conv_store("emb_" + std::to_string(i), prev, nullptr, i == 0 ? 1 : 2, o, nullptr, ACT_LRELU, nullptr,
+                    dual ? &o2 : nullptr);
+      prev = dual ? o2 : o;
       cond.push_back(o);
-      prev = o;
     }
   }
   // -- main branch --
@@ -716,6 +737,7 @@ static int build_plan(Generator* G, int B, int H, int W, void* wsbase, size_t* b
       double* st = mst[bn + std::to_string(i)];
       pb.conv_store(nm, cur, nullptr, i == 0 ? 1 : 2, raw, st, ACT_NONE, nullptr);
       View o = (i == c.mask_down) ? PlanBuilder::slice(cat, br * mch, mch) : pb.alloc(nm, h, w, ch);
+      if (i != c.mask_down) o.parity = true;  // consumed only by the next (stride-2) conv
       pb.in_apply(raw, st, f + bn + "." + std::to_string(i) + ".layers.norm", nullptr, nullptr, "", o, 1, false);
       cur = o;
     }
@@ -961,6 +983,7 @@ int conv_test(const void* x, const float* w, const float* bias, void* out, doubl
   in.H = Hin;
   in.W = Win;
   in.C = in.Ctot = Cin;
+  in.parity = stride == 2;
   View o;
   o.p = static_cast<act_t*>(out);
   o.B = B;

@@ -12,7 +12,7 @@ import torch.nn.functional as F
 
 from oracle import generator_oracle as go
 from oracle import raster_oracle as ro
-from rib.layout import from_planar, to_planar
+from rib.layout import from_planar, to_parity_planar, to_planar
 from rib.synth import synth_flow, synth_image, synth_joints
 
 pytestmark = pytest.mark.gpu
@@ -112,7 +112,8 @@ def _run_conv(dev, x_nchw, w, bias, k, stride, act, want_stats, simt):
     dt = _act_dtype()
     b, cin, h, wd = x_nchw.shape
     cout = w.shape[0]
-    x = to_planar(x_nchw, dt).to(dev)
+    # a stride-2 convolution reads its input from the parity-planar layout its producer writes
+    x = (to_parity_planar(x_nchw, dt) if stride == 2 else to_planar(x_nchw, dt)).to(dev)
     out = torch.zeros(b, cout // 8, h // stride, wd // stride, 8, dtype=dt, device=dev)
     stats = torch.zeros(b, cout, 2, dtype=torch.float64, device=dev) if want_stats else None
     scratch = torch.empty(lib.rib_conv_test_scratch_bytes(cin, cout, k) + 1024, dtype=torch.uint8, device=dev)
@@ -136,7 +137,7 @@ CONV_CASES = [
     (1, 64, 64, 32, 32, 3, 1),     # 64-channel stage, 32-channel K groups
     (1, 128, 256, 16, 16, 3, 1),   # streamed weights, several stages, two N tiles
     (1, 256, 256, 32, 32, 3, 1),   # streamed weights with two M sub-tiles per super-tile (MT=2)
-    (2, 64, 128, 32, 32, 3, 2),    # stride 2 through the four parity views
+    (2, 64, 128, 32, 32, 3, 2),    # stride 2 through the four parity tiles
     (1, 512, 64, 16, 16, 1, 1),    # 1x1 (SPADE-shaped K), resident weights
     (2, 512, 128, 64, 16, 1, 1),   # 1x1, streamed weights, MT=2
     (1, 32, 16, 20, 30, 3, 1),     # ragged: H, W not multiples of the tile (HSM.yaml's 320x480 / 16)
