@@ -1,7 +1,10 @@
 // Implicit-GEMM convolution on tcgen05 / TMEM fed by TMA (sm_100a).  See conv_gemm.cuh.
 //
-// CTA = 192 threads, persistent over super-tiles: warp 0 = TMA producer (one lane), warp 1 = TMEM
-// allocator + tcgen05.mma issuer (one lane), warps 2..5 = epilogue (TMEM lane quarter = warp_idx & 3).
+// CTA = 64 + 128 * kEpiGroups threads, persistent over super-tiles: warp 0 = TMA producer (one lane), warp 1 =
+// TMEM allocator + tcgen05.mma issuer (one lane), then kEpiGroups epilogue groups of four warps (TMEM lane
+// quarter = warp_idx & 3); group g drains every kEpiGroups-th tile of the CTA.  Two groups (one per accumulator
+// buffer) were measured: no gain for the one-CTA-per-SM layers (they are MMA / TMA bound) and a loss for the
+// small layers (fewer CTAs per SM), so one group is built.
 // Barriers: full/empty per ring slot (TMA <-> MMA), tmem_full/tmem_empty per accumulator buffer
 // (MMA <-> epilogue), one barrier for the resident weights.
 #include "conv_gemm.cuh"
@@ -12,7 +15,8 @@
 
 namespace rib {
 
-static constexpr int kThreads = 192;
+static constexpr int kEpiGroups = 1;                       // epilogue groups (4 warps each), one per TMEM accumulator buffer
+static constexpr int kThreads = 64 + 128 * kEpiGroups;
 static constexpr int kNumSms = 148;
 
 // Geometry of tap t of a stage: which halo tile of the slot it reads and the pixel offset of its
@@ -113,7 +117,8 @@ __device__ void simt_chunk(const ConvGemmParams& p, int n, int oy, int ox, int c
   }
 }
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// named barrier of one epilogue group (128 threads)
+__device__ __forceinline__ void epi_bar(int group) { asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory"); }
 
 // Per-warp staging buffer for the instance-norm statistics: 32 rows (pixels) x 16 columns fp32 with a
 // 20-float row pitch (conflict-free 16-byte row writes and scalar column reads).
@@ -160,7 +165,7 @@ __device__ __forceinline__ void issue_group_nt(int nt, const IssueCtx& c, uint32
 }
 
 template <int MODE, int BN, bool SIMT>
-__global__ void __launch_bounds__(kThreads, SIMT ? 1 : (BN <= 32 ? 3 : 2)) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+__global__ void __launch_bounds__(kThreads, SIMT ? 1 : (kEpiGroups == 1 ? (BN <= 32 ? 3 : 2) : (BN <= 32 ? 2 : 1))) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -174,7 +179,7 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (BN <= 32 ? 3 : 2)) conv_
   uint8_t* sB = sA + (((size_t)p.a_ring * p.g_slot_bytes + 1023) & ~(size_t)1023);  // swizzled tiles: 1024-byte aligned
   uint8_t* sStat = sB + (size_t)(p.b_resident ? n_bt : 0) * p.b_tap_bytes;
   const bool want_stats = MODE == EPI_STORE && p.stats != nullptr;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + (want_stats ? 4 * kStatWarpFloats * 4 : 0));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + (want_stats ? 4 * kEpiGroups * kStatWarpFloats * 4 : 0));
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + p.a_ring;
   uint64_t* tmem_full_bar = a_empty + p.a_ring;  // [2]
@@ -182,8 +187,8 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (BN <= 32 ? 3 : 2)) conv_
   uint64_t* bres_bar = tmem_empty_bar + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bres_bar + 1);
   float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr + 4) + 15) & ~(uintptr_t)15);  // [BN], 16-byte aligned
-  float* s_aux = s_bias + BN;                              // STORE: [4 warps][2*BN] stats; SPADE: [2*CT] rstd, -mean*rstd
-  uint32_t* s_tapoff = reinterpret_cast<uint32_t*>(s_aux + 8 * BN);  // [10] A start offset (16-byte units) of tap t; [9]: 1x1 second source
+  float* s_aux = s_bias + BN;                              // per epilogue group: STORE [4 warps][2*BN] stats; SPADE [2*CT] rstd, -mean*rstd
+  uint32_t* s_tapoff = reinterpret_cast<uint32_t*>(s_aux + kEpiGroups * 8 * BN);  // [10] A start offset (16-byte units) of tap t; [9]: 1x1 second source
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -220,7 +225,7 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (BN <= 32 ? 3 : 2)) conv_
       tmem_relinquish();
     }
   }
-  if (warp >= 2) {
+  if (warp >= 2 && warp < 6) {
     const int e = threadIdx.x - 64;
     if (e < 10) {
       const TapGeom tg = tap_geom(p, e == 9, e == 9 ? 0 : e);
@@ -260,7 +265,7 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (BN <= 32 ? 3 : 2)) conv_
       int tile_y = rem0 / tiles_x, tile_x = rem0 - tile_y * tiles_x;
       const int tiles_y = p.tiles_y;
       for (int mt = t_begin; mt < t_end; ++mt) {
-        const int oy0 = tile_y * kTileH * MT, ox0 = tile_x * kTileW;
+        const int oy0 = tile_y * p.th * MT, ox0 = tile_x * p.tw;
         for (int g = 0; g < G; ++g) {
           mbar_wait(a_empty0 + 8u * a_slot, a_phase ^ 1u);
           const uint32_t fb = a_full0 + 8u * a_slot;
@@ -326,7 +331,7 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (BN <= 32 ? 3 : 2)) conv_
       c.b_tap16 = p.b_tap_bytes >> 4;
       c.bn = BN;
       const uint32_t a_kk_step = (2u * p.lbo) >> 4;             // K = 16 is two 8-channel planes
-      const uint32_t m_step = (uint32_t)(kTileH * p.halo_w);    // 16-byte pixels between stacked sub-tiles
+      const uint32_t m_step = (uint32_t)(p.th * p.halo_w);    // 16-byte pixels between stacked sub-tiles
       uint32_t tap[9], mk[8];
 #pragma unroll
       for (int t = 0; t < 9; ++t) tap[t] = s_tapoff[t];
@@ -379,12 +384,14 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (BN <= 32 ? 3 : 2)) conv_
   } else {
     // ===================== Epilogue =====================
     const int q = warp & 3;
-    const int e = threadIdx.x - 64;
+    const int eg = (warp - 2) >> 2;                     // epilogue group = accumulator buffer it drains
+    const int e = (threadIdx.x - 64) & 127;             // thread index inside the group
     const int prow = q * 32 + lane;           // row of the M=128 sub-tile = TMEM lane
-    const int ty = prow >> 3, tx = prow & 7;  // 16 x 8 pixel tile
+    const int ty = p.tw == 8 ? prow >> 3 : prow >> 5, tx = prow & (p.tw - 1);  // 16 x 8 (or 4 x 32) pixel tile
     const size_t HW8 = (size_t)p.H * p.W * 8;
     const float slope = p.act == ACT_LRELU ? 0.2f : 1.0f;  // lrelu(v) = max(v, 0.2 v); identity = max(v, v)
     float* sbuf = reinterpret_cast<float*>(sStat) + (warp - 2) * kStatWarpFloats;
+    float* s_auxg = s_aux + eg * 8 * BN;                // this group's scratch (statistics slots / SPADE coefficients)
     // column sums: lane l owns column (l & 15) of every chunk for half of the 32 rows
     const int st_col = lane & 15, st_half = lane >> 4;
     float acc1[NCH], acc2[NCH];
@@ -407,7 +414,7 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (BN <= 32 ? 3 : 2)) conv_
     // Deterministic: every warp parks its column sums in its own slot, then one thread per column adds the
     // four slots in a fixed order and issues the fp64 atomics (whose rounding is far below fp32 resolution).
     auto flush_stats = [&](int n_img) {
-      float* slot = s_aux + (warp - 2) * 2 * BN;
+      float* slot = s_auxg + ((warp - 2) & 3) * 2 * BN;
       if (kRegStats) {
 #pragma unroll
         for (int j = 0; j < NCH; ++j) {
@@ -432,27 +439,38 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (BN <= 32 ? 3 : 2)) conv_
           acc1[j] = acc2[j] = 0.f;
         }
       }
-      epi_bar();
+      epi_bar(eg);
       for (int c = e; c < BN; c += 128) {
         const int col = ntile * BN + c;
         if (col < p.n_valid) {
-          const float t1 = ((s_aux[c] + s_aux[2 * BN + c]) + s_aux[4 * BN + c]) + s_aux[6 * BN + c];
-          const float t2 = ((s_aux[BN + c] + s_aux[3 * BN + c]) + s_aux[5 * BN + c]) + s_aux[7 * BN + c];
+          const float t1 = ((s_auxg[c] + s_auxg[2 * BN + c]) + s_auxg[4 * BN + c]) + s_auxg[6 * BN + c];
+          const float t2 = ((s_auxg[BN + c] + s_auxg[3 * BN + c]) + s_auxg[5 * BN + c]) + s_auxg[7 * BN + c];
           atomicAdd(&p.stats[((size_t)n_img * p.n_valid + col) * 2 + 0], (double)t1);
           atomicAdd(&p.stats[((size_t)n_img * p.n_valid + col) * 2 + 1], (double)t2);
         }
       }
-      epi_bar();
+      epi_bar(eg);
     };
 
-    // tile coordinates advance incrementally (no divisions per tile)
-    int n = t_begin / tiles_per_img;
-    int tile_y = (t_begin - n * tiles_per_img) / p.tiles_x;
-    int tile_x = (t_begin - n * tiles_per_img) - tile_y * p.tiles_x;
-    for (int mt = t_begin; mt < t_end; ++mt, ++it) {
+    // group eg takes tiles t_begin + eg, t_begin + eg + 2, ...; tile coordinates advance incrementally
+    const int t_first = t_begin + eg;
+    int n = t_first / tiles_per_img;
+    int tile_y = (t_first - n * tiles_per_img) / p.tiles_x;
+    int tile_x = (t_first - n * tiles_per_img) - tile_y * p.tiles_x;
+    auto advance_tile = [&]() {
+      if (++tile_x == p.tiles_x) {
+        tile_x = 0;
+        if (++tile_y == p.tiles_y) {
+          tile_y = 0;
+          ++n;
+        }
+      }
+    };
+    it = eg;
+    for (int mt = t_first; mt < t_end; mt += kEpiGroups, it += kEpiGroups) {
       const int buf = it & 1;
       const uint32_t use = (uint32_t)(it >> 1);
-      const int oy0 = tile_y * kTileH * p.MT, ox0 = tile_x * kTileW;
+      const int oy0 = tile_y * p.th * p.MT, ox0 = tile_x * p.tw;
 
       if (n != cur_n) {  // uniform over the 128 epilogue threads
         if (MODE == EPI_STORE && want_stats && cur_n >= 0) flush_stats(cur_n);
@@ -460,7 +478,7 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (BN <= 32 ? 3 : 2)) conv_
           const int tiles_per_q = p.C / CT;
           const int c0 = (ntile % tiles_per_q) * CT;
           const double cnt = (double)p.Hx * (double)p.Wx;
-          epi_bar();
+          epi_bar(eg);
           for (int c = e; c < CT; c += 128) {
             const double s = p.xstats[((size_t)n * p.C + c0 + c) * 2 + 0];
             const double ss = p.xstats[((size_t)n * p.C + c0 + c) * 2 + 1];
@@ -468,10 +486,10 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (BN <= 32 ? 3 : 2)) conv_
             double var = ss / cnt - mean * mean;
             var = var < 0.0 ? 0.0 : var;
             const double rstd = 1.0 / sqrt(var + (double)p.eps);
-            s_aux[c] = (float)rstd;
-            s_aux[CT + c] = (float)(-mean * rstd);
+            s_auxg[c] = (float)rstd;
+            s_auxg[CT + c] = (float)(-mean * rstd);
           }
-          epi_bar();
+          epi_bar(eg);
         }
         cur_n = n;
       }
@@ -481,7 +499,7 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (BN <= 32 ? 3 : 2)) conv_
       constexpr int NXC = MODE == EPI_SPADE ? CT / 16 : 1;
       uint4 xcur[NXC][2], xnext[NXC][2];
       auto load_x = [&](int m, uint4 (*dst)[2]) {
-        const int oy = oy0 + m * kTileH + ty, ox = ox0 + tx;
+        const int oy = oy0 + m * p.th + ty, ox = ox0 + tx;
         const bool valid = (oy < p.H) && (ox < p.W);
         const int tiles_per_q = p.C / CT;
         const int c0 = (ntile % tiles_per_q) * CT;
@@ -503,7 +521,7 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (BN <= 32 ? 3 : 2)) conv_
         tc_fence_after();
       }
       for (int m = 0; m < p.MT; ++m) {
-        const int oy = oy0 + m * kTileH + ty, ox = ox0 + tx;
+        const int oy = oy0 + m * p.th + ty, ox = ox0 + tx;
         const bool valid = (oy < p.H) && (ox < p.W);
         const size_t pix8 = ((size_t)oy * p.W + ox) * 8;
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols + m * BN);
@@ -630,8 +648,8 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (BN <= 32 ? 3 : 2)) conv_
 #pragma unroll
               for (int c4 = 0; c4 < 4; ++c4) {
                 const int cb = j * 16 + c4 * 4;
-                const float4 rs = *reinterpret_cast<const float4*>(s_aux + cb);        // rstd
-                const float4 ms = *reinterpret_cast<const float4*>(s_aux + CT + cb);   // -mean * rstd
+                const float4 rs = *reinterpret_cast<const float4*>(s_auxg + cb);        // rstd
+                const float4 ms = *reinterpret_cast<const float4*>(s_auxg + CT + cb);   // -mean * rstd
                 const float4 bg = *reinterpret_cast<const float4*>(s_bias + cb);       // gamma bias + 1
                 const float4 bb = *reinterpret_cast<const float4*>(s_bias + CT + cb);  // beta bias
                 float xa, xb, xc, xd;
@@ -678,13 +696,8 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (BN <= 32 ? 3 : 2)) conv_
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[buf]));
       }
-      if (++tile_x == p.tiles_x) {
-        tile_x = 0;
-        if (++tile_y == p.tiles_y) {
-          tile_y = 0;
-          ++n;
-        }
-      }
+#pragma unroll
+      for (int k = 0; k < kEpiGroups; ++k) advance_tile();
     }
     if (MODE == EPI_STORE && want_stats && cur_n >= 0) flush_stats(cur_n);
     tc_fence_before();
@@ -795,9 +808,9 @@ int make_tmap_w(CUtensorMap* m, const act_t* w, int K, int N, int bkc, int boxN,
   return 0;
 }
 
-static constexpr size_t kStatStageBytes = 4 * kStatWarpFloats * 4;
+static constexpr size_t kStatStageBytes = (size_t)4 * kEpiGroups * kStatWarpFloats * 4;
 static constexpr size_t kSmallResident = (size_t)72 * 1024;   // weights of an N tile that leave room for several CTAs per SM
-static constexpr size_t kBigResident = (size_t)152 * 1024;    // ... that still fit beside two halo-tile slots (one CTA per SM)
+static constexpr size_t kBigResident = (size_t)148 * 1024;    // ... that still fit beside two halo-tile slots (one CTA per SM)
 
 // Channels per group.  Also fixes the K order of the packed weights, so it may only depend on the layer shape.
 int choose_bkc(int cin0, int cin1, int taps, int BN, int stride) {
@@ -835,26 +848,34 @@ int conv_gemm_configure(ConvGemmParams* p, int B, int Hout, int Wout, int cin0, 
   const size_t b_all = (size_t)n_bt * p->b_tap_bytes;
   const int G = p->stages0 + p->stages1;
   const int ntile_a = stride == 2 ? 4 : 1;
+  // Sub-tile shape.  A 3x3 tile is 16 rows x 8 pixels (every tile row is one 8-row UMMA group, the halo row pitch is
+  // the group stride).  A 1x1 tile has no halo, so its 8-pixel groups may also sit side by side: 4 rows x 32 pixels
+  // quarters the number of rows TMA has to fetch per tile (512-byte instead of 128-byte rows) and makes the
+  // epilogue's x loads / stores 512-byte contiguous per warp.
+  p->tw = (taps == 1 && Wout % 32 == 0) ? 32 : kTileW;
+  p->th = 128 / p->tw;
   // geometry of one halo-tile slot for a given number of stacked sub-tiles
   auto set_geometry = [&](int MT) {
     p->MT = MT;
-    const int hw = stride == 1 ? kTileW + 2 * p->halo : kTileW + 1;
-    const int hh = stride == 1 ? kTileH * MT + 2 * p->halo : kTileH * MT + 1;
+    const int hw = stride == 1 ? p->tw + 2 * p->halo : p->tw + 1;
+    const int hh = stride == 1 ? p->th * MT + 2 * p->halo : p->th * MT + 1;
     p->halo_w = hw;
     p->lbo = (uint32_t)(hw * hh * 16);
-    p->sbo = (uint32_t)(hw * 16);
+    // stride between 8-pixel groups: the next tile row (3x3), or the next 8 pixels of the same row (32-wide 1x1 tile,
+    // whose rows are contiguous in shared memory)
+    p->sbo = p->tw == kTileW ? (uint32_t)(hw * 16) : 128u;
     const uint32_t tile_raw = (uint32_t)(hw * hh * 16 * (bkc / 8));
     p->a_tile_bytes = (tile_raw + 127u) & ~127u;
     p->a_slot_bytes = ((uint32_t)ntile_a * p->a_tile_bytes + 127u) & ~127u;
     p->a_tx_bytes = (uint32_t)ntile_a * tile_raw;
-    p->tiles_x = ceil_div(Wout, kTileW);
-    p->tiles_y = ceil_div(Hout, kTileH * MT);
+    p->tiles_x = ceil_div(Wout, p->tw);
+    p->tiles_y = ceil_div(Hout, p->th * MT);
     p->b_off = 0;
     p->g_slot_bytes = p->a_slot_bytes;
   };
-  const size_t kSmemMax = (size_t)227 * 1024, kOverhead = 8 * 1024;  // barriers, bias, statistics slots, alignment
+  const size_t kSmemMax = (size_t)227 * 1024, kOverhead = 12 * 1024;  // barriers, bias, statistics slots, alignment
   // (stride 2 is not bound by weight traffic: stacking sub-tiles does not help it)
-  const bool can_mt2 = Hout >= 2 * kTileH && stride == 1;
+  const bool can_mt2 = Hout >= 2 * p->th && stride == 1;
   p->b_ring = 1;  // unused
   if (b_all <= kSmallResident) {
     // small weights stay resident; bandwidth-bound layers: keep the CTA near 100 KB so that several fit on an SM
@@ -899,7 +920,7 @@ size_t conv_gemm_smem_bytes(const ConvGemmParams& p) {
                  (size_t)(p.b_resident ? n_bt : 0) * p.b_tap_bytes;
   size_t stat = p.stats != nullptr ? kStatStageBytes : 0;
   size_t bars = (size_t)(2 * p.a_ring + 5) * 8 + 32;
-  size_t scratch = (size_t)p.BN * 4 * 9 + 64 + 64;
+  size_t scratch = (size_t)p.BN * 4 * (1 + 8 * kEpiGroups) + 64 + 64;
   return 1024 + tiles + stat + bars + scratch;
 }
 

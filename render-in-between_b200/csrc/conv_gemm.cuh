@@ -49,6 +49,7 @@ struct alignas(64) ConvGemmParams {
   CUtensorMap bmap;     // packed weights, 3-D view (BKc, Npad, Ktotal/BKc)
   int B, H, W;          // output spatial size
   int tiles_x, tiles_y; // super-tiles per image
+  int tw, th;           // pixels per sub-tile row / rows per M=128 sub-tile (8 x 16, or 32 x 4 for 1x1 convolutions)
   int MT;               // M=128 sub-tiles per super-tile (stacked vertically): 1 or 2
   int BN, n_tiles;
   int BKc;              // channels per group = per halo tile (16/32/64)
