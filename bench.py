@@ -49,7 +49,7 @@ def peaks():
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+    Q = ('timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
 
@@ -61,12 +61,22 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                       '--format=csv,noheader,nounits', '-lms', '50'], stdout=self.f,
+                                       '--format=csv,noheader,nounits', '-lms', '20'], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
-    def stop(self):
+    @staticmethod
+    def _epoch(ts):
+        import datetime
+        try:
+            return datetime.datetime.strptime(ts.strip(), '%Y/%m/%d %H:%M:%S.%f').timestamp()
+        except ValueError:
+            return None
+
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples taken in the wall-clock window [t0, t1] (the timed region); the sampler itself is
+        started before the warm-up because nvidia-smi needs a moment to come up."""
         out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
         if self.p is None:
             return out
@@ -82,6 +92,9 @@ class ClockSampler:
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         for r in rows:
             if len(r) < 9:
+                continue
+            ts = self._epoch(r[0])
+            if t0 is not None and ts is not None and not (t0 - 0.05 <= ts <= t1 + 0.05):
                 continue
             try:
                 sm.append(float(r[1]))
@@ -321,15 +334,17 @@ def main():
         return float(ms.item())
 
     with torch.no_grad():
-        for _ in range(args.warmup):
-            step_resident()
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
+        for _ in range(args.warmup):
+            step_resident()
         l0 = lib.rib_kernel_launch_count()
+        w0 = time.time()
         ms = timed(step_resident, args.steps)
+        w1 = time.time()
         launches = lib.rib_kernel_launch_count() - l0
-        clocks = sampler.stop() if rank == 0 else None
+        clocks = sampler.stop(w0, w1) if rank == 0 else None
         for _ in range(2):
             step_e2e()
         barrier()
@@ -357,6 +372,12 @@ def main():
     e2e_value = frames / (ms_e2e * 1e-3)
     tc_peak, hbm_peak, peak_src = peaks()
     conv_flop_per_step = CONV_FLOP_PER_FRAME * GEN_FRAMES
+    # DRAM traffic of the implicit-GEMM launches: from the committed ncu launch list of this same command
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, 'profiles', 'conv_gemm_traffic.json')
+    if os.path.isfile(tpath):
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj.get('dram_bytes_per_launch'), tj.get('source')
     launches_per_step = conv_n.value / max(args.steps, 1)
     conv_ms_per_step = conv_ms.value / max(args.steps, 1)
     achieved = conv_flop_per_step / (conv_ms_per_step * 1e-3) / 1e12
@@ -377,7 +398,8 @@ def main():
             'launches_per_step': launches_per_step, 'kernel_ms_per_step': conv_ms_per_step,
             'algorithmic_flop_per_step': conv_flop_per_step,
             'share_of_step': conv_ms_per_step / (ms / args.steps),
-            'traffic': None,
+            'traffic': traffic, 'traffic_unit': 'bytes per launch (mean over the %d launches of a step)' % round(launches_per_step),
+            'traffic_source': traffic_src,
             'note': 'achieved = 883.5 kFLOP/pixel x 512x512 x 32 frames / summed CUDA-event time of all conv_gemm '
                     'launches of a step (events on the launching stream, separate pass of the same steps)'},
     }

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define RIB_ABI_VERSION 2
+#define RIB_ABI_VERSION 3
 
 /* Message of the last failing call on this host thread ("" if none). */
 const char* rib_last_error(void);
@@ -36,9 +36,9 @@ long long rib_kernel_launch_count(void);
  *   label         device  f32 [B][22][H][W]  = [skeleton RGB normalised to [-1,1] | 19 heat-maps]; may be NULL
  *   label_planar  device  16-bit [B][4][H][W][8]: the same label rounded to the generator's activation type
  *                 in its input layout (32 channels, 22..31 zero) (see rib_generator_bind); may be NULL
- *   workspace     device scratch of rib_rasterize_workspace_bytes(B) bytes, 16-byte aligned
+ *   workspace     device scratch of rib_rasterize_workspace_bytes(B, H, W) bytes, 16-byte aligned
  */
-long long rib_rasterize_workspace_bytes(int B);
+long long rib_rasterize_workspace_bytes(int B, int H, int W);
 int rib_rasterize(const double* joints, int B, int H, int W, const double* gauss_taps, double skeleton_thres,
                   double foot_thres, float* label, void* label_planar, void* workspace, long long workspace_bytes,
                   void* stream);
@@ -135,6 +135,9 @@ int rib_generator_debug_tensor(rib_generator* g, const char* name, const void** 
 /* Text description (one line per planned kernel launch, in launch order) of the plan built by the last
  * rib_generator_forward: layer name, tiling, algorithmic FLOPs.  Joined with ncu launch lists by tools/. */
 int rib_generator_plan_text(rib_generator* g, char* buf, long long cap);
+/* The plan-time auto-tuner's log: one line per tuned launch shape of this process (candidate tilings with their
+ * measured device times and the choice).  RIB_AUTOTUNE=0 in the environment disables the tuner. */
+int rib_tune_log(char* buf, long long cap);
 /* 1 if activations are stored as IEEE fp16, 0 for bf16. */
 int rib_act_is_fp16(void);
 /* Stand-alone launch of the implicit-GEMM convolution for unit tests:

@@ -74,22 +74,28 @@ def embed(sd, arch, x, name='ref_embedding'):
     return out
 
 
-def mask_net(sd, arch, label, img9):
+def mask_net(sd, arch, label, img9, taps=None):
     f = 'flow_network_temp'
     a, b = label, img9
     for i in range(arch.mask_down + 1):
         a = _cna(sd, '%s.down_lbl.%d' % (f, i), a, stride=1 if i == 0 else 2)
         b = _cna(sd, '%s.down_img.%d' % (f, i), b, stride=1 if i == 0 else 2)
     x = torch.cat([a, b], dim=1)
+    if taps is not None:
+        taps['mask.cat'] = x
     for i in range(arch.mask_res):
         p = '%s.res_flow.%d' % (f, i)
         dx = _cna(sd, p + '.conv_block_0', x)
         dx = _cna(sd, p + '.conv_block_1', dx, act=False)
         xs = _cna(sd, p + '.conv_block_s', x, act=False) if i == 0 else x
         x = xs + dx
+        if taps is not None:
+            taps['mask.res.%d' % i] = x
     for n in range(arch.mask_down):
         x = F.interpolate(x, scale_factor=2)
         x = _cna(sd, '%s.up_flow.%d' % (f, 2 * n + 1), x)
+        if taps is not None:
+            taps['mask.up.%d' % n] = x
     return torch.sigmoid(_conv(sd, f + '.conv_mask.0.layers.conv', x, sn=False))
 
 
@@ -122,7 +128,7 @@ def generator_forward(sd, arch, label, img_fake, img_prev, taps=None):
         if i != 0:
             x = F.interpolate(x, scale_factor=2)
     img_final = torch.tanh(_conv(sd, 'conv_img.layers.conv', _lrelu(x), sn=False))
-    mask = mask_net(sd, arch, label, torch.cat([img_prev, img_fake, img_final], dim=1))
+    mask = mask_net(sd, arch, label, torch.cat([img_prev, img_fake, img_final], dim=1), taps=taps)
     return img_final, mask
 
 

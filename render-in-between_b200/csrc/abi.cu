@@ -32,7 +32,9 @@ const char* rib_last_error(void) { return rib::last_error(); }
 int rib_abi_version(void) { return RIB_ABI_VERSION; }
 long long rib_kernel_launch_count(void) { return conv_gemm_launch_count() + misc_launch_count(); }
 
-long long rib_rasterize_workspace_bytes(int B) { return B > 0 ? raster_workspace_bytes(B) : -1; }
+long long rib_rasterize_workspace_bytes(int B, int H, int W) {
+  return B > 0 && H > 0 && W > 0 ? raster_workspace_bytes(B, H, W) : -1;
+}
 
 int rib_rasterize(const double* joints, int B, int H, int W, const double* gauss_taps, double skeleton_thres,
                   double foot_thres, float* label, void* label_planar, void* workspace, long long workspace_bytes,
@@ -131,6 +133,14 @@ int rib_generator_plan_text(rib_generator* g, char* buf, long long cap) {
   RIB_GUARD_BEGIN
   RIB_REQUIRE(g && buf && cap > 0, "rib_generator_plan_text: bad argument");
   return generator_plan_text(reinterpret_cast<Generator*>(g), buf, cap);
+  RIB_GUARD_END
+}
+
+int rib_tune_log(char* buf, long long cap) {
+  RIB_GUARD_BEGIN
+  RIB_REQUIRE(buf && cap > 0, "rib_tune_log: bad argument");
+  RIB_REQUIRE(generator_tune_log(buf, cap) == 0, "rib_tune_log: buffer too small");
+  return 0;
   RIB_GUARD_END
 }
 

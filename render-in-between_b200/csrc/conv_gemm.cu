@@ -10,6 +10,7 @@
 #include "conv_gemm.cuh"
 
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -24,9 +25,13 @@ static constexpr int kNumSms = 148;
 struct TapGeom {
   int tile, poff;
 };
-__device__ __forceinline__ TapGeom tap_geom(const ConvGemmParams& p, bool src1, int t) {
+__device__ __forceinline__ TapGeom tap_geom(const ConvGemmParams& p, bool src1, int t, int par) {
   TapGeom g;
   g.tile = 0;
+  if (p.ntaps == 4) {  // sub-pixel conv: tap (a, b) of output parity (py, px) reads low-res pixel (y - 1 + py + a, x - 1 + px + b)
+    g.poff = ((par >> 1) + (t >> 1)) * p.halo_w + (par & 1) + (t & 1);
+    return g;
+  }
   if (src1) {  // 1x1 second source, loaded with the same halo box: centre pixel
     g.poff = p.halo ? p.halo_w + 1 : 0;
     return g;
@@ -87,14 +92,18 @@ __device__ __forceinline__ const act_t* planar_at(const PlanarRef& r, int n, int
 
 // Bring-up mainloop: plain loads and FMAs for one pixel x 16 columns (selected only through
 // rib_debug_set_simt(); used to bisect tcgen05/TMA problems, never in the measured path).
-__device__ void simt_chunk(const ConvGemmParams& p, int n, int oy, int ox, int col0, float* acc) {
+__device__ void simt_chunk(const ConvGemmParams& p, int n, int oy, int ox, int col0, float* acc, int par = 0) {
 #pragma unroll
   for (int c = 0; c < 16; ++c) acc[c] = 0.f;
   const int cin0 = p.stages0 * p.BKc, cin1 = p.stages1 * p.BKc;
   for (int ci = 0; ci < cin0; ++ci) {
     const int grp = ci / p.BKc, cc = ci - grp * p.BKc;
     for (int t = 0; t < p.ntaps; ++t) {
-      const int r = p.ntaps == 9 ? t / 3 : 1, s = p.ntaps == 9 ? t - 3 * (t / 3) : 1;
+      int r = p.ntaps == 9 ? t / 3 : 1, s = p.ntaps == 9 ? t - 3 * (t / 3) : 1;
+      if (p.ntaps == 4) {
+        r = (par >> 1) + (t >> 1);
+        s = (par & 1) + (t & 1);
+      }
       const int iy = oy * p.stride + r - 1, ix = ox * p.stride + s - 1;
       if (iy < 0 || ix < 0 || iy >= p.Hin || ix >= p.Win) continue;
       // a stride-2 input is parity-planar: [plane][py][px][H/2][W/2][8]
@@ -161,6 +170,7 @@ template <int KK, int MT>
 __device__ __forceinline__ void issue_group_nt(int nt, const IssueCtx& c, uint32_t a_lo, const uint32_t* tap,
                                                const uint32_t* mk, uint32_t b_lo, uint32_t d0, uint32_t acc_first) {
   if (nt == 9) issue_group<9, KK, MT>(c, a_lo, tap, mk, b_lo, d0, acc_first);
+  else if (nt == 4) issue_group<4, KK, MT>(c, a_lo, tap, mk, b_lo, d0, acc_first);
   else issue_group<1, KK, MT>(c, a_lo, tap, mk, b_lo, d0, acc_first);
 }
 
@@ -193,6 +203,10 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (kEpiGroups == 1 ? (BN <=
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int ntile = blockIdx.x % p.n_tiles;
+  // sub-pixel conv: the N tiles of output parity `par` cover channels [ncol0, ncol0 + BN) of that parity's map
+  const int tiles_per_par = p.subpix ? p.n_tiles >> 2 : p.n_tiles;
+  const int par = ntile / tiles_per_par;
+  const int ncol0 = (ntile - par * tiles_per_par) * BN;
   const int cta_m = blockIdx.x / p.n_tiles;
   const int cta_groups = gridDim.x / p.n_tiles;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
@@ -228,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (kEpiGroups == 1 ? (BN <=
   if (warp >= 2 && warp < 6) {
     const int e = threadIdx.x - 64;
     if (e < 10) {
-      const TapGeom tg = tap_geom(p, e == 9, e == 9 ? 0 : e);
+      const TapGeom tg = tap_geom(p, e == 9, e == 9 ? 0 : e, par);
       s_tapoff[e] = (uint32_t)tg.tile * (p.a_tile_bytes >> 4) + (uint32_t)tg.poff;
     }
     for (int c = e; c < BN; c += 128) s_bias[c] = p.bias[ntile * BN + c];
@@ -389,6 +403,7 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (kEpiGroups == 1 ? (BN <=
     const int prow = q * 32 + lane;           // row of the M=128 sub-tile = TMEM lane
     const int ty = p.tw == 8 ? prow >> 3 : prow >> 5, tx = prow & (p.tw - 1);  // 16 x 8 (or 4 x 32) pixel tile
     const size_t HW8 = (size_t)p.H * p.W * 8;
+    const size_t oplane = p.subpix ? 4 * HW8 : HW8;   // EPI_STORE: elements between output planes
     const float slope = p.act == ACT_LRELU ? 0.2f : 1.0f;  // lrelu(v) = max(v, 0.2 v); identity = max(v, v)
     float* sbuf = reinterpret_cast<float*>(sStat) + (warp - 2) * kStatWarpFloats;
     float* s_auxg = s_aux + eg * 8 * BN;                // this group's scratch (statistics slots / SPADE coefficients)
@@ -441,7 +456,7 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (kEpiGroups == 1 ? (BN <=
       }
       epi_bar(eg);
       for (int c = e; c < BN; c += 128) {
-        const int col = ntile * BN + c;
+        const int col = ncol0 + c;
         if (col < p.n_valid) {
           const float t1 = ((s_auxg[c] + s_auxg[2 * BN + c]) + s_auxg[4 * BN + c]) + s_auxg[6 * BN + c];
           const float t2 = ((s_auxg[BN + c] + s_auxg[3 * BN + c]) + s_auxg[5 * BN + c]) + s_auxg[7 * BN + c];
@@ -527,7 +542,9 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (kEpiGroups == 1 ? (BN <=
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols + m * BN);
 
         if (MODE == EPI_STORE) {
-          act_t* obase = p.out.p + (size_t)n * p.out.bstride + (size_t)((ntile * BN) >> 3) * HW8 + pix8;
+          // (sub-pixel conv: planes of the (2H, 2W) output are 4 HW8 apart and parity `par` is a dense H x W image)
+          act_t* obase = p.subpix ? p.out.p + (size_t)n * p.out.bstride + ((size_t)(ncol0 >> 3) * 4 + par) * HW8 + pix8
+                                  : p.out.p + (size_t)n * p.out.bstride + (size_t)((ntile * BN) >> 3) * HW8 + pix8;
           // parity-planar copy for a stride-2 consumer: [plane][py][px][H/2][W/2][8]
           act_t* obase2 = nullptr;
           if (p.has_out2)
@@ -546,7 +563,7 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (kEpiGroups == 1 ? (BN <=
             }
             float v[16];
             if (SIMT) {
-              simt_chunk(p, n, oy, ox, ntile * BN + j * 16, v);
+              simt_chunk(p, n, oy, ox, ntile * BN + j * 16, v, par);
             } else {
               tmem_ld16_wait(r[j & 1]);
               if (j + 1 < NCH) tmem_ld16_issue(trow + (uint32_t)((j + 1) * 16), r[(j + 1) & 1]);
@@ -607,8 +624,8 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (kEpiGroups == 1 ? (BN <=
               }
 #pragma unroll
               for (int c = 0; c < 8; ++c) o[c] = pack2(v[2 * c], v[2 * c + 1]);
-              *reinterpret_cast<uint4*>(obase + (size_t)(2 * j) * HW8) = make_uint4(o[0], o[1], o[2], o[3]);
-              *reinterpret_cast<uint4*>(obase + (size_t)(2 * j + 1) * HW8) = make_uint4(o[4], o[5], o[6], o[7]);
+              *reinterpret_cast<uint4*>(obase + (size_t)(2 * j) * oplane) = make_uint4(o[0], o[1], o[2], o[3]);
+              *reinterpret_cast<uint4*>(obase + (size_t)(2 * j + 1) * oplane) = make_uint4(o[4], o[5], o[6], o[7]);
               if (p.has_out2) {
                 *reinterpret_cast<uint4*>(obase2 + (size_t)(2 * j) * HW8) = make_uint4(o[0], o[1], o[2], o[3]);
                 *reinterpret_cast<uint4*>(obase2 + (size_t)(2 * j + 1) * HW8) = make_uint4(o[4], o[5], o[6], o[7]);
@@ -825,8 +842,9 @@ int choose_bkc(int cin0, int cin1, int taps, int BN, int stride) {
 }
 
 int conv_gemm_configure(ConvGemmParams* p, int B, int Hout, int Wout, int cin0, int cin1, int taps, int stride,
-                        int BN, int n_pad) {
-  RIB_REQUIRE(taps == 1 || taps == 9, "conv_gemm: 1x1 or 3x3 only");
+                        int BN, int n_pad, const ConvTune* tune) {
+  RIB_REQUIRE(taps == 1 || taps == 9 || taps == 4, "conv_gemm: 1x1, 3x3 or sub-pixel 2x2 only");
+  RIB_REQUIRE(taps != 4 || (stride == 1 && cin1 == 0 && (n_pad / BN) % 4 == 0), "conv_gemm: bad sub-pixel conv");
   RIB_REQUIRE(stride == 1 || (stride == 2 && taps == 9 && cin1 == 0), "conv_gemm: stride 2 needs a plain 3x3");
   RIB_REQUIRE(BN >= 16 && BN <= 128 && (BN & (BN - 1)) == 0 && n_pad % BN == 0, "conv_gemm: bad BN");
   const int bkc = choose_bkc(cin0, cin1, taps, BN, stride);
@@ -842,7 +860,8 @@ int conv_gemm_configure(ConvGemmParams* p, int B, int Hout, int Wout, int cin0, 
   p->stages1 = cin1 / bkc;
   p->ntaps = taps;
   p->stride = stride;
-  p->halo = taps == 9 ? 1 : 0;
+  p->halo = taps == 1 ? 0 : 1;
+  p->subpix = taps == 4 ? 1 : 0;
   p->b_tap_bytes = (uint32_t)(BN * bkc * 2);
   const int n_bt = p->stages0 * taps + p->stages1;
   const size_t b_all = (size_t)n_bt * p->b_tap_bytes;
@@ -874,13 +893,22 @@ int conv_gemm_configure(ConvGemmParams* p, int B, int Hout, int Wout, int cin0, 
     p->g_slot_bytes = p->a_slot_bytes;
   };
   const size_t kSmemMax = (size_t)227 * 1024, kOverhead = 12 * 1024;  // barriers, bias, statistics slots, alignment
-  // (stride 2 is not bound by weight traffic: stacking sub-tiles does not help it)
-  const bool can_mt2 = Hout >= 2 * p->th && stride == 1;
+  const bool can_mt2 = Hout >= 2 * p->th;
   p->b_ring = 1;  // unused
-  if (b_all <= kSmallResident) {
-    // small weights stay resident; bandwidth-bound layers: keep the CTA near 100 KB so that several fit on an SM
+  // Residency policy: 1 = weights resident, CTA kept near 100 KB so that several fit on an SM (bandwidth-bound layers);
+  // 2 = weights resident, one CTA per SM with the rest of shared memory as halo ring; 3 = weights streamed with the
+  // halo tiles.  Defaults by weight size; a ConvTune (the plan-time auto-tuner, generator.cu) may override policy and MT.
+  int policy = b_all <= kSmallResident ? 1 : (b_all <= kBigResident ? 2 : 3);
+  if (tune != nullptr && tune->policy != 0) policy = tune->policy;
+  RIB_REQUIRE(policy >= 1 && policy <= 3 && (policy == 3 ? b_all > kSmallResident : b_all <= kBigResident),
+              "conv_gemm: residency policy does not apply to this layer");
+  int mt = policy == 1 ? 1 : (can_mt2 ? 2 : 1);
+  const bool mt_forced = tune != nullptr && tune->mt != 0;
+  if (mt_forced) mt = tune->mt;
+  RIB_REQUIRE(mt == 1 || (mt == 2 && can_mt2), "conv_gemm: cannot stack two sub-tiles here");
+  if (policy == 1) {
     p->b_resident = 1;
-    set_geometry(1);
+    set_geometry(mt);
     const size_t budget = (size_t)100 * 1024 - b_all - kStatStageBytes;
     int ring = (int)(budget / p->a_slot_bytes);
     const int want = G <= 2 ? 4 : 2 * G;
@@ -888,25 +916,30 @@ int conv_gemm_configure(ConvGemmParams* p, int B, int Hout, int Wout, int cin0, 
     if (ring > 8) ring = 8;
     if (ring < 2) ring = 2;
     p->a_ring = ring;
-  } else if (b_all <= kBigResident) {
-    // medium weights: one CTA per SM keeps its whole N tile of weights in shared memory (no weight traffic per
-    // output tile at all); the remaining space is the halo-tile ring
+    RIB_REQUIRE(b_all + kStatStageBytes + kOverhead + (size_t)ring * p->a_slot_bytes <= kSmemMax,
+                "conv_gemm: halo ring does not fit beside the resident weights");
+  } else if (policy == 2) {
     p->b_resident = 1;
     const size_t fixed = b_all + kStatStageBytes + kOverhead;
-    set_geometry(can_mt2 ? 2 : 1);
-    if (fixed + 2 * (size_t)p->a_slot_bytes > kSmemMax) set_geometry(1);
+    set_geometry(mt);
+    if (!mt_forced && fixed + 2 * (size_t)p->a_slot_bytes > kSmemMax) set_geometry(1);
     RIB_REQUIRE(fixed + 2 * (size_t)p->a_slot_bytes <= kSmemMax, "conv_gemm: resident weights do not fit");
     int ring = (int)((kSmemMax - fixed) / p->a_slot_bytes);
     p->a_ring = ring > 4 ? 4 : ring;
   } else {
-    // large weights are streamed: a ring slot holds the halo tile of a channel group AND that group's weight
-    // sub-tiles (one barrier round trip per group); two stacked sub-tiles halve the weight traffic per pixel
+    // a ring slot holds the halo tile(s) of a channel group AND that group's weight sub-tiles (one barrier round trip
+    // per group); two stacked sub-tiles halve the weight traffic per pixel (measured: also for stride 2, whose four
+    // parity tiles otherwise make the layer L2-bound)
     p->b_resident = 0;
-    set_geometry(can_mt2 ? 2 : 1);
-    p->b_off = (p->a_slot_bytes + 1023u) & ~1023u;
-    p->g_slot_bytes = p->b_off + (uint32_t)taps * p->b_tap_bytes;
     const size_t budget = kSmemMax - kStatStageBytes - kOverhead;
-    int ring = (int)(budget / p->g_slot_bytes);
+    for (;;) {
+      set_geometry(mt);
+      p->b_off = (p->a_slot_bytes + 1023u) & ~1023u;
+      p->g_slot_bytes = p->b_off + (uint32_t)taps * p->b_tap_bytes;
+      if (budget / p->g_slot_bytes >= 2 || mt == 1 || mt_forced) break;
+      mt = 1;
+    }
+    const int ring = (int)(budget / p->g_slot_bytes);
     RIB_REQUIRE(ring >= 2, "conv_gemm: streamed group slots do not fit");
     p->a_ring = ring > 4 ? 4 : ring;
   }

@@ -25,6 +25,10 @@
 //   EPI_SPADE  the GEMM produces [gamma|beta] = conv1x1(cond); the epilogue applies
 //              lrelu?((x - mean) * rstd * (1 + gamma) + beta)   activation_norm.py:211-234
 //              (x may be read through a nearest x2 up-sampling, generator.py:249)
+//              sub-pixel form (ConvGemmParams::subpix) of "nearest x2 -> conv3x3" (generator.py:478-481 up_flow): output
+//              pixel (2y+py, 2x+px) only sees the 2x2 low-resolution neighbourhood {y-1+py, y+py} x {x-1+px, x+px} with
+//              the 3x3 weights summed per source pixel, so the up-sampled map is never written or read and the MACs
+//              drop by 9/4
 //   EPI_FINAL  bias -> tanh / sigmoid -> fp32 NCHW (+ optional 16-bit planar copy)  generator.py:228, :484-485
 #pragma once
 #include "common.cuh"
@@ -55,6 +59,9 @@ struct alignas(64) ConvGemmParams {
   int BKc;              // channels per group = per halo tile (16/32/64)
   int stages0, stages1; // channel groups of source 0 / source 1
   int ntaps, stride, halo;
+  int subpix;           // 1: 3x3 conv on a nearest-x2 up-sampled map, folded into four 2x2 convs on the LOW-resolution map
+                        //    (ntaps = 4; N tile -> output parity (py, px) = ntile / (n_tiles / 4); the output, twice the
+                        //    size of H x W, is written parity-planar [plane][py][px][H][W][8])
   int s2_parity;        // stride 2: 1 = the input is a parity-planar map, 0 = strided parity views of a normal map
   int a_ring, b_ring;   // ring slots (one channel group each); b_ring is unused
   int b_resident;       // 1: all weight sub-tiles of this CTA's N tile stay in shared memory
@@ -108,9 +115,17 @@ int make_tmap_act_s2_strided(CUtensorMap* m, const act_t* base, int C, int W, in
 int make_tmap_w(CUtensorMap* m, const act_t* w, int K, int N, int bkc, int boxN, int taps);
 // Channels per pipeline stage for a layer (also fixes the K ordering of the packed weights).
 int choose_bkc(int cin0, int cin1, int taps, int BN, int stride);
-// Fills the tiling / pipeline fields of p (everything except tensor maps and epilogue pointers).
+// Tiling choices the plan-time auto-tuner may override (0 = the default heuristic):
+//   mt      M=128 sub-tiles stacked per super-tile (1 or 2)
+//   policy  1 = resident weights, ~100 KB CTAs (several per SM); 2 = resident weights, one CTA per SM, deep halo ring;
+//           3 = weights streamed with the halo tiles
+struct ConvTune {
+  int mt = 0, policy = 0;
+};
+// Fills the tiling / pipeline fields of p (everything except tensor maps and epilogue pointers).  Returns non-zero
+// when the requested tuning does not fit the layer.
 int conv_gemm_configure(ConvGemmParams* p, int B, int Hout, int Wout, int cin0, int cin1, int taps, int stride,
-                        int BN, int n_pad);
+                        int BN, int n_pad, const ConvTune* tune = nullptr);
 size_t conv_gemm_smem_bytes(const ConvGemmParams& p);
 int launch_conv_gemm(const ConvGemmParams& p, int mode, cudaStream_t stream);
 long long conv_gemm_launch_count();

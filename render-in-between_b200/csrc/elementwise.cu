@@ -134,8 +134,78 @@ __global__ void in_apply_kernel(const InApplyParams p) {
   }
 }
 
+// Same operation for the parity-planar output of a sub-pixel conv: one thread reads the two x parities of an output
+// pixel pair (two coalesced streams) and writes 32 contiguous bytes of the normal map.
+__global__ void in_apply_unparity_kernel(const InApplyParams p) {
+  extern __shared__ float s_coef[];  // [2][C]: scale, shift
+  const int n = blockIdx.y;
+  const double cnt = (double)p.H * (double)p.W;
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x)
+    in_coeffs(p.astats, p.aw, p.ab, n, p.C, c, cnt, p.eps, &s_coef[c], &s_coef[p.C + c]);
+  __syncthreads();
+  const size_t HW = (size_t)p.H * p.W, Q = HW >> 2;
+  const int Wh = p.W >> 1;
+  const size_t npair = (size_t)(p.C / 8) * p.H * Wh;
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  constexpr int U = 2;
+  const act_t* ab = p.a + (size_t)n * p.a_bs;
+  act_t* ob = p.out + (size_t)n * p.o_bs;
+  for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < npair; i0 += U * step) {
+    uint4 v0[U], v1[U];
+    size_t dst[U];
+    int c0[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t i = i0 + u * step;
+      if (i < npair) {
+        const int x2 = (int)(i % Wh);
+        const size_t r = i / Wh;
+        const int y = (int)(r % p.H);
+        const size_t pl = r / p.H;
+        const size_t src = pl * HW + (size_t)((y & 1) * 2) * Q + (size_t)(y >> 1) * Wh + x2;
+        v0[u] = *reinterpret_cast<const uint4*>(ab + src * 8);
+        v1[u] = *reinterpret_cast<const uint4*>(ab + (src + Q) * 8);
+        dst[u] = (pl * HW + (size_t)y * p.W + 2 * x2) * 8;
+        c0[u] = (int)pl * 8;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i0 + u * step >= npair) break;
+      const uint32_t au[8] = {v0[u].x, v0[u].y, v0[u].z, v0[u].w, v1[u].x, v1[u].y, v1[u].z, v1[u].w};
+      uint32_t o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float a, b;
+        unpack2(au[k], a, b);
+        const int c = c0[u] + 2 * (k & 3);
+        a = a * s_coef[c] + s_coef[p.C + c];
+        b = b * s_coef[c + 1] + s_coef[p.C + c + 1];
+        if (p.act) {
+          a = lrelu02(a);
+          b = lrelu02(b);
+        }
+        o[k] = pack2(a, b);
+      }
+      *reinterpret_cast<uint4*>(ob + dst[u]) = make_uint4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<uint4*>(ob + dst[u] + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+  }
+}
+
 int launch_in_apply(const InApplyParams& p, cudaStream_t s) {
   RIB_REQUIRE(p.C % 8 == 0, "in_apply: channels must be a multiple of 8");
+  if (p.in_parity) {
+    RIB_REQUIRE(p.b == nullptr && !p.ups && !p.out_parity && p.H % 2 == 0 && p.W % 2 == 0,
+                "in_apply: the parity-planar input form is single-term, same-size, normal output");
+    const size_t npair = (size_t)p.H * (p.W / 2) * (p.C / 8);
+    unsigned gx = (unsigned)((npair + 255) / 256);
+    unsigned want = (148u * 8u + (unsigned)p.B - 1u) / (unsigned)p.B;
+    if (gx > want) gx = want;
+    in_apply_unparity_kernel<<<dim3(gx, (unsigned)p.B), 256, 2 * p.C * sizeof(float), s>>>(p);
+    RIB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   const size_t nvec = (size_t)p.H * p.W * (p.C / 8);
   const int threads = 256;
   // every block first derives the normalisation coefficients of its image (fp64 divide + sqrt per channel),
@@ -390,6 +460,28 @@ __device__ __forceinline__ int pack_row(const PackWeightParams& p, int co) {
   return p.row_off + (c / p.spade_CT) * 2 * p.spade_CT + half * p.spade_CT + c % p.spade_CT;
 }
 
+__global__ void pack_weight_subpix_kernel(const PackWeightParams p) {
+  const float scale = p.sigma_inv ? p.sigma_inv[0] : 1.f;
+  const int py = p.subpix_parity >> 1, px = p.subpix_parity & 1;
+  const size_t total = (size_t)p.Cout * p.Cin * 4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int tap = (int)(i & 3), a = tap >> 1, b = tap & 1;
+    const size_t r = i >> 2;
+    const int ci = (int)(r % p.Cin), co = (int)(r / p.Cin);
+    // source rows / columns of the 3x3 kernel that land on low-resolution neighbour a / b for this output parity
+    const int r0 = py == 0 ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2), r1 = py == 0 ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
+    const int s0 = px == 0 ? (b == 0 ? 0 : 1) : (b == 0 ? 0 : 2), s1 = px == 0 ? (b == 0 ? 0 : 2) : (b == 0 ? 1 : 2);
+    const float* w9 = p.w + r * 9;
+    float acc = 0.f;
+    for (int rr = r0; rr <= r1; ++rr)
+      for (int ss = s0; ss <= s1; ++ss) acc += p.sigma_inv ? w9[rr * 3 + ss] * scale : w9[rr * 3 + ss];
+    p.dst[(size_t)pack_row(p, co) * p.ktotal + p.koff + ((ci / p.bkc) * 4 + tap) * p.bkc + ci % p.bkc] = f2act(acc);
+  }
+  if (p.bias_dst != nullptr)
+    for (int co = blockIdx.x * blockDim.x + threadIdx.x; co < p.Cout; co += gridDim.x * blockDim.x)
+      p.bias_dst[pack_row(p, co)] = p.bias ? p.bias[co] : 0.f;
+}
+
 __global__ void pack_weight_kernel(const PackWeightParams p) {
   const float scale = p.sigma_inv ? p.sigma_inv[0] : 1.f;
   const size_t total = (size_t)p.Cout * p.Cin * p.taps;
@@ -416,7 +508,12 @@ int launch_pack_weight(const PackWeightParams& p, cudaStream_t s) {
   const size_t total = (size_t)p.Cout * p.Cin * p.taps;
   unsigned blocks = (unsigned)((total + 255) / 256);
   if (blocks > 2048u) blocks = 2048u;
-  pack_weight_kernel<<<blocks, 256, 0, s>>>(p);
+  if (p.subpix) {
+    RIB_REQUIRE(p.taps == 9 && p.spade_C == 0 && !p.bias_accumulate, "pack: the sub-pixel form needs a plain 3x3 conv");
+    pack_weight_subpix_kernel<<<blocks, 256, 0, s>>>(p);
+  } else {
+    pack_weight_kernel<<<blocks, 256, 0, s>>>(p);
+  }
   RIB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -28,6 +28,7 @@ struct InApplyParams {
   int B, H, W, C;  // input spatial size
   int act;         // 0 none, 1 leaky-relu(0.2) on the first term
   int ups;         // 1: write each pixel to the 2x2 block of a (2H, 2W) output
+  int in_parity;   // 1: `a` is a parity-planar (H, W) map (the output of a sub-pixel conv); the output is a normal map
   int out_parity;  // 1: write the output in parity-planar layout [plane][py][px][H/2][W/2][8] (feeds a stride-2 conv)
   float eps;
 };
@@ -66,6 +67,10 @@ struct PackWeightParams {
   int ktotal, koff, bkc, row_off;
   int spade_C, spade_CT;  // 0 for plain convs
   int bias_accumulate;    // add into bias_dst instead of overwriting (fused shortcut)
+  // Sub-pixel form of "nearest x2 -> conv3x3" (taps == 9 in the source): emit the 2x2 kernel of output parity
+  // (py, px) = (subpix_parity >> 1, subpix_parity & 1), K order (channel group, tap (a, b), channel) with 4 taps:
+  //   w2[a][b] = sum of w[r][s] over r in R(py, a), s in R(px, b);  R(0,0)={0} R(0,1)={1,2} R(1,0)={0,1} R(1,1)={2}
+  int subpix, subpix_parity;
 };
 int launch_pack_weight(const PackWeightParams& p, cudaStream_t s);
 

@@ -18,6 +18,7 @@
 #include <atomic>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <unordered_map>
 #include <vector>
 
@@ -65,6 +66,9 @@ struct Op {
   // gemm
   ConvGemmParams g;
   int mode = 0;
+  const GemmLayer* layer = nullptr;  // for re-tiling (auto-tuner)
+  View in0, in1;
+  bool has_in1 = false;
   // in_apply
   InApplyParams ia;
   // pool
@@ -156,6 +160,7 @@ struct PackJob {  // one reference conv placed inside a GEMM layer
   bool sn;
   int cout, cin, taps, koff, cin_pad /* padded input channels (informational) */, row_off, spade_C, spade_CT;
   bool bias_acc;
+  int subpix = 0, parity = 0;  // sub-pixel form of a conv that follows nearest x2 (see PackWeightParams)
 };
 
 int spade_ct(int C) { return std::min(C, 64); }
@@ -252,8 +257,12 @@ int generator_create(const rib_gen_config* cfg, const rib_tensor* tensors, int n
   for (int k = 0; k < c.mask_down; ++k) {
     const int i = c.mask_down - 1 - k;
     const std::string ln = "mask.up." + std::to_string(k);
-    add_layer(G, ln, mask_nfilt(c, i), mask_nfilt(c, i), mask_nfilt(c, i + 1), 9, 0);
-    jobs.push_back({ln, f + "up_flow." + std::to_string(2 * k + 1) + ".layers.conv", true, mask_nfilt(c, i), mask_nfilt(c, i + 1), 9, 0, mask_nfilt(c, i + 1), 0, 0, 0, false});
+    // nn.Upsample(2) -> conv3x3 (generator.py:478-481) runs as four 2x2 convs on the low-resolution map, one per output
+    // parity: N = 4 x Cout, K = 4 x Cin
+    const int co = mask_nfilt(c, i), ci = mask_nfilt(c, i + 1);
+    add_layer(G, ln, co, 4 * co, ci, 4, 0, std::min(co, 128));
+    for (int par = 0; par < 4; ++par)
+      jobs.push_back({ln, f + "up_flow." + std::to_string(2 * k + 1) + ".layers.conv", true, co, ci, 9, 0, ci, par * co, 0, 0, false, 1, par});
   }
   add_layer(G, "mask.conv_mask", 1, 16, c.mask_nf, 9, 0);
   jobs.push_back({"mask.conv_mask", f + "conv_mask.0.layers.conv", false, 1, c.mask_nf, 9, 0, c.mask_nf, 0, 0, 0, false});
@@ -325,6 +334,8 @@ int generator_create(const rib_gen_config* cfg, const rib_tensor* tensors, int n
     pp.spade_C = pj.spade_C;
     pp.spade_CT = pj.spade_CT;
     pp.bias_accumulate = pj.bias_acc ? 1 : 0;
+    pp.subpix = pj.subpix;
+    pp.subpix_parity = pj.parity;
     rc = launch_pack_weight(pp, stream);
     if (rc) return fail(rc);
   }
@@ -429,23 +440,49 @@ struct PlanBuilder {
     p.bias = L.bias;
     p.n_valid = L.n_valid;
     p.eps = 1e-5f;
-    if (real && rc == 0) {
-      const int halo_h = (int)(p.lbo / 16u) / p.halo_w;
-      if (stride == 1) {
-        rc = make_tmap_act_s1(&p.amap[0], in0.p, in0.C, in0.W, in0.H, B, in0.bstride(), p.BKc, p.halo_w, halo_h);
-        if (!rc && in1)
-          rc = make_tmap_act_s1(&p.amap[1], in1->p, in1->C, in1->W, in1->H, B, in1->bstride(), p.BKc, p.halo_w, halo_h);
-      } else {
-        for (int py = 0; py < 2 && !rc; ++py)
-          for (int px = 0; px < 2 && !rc; ++px)
-            rc = in0.parity ? make_tmap_act_s2(&p.amap[py * 2 + px], in0.p, in0.C, in0.W, in0.H, B, in0.bstride(), py, px,
-                                               p.BKc, p.halo_w, halo_h)
-                            : make_tmap_act_s2_strided(&p.amap[py * 2 + px], in0.p, in0.C, in0.W, in0.H, B,
-                                                       in0.bstride(), py, px, p.BKc, p.halo_w, halo_h);
-      }
-      if (!rc) rc = make_tmap_w(&p.bmap, L.w, L.ktotal, L.n_pad, p.BKc, BN, L.taps);
-    }
+    if (real && rc == 0) rc = make_maps(&p, L, in0, in1);
+    last_layer = &L;
+    last_in0 = in0;
+    last_has_in1 = in1 != nullptr;
+    if (in1) last_in1 = *in1;
     return p;
+  }
+
+  // inputs of the most recent gemm_common() call (copied into the Op by push_gemm / conv_final)
+  const GemmLayer* last_layer = nullptr;
+  View last_in0, last_in1;
+  bool last_has_in1 = false;
+
+  // Tensor maps for the tiling currently in p (they depend on the halo box, i.e. on MT).
+  int make_maps(ConvGemmParams* p, const GemmLayer& L, const View& in0, const View* in1) {
+    int r = 0;
+    const int halo_h = (int)(p->lbo / 16u) / p->halo_w;
+    if (p->stride == 1) {
+      r = make_tmap_act_s1(&p->amap[0], in0.p, in0.C, in0.W, in0.H, B, in0.bstride(), p->BKc, p->halo_w, halo_h);
+      if (!r && in1)
+        r = make_tmap_act_s1(&p->amap[1], in1->p, in1->C, in1->W, in1->H, B, in1->bstride(), p->BKc, p->halo_w, halo_h);
+    } else {
+      for (int py = 0; py < 2 && !r; ++py)
+        for (int px = 0; px < 2 && !r; ++px)
+          r = in0.parity ? make_tmap_act_s2(&p->amap[py * 2 + px], in0.p, in0.C, in0.W, in0.H, B, in0.bstride(), py, px,
+                                            p->BKc, p->halo_w, halo_h)
+                         : make_tmap_act_s2_strided(&p->amap[py * 2 + px], in0.p, in0.C, in0.W, in0.H, B, in0.bstride(),
+                                                    py, px, p->BKc, p->halo_w, halo_h);
+    }
+    if (!r) r = make_tmap_w(&p->bmap, L.w, L.ktotal, L.n_pad, p->BKc, p->BN, L.taps);
+    return r;
+  }
+
+  // The same launch with another tiling: configure() rewrites only the geometry fields, the epilogue stays.
+  int retile(const Op& op, const ConvTune& t, ConvGemmParams* out) {
+    ConvGemmParams p = op.g;
+    const GemmLayer& L = *op.layer;
+    int r = conv_gemm_configure(&p, B, p.H, p.W, L.cin0, L.cin1, L.taps, L.stride, p.BN, L.n_pad, &t);
+    if (r || p.BKc != L.bkc) return r ? r : -4;
+    r = make_maps(&p, L, op.in0, op.has_in1 ? &op.in1 : nullptr);
+    if (r) return r;
+    *out = p;
+    return 0;
   }
 
   void push_gemm(const ConvGemmParams& p, int mode, const std::string& name) {
@@ -454,6 +491,10 @@ struct PlanBuilder {
     op.name = name;
     op.g = p;
     op.mode = mode;
+    op.layer = last_layer;
+    op.in0 = last_in0;
+    op.in1 = last_in1;
+    op.has_in1 = last_has_in1;
     ops.push_back(op);
   }
 
@@ -469,6 +510,20 @@ struct PlanBuilder {
     p.act = act;
     p.has_res = res ? 1 : 0;
     if (res) p.res = res->ref();
+    push_gemm(p, EPI_STORE, lname);
+  }
+
+  // conv3x3(nearest_x2(in0)) + bias as a sub-pixel conv: `out` is the parity-planar (2H, 2W) raw map
+  void conv_subpix(const std::string& lname, const View& in0, const View& out, double* stats) {
+    const GemmLayer& L = G->layers.at(lname);
+    if (out.H != 2 * in0.H || out.W != 2 * in0.W || !out.parity || out.C != L.n_valid) {
+      set_error("plan: bad sub-pixel conv output in " + lname);
+      rc = -4;
+    }
+    ConvGemmParams p = gemm_common(L, in0, nullptr, 1, in0.H, in0.W, L.BN);
+    p.out = out.ref();
+    p.stats = stats;
+    p.act = ACT_NONE;
     push_gemm(p, EPI_STORE, lname);
   }
 
@@ -540,6 +595,7 @@ struct PlanBuilder {
     p.C = a.C;
     p.act = act;
     p.ups = ups ? 1 : 0;
+    p.in_parity = a.parity ? 1 : 0;
     p.out_parity = out.parity ? 1 : 0;
     p.eps = 1e-5f;
     ops.push_back(op);
@@ -576,6 +632,122 @@ struct PlanBuilder {
 };
 
 }  // namespace
+
+// ---- plan-time auto-tuner ---------------------------------------------------------------------
+// Which tiling is fastest for a layer (stacked sub-tiles or not, several ~100 KB CTAs per SM or one big one, weights
+// resident or streamed) depends on how its halo ring, TMEM footprint and epilogue balance out; the measurements in
+// profiles/r1f_autotune_candidates.txt show no simple rule.  So the first plan for a given launch shape times the
+// candidates on the real buffers (CUDA events, best of 3) and every later plan of this process re-uses the choice.
+// RIB_AUTOTUNE=0 keeps the default heuristics of conv_gemm_configure().
+namespace {
+
+std::mutex g_tune_mu;
+std::map<std::string, ConvTune> g_tune_cache;
+std::string g_tune_log;
+
+bool autotune_enabled() {
+  static const bool on = !(getenv("RIB_AUTOTUNE") != nullptr && atoi(getenv("RIB_AUTOTUNE")) == 0);
+  return on;
+}
+
+std::string tune_key(const Op& op) {
+  const ConvGemmParams& p = op.g;
+  const GemmLayer& L = *op.layer;
+  char buf[256];
+  snprintf(buf, sizeof(buf), "m%d B%d H%d W%d c%d+%d t%d s%d BN%d N%d r%d o%d st%d u%d q%d par%d", op.mode, p.B, p.H, p.W,
+           L.cin0, L.cin1, L.taps, L.stride, p.BN, L.n_pad, p.has_res, p.has_out2, p.stats != nullptr, p.ups,
+           op.mode == EPI_SPADE ? p.n_tiles * p.BN / (2 * p.C) : 0, p.s2_parity);
+  return buf;
+}
+
+float time_gemm(const ConvGemmParams& p, int mode, cudaStream_t s) {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return -1.f;
+  float best = -1.f;
+  if (launch_conv_gemm(p, mode, s) == 0) {  // warm-up (also sets the kernel's shared-memory attribute)
+    for (int r = 0; r < 3; ++r) {
+      cudaEventRecord(e0, s);
+      if (launch_conv_gemm(p, mode, s) != 0) break;
+      cudaEventRecord(e1, s);
+      if (cudaEventSynchronize(e1) != cudaSuccess) break;
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (best < 0.f || ms < best) best = ms;
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return best;
+}
+
+bool same_tiling(const ConvGemmParams& a, const ConvGemmParams& b) {
+  return a.MT == b.MT && a.a_ring == b.a_ring && a.g_slot_bytes == b.g_slot_bytes && a.b_resident == b.b_resident;
+}
+
+void autotune(PlanBuilder& pb, cudaStream_t stream) {
+  std::lock_guard<std::mutex> lk(g_tune_mu);
+  for (Op& op : pb.ops) {
+    if (op.kind != OP_GEMM || op.mode == EPI_FINAL || op.layer == nullptr) continue;
+    const std::string key = tune_key(op);
+    auto it = g_tune_cache.find(key);
+    if (it != g_tune_cache.end()) {
+      if (it->second.mt != 0 || it->second.policy != 0) {
+        ConvGemmParams q;
+        if (pb.retile(op, it->second, &q) == 0) op.g = q;
+      }
+      continue;
+    }
+    const float t_def = time_gemm(op.g, op.mode, stream);
+    ConvTune best_tune;  // zeros = keep the default
+    ConvGemmParams best_p = op.g;
+    float best_t = t_def;
+    std::vector<ConvGemmParams> tried{op.g};
+    char line[160];
+    snprintf(line, sizeof(line), "%-20s default MT%d ring%d res%d %.1f us |", op.name.c_str(), op.g.MT, op.g.a_ring,
+             op.g.b_resident, t_def * 1e3f);
+    std::string log = line;
+    if (t_def > 0.f) {
+      for (int policy = 1; policy <= 3; ++policy)
+        for (int mt = 1; mt <= 2; ++mt) {
+          ConvTune t;
+          t.mt = mt;
+          t.policy = policy;
+          ConvGemmParams q;
+          if (pb.retile(op, t, &q) != 0) continue;
+          bool dup = false;
+          for (const ConvGemmParams& o : tried) dup = dup || same_tiling(o, q);
+          if (dup) continue;
+          tried.push_back(q);
+          const float tq = time_gemm(q, op.mode, stream);
+          snprintf(line, sizeof(line), " p%d MT%d ring%d %.1f", policy, mt, q.a_ring, tq * 1e3f);
+          log += line;
+          if (tq > 0.f && tq < best_t) {
+            best_t = tq;
+            best_tune = t;
+            best_p = q;
+          }
+        }
+    }
+    if (best_t >= 0.97f * t_def) {  // not worth leaving the default (and keeps the choice stable run to run)
+      best_tune = ConvTune();
+      best_p = op.g;
+    }
+    snprintf(line, sizeof(line), " -> p%d MT%d", best_tune.policy, best_tune.mt);
+    g_tune_log += log + line + "\n";
+    g_tune_cache[key] = best_tune;
+    op.g = best_p;
+  }
+  set_error("");  // candidates that did not fit left messages behind
+}
+
+}  // namespace
+
+int generator_tune_log(char* buf, long long cap) {
+  std::lock_guard<std::mutex> lk(g_tune_mu);
+  if ((long long)g_tune_log.size() + 1 > cap) return -1;
+  memcpy(buf, g_tune_log.c_str(), g_tune_log.size() + 1);
+  return 0;
+}
 
 static int build_plan(Generator* G, int B, int H, int W, void* wsbase, size_t* bytes_out, cudaStream_t stream) {
   const rib_gen_config& c = G->cfg;
@@ -753,15 +925,15 @@ static int build_plan(Generator* G, int B, int H, int W, void* wsbase, size_t* b
     View raw1 = pb.alloc(rn + ".raw1", rh, rw, mch);
     pb.conv_store(rn + ".conv1", t0, nullptr, 1, raw1, mst["res" + std::to_string(i) + "c1"], ACT_NONE, nullptr);
     const bool last = (i + 1 == c.mask_res);
-    // the last block's output is only consumed through nn.Upsample(2): store it up-sampled
-    View o = last ? pb.alloc(rn, 2 * rh, 2 * rw, mch) : pb.alloc(rn, rh, rw, mch);
+    (void)last;  // the last block's output is only consumed through nn.Upsample(2), which the sub-pixel conv absorbs
+    View o = pb.alloc(rn, rh, rw, mch);
     if (i == 0) {
       View raws = pb.alloc(rn + ".raws", rh, rw, mch);
       pb.conv_store(rn + ".convs", r, nullptr, 1, raws, mst["res0cs"], ACT_NONE, nullptr);
       pb.in_apply(raw1, mst["res0c1"], rp + ".conv_block_1.layers.norm", &raws, mst["res0cs"],
-                  rp + ".conv_block_s.layers.norm", o, 0, last);
+                  rp + ".conv_block_s.layers.norm", o, 0, false);
     } else {
-      pb.in_apply(raw1, mst["res" + std::to_string(i) + "c1"], rp + ".conv_block_1.layers.norm", &r, nullptr, "", o, 0, last);
+      pb.in_apply(raw1, mst["res" + std::to_string(i) + "c1"], rp + ".conv_block_1.layers.norm", &r, nullptr, "", o, 0, false);
     }
     r = o;
   }
@@ -770,11 +942,11 @@ static int build_plan(Generator* G, int B, int H, int W, void* wsbase, size_t* b
     const int h = H >> i, w = W >> i, ch = mask_nfilt(c, i);
     const std::string nm = "mask.up." + std::to_string(k);
     View raw = pb.alloc(nm + ".raw", h, w, ch);
-    pb.conv_store(nm, r, nullptr, 1, raw, mst["up" + std::to_string(k)], ACT_NONE, nullptr);
-    const bool ups = (k + 1 != c.mask_down);
-    View o = pb.alloc(nm, ups ? 2 * h : h, ups ? 2 * w : w, ch);
+    raw.parity = true;
+    pb.conv_subpix(nm, r, raw, mst["up" + std::to_string(k)]);
+    View o = pb.alloc(nm, h, w, ch);
     pb.in_apply(raw, mst["up" + std::to_string(k)], f + "up_flow." + std::to_string(2 * k + 1) + ".layers.norm", nullptr, nullptr,
-                "", o, 1, ups);
+                "", o, 1, false);
     r = o;
   }
   pb.conv_final("mask.conv_mask", r, ACT_SIGMOID, EXT_OUT_MASK, nullptr, 0);
@@ -782,7 +954,7 @@ static int build_plan(Generator* G, int B, int H, int W, void* wsbase, size_t* b
   if (pb.rc) return pb.rc;
   *bytes_out = align_up(pb.ws.off, 1024);
   if (wsbase) {
-    (void)stream;  // padding channels of the staging buffers are written by the pack kernels
+    if (!g_debug_simt && autotune_enabled()) autotune(pb, stream);
     G->ops.swap(pb.ops);
     G->debug_views.swap(pb.views);
     G->pB = B;

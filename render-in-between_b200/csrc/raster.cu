@@ -19,8 +19,10 @@
 // for the pixel's first stamp.  So instead of replaying stamps serially, three data-parallel passes:
 //   prep   per frame: the integer curve of every limb as a lookup table f_e[major coord] -> minor coord
 //   mark   per pixel: enumerate the stamps touching it in order; every stamp after the first one is, by
-//          definition, a stamp that hit an older pixel -> set its flag
-//   paint  per pixel: enumerate again, first stamp -> colour (or colour >> 1 if its flag is set), then average
+//          definition, a stamp that hit an older pixel -> set its flag.  The pixel's colour only depends on the flag
+//          of its FIRST stamp, so both outcomes (first stamp painted as colour / as colour >> 1, then the averaging
+//          chain) are computed here and parked with the first stamp's id in one 64-bit word per pixel
+//   paint  per pixel: pick the outcome by the first stamp's flag; heat-map channels; all stores
 // A stamp (i, j) of a limb touches pixel (y, x) iff f[x - j] == y - i (roles of x / y swapped for steep limbs):
 // 8 table look-ups per limb give the 64-bit set of body stamps, whose bit order is the stamp order.
 #include "raster.cuh"
@@ -62,7 +64,12 @@ struct FrameScratch {
   float win[kJoints][kWin];
 };
 
-long long raster_workspace_bytes(int B) { return (long long)B * (long long)sizeof(FrameScratch); }
+// Workspace = B FrameScratch records, then one 64-bit word per pixel in which `mark` leaves what `paint` needs
+// (see raster_mark_kernel).
+static size_t scratch_bytes(int B) { return ((size_t)B * sizeof(FrameScratch) + 255) & ~(size_t)255; }
+long long raster_workspace_bytes(int B, int H, int W) {
+  return (long long)(scratch_bytes(B) + (size_t)B * H * W * sizeof(unsigned long long));
+}
 
 __device__ __forceinline__ int reflect_idx(int i, int n) {  // ndimage 'reflect': d c b a | a b c d | d c b a
   const int period = 2 * n;
@@ -397,8 +404,12 @@ __device__ __forceinline__ void tile_edges(const FrameScratch* fs, int y0, int x
   __syncthreads();
 }
 
-// mark: every stamp that is not the first one of some pixel hit an older pixel.
-__global__ void __launch_bounds__(256) raster_mark_kernel(FrameScratch* __restrict__ scratch, int H, int W) {
+// mark: every stamp that is not the first one of some pixel hit an older pixel.  Per pixel it leaves
+//   bits 0-23 colour if the first stamp painted `col`, 24-47 colour if it painted col >> 1, 48-52 limb and 53-62 key
+//   of the first stamp, bit 63 = touched at all
+// in `cache` (only tiles that some limb can touch are written; paint skips the others the same way).
+__global__ void __launch_bounds__(256) raster_mark_kernel(FrameScratch* __restrict__ scratch,
+                                                          unsigned long long* __restrict__ cache, int H, int W) {
   __shared__ TileEdges te;
   __shared__ EdgeMeta s_meta[kEdges];
   FrameScratch* fs = scratch + blockIdx.z;
@@ -408,23 +419,46 @@ __global__ void __launch_bounds__(256) raster_mark_kernel(FrameScratch* __restri
   const int y = y0 + (threadIdx.x >> 5);
   const int xb = x0 + (threadIdx.x & 31) * kPxPerThread;
   if (y >= H) return;
+  unsigned long long word[kPxPerThread];
+#pragma unroll
   for (int p = 0; p < kPxPerThread; ++p) {
     const int x = xb + p;
-    if (x >= W) break;
+    word[p] = 0ull;
+    if (x >= W) continue;
     int count = 0;
+    uint32_t ca = 0u, cb = 0u, first = 0u;
     for (int k = 0; k < te.n; ++k) {
       const EdgeMeta& m = s_meta[k];
       if (x < m.bx0 || x > m.bx1 || y < m.by0 || y > m.by1) continue;
       const int e = te.idx[k];
+      const uint32_t col = (uint32_t)c_colors[e][0] | ((uint32_t)c_colors[e][1] << 8) | ((uint32_t)c_colors[e][2] << 16);
       visit_limb(m, fs->f[e], y, x, H, W, [&](int key) {
-        if (count++ > 0) fs->flag[e][key] = 1;
+        if (count++ == 0) {
+          first = (uint32_t)e | ((uint32_t)key << 5);
+          ca = col;
+          cb = avg_color(0u, col);
+        } else {
+          fs->flag[e][key] = 1;
+          ca = avg_color(ca, col);
+          cb = avg_color(cb, col);
+        }
       });
     }
+    if (count > 0)
+      word[p] = (unsigned long long)ca | ((unsigned long long)cb << 24) | ((unsigned long long)first << 48) | (1ull << 63);
+  }
+  unsigned long long* cp = cache + ((size_t)blockIdx.z * H + y) * W + xb;
+  if (xb + kPxPerThread <= W && (W & 3) == 0) {
+    *reinterpret_cast<ulonglong2*>(cp) = make_ulonglong2(word[0], word[1]);
+    *reinterpret_cast<ulonglong2*>(cp + 2) = make_ulonglong2(word[2], word[3]);
+  } else {
+    for (int p = 0; p < kPxPerThread && xb + p < W; ++p) cp[p] = word[p];
   }
 }
 
 // paint: all 22 channels of every pixel, as fp32 NCHW and / or the generator's 16-bit planar input.
 __global__ void __launch_bounds__(256) raster_paint_kernel(const FrameScratch* __restrict__ scratch,
+                                                           const unsigned long long* __restrict__ cache,
                                                            float* __restrict__ label, act_t* __restrict__ planar,
                                                            int H, int W) {
   __shared__ TileEdges te;
@@ -443,22 +477,23 @@ __global__ void __launch_bounds__(256) raster_paint_kernel(const FrameScratch* _
   if (y >= H || xb >= W) return;
   uint32_t rgb[kPxPerThread];
 #pragma unroll
-  for (int p = 0; p < kPxPerThread; ++p) {
-    const int x = xb + p;
-    rgb[p] = 0u;
-    if (x < W) {
-      int count = 0;
-      for (int k = 0; k < te.n; ++k) {
-        const EdgeMeta& m = s_meta[k];
-        if (x < m.bx0 || x > m.bx1 || y < m.by0 || y > m.by1) continue;
-        const int e = te.idx[k];
-        const uint32_t col =
-            (uint32_t)c_colors[e][0] | ((uint32_t)c_colors[e][1] << 8) | ((uint32_t)c_colors[e][2] << 16);
-        visit_limb(m, fs->f[e], y, x, H, W, [&](int key) {
-          if (count++ == 0) rgb[p] = fs->flag[e][key] ? avg_color(0u, col) : col;
-          else rgb[p] = avg_color(rgb[p], col);
-        });
-      }
+  for (int p = 0; p < kPxPerThread; ++p) rgb[p] = 0u;
+  if (te.n > 0) {  // same test as in mark: only then was the cache written
+    const unsigned long long* cp = cache + ((size_t)b * H + y) * W + xb;
+    unsigned long long word[kPxPerThread];
+    if (xb + kPxPerThread <= W && (W & 3) == 0) {
+      const ulonglong2 w0 = *reinterpret_cast<const ulonglong2*>(cp), w1 = *reinterpret_cast<const ulonglong2*>(cp + 2);
+      word[0] = w0.x, word[1] = w0.y, word[2] = w1.x, word[3] = w1.y;
+    } else {
+#pragma unroll
+      for (int p = 0; p < kPxPerThread; ++p) word[p] = xb + p < W ? cp[p] : 0ull;
+    }
+#pragma unroll
+    for (int p = 0; p < kPxPerThread; ++p) {
+      if (!(word[p] >> 63)) continue;
+      const uint32_t first = (uint32_t)(word[p] >> 48) & 0x7fffu;
+      const bool hit_older = fs->flag[first & 31u][first >> 5] != 0;
+      rgb[p] = (uint32_t)(hit_older ? word[p] >> 24 : word[p]) & 0xffffffu;
     }
   }
   const size_t HW = (size_t)H * W;
@@ -512,17 +547,18 @@ int launch_rasterize(const double* joints_dev, int B, int H, int W, const double
   RIB_REQUIRE(H >= 2 && W >= 2 && B >= 1, "rasterize: bad shape");
   RIB_REQUIRE(H <= kMaxDim && W <= kMaxDim, "rasterize: images larger than 1024 px are not supported");
   RIB_REQUIRE(label != nullptr || label_planar != nullptr, "rasterize: no output requested");
-  RIB_REQUIRE(workspace != nullptr && workspace_bytes >= raster_workspace_bytes(B), "rasterize: workspace too small");
+  RIB_REQUIRE(workspace != nullptr && workspace_bytes >= raster_workspace_bytes(B, H, W), "rasterize: workspace too small");
   RIB_REQUIRE(((uintptr_t)workspace & 15) == 0, "rasterize: workspace must be 16-byte aligned");
   GaussTable tab;
   for (int i = 0; i < kTaps; ++i) tab.w[i] = wtab41_host[i];
   FrameScratch* fs = static_cast<FrameScratch*>(workspace);
+  unsigned long long* cache = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(workspace) + scratch_bytes(B));
   raster_prep_kernel<<<dim3(kJoints + 1, B), 256, 0, stream>>>(joints_dev, tab, skeleton_thres, foot_thres, fs, H, W);
   RIB_CHECK_CUDA(cudaGetLastError());
   const dim3 grid(ceil_div(W, kTileCols), ceil_div(H, kTileRows), B);
-  raster_mark_kernel<<<grid, 256, 0, stream>>>(fs, H, W);
+  raster_mark_kernel<<<grid, 256, 0, stream>>>(fs, cache, H, W);
   RIB_CHECK_CUDA(cudaGetLastError());
-  raster_paint_kernel<<<grid, 256, 0, stream>>>(fs, label, label_planar, H, W);
+  raster_paint_kernel<<<grid, 256, 0, stream>>>(fs, cache, label, label_planar, H, W);
   RIB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -5,7 +5,7 @@
 namespace rib {
 
 // Bytes of device scratch launch_rasterize needs for B frames (limb tables, stamp flags, heat-map windows).
-long long raster_workspace_bytes(int B);
+long long raster_workspace_bytes(int B, int H, int W);
 
 // joints_dev: device [B][19][3] float64 (x, y, confidence) in model-pixel coordinates.
 // wtab41_host: host [41] float64 normalised Gaussian taps (scipy _gaussian_kernel1d(sigma=5, radius=20)).

@@ -16,6 +16,7 @@ SYMBOLS = [
     'rib_generator_create', 'rib_generator_destroy', 'rib_generator_workspace_bytes', 'rib_generator_bind', 'rib_generator_forward',
     'rib_debug_set_simt', 'rib_debug_get_simt', 'rib_generator_debug_tensor', 'rib_generator_plan_text', 'rib_act_is_fp16',
     'rib_conv_test_scratch_bytes', 'rib_conv_test', 'rib_profile_enable', 'rib_profile_collect', 'rib_profile_collect_launches',
+    'rib_tune_log',
 ]
 
 
@@ -43,7 +44,7 @@ def _load():
     lib.rib_rasterize.restype = i32
     lib.rib_rasterize.argtypes = [vp, i32, i32, i32, C.POINTER(f64), f64, f64, vp, vp, vp, i64, vp]
     lib.rib_rasterize_workspace_bytes.restype = i64
-    lib.rib_rasterize_workspace_bytes.argtypes = [i32]
+    lib.rib_rasterize_workspace_bytes.argtypes = [i32, i32, i32]
     lib.rib_warp.restype = i32
     lib.rib_warp.argtypes = [vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, vp]
     lib.rib_composite.restype = i32
@@ -63,6 +64,8 @@ def _load():
     lib.rib_debug_get_simt.restype = i32
     lib.rib_generator_debug_tensor.restype = i32
     lib.rib_generator_debug_tensor.argtypes = [vp, C.c_char_p, C.POINTER(vp)] + [C.POINTER(i32)] * 5
+    lib.rib_tune_log.restype = i32
+    lib.rib_tune_log.argtypes = [C.c_char_p, i64]
     lib.rib_generator_plan_text.restype = i32
     lib.rib_generator_plan_text.argtypes = [vp, C.c_char_p, i64]
     lib.rib_act_is_fp16.restype = i32

@@ -161,6 +161,13 @@ class Generator(nn.Module):
         check(lib.rib_generator_plan_text(self._handle, buf, len(buf)), 'rib_generator_plan_text')
         return buf.value.decode()
 
+    @staticmethod
+    def tune_log():
+        """The auto-tuner's candidates / timings / choices for every launch shape tuned in this process."""
+        buf = C.create_string_buffer(1 << 20)
+        check(lib.rib_tune_log(buf, len(buf)), 'rib_tune_log')
+        return buf.value.decode()
+
     def debug_tensor(self, name):
         """Intermediate activation of the last forward as an fp32 NCHW tensor (tests only)."""
         ptr, b, h, w, c, ld = C.c_void_p(), C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()

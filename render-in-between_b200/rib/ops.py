@@ -32,10 +32,11 @@ def gaussian_taps(sigma=HSM_RASTER['gauss_sigma'], truncate=4.0):
 _raster_ws = {}
 
 
-def _raster_workspace(b, device):
-    """Per-device scratch for the rasteriser (limb tables, stamp flags, heat-map windows); grown on demand."""
+def _raster_workspace(b, h, w, device):
+    """Per-device scratch for the rasteriser (limb tables, stamp flags, heat-map windows, one word per pixel);
+    grown on demand."""
     key = (device.type, device.index)
-    need = int(lib.rib_rasterize_workspace_bytes(b))
+    need = int(lib.rib_rasterize_workspace_bytes(b, h, w))
     ws = _raster_ws.get(key)
     if ws is None or ws.numel() < need:
         ws = torch.empty(need, dtype=torch.uint8, device=device)
@@ -63,7 +64,7 @@ def rasterize(joints, height, width, skeleton_thres=HSM_RASTER['skeleton_thres']
     taps = gaussian_taps()
     if taps.shape[0] != 41:
         raise ValueError('rasteriser supports sigma=5 (41 taps) only')
-    ws = _raster_workspace(b, joints.device)
+    ws = _raster_workspace(b, height, width, joints.device)
     with torch.cuda.device(joints.device):
         check(lib.rib_rasterize(joints.data_ptr(), b, height, width, taps.ctypes.data_as(C.POINTER(C.c_double)),
                                 float(skeleton_thres), float(foot_thres), label.data_ptr() if want_label else None,

@@ -80,7 +80,8 @@ def test_generator_matches_reference_fixture(dev, gen, golden_dir, arch, synth_s
     lines = []
     worst = 0.0
     for name in ['cond_0', 'cond_1', 'cond_2', 'cond_3', 'cond_4', 'down_first', 'down_0', 'down_1', 'down_2',
-                 'down_3', 'down_4', 'res_0', 'res_1', 'up_4', 'up_3', 'up_2', 'up_1']:
+                 'down_3', 'down_4', 'res_0', 'res_1', 'up_4', 'up_3', 'up_2', 'up_1', 'mask.cat', 'mask.res.0',
+                 'mask.res.3', 'mask.up.0', 'mask.up.1', 'mask.up.2']:
         got = gen.debug_tensor(name).cpu()
         lines.append(_report(name, got, taps[name]))
         rel = (got - taps[name]).pow(2).mean().sqrt().item() / taps[name].pow(2).mean().sqrt().item()

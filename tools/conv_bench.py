@@ -58,6 +58,8 @@ def main():
     print(txt.splitlines()[-1], 'lib', os.environ.get('RIB_LIB', 'default'))
     if a.out:
         open(a.out, 'w').write(txt + '\n')
+        open(a.out + '.plan', 'w').write(gen.plan_text())
+        open(a.out + '.tune', 'w').write(gen.tune_log())
 
 
 if __name__ == '__main__':
