@@ -51,6 +51,42 @@ int launch_pack_nchw(const PackSrc* srcs, int nsrc, act_t* dst, long long dst_bs
   return 0;
 }
 
+__global__ void pack_images_kernel(const float* __restrict__ fake, const float* __restrict__ prev,
+                                   act_t* __restrict__ emb, long long emb_bs, act_t* __restrict__ msk, long long msk_bs,
+                                   int HW, size_t total) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over B * HW / 4
+  if (i >= total) return;
+  const int q4 = HW >> 2;
+  const size_t n = i / q4;
+  const int pix = (int)(i - n * q4) * 4;
+  float f[3][4], p[3][4];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(fake + (n * 3 + c) * (size_t)HW + pix));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(prev + (n * 3 + c) * (size_t)HW + pix));
+    f[c][0] = a.x, f[c][1] = a.y, f[c][2] = a.z, f[c][3] = a.w;
+    p[c][0] = b.x, p[c][1] = b.y, p[c][2] = b.z, p[c][3] = b.w;
+  }
+  uint4* eo = reinterpret_cast<uint4*>(emb + n * emb_bs + (size_t)pix * 8);
+  uint4* mo = reinterpret_cast<uint4*>(msk + n * msk_bs + (size_t)pix * 8);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    eo[k] = make_uint4(pack2(f[0][k], f[1][k]), pack2(f[2][k], p[0][k]), pack2(p[1][k], p[2][k]), 0u);
+    mo[k] = make_uint4(pack2(p[0][k], p[1][k]), pack2(p[2][k], f[0][k]), pack2(f[1][k], f[2][k]), 0u);
+  }
+}
+
+int launch_pack_images(const float* fake, const float* prev, act_t* emb, long long emb_bstride, act_t* mask,
+                       long long mask_bstride, int B, int H, int W, cudaStream_t s) {
+  RIB_REQUIRE((H * W) % 4 == 0, "pack_images: H*W must be a multiple of 4");
+  RIB_REQUIRE((((uintptr_t)fake | (uintptr_t)prev) & 15) == 0, "pack_images: inputs must be 16-byte aligned");
+  const size_t total = (size_t)B * (H * W / 4);
+  pack_images_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(fake, prev, emb, emb_bstride, mask, mask_bstride,
+                                                                     H * W, total);
+  RIB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Instance-norm application
 // ---------------------------------------------------------------------------------------------

@@ -18,6 +18,14 @@ struct PackSrc {
 int launch_pack_nchw(const PackSrc* srcs, int nsrc, act_t* dst, long long dst_bstride, int c_off, int plane0,
                      int nplanes, int B, int H, int W, cudaStream_t s);
 
+// Both image inputs of the generator in one pass (generator.py:197 and :232): img_fake, img_prev fp32 [B,3,H,W] ->
+//   emb plane 0  = [fake(3), prev(3), 0, 0]          (cat([img_fake, img_prev]) for ref_embedding)
+//   mask plane 0 = [prev(3), fake(3), 0, 0]          (cat([img_prev, img_fake, img_final]); img_final is written into
+//                                                     channels 6..8 by conv_img's epilogue)
+// Four pixels per thread (16-byte loads, 64-byte stores).  The all-zero second planes are not touched.
+int launch_pack_images(const float* fake, const float* prev, act_t* emb, long long emb_bstride, act_t* mask,
+                       long long mask_bstride, int B, int H, int W, cudaStream_t s);
+
 // Instance-norm (affine) application for the C-N-A blocks of the mask network
 // (conv.py:56-69 with order 'CNA'; residual.py:146-151 for the two-term form):
 //   out = act(IN_a(a)) [+ IN_b(b) | + b]   with optional nearest x2 up-sampling on the store

@@ -49,7 +49,7 @@ struct GemmLayer {
   size_t w_off = 0, b_off = 0;
 };
 
-enum OpKind { OP_MEMSET, OP_PACK, OP_GEMM, OP_IN_APPLY, OP_POOL };
+enum OpKind { OP_MEMSET, OP_PACK, OP_PACK_IMAGES, OP_GEMM, OP_IN_APPLY, OP_POOL };
 enum ExtPtr { EXT_NONE = 0, EXT_LABEL, EXT_FAKE, EXT_PREV, EXT_OUT_IMG, EXT_OUT_MASK };
 
 struct Op {
@@ -63,6 +63,10 @@ struct Op {
   int pk_nsrc = 0, pk_ext[3] = {0, 0, 0}, pk_C[3] = {0, 0, 0}, pk_nplanes = 0;
   long long pk_bs = 0;
   act_t* pk_dst = nullptr;
+  // pack_images
+  act_t* pi_emb = nullptr;
+  act_t* pi_mask = nullptr;
+  long long pi_emb_bs = 0, pi_mask_bs = 0;
   // gemm
   ConvGemmParams g;
   int mode = 0;
@@ -106,6 +110,14 @@ struct Generator {
   std::vector<Op> ops;
   std::map<std::string, View> debug_views;
   bool plan_simt = false;
+  // planes that are all-zero padding for the life of the plan: cleared by the first forward after a plan (re)build
+  struct ZeroPlane {
+    void* ptr;
+    size_t pitch, width;
+    int rows;
+  };
+  std::vector<ZeroPlane> zero_once;
+  bool zero_pending = false;
 };
 
 namespace {
@@ -809,10 +821,16 @@ static int build_plan(Generator* G, int B, int H, int W, void* wsbase, size_t* b
   {
     const int e_lab[1] = {EXT_LABEL}, c_lab[1] = {c.label_nc};
     pb.pack(1, e_lab, c_lab, lab);
-    const int e_emb[2] = {EXT_FAKE, EXT_PREV}, c_img[2] = {c.img_nc, c.img_nc};
-    pb.pack(2, e_emb, c_img, emb_in);   // cat([img_fake, img_prev])            generator.py:197
-    const int e_msk[2] = {EXT_PREV, EXT_FAKE};
-    pb.pack(2, e_msk, c_img, mask_in);  // cat([img_prev, img_fake, img_final])  generator.py:232 (img_final: conv_img)
+    // cat([img_fake, img_prev]) (generator.py:197) and cat([img_prev, img_fake, img_final]) (:232; img_final comes from
+    // conv_img's epilogue) in one pass over the two images; channels 8..15 of both are padding (mask_in's channel 8 is
+    // img_final's third channel) and are zeroed once per plan
+    Op op;
+    op.kind = OP_PACK_IMAGES;
+    op.pi_emb = emb_in.p;
+    op.pi_emb_bs = emb_in.bstride();
+    op.pi_mask = mask_in.p;
+    op.pi_mask_bs = mask_in.bstride();
+    pb.ops.push_back(op);
   }
 
   // -- ref_embedding: 5 convs + LeakyReLU (generator.py:360-377) --
@@ -956,6 +974,10 @@ static int build_plan(Generator* G, int B, int H, int W, void* wsbase, size_t* b
   if (wsbase) {
     if (!g_debug_simt && autotune_enabled()) autotune(pb, stream);
     G->ops.swap(pb.ops);
+    G->zero_once.clear();
+    for (const View* v : {&emb_in, &mask_in})
+      G->zero_once.push_back({v->p + (size_t)H * W * 8, (size_t)v->bstride() * sizeof(act_t), (size_t)H * W * 8 * sizeof(act_t), B});
+    G->zero_pending = true;
     G->debug_views.swap(pb.views);
     G->pB = B;
     G->pH = H;
@@ -1007,9 +1029,18 @@ int generator_forward(Generator* G, int B, int H, int W, const float* label, con
   RIB_REQUIRE(G && img_fake && img_prev && out_img && out_mask && ws, "forward: null argument");
   int prc = ensure_plan(G, B, H, W, ws, ws_bytes, stream);
   if (prc) return prc;
+  if (G->zero_pending) {
+    for (const Generator::ZeroPlane& z : G->zero_once)
+      RIB_CHECK_CUDA(cudaMemset2DAsync(z.ptr, z.pitch, 0, z.width, (size_t)z.rows, stream));
+    G->zero_pending = false;
+  }
   for (const Op& op : G->ops) {
     int rc = 0;
     switch (op.kind) {
+      case OP_PACK_IMAGES:
+        rc = launch_pack_images(img_fake, img_prev, op.pi_emb, op.pi_emb_bs, op.pi_mask, op.pi_mask_bs, B, H, W, stream);
+        count_misc_launch(1);
+        break;
       case OP_MEMSET:
         RIB_CHECK_CUDA(cudaMemsetAsync(op.ms_ptr, 0, op.ms_bytes, stream));
         break;
@@ -1060,6 +1091,9 @@ int generator_plan_text(Generator* G, char* buf, long long cap) {
         break;
       case OP_PACK:
         snprintf(line, sizeof(line), "pack planes=%d\n", op.pk_nplanes);
+        break;
+      case OP_PACK_IMAGES:
+        snprintf(line, sizeof(line), "pack_images\n");
         break;
       case OP_GEMM: {
         const ConvGemmParams& p = op.g;

@@ -404,6 +404,49 @@ __device__ __forceinline__ void tile_edges(const FrameScratch* fs, int y0, int x
   __syncthreads();
 }
 
+// Conservative x-interval [lo, hi] of row y outside of which limb m touches no pixel (lo > hi: nothing on this row).
+// Body: a stamp (i, j) in [-4, 3]^2 of curve point (mm, f[mm]) with f[mm] within ~2 of a*mm + b and |a| <= 1, i.e. the
+// same band |minor - (a*major + b)| <= 11 that visit_limb tests, widened to 12; end caps: |i|, |j| <= 12 around the two
+// end points.  Rows whose y is clamped (first / last row collect everything drawn beyond them) fall back to the
+// bounding box; sources beyond the left / right border are clamped onto the border pixel by clamping the interval.
+__device__ __forceinline__ void row_interval(const EdgeMeta& m, int y, int H, int W, int* lo, int* hi) {
+  int l = 1 << 20, h = -(1 << 20);
+  if (y < m.by0 || y > m.by1) {
+    // nothing
+  } else if (y <= 0 || y >= H - 1) {
+    l = m.bx0;
+    h = m.bx1;
+  } else {
+    if (abs(y - m.ey0) <= 12) l = min(l, m.ex0 - 12), h = max(h, m.ex0 + 12);
+    if (abs(y - m.ey1) <= 12) l = min(l, m.ex1 - 12), h = max(h, m.ex1 + 12);
+    const float fy = (float)y;
+    if (m.swap) {  // major axis y: x ~ a*y + b
+      if (y >= m.mlo - 4 && y <= m.mhi + 3) {
+        const float c = m.a * fy + m.b;
+        l = min(l, (int)floorf(c - 12.f));
+        h = max(h, (int)ceilf(c + 12.f));
+      }
+    } else {       // major axis x: y ~ a*x + b
+      int bl = m.mlo - 4, bh = m.mhi + 3;
+      if (fabsf(m.a) > 1e-3f) {
+        const float x0 = (fy - m.b - 12.f) / m.a, x1 = (fy - m.b + 12.f) / m.a;
+        bl = max(bl, (int)floorf(fminf(x0, x1)) - 1);
+        bh = min(bh, (int)ceilf(fmaxf(x0, x1)) + 1);
+      } else if (fabsf(fy - (m.a * 0.5f * (float)(m.mlo + m.mhi) + m.b)) > 14.f) {
+        bh = bl - 1;   // (the line moves by at most ~1 px over its whole length)
+      }
+      if (bl <= bh) l = min(l, bl), h = max(h, bh);
+    }
+  }
+  if (l > h) {
+    *lo = 1;
+    *hi = 0;
+  } else {
+    *lo = min(max(l, 0), W - 1);
+    *hi = min(max(h, 0), W - 1);
+  }
+}
+
 // mark: every stamp that is not the first one of some pixel hit an older pixel.  Per pixel it leaves
 //   bits 0-23 colour if the first stamp painted `col`, 24-47 colour if it painted col >> 1, 48-52 limb and 53-62 key
 //   of the first stamp, bit 63 = touched at all
@@ -419,34 +462,45 @@ __global__ void __launch_bounds__(256) raster_mark_kernel(FrameScratch* __restri
   const int y = y0 + (threadIdx.x >> 5);
   const int xb = x0 + (threadIdx.x & 31) * kPxPerThread;
   if (y >= H) return;
-  unsigned long long word[kPxPerThread];
+  // One lane per limb works out the x-interval of this row outside of which the limb touches nothing (the whole warp
+  // is on row y); the limbs are then walked in drawing order with two shuffles each, and a lane only enters
+  // visit_limb for pixels inside the interval.
+  const int lane = threadIdx.x & 31;
+  int my_lo = 1, my_hi = 0;
+  if (lane < te.n) row_interval(s_meta[lane], y, H, W, &my_lo, &my_hi);
+  int count[kPxPerThread];
+  uint32_t ca[kPxPerThread], cb[kPxPerThread], first[kPxPerThread];
 #pragma unroll
-  for (int p = 0; p < kPxPerThread; ++p) {
-    const int x = xb + p;
-    word[p] = 0ull;
-    if (x >= W) continue;
-    int count = 0;
-    uint32_t ca = 0u, cb = 0u, first = 0u;
-    for (int k = 0; k < te.n; ++k) {
-      const EdgeMeta& m = s_meta[k];
-      if (x < m.bx0 || x > m.bx1 || y < m.by0 || y > m.by1) continue;
-      const int e = te.idx[k];
-      const uint32_t col = (uint32_t)c_colors[e][0] | ((uint32_t)c_colors[e][1] << 8) | ((uint32_t)c_colors[e][2] << 16);
+  for (int p = 0; p < kPxPerThread; ++p) count[p] = 0, ca[p] = cb[p] = first[p] = 0u;
+  for (int k = 0; k < te.n; ++k) {
+    const int lo = __shfl_sync(0xffffffffu, my_lo, k), hi = __shfl_sync(0xffffffffu, my_hi, k);
+    if (xb + kPxPerThread - 1 < lo || xb > hi) continue;
+    const EdgeMeta& m = s_meta[k];
+    const int e = te.idx[k];
+    const uint32_t col = (uint32_t)c_colors[e][0] | ((uint32_t)c_colors[e][1] << 8) | ((uint32_t)c_colors[e][2] << 16);
+#pragma unroll
+    for (int p = 0; p < kPxPerThread; ++p) {
+      const int x = xb + p;
+      if (x < lo || x > hi || x >= W) continue;
       visit_limb(m, fs->f[e], y, x, H, W, [&](int key) {
-        if (count++ == 0) {
-          first = (uint32_t)e | ((uint32_t)key << 5);
-          ca = col;
-          cb = avg_color(0u, col);
+        if (count[p]++ == 0) {
+          first[p] = (uint32_t)e | ((uint32_t)key << 5);
+          ca[p] = col;
+          cb[p] = avg_color(0u, col);
         } else {
           fs->flag[e][key] = 1;
-          ca = avg_color(ca, col);
-          cb = avg_color(cb, col);
+          ca[p] = avg_color(ca[p], col);
+          cb[p] = avg_color(cb[p], col);
         }
       });
     }
-    if (count > 0)
-      word[p] = (unsigned long long)ca | ((unsigned long long)cb << 24) | ((unsigned long long)first << 48) | (1ull << 63);
   }
+  unsigned long long word[kPxPerThread];
+#pragma unroll
+  for (int p = 0; p < kPxPerThread; ++p)
+    word[p] = count[p] > 0 ? (unsigned long long)ca[p] | ((unsigned long long)cb[p] << 24) |
+                                 ((unsigned long long)first[p] << 48) | (1ull << 63)
+                           : 0ull;
   unsigned long long* cp = cache + ((size_t)blockIdx.z * H + y) * W + xb;
   if (xb + kPxPerThread <= W && (W & 3) == 0) {
     *reinterpret_cast<ulonglong2*>(cp) = make_ulonglong2(word[0], word[1]);
