@@ -120,6 +120,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 
 // One lane of the (converged) warp is elected; all lanes must call it.
+// Orders this thread's generic-proxy shared-memory writes before later async-proxy (TMA / tcgen05.mma) reads.
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(

@@ -19,6 +19,7 @@ namespace rib {
 static constexpr int kEpiGroups = 1;                       // epilogue groups (4 warps each), one per TMEM accumulator buffer
 static constexpr int kThreads = 64 + 128 * kEpiGroups;
 static constexpr int kNumSms = 148;
+static constexpr int kXfThreads = 256;                     // transform warps of the XF kernels (after the epilogue warps)
 
 // Geometry of tap t of a stage: which halo tile of the slot it reads and the pixel offset of its
 // top-left corner inside that tile.
@@ -112,7 +113,19 @@ __device__ void simt_chunk(const ConvGemmParams& p, int n, int oy, int ox, int c
                                   ((size_t)(ci >> 3) * p.Hin * p.Win + (size_t)((iy & 1) * 2 + (ix & 1)) * (p.Hin / 2) * (p.Win / 2) +
                                    (size_t)(iy >> 1) * (p.Win / 2) + (ix >> 1)) * 8 + (ci & 7)
                             : planar_at(p.src0, n, ci, p.Hin, p.Win, iy, ix);
-      const float av = act2f(*ap);
+      float av = act2f(*ap);
+      if (p.xf_stats != nullptr) {  // A-operand transform, same arithmetic as the transform warps (result rounded to 16 bits)
+        const double cnt = (double)p.Hin * (double)p.Win;
+        const double s1 = p.xf_stats[((size_t)n * cin0 + ci) * 2], s2 = p.xf_stats[((size_t)n * cin0 + ci) * 2 + 1];
+        const double mean = s1 / cnt;
+        double var = s2 / cnt - mean * mean;
+        var = var < 0.0 ? 0.0 : var;
+        const double rstd = 1.0 / sqrt(var + (double)p.eps);
+        const double g = p.xf_w ? (double)p.xf_w[ci] : 1.0, be = p.xf_b ? (double)p.xf_b[ci] : 0.0;
+        av = fmaf(av, (float)(g * rstd), (float)(be - mean * g * rstd));
+        if (p.xf_act) av = fmaxf(av, 0.2f * av);
+        av = act2f(f2act(av));
+      }
       const int k = (grp * p.ntaps + t) * p.BKc + cc;
 #pragma unroll
       for (int c = 0; c < 16; ++c) acc[c] += av * act2f(p.wpk[(size_t)(col0 + c) * p.ktotal + k]);
@@ -174,8 +187,8 @@ __device__ __forceinline__ void issue_group_nt(int nt, const IssueCtx& c, uint32
   else issue_group<1, KK, MT>(c, a_lo, tap, mk, b_lo, d0, acc_first);
 }
 
-template <int MODE, int BN, bool SIMT>
-__global__ void __launch_bounds__(kThreads, SIMT ? 1 : (kEpiGroups == 1 ? (BN <= 32 ? 3 : 2) : (BN <= 32 ? 2 : 1))) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+template <int MODE, int BN, bool SIMT, bool XF>
+__global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF) ? 1 : (kEpiGroups == 1 ? (BN <= 32 ? 3 : 2) : (BN <= 32 ? 2 : 1))) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -192,13 +205,15 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (kEpiGroups == 1 ? (BN <=
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStat + (want_stats ? 4 * kEpiGroups * kStatWarpFloats * 4 : 0));
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + p.a_ring;
-  uint64_t* tmem_full_bar = a_empty + p.a_ring;  // [2]
+  uint64_t* a_ready = a_empty + p.a_ring;        // XF only: halo tile transformed, MMA may read it
+  uint64_t* tmem_full_bar = a_ready + (XF ? p.a_ring : 0);  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [2]
   uint64_t* bres_bar = tmem_empty_bar + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bres_bar + 1);
   float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr + 4) + 15) & ~(uintptr_t)15);  // [BN], 16-byte aligned
   float* s_aux = s_bias + BN;                              // per epilogue group: STORE [4 warps][2*BN] stats; SPADE [2*CT] rstd, -mean*rstd
   uint32_t* s_tapoff = reinterpret_cast<uint32_t*>(s_aux + kEpiGroups * 8 * BN);  // [10] A start offset (16-byte units) of tap t; [9]: 1x1 second source
+  float* s_xf = reinterpret_cast<float*>(s_tapoff + 12);   // XF: [2][cin0] scale, shift of the current image
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -226,6 +241,7 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (kEpiGroups == 1 ? (BN <=
       for (int i = 0; i < p.a_ring; ++i) {
         mbar_init(smem_u32(&a_full[i]), 1);
         mbar_init(smem_u32(&a_empty[i]), 1);
+        if (XF) mbar_init(smem_u32(&a_ready[i]), kXfThreads / 32);
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(smem_u32(&tmem_full_bar[i]), 1);
@@ -329,7 +345,7 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (kEpiGroups == 1 ? (BN <=
       const bool b_resident = p.b_resident != 0;
       const uint32_t g_slot16 = p.g_slot_bytes >> 4, b_off16 = p.b_off >> 4;
       const uint32_t sA16 = smem_u32(sA) >> 4, sB16 = smem_u32(sB) >> 4;
-      const uint32_t a_full0 = smem_u32(a_full), a_empty0 = smem_u32(a_empty);
+      const uint32_t a_full0 = XF ? smem_u32(a_ready) : smem_u32(a_full), a_empty0 = smem_u32(a_empty);
       const uint32_t tfull0 = smem_u32(tmem_full_bar), tempty0 = smem_u32(tmem_empty_bar);
       const uint32_t b_row_bytes = (uint32_t)p.BKc * 2u;
       const int kk_steps = p.BKc >> 4;
@@ -395,6 +411,114 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (kEpiGroups == 1 ? (BN <=
       }
     }
     __syncwarp();
+  } else if (XF && warp >= 2 + 4 * kEpiGroups) {
+    // ===================== A-operand transform =====================
+    // Four warps rewrite every halo tile in place: x -> lrelu?(x * scale[c] + shift[c]) for in-image pixels (padding
+    // stays zero), one 8-channel plane per warp at a time with its 16 coefficients in registers.
+    if (!SIMT) {
+      const int xw = warp - (2 + 4 * kEpiGroups);
+      const int stages0 = p.stages0, a_ring = p.a_ring, BKc = p.BKc, MT = p.MT, tiles_x = p.tiles_x, tiles_y = p.tiles_y;
+      const int planes = BKc >> 3, ntile_a = p.stride == 2 ? 4 : 1;
+      const int hw = p.halo_w, npix = (int)(p.lbo >> 4), halo = p.halo, hh = npix / hw;
+      const int S = planes * ntile_a >= 8 ? 1 : (planes * ntile_a >= 4 ? 2 : 4), s_shift = S == 1 ? 0 : (S == 2 ? 1 : 2);
+      const int nitems = planes * ntile_a * S, chunk = (npix + S - 1) / S;
+      const float inv_hw = 1.0f / (float)hw;
+      const int Hs = p.stride == 2 ? p.Hin >> 1 : p.Hin, Ws = p.stride == 2 ? p.Win >> 1 : p.Win;  // extent a tile indexes
+      const int org = p.stride == 2 ? 1 : halo;
+      const int cin0 = stages0 * BKc;
+      const double cnt = (double)p.Hin * (double)p.Win;
+      const bool lrelu = p.xf_act != 0;
+      int a_slot = 0;
+      uint32_t a_phase = 0;
+      int n = t_begin / tiles_per_img;
+      int rem0 = t_begin - n * tiles_per_img;
+      int tile_y = rem0 / tiles_x, tile_x = rem0 - tile_y * tiles_x;
+      int cur_n = -1;
+      for (int mt = t_begin; mt < t_end; ++mt) {
+        if (n != cur_n) {  // uniform over the four warps
+          asm volatile("bar.sync 8, %0;" ::"n"(kXfThreads) : "memory");   // nobody still reads the previous image's coefficients
+          for (int c = threadIdx.x - (kThreads); c < cin0; c += kXfThreads) {
+            const double s1 = p.xf_stats[((size_t)n * cin0 + c) * 2], s2 = p.xf_stats[((size_t)n * cin0 + c) * 2 + 1];
+            const double mean = s1 / cnt;
+            double var = s2 / cnt - mean * mean;
+            var = var < 0.0 ? 0.0 : var;
+            const double rstd = 1.0 / sqrt(var + (double)p.eps);
+            const double g = p.xf_w ? (double)p.xf_w[c] : 1.0, be = p.xf_b ? (double)p.xf_b[c] : 0.0;
+            s_xf[c] = (float)(g * rstd);
+            s_xf[cin0 + c] = (float)(be - mean * g * rstd);
+          }
+          asm volatile("bar.sync 8, %0;" ::"n"(kXfThreads) : "memory");
+          cur_n = n;
+        }
+        const int oy0 = tile_y * p.th * MT - org, ox0 = tile_x * p.tw - org;   // image coordinates of halo pixel (0, 0)
+        for (int g = 0; g < stages0; ++g) {
+          mbar_wait(smem_u32(&a_full[a_slot]), a_phase);
+          uint8_t* slot = sA + (size_t)a_slot * p.g_slot_bytes;
+          // work items: (parity tile, plane, pixel range); S ranges per plane so that all warps have work
+          const bool interior = oy0 >= 0 && ox0 >= 0 && oy0 + hh <= Hs && ox0 + hw <= Ws;
+          for (int it = xw; it < nitems; it += kXfThreads / 32) {
+            const int pi = it >> s_shift, sidx = it & (S - 1);
+            const int q = pi / planes, pl = pi - q * planes;
+            const float* cs = s_xf + g * BKc + pl * 8;
+            const float4 sc0 = *reinterpret_cast<const float4*>(cs), sc1 = *reinterpret_cast<const float4*>(cs + 4);
+            const float4 sh0 = *reinterpret_cast<const float4*>(cs + cin0), sh1 = *reinterpret_cast<const float4*>(cs + cin0 + 4);
+            const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+            const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+            uint4* tile = reinterpret_cast<uint4*>(slot + (size_t)q * p.a_tile_bytes + (size_t)pl * p.lbo);
+            const int p_lo = sidx * chunk, p_hi = min(npix, p_lo + chunk);
+            auto xform = [&](uint4 v) {
+              const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+              uint32_t o[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                float a, b;
+                unpack2(u[k], a, b);
+                a = fmaf(a, sc[2 * k], sh[2 * k]);
+                b = fmaf(b, sc[2 * k + 1], sh[2 * k + 1]);
+                if (lrelu) {
+                  a = fmaxf(a, 0.2f * a);
+                  b = fmaxf(b, 0.2f * b);
+                }
+                o[k] = pack2(a, b);
+              }
+              return make_uint4(o[0], o[1], o[2], o[3]);
+            };
+            if (interior) {  // four independent vectors in flight per lane
+              for (int base = p_lo + lane; base < p_hi; base += 128) {
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  if (base + 32 * u < p_hi) v[u] = tile[base + 32 * u];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  if (base + 32 * u < p_hi) tile[base + 32 * u] = xform(v[u]);
+              }
+            } else {
+              for (int pix = p_lo + lane; pix < p_hi; pix += 32) {
+                const int hy = (int)(((float)pix + 0.5f) * inv_hw), hx = pix - hy * hw;
+                const int iy = oy0 + hy, ix = ox0 + hx;
+                if ((unsigned)iy >= (unsigned)Hs || (unsigned)ix >= (unsigned)Ws) continue;   // zero padding stays zero
+                tile[pix] = xform(tile[pix]);
+              }
+            }
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&a_ready[a_slot]));
+          if (++a_slot == a_ring) {
+            a_slot = 0;
+            a_phase ^= 1u;
+          }
+        }
+        if (++tile_x == tiles_x) {
+          tile_x = 0;
+          if (++tile_y == tiles_y) {
+            tile_y = 0;
+            ++n;
+          }
+        }
+      }
+    }
   } else {
     // ===================== Epilogue =====================
     const int q = warp & 3;
@@ -460,8 +584,8 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (kEpiGroups == 1 ? (BN <=
         if (col < p.n_valid) {
           const float t1 = ((s_auxg[c] + s_auxg[2 * BN + c]) + s_auxg[4 * BN + c]) + s_auxg[6 * BN + c];
           const float t2 = ((s_auxg[BN + c] + s_auxg[3 * BN + c]) + s_auxg[5 * BN + c]) + s_auxg[7 * BN + c];
-          atomicAdd(&p.stats[((size_t)n_img * p.n_valid + col) * 2 + 0], (double)t1);
-          atomicAdd(&p.stats[((size_t)n_img * p.n_valid + col) * 2 + 1], (double)t2);
+          atomicAdd(&p.stats[((size_t)n_img * p.stats_ld + col) * 2 + 0], (double)t1);
+          atomicAdd(&p.stats[((size_t)n_img * p.stats_ld + col) * 2 + 1], (double)t2);
         }
       }
       epi_bar(eg);
@@ -545,6 +669,9 @@ __global__ void __launch_bounds__(kThreads, SIMT ? 1 : (kEpiGroups == 1 ? (BN <=
           // (sub-pixel conv: planes of the (2H, 2W) output are 4 HW8 apart and parity `par` is a dense H x W image)
           act_t* obase = p.subpix ? p.out.p + (size_t)n * p.out.bstride + ((size_t)(ncol0 >> 3) * 4 + par) * HW8 + pix8
                                   : p.out.p + (size_t)n * p.out.bstride + (size_t)((ntile * BN) >> 3) * HW8 + pix8;
+          if (p.out_parity)
+            obase = p.out.p + (size_t)n * p.out.bstride + (size_t)((ntile * BN) >> 3) * HW8 +
+                    (size_t)((oy & 1) * 2 + (ox & 1)) * (HW8 >> 2) + ((size_t)(oy >> 1) * (p.W >> 1) + (ox >> 1)) * 8;
           // parity-planar copy for a stride-2 consumer: [plane][py][px][H/2][W/2][8]
           act_t* obase2 = nullptr;
           if (p.has_out2)
@@ -952,8 +1079,9 @@ size_t conv_gemm_smem_bytes(const ConvGemmParams& p) {
   size_t tiles = (((size_t)p.a_ring * p.g_slot_bytes + 1023) & ~(size_t)1023) +
                  (size_t)(p.b_resident ? n_bt : 0) * p.b_tap_bytes;
   size_t stat = p.stats != nullptr ? kStatStageBytes : 0;
-  size_t bars = (size_t)(2 * p.a_ring + 5) * 8 + 32;
-  size_t scratch = (size_t)p.BN * 4 * (1 + 8 * kEpiGroups) + 64 + 64;
+  const bool xf = p.xf_stats != nullptr;
+  size_t bars = (size_t)((xf ? 3 : 2) * p.a_ring + 5) * 8 + 32;
+  size_t scratch = (size_t)p.BN * 4 * (1 + 8 * kEpiGroups) + 64 + 64 + (xf ? (size_t)2 * p.stages0 * p.BKc * 4 : 0);
   return 1024 + tiles + stat + bars + scratch;
 }
 
@@ -990,10 +1118,10 @@ int conv_gemm_profile_collect(double* total_ms, long long* launches, float* per_
 
 // Resident CTAs per SM for a given dynamic shared-memory size: limited by shared memory (227 KB usable,
 // 1 KB reserved per CTA), registers (64 K per SM) and TMEM columns (512 per SM).
-static int ctas_per_sm(const void* fn, size_t smem, int tmem_cols, int* occ) {
+static int ctas_per_sm(const void* fn, size_t smem, int tmem_cols, int threads, int* occ) {
   cudaFuncAttributes fa;
   RIB_CHECK_CUDA(cudaFuncGetAttributes(&fa, fn));
-  const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * kThreads;
+  const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * threads;
   int o = (int)((size_t)227 * 1024 / (smem + 1024));
   if (regs_per_cta > 0 && o > 65536 / regs_per_cta) o = 65536 / regs_per_cta;
   if (o > 512 / tmem_cols) o = 512 / tmem_cols;
@@ -1006,22 +1134,30 @@ static int ctas_per_sm(const void* fn, size_t smem, int tmem_cols, int* occ) {
 typedef void (*ConvKernel)(const ConvGemmParams);
 
 template <bool SIMT>
-static ConvKernel pick_kernel(int mode, int BN) {
+static ConvKernel pick_kernel(int mode, int BN, bool xf) {
+  if (xf) {  // the A-operand transform is built for the layers that use it: plain-store convs with 64 / 128 columns
+    if (mode != EPI_STORE) return nullptr;
+    switch (BN) {
+      case 64: return conv_gemm_kernel<EPI_STORE, 64, SIMT, true>;
+      case 128: return conv_gemm_kernel<EPI_STORE, 128, SIMT, true>;
+    }
+    return nullptr;
+  }
   if (mode == EPI_STORE) {
     switch (BN) {
-      case 16: return conv_gemm_kernel<EPI_STORE, 16, SIMT>;
-      case 32: return conv_gemm_kernel<EPI_STORE, 32, SIMT>;
-      case 64: return conv_gemm_kernel<EPI_STORE, 64, SIMT>;
-      case 128: return conv_gemm_kernel<EPI_STORE, 128, SIMT>;
+      case 16: return conv_gemm_kernel<EPI_STORE, 16, SIMT, false>;
+      case 32: return conv_gemm_kernel<EPI_STORE, 32, SIMT, false>;
+      case 64: return conv_gemm_kernel<EPI_STORE, 64, SIMT, false>;
+      case 128: return conv_gemm_kernel<EPI_STORE, 128, SIMT, false>;
     }
   } else if (mode == EPI_SPADE) {
     switch (BN) {
-      case 32: return conv_gemm_kernel<EPI_SPADE, 32, SIMT>;
-      case 64: return conv_gemm_kernel<EPI_SPADE, 64, SIMT>;
-      case 128: return conv_gemm_kernel<EPI_SPADE, 128, SIMT>;
+      case 32: return conv_gemm_kernel<EPI_SPADE, 32, SIMT, false>;
+      case 64: return conv_gemm_kernel<EPI_SPADE, 64, SIMT, false>;
+      case 128: return conv_gemm_kernel<EPI_SPADE, 128, SIMT, false>;
     }
   } else if (mode == EPI_FINAL && BN == 16) {
-    return conv_gemm_kernel<EPI_FINAL, 16, SIMT>;
+    return conv_gemm_kernel<EPI_FINAL, 16, SIMT, false>;
   }
   return nullptr;
 }
@@ -1034,7 +1170,10 @@ int launch_conv_gemm(const ConvGemmParams& p, int mode, cudaStream_t stream) {
   RIB_REQUIRE(p.n_tiles >= 1, "conv_gemm: no N tiles");
   RIB_REQUIRE(mode != EPI_SPADE || (p.BN == 2 * p.CT && p.CT % 16 == 0 && p.C % p.CT == 0),
               "conv_gemm: EPI_SPADE needs BN == 2*CT");
-  ConvKernel fn = p.debug_simt ? pick_kernel<true>(mode, p.BN) : pick_kernel<false>(mode, p.BN);
+  const bool xf = p.xf_stats != nullptr;
+  RIB_REQUIRE(!xf || (p.stages1 == 0 && p.subpix == 0), "conv_gemm: the A-operand transform needs a single source");
+  RIB_REQUIRE(!p.out_parity || (p.H % 2 == 0 && p.W % 2 == 0 && !p.subpix), "conv_gemm: bad parity-planar output");
+  ConvKernel fn = p.debug_simt ? pick_kernel<true>(mode, p.BN, xf) : pick_kernel<false>(mode, p.BN, xf);
   RIB_REQUIRE(fn != nullptr, "conv_gemm: no kernel for this (epilogue, BN)");
   const size_t smem = conv_gemm_smem_bytes(p);
   RIB_REQUIRE(smem <= 227 * 1024, "conv_gemm: shared memory budget exceeded");
@@ -1053,14 +1192,15 @@ int launch_conv_gemm(const ConvGemmParams& p, int mode, cudaStream_t stream) {
   int tmem_cols = 32;
   while (tmem_cols < 2 * p.MT * p.BN) tmem_cols <<= 1;
   int occ = 1;
-  int rc = ctas_per_sm((const void*)fn, smem, tmem_cols, &occ);
+  const int threads = kThreads + (xf ? kXfThreads : 0);
+  int rc = ctas_per_sm((const void*)fn, smem, tmem_cols, threads, &occ);
   if (rc) return rc;
   const long long m_tiles = (long long)p.tiles_x * p.tiles_y * p.B;
   long long groups = ((long long)kNumSms * occ) / p.n_tiles;
   if (groups < 1) groups = 1;
   if (groups > m_tiles) groups = m_tiles;
   dim3 grid((unsigned)(groups * p.n_tiles));
-  dim3 block(kThreads);
+  dim3 block(threads);
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (g_profile) {
     RIB_CHECK_CUDA(cudaEventCreate(&ev0));

@@ -83,11 +83,20 @@ struct alignas(64) ConvGemmParams {
   const float* bias;   // [Npad]
   int n_valid;         // real output columns (<= Npad)
   int act;
+  // A-operand transform: source 0 holds RAW conv outputs; lrelu?(instance_norm_affine(x)) (the N-A of a C-N-A block,
+  // conv.py:56-69) is applied to every halo tile in shared memory between its TMA load and the MMAs, so the
+  // normalised map is never written to HBM.  Zero padding stays zero.  Null xf_stats = no transform.
+  const double* xf_stats;   // [B][cin0][2] of source 0
+  const float* xf_w;        // [cin0] affine weight / bias
+  const float* xf_b;
+  int xf_act;
   // EPI_STORE
   PlanarRef out;
   PlanarRef res; int has_res;
   PlanarRef out2; int has_out2;  // optional second copy of the output in parity-planar layout (feeds a stride-2 conv)
-  double* stats;       // [B][n_valid][2] (sum, sum of squares) or null
+  double* stats;       // [B][stats_ld][2] (sum, sum of squares; this launch's channel 0 first) or null
+  int stats_ld;        // channels per image of the statistics buffer (>= n_valid: several producers may share one)
+  int out_parity;      // 1: `out` is parity-planar [plane][py][px][H/2][W/2][8] (its only consumer is a stride-2 conv)
   // EPI_SPADE
   PlanarRef x; int Hx, Wx, ups;
   const double* xstats;  // [B][C][2]

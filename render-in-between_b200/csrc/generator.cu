@@ -103,6 +103,8 @@ struct Generator {
   std::unordered_map<std::string, const float*> in_affine;  // IN weight / bias device pointers (caller-owned fp32)
   uint8_t* arena = nullptr;
   size_t arena_bytes = 0;
+  float* cat_w = nullptr;  // IN affine weight / bias of cat([down_lbl, down_img]) in one table (RIB_XF=2)
+  float* cat_b = nullptr;
   // cached plan
   int pB = 0, pH = 0, pW = 0;
   void* pws = nullptr;
@@ -293,6 +295,9 @@ int generator_create(const rib_gen_config* cfg, const rib_tensor* tensors, int n
   off = align_up(off, 256);
   const size_t sigma_off = off;
   off += jobs.size() * sizeof(float);
+  off = align_up(off, 256);
+  const size_t cat_off = off;
+  off += (size_t)4 * mask_nfilt(c, c.mask_down) * sizeof(float);
   G->arena_bytes = off;
   cudaError_t ce = cudaMalloc(&G->arena, G->arena_bytes);
   if (ce != cudaSuccess) {
@@ -370,6 +375,14 @@ int generator_create(const rib_gen_config* cfg, const rib_tensor* tensors, int n
     for (int k = 0; k < c.mask_down; ++k)
       reg(f + "up_flow." + std::to_string(2 * k + 1) + ".layers.norm", mask_nfilt(c, c.mask_down - 1 - k));
     if (err) return fail(err);
+    G->cat_w = reinterpret_cast<float*>(G->arena + cat_off);
+    G->cat_b = G->cat_w + 2 * mch;
+    for (int br = 0; br < 2; ++br) {
+      const std::string pre = f + (br == 0 ? "down_lbl." : "down_img.") + std::to_string(c.mask_down) + ".layers.norm";
+      if (cudaMemcpyAsync(G->cat_w + br * mch, G->in_affine.at(pre + ".weight"), mch * sizeof(float), cudaMemcpyDeviceToDevice, stream) != cudaSuccess ||
+          cudaMemcpyAsync(G->cat_b + br * mch, G->in_affine.at(pre + ".bias"), mch * sizeof(float), cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
+        return fail(-2);
+    }
   }
   ce = cudaStreamSynchronize(stream);
   if (ce != cudaSuccess) {
@@ -451,6 +464,7 @@ struct PlanBuilder {
     p.ktotal = L.ktotal;
     p.bias = L.bias;
     p.n_valid = L.n_valid;
+    p.stats_ld = L.n_valid;
     p.eps = 1e-5f;
     if (real && rc == 0) rc = make_maps(&p, L, in0, in1);
     last_layer = &L;
@@ -510,12 +524,32 @@ struct PlanBuilder {
     ops.push_back(op);
   }
 
-  // conv (+bias, optional residual/second source) -> 16-bit NHWC store, optional statistics
+  // The consumer-side form of the N-A of a C-N-A block: in0 holds the producer's RAW output and the conv kernel
+  // normalises (+ LeakyReLU) every halo tile in shared memory (ConvGemmParams::xf_*).
+  struct Xf {
+    const double* stats = nullptr;
+    const float* w = nullptr;
+    const float* b = nullptr;
+    int act = 0;
+  };
+
+  // conv (+bias, optional residual/second source) -> 16-bit planar store, optional statistics.  out.parity: the output
+  // is written parity-planar (only a stride-2 conv reads it).  stats_ld: channels per image of the statistics buffer
+  // when this layer's statistics are a slice of a wider one (0 = its own).
   void conv_store(const std::string& lname, const View& in0, const View* in1, int stride, const View& out,
-                  double* stats, int act, const View* res, const View* out2 = nullptr) {
+                  double* stats, int act, const View* res, const View* out2 = nullptr, const Xf* xf = nullptr,
+                  int stats_ld = 0) {
     const GemmLayer& L = G->layers.at(lname);
     ConvGemmParams p = gemm_common(L, in0, in1, stride, out.H, out.W, L.BN);
     p.out = out.ref();
+    p.out_parity = out.parity ? 1 : 0;
+    if (stats_ld) p.stats_ld = stats_ld;
+    if (xf) {
+      p.xf_stats = xf->stats;
+      p.xf_w = xf->w;
+      p.xf_b = xf->b;
+      p.xf_act = xf->act;
+    }
     p.has_out2 = out2 ? 1 : 0;
     if (out2) p.out2 = out2->ref();
     p.stats = stats;
@@ -668,7 +702,7 @@ std::string tune_key(const Op& op) {
   char buf[256];
   snprintf(buf, sizeof(buf), "m%d B%d H%d W%d c%d+%d t%d s%d BN%d N%d r%d o%d st%d u%d q%d par%d", op.mode, p.B, p.H, p.W,
            L.cin0, L.cin1, L.taps, L.stride, p.BN, L.n_pad, p.has_res, p.has_out2, p.stats != nullptr, p.ups,
-           op.mode == EPI_SPADE ? p.n_tiles * p.BN / (2 * p.C) : 0, p.s2_parity);
+           op.mode == EPI_SPADE ? p.n_tiles * p.BN / (2 * p.C) : 0, p.s2_parity + 2 * (p.xf_stats != nullptr) + 4 * p.out_parity);
   return buf;
 }
 
@@ -807,6 +841,7 @@ static int build_plan(Generator* G, int B, int H, int W, void* wsbase, size_t* b
     for (int i = 0; i <= c.mask_down; ++i) mst[bn + std::to_string(i)] = pb.alloc_stats(mask_nfilt(c, i));
   }
   const int mch = mask_nfilt(c, c.mask_down);
+  double* st_cat = pb.alloc_stats(2 * mch);   // statistics of both branches' last level, in cat order (RIB_XF=2)
   for (int i = 0; i < c.mask_res; ++i) {
     mst["res" + std::to_string(i) + "c0"] = pb.alloc_stats(mch);
     mst["res" + std::to_string(i) + "c1"] = pb.alloc_stats(mch);
@@ -916,38 +951,73 @@ static int build_plan(Generator* G, int B, int H, int W, void* wsbase, size_t* b
   pb.conv_final("conv_img", x, ACT_TANH, EXT_OUT_IMG, &mask_in, 2 * c.img_nc);
 
   // -- mask network (generator.py:493-510) --
+  // down_lbl / down_img (C-N-A, stride 2 from level 1 on): a level's conv stores its RAW output parity-planar (+ its
+  // statistics) and the next level's conv applies the instance norm + LeakyReLU to its halo tiles in shared memory
+  // (Xf), which removes a read + write of every full-resolution map.  Measured (profiles/r1h_xf_layers.txt): the
+  // transform costs an MMA-bound layer 15-25 % (tcgen05 already uses the whole shared-memory bandwidth), so the last
+  // level and the res_flow blocks keep the separate in_apply pass.
+  // RIB_XF = 0: separate in_apply everywhere; 1 (default): transform in the stride-2 down convs; 2: also in the
+  // res_flow convs (the statistics of both branches' last level then share one buffer in cat order).
+  static const int xf_mode = getenv("RIB_XF") ? atoi(getenv("RIB_XF")) : 1;
   View cat = pb.alloc("mask.cat", H >> c.mask_down, W >> c.mask_down, 2 * mch);
   for (int br = 0; br < 2; ++br) {
     const std::string bn = br == 0 ? "down_lbl" : "down_img";
     View cur = br == 0 ? lab : mask_in;
+    PlanBuilder::Xf xf_prev;
     for (int i = 0; i <= c.mask_down; ++i) {
       const int h = H >> i, w = W >> i, ch = mask_nfilt(c, i);
       const std::string nm = "mask." + bn + "." + std::to_string(i);
-      View raw = pb.alloc(nm + ".raw", h, w, ch);
-      double* st = mst[bn + std::to_string(i)];
-      pb.conv_store(nm, cur, nullptr, i == 0 ? 1 : 2, raw, st, ACT_NONE, nullptr);
-      View o = (i == c.mask_down) ? PlanBuilder::slice(cat, br * mch, mch) : pb.alloc(nm, h, w, ch);
-      if (i != c.mask_down) o.parity = true;  // consumed only by the next (stride-2) conv
-      pb.in_apply(raw, st, f + bn + "." + std::to_string(i) + ".layers.norm", nullptr, nullptr, "", o, 1, false);
-      cur = o;
+      const std::string pre = f + bn + "." + std::to_string(i) + ".layers.norm";
+      const bool lastl = i == c.mask_down;
+      const bool raw_in_cat = lastl && xf_mode >= 2;
+      View raw = raw_in_cat ? PlanBuilder::slice(cat, br * mch, mch) : pb.alloc(nm + ".raw", h, w, ch);
+      if (!lastl && xf_mode >= 1) raw.parity = true;  // consumed only by the next (stride-2) conv
+      double* st = raw_in_cat ? st_cat + (size_t)br * mch * 2 : mst[bn + std::to_string(i)];
+      pb.conv_store(nm, cur, nullptr, i == 0 ? 1 : 2, raw, st, ACT_NONE, nullptr, nullptr,
+                    (i == 0 || xf_mode < 1) ? nullptr : &xf_prev, raw_in_cat ? 2 * mch : 0);
+      xf_prev.stats = st;
+      xf_prev.w = G->in_affine.at(pre + ".weight");
+      xf_prev.b = G->in_affine.at(pre + ".bias");
+      xf_prev.act = 1;
+      cur = raw;
+      if (xf_mode < 1 || (lastl && xf_mode < 2)) {
+        View o = lastl ? PlanBuilder::slice(cat, br * mch, mch) : pb.alloc(nm, h, w, ch);
+        if (!lastl) o.parity = true;
+        pb.in_apply(raw, st, pre, nullptr, nullptr, "", o, 1, false);
+        cur = o;
+      }
     }
   }
+  PlanBuilder::Xf xf_cat;
+  xf_cat.stats = st_cat;
+  xf_cat.w = G->cat_w;
+  xf_cat.b = G->cat_b;
+  xf_cat.act = 1;
+  const PlanBuilder::Xf* xfc = xf_mode >= 2 ? &xf_cat : nullptr;
   View r = cat;
   const int rh = H >> c.mask_down, rw = W >> c.mask_down;
   for (int i = 0; i < c.mask_res; ++i) {
     const std::string rn = "mask.res." + std::to_string(i), rp = f + "res_flow." + std::to_string(i);
+    double* st0 = mst["res" + std::to_string(i) + "c0"];
     View raw0 = pb.alloc(rn + ".raw0", rh, rw, mch);
-    pb.conv_store(rn + ".conv0", r, nullptr, 1, raw0, mst["res" + std::to_string(i) + "c0"], ACT_NONE, nullptr);
-    View t0 = pb.alloc(rn + ".t0", rh, rw, mch);
-    pb.in_apply(raw0, mst["res" + std::to_string(i) + "c0"], rp + ".conv_block_0.layers.norm", nullptr, nullptr, "", t0, 1, false);
+    pb.conv_store(rn + ".conv0", r, nullptr, 1, raw0, st0, ACT_NONE, nullptr, nullptr, i == 0 ? xfc : nullptr);
     View raw1 = pb.alloc(rn + ".raw1", rh, rw, mch);
-    pb.conv_store(rn + ".conv1", t0, nullptr, 1, raw1, mst["res" + std::to_string(i) + "c1"], ACT_NONE, nullptr);
-    const bool last = (i + 1 == c.mask_res);
-    (void)last;  // the last block's output is only consumed through nn.Upsample(2), which the sub-pixel conv absorbs
-    View o = pb.alloc(rn, rh, rw, mch);
+    if (xf_mode >= 2) {
+      PlanBuilder::Xf xf0;
+      xf0.stats = st0;
+      xf0.w = G->in_affine.at(rp + ".conv_block_0.layers.norm.weight");
+      xf0.b = G->in_affine.at(rp + ".conv_block_0.layers.norm.bias");
+      xf0.act = 1;
+      pb.conv_store(rn + ".conv1", raw0, nullptr, 1, raw1, mst["res" + std::to_string(i) + "c1"], ACT_NONE, nullptr, nullptr, &xf0);
+    } else {
+      View t0 = pb.alloc(rn + ".t0", rh, rw, mch);
+      pb.in_apply(raw0, st0, rp + ".conv_block_0.layers.norm", nullptr, nullptr, "", t0, 1, false);
+      pb.conv_store(rn + ".conv1", t0, nullptr, 1, raw1, mst["res" + std::to_string(i) + "c1"], ACT_NONE, nullptr);
+    }
+    View o = pb.alloc(rn, rh, rw, mch);   // (the last block's x2 up-sampling is absorbed by the sub-pixel conv)
     if (i == 0) {
       View raws = pb.alloc(rn + ".raws", rh, rw, mch);
-      pb.conv_store(rn + ".convs", r, nullptr, 1, raws, mst["res0cs"], ACT_NONE, nullptr);
+      pb.conv_store(rn + ".convs", r, nullptr, 1, raws, mst["res0cs"], ACT_NONE, nullptr, nullptr, xfc);
       pb.in_apply(raw1, mst["res0c1"], rp + ".conv_block_1.layers.norm", &raws, mst["res0cs"],
                   rp + ".conv_block_s.layers.norm", o, 0, false);
     } else {
