@@ -138,6 +138,12 @@ int rib_generator_plan_text(rib_generator* g, char* buf, long long cap);
 /* The plan-time auto-tuner's log: one line per tuned launch shape of this process (candidate tilings with their
  * measured device times and the choice).  RIB_AUTOTUNE=0 in the environment disables the tuner. */
 int rib_tune_log(char* buf, long long cap);
+/* The tuning table of this process as text ("<launch-shape key>\t<mt>\t<policy>" per line) and its import, which
+ * returns the number of entries read (>= 0).  A table imported before the first forward makes the tiling choices
+ * identical across processes / ranks and skips the timing runs for the shapes it lists; the host mirror loads
+ * render-in-between_b200/rib/tune_b200.txt (and $RIB_TUNE_FILE, which it also rewrites at exit). */
+int rib_tune_export(char* buf, long long cap);
+int rib_tune_import(const char* text);
 /* 1 if activations are stored as IEEE fp16, 0 for bf16. */
 int rib_act_is_fp16(void);
 /* Stand-alone launch of the implicit-GEMM convolution for unit tests:

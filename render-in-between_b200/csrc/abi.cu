@@ -144,6 +144,21 @@ int rib_tune_log(char* buf, long long cap) {
   RIB_GUARD_END
 }
 
+int rib_tune_export(char* buf, long long cap) {
+  RIB_GUARD_BEGIN
+  RIB_REQUIRE(buf && cap > 0, "rib_tune_export: bad argument");
+  RIB_REQUIRE(generator_tune_export(buf, cap) == 0, "rib_tune_export: buffer too small");
+  return 0;
+  RIB_GUARD_END
+}
+
+int rib_tune_import(const char* text) {
+  RIB_GUARD_BEGIN
+  RIB_REQUIRE(text != nullptr, "rib_tune_import: null argument");
+  return generator_tune_import(text);
+  RIB_GUARD_END
+}
+
 int rib_act_is_fp16(void) {
 #ifdef RIB_ACT_FP16
   return 1;

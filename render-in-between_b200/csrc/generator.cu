@@ -788,6 +788,37 @@ void autotune(PlanBuilder& pb, cudaStream_t stream) {
 
 }  // namespace
 
+// Tuning table as text, one line per launch shape: "<key>\t<mt>\t<policy>".  Importing a table (before the first
+// plan) makes the choices reproducible across processes and ranks and skips the timing runs for known shapes.
+int generator_tune_export(char* buf, long long cap) {
+  std::lock_guard<std::mutex> lk(g_tune_mu);
+  std::string out;
+  for (const auto& kv : g_tune_cache) out += kv.first + "\t" + std::to_string(kv.second.mt) + "\t" + std::to_string(kv.second.policy) + "\n";
+  if ((long long)out.size() + 1 > cap) return -1;
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return 0;
+}
+
+int generator_tune_import(const char* text) {
+  std::lock_guard<std::mutex> lk(g_tune_mu);
+  int n = 0;
+  const char* p = text;
+  while (*p) {
+    const char* e = strchr(p, '\n');
+    std::string line = e ? std::string(p, e - p) : std::string(p);
+    p = e ? e + 1 : p + line.size();
+    const size_t t1 = line.find('\t'), t2 = t1 == std::string::npos ? t1 : line.find('\t', t1 + 1);
+    if (t2 == std::string::npos) continue;
+    ConvTune t;
+    t.mt = atoi(line.substr(t1 + 1, t2 - t1 - 1).c_str());
+    t.policy = atoi(line.substr(t2 + 1).c_str());
+    if (t.mt < 0 || t.mt > 2 || t.policy < 0 || t.policy > 3) continue;
+    g_tune_cache[line.substr(0, t1)] = t;
+    ++n;
+  }
+  return n;
+}
+
 int generator_tune_log(char* buf, long long cap) {
   std::lock_guard<std::mutex> lk(g_tune_mu);
   if ((long long)g_tune_log.size() + 1 > cap) return -1;

@@ -18,6 +18,8 @@ int generator_bind(Generator* g, int B, int H, int W, void* ws, long long ws_byt
 int generator_debug_tensor(Generator* g, const char* name, const void** ptr, int* B, int* H, int* W, int* C, int* ld);
 int generator_plan_text(Generator* g, char* buf, long long cap);
 int generator_tune_log(char* buf, long long cap);
+int generator_tune_export(char* buf, long long cap);
+int generator_tune_import(const char* text);
 long long conv_test_scratch_bytes(int Cin, int Cout, int k);
 int conv_test(const void* x, const float* w, const float* bias, void* out, double* stats, int B, int Hin, int Win,
               int Cin, int Cout, int k, int stride, int act, void* scratch, cudaStream_t stream);

@@ -460,53 +460,42 @@ __global__ void __launch_bounds__(256) raster_mark_kernel(FrameScratch* __restri
   tile_edges(fs, y0, x0, H, W, &te, s_meta);
   if (te.n == 0) return;
   const int y = y0 + (threadIdx.x >> 5);
-  const int xb = x0 + (threadIdx.x & 31) * kPxPerThread;
   if (y >= H) return;
   // One lane per limb works out the x-interval of this row outside of which the limb touches nothing (the whole warp
-  // is on row y); the limbs are then walked in drawing order with two shuffles each, and a lane only enters
-  // visit_limb for pixels inside the interval.
+  // is on row y).  The warp then walks its 128 columns in four 32-pixel segments, one pixel per lane: a limb is only
+  // enumerated in the segments its interval reaches, in drawing order (two shuffles per limb and segment).
   const int lane = threadIdx.x & 31;
   int my_lo = 1, my_hi = 0;
   if (lane < te.n) row_interval(s_meta[lane], y, H, W, &my_lo, &my_hi);
-  int count[kPxPerThread];
-  uint32_t ca[kPxPerThread], cb[kPxPerThread], first[kPxPerThread];
-#pragma unroll
-  for (int p = 0; p < kPxPerThread; ++p) count[p] = 0, ca[p] = cb[p] = first[p] = 0u;
-  for (int k = 0; k < te.n; ++k) {
-    const int lo = __shfl_sync(0xffffffffu, my_lo, k), hi = __shfl_sync(0xffffffffu, my_hi, k);
-    if (xb + kPxPerThread - 1 < lo || xb > hi) continue;
-    const EdgeMeta& m = s_meta[k];
-    const int e = te.idx[k];
-    const uint32_t col = (uint32_t)c_colors[e][0] | ((uint32_t)c_colors[e][1] << 8) | ((uint32_t)c_colors[e][2] << 16);
-#pragma unroll
-    for (int p = 0; p < kPxPerThread; ++p) {
-      const int x = xb + p;
+  unsigned long long* crow = cache + ((size_t)blockIdx.z * H + y) * W;
+  for (int seg = 0; seg < kTileCols / 32; ++seg) {
+    const int xs = x0 + seg * 32;
+    if (xs >= W) break;
+    const int x = xs + lane;
+    int count = 0;
+    uint32_t ca = 0u, cb = 0u, first = 0u;
+    for (int k = 0; k < te.n; ++k) {
+      const int lo = __shfl_sync(0xffffffffu, my_lo, k), hi = __shfl_sync(0xffffffffu, my_hi, k);
+      if (xs + 31 < lo || xs > hi) continue;   // uniform
       if (x < lo || x > hi || x >= W) continue;
+      const EdgeMeta& m = s_meta[k];
+      const int e = te.idx[k];
+      const uint32_t col = (uint32_t)c_colors[e][0] | ((uint32_t)c_colors[e][1] << 8) | ((uint32_t)c_colors[e][2] << 16);
       visit_limb(m, fs->f[e], y, x, H, W, [&](int key) {
-        if (count[p]++ == 0) {
-          first[p] = (uint32_t)e | ((uint32_t)key << 5);
-          ca[p] = col;
-          cb[p] = avg_color(0u, col);
+        if (count++ == 0) {
+          first = (uint32_t)e | ((uint32_t)key << 5);
+          ca = col;
+          cb = avg_color(0u, col);
         } else {
           fs->flag[e][key] = 1;
-          ca[p] = avg_color(ca[p], col);
-          cb[p] = avg_color(cb[p], col);
+          ca = avg_color(ca, col);
+          cb = avg_color(cb, col);
         }
       });
     }
-  }
-  unsigned long long word[kPxPerThread];
-#pragma unroll
-  for (int p = 0; p < kPxPerThread; ++p)
-    word[p] = count[p] > 0 ? (unsigned long long)ca[p] | ((unsigned long long)cb[p] << 24) |
-                                 ((unsigned long long)first[p] << 48) | (1ull << 63)
-                           : 0ull;
-  unsigned long long* cp = cache + ((size_t)blockIdx.z * H + y) * W + xb;
-  if (xb + kPxPerThread <= W && (W & 3) == 0) {
-    *reinterpret_cast<ulonglong2*>(cp) = make_ulonglong2(word[0], word[1]);
-    *reinterpret_cast<ulonglong2*>(cp + 2) = make_ulonglong2(word[2], word[3]);
-  } else {
-    for (int p = 0; p < kPxPerThread && xb + p < W; ++p) cp[p] = word[p];
+    if (x < W)
+      crow[x] = count > 0 ? (unsigned long long)ca | ((unsigned long long)cb << 24) | ((unsigned long long)first << 48) | (1ull << 63)
+                          : 0ull;
   }
 }
 

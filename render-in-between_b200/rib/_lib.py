@@ -16,7 +16,7 @@ SYMBOLS = [
     'rib_generator_create', 'rib_generator_destroy', 'rib_generator_workspace_bytes', 'rib_generator_bind', 'rib_generator_forward',
     'rib_debug_set_simt', 'rib_debug_get_simt', 'rib_generator_debug_tensor', 'rib_generator_plan_text', 'rib_act_is_fp16',
     'rib_conv_test_scratch_bytes', 'rib_conv_test', 'rib_profile_enable', 'rib_profile_collect', 'rib_profile_collect_launches',
-    'rib_tune_log',
+    'rib_tune_log', 'rib_tune_export', 'rib_tune_import',
 ]
 
 
@@ -66,6 +66,10 @@ def _load():
     lib.rib_generator_debug_tensor.argtypes = [vp, C.c_char_p, C.POINTER(vp)] + [C.POINTER(i32)] * 5
     lib.rib_tune_log.restype = i32
     lib.rib_tune_log.argtypes = [C.c_char_p, i64]
+    lib.rib_tune_export.restype = i32
+    lib.rib_tune_export.argtypes = [C.c_char_p, i64]
+    lib.rib_tune_import.restype = i32
+    lib.rib_tune_import.argtypes = [C.c_char_p]
     lib.rib_generator_plan_text.restype = i32
     lib.rib_generator_plan_text.argtypes = [vp, C.c_char_p, i64]
     lib.rib_act_is_fp16.restype = i32
@@ -83,6 +87,30 @@ def _load():
 
 
 lib = _load()
+
+# Tuning table (see rib_tune_import): the shipped table for the benchmark shapes, then the user's file.  With
+# RIB_TUNE_FILE set, everything tuned in this process is written back to that file at exit.
+TUNE_TABLE = os.path.join(_HERE, 'tune_b200.txt')
+
+
+def _load_tune_tables():
+    import atexit
+    user = os.environ.get('RIB_TUNE_FILE')
+    for path in (TUNE_TABLE, user):
+        if path and os.path.isfile(path):
+            with open(path, 'rb') as f:
+                lib.rib_tune_import(f.read() + b'\0')
+    if user:
+        def _save():
+            buf = C.create_string_buffer(1 << 20)
+            if lib.rib_tune_export(buf, len(buf)) == 0 and buf.value:
+                with open(user, 'wb') as f:
+                    f.write(buf.value)
+        atexit.register(_save)
+
+
+if os.environ.get('RIB_AUTOTUNE', '1') != '0':
+    _load_tune_tables()
 
 
 def check(rc, what):

@@ -24,6 +24,21 @@ def main(path, tag, steps):
     for x in r:
         d = rows.setdefault(x[ix['ID']], {'name': x[ix['Kernel Name']]})
         d[x[ix['Metric Name']]] = float(x[ix['Metric Value']].replace(',', ''))
+    # A step starts with the key-frame pass of ClipRenderer.render (a composite launch that follows a non-raster
+    # kernel); only complete steps with the modal launch count are kept, which drops model creation and the
+    # auto-tuner's candidate launches of the first step.
+    allrows = list(rows.values())
+    def short(d):
+        m = re.search(r'rib::(\w+)', d['name'])
+        return m.group(1) if m else d['name'][:40]
+    starts = [i for i, d in enumerate(allrows) if short(d) == 'composite_kernel' and
+              (i + 1 < len(allrows) and short(allrows[i + 1]) != 'composite_kernel')]
+    segs = [allrows[a:b] for a, b in zip(starts, starts[1:] + [len(allrows)])]
+    from collections import Counter
+    modal = Counter(len(x) for x in segs).most_common(1)[0][0]
+    segs = [x for x in segs if len(x) == modal]
+    steps = len(segs)
+    rows = OrderedDict((i, d) for i, d in enumerate(d for seg in segs for d in seg))
     agg = defaultdict(lambda: {'launches': 0, 'us': 0.0, 'dram_read': 0.0, 'dram_write': 0.0})
     for d in rows.values():
         m = re.search(r'rib::(\w+)', d['name'])
@@ -33,7 +48,7 @@ def main(path, tag, steps):
         a['dram_read'] += d.get('dram__bytes_read.sum', 0)
         a['dram_write'] += d.get('dram__bytes_write.sum', 0)
     once = ('sn_sigma_inv_kernel', 'pack_weight_kernel', 'pack_weight_subpix_kernel')   # model creation, not per step
-    out = {'source': os.path.basename(path), 'steps_under_ncu': steps, 'per_step': {}, 'once': {}}
+    out = {'source': os.path.basename(path), 'clean_steps_averaged': steps, 'launches_per_step': modal, 'per_step': {}, 'once': {}}
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1]['us']):
         if k in once:
             out['once'][k] = {'launches': a['launches'], 'us': round(a['us'], 1)}
