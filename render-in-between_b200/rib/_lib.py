@@ -96,7 +96,7 @@ TUNE_TABLE = os.path.join(_HERE, 'tune_b200.txt')
 def _load_tune_tables():
     import atexit
     user = os.environ.get('RIB_TUNE_FILE')
-    for path in (TUNE_TABLE, user):
+    for path in ((None if os.environ.get('RIB_NO_TUNE_TABLE') else TUNE_TABLE), user):
         if path and os.path.isfile(path):
             with open(path, 'rb') as f:
                 lib.rib_tune_import(f.read() + b'\0')
