@@ -816,19 +816,33 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
             xcur[j][0] = xnext[j][0];
             xcur[j][1] = xnext[j][1];
           }
-        } else {  // EPI_FINAL (BN == 16)
+        } else {  // EPI_FINAL (BN == 16, at most 4 real output channels)
           float v[16];
           if (SIMT) simt_chunk(p, n, oy, ox, 0, v);
           else tmem_ld16(trow, v);
           if (valid) {
+            // (kept small on purpose: the 16-way unrolled form of this block thrashed the instruction cache)
+            float y[4];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) {
+            for (int c = 0; c < 4; ++c) y[c] = v[c] + s_bias[c];
+            if (p.act == ACT_TANH) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) y[c] = tanhf(y[c]);
+            } else if (p.act == ACT_SIGMOID) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) y[c] = 1.f / (1.f + expf(-y[c]));
+            } else if (p.act == ACT_LRELU) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) y[c] = lrelu02(y[c]);
+            }
+            float* of = p.out_f32 + ((size_t)n * p.n_valid * p.H + oy) * p.W + ox;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
               if (c < p.n_valid) {
-                const float y = apply_act(v[c] + s_bias[c], p.act);
-                p.out_f32[(((size_t)n * p.n_valid + c) * p.H + oy) * p.W + ox] = y;
+                of[(size_t)c * p.H * p.W] = y[c];
                 if (p.has_out_act) {
                   const int cc = p.out_act_coff + c;
-                  p.out_act.p[(size_t)n * p.out_act.bstride + (size_t)(cc >> 3) * HW8 + pix8 + (cc & 7)] = f2act(y);
+                  p.out_act.p[(size_t)n * p.out_act.bstride + (size_t)(cc >> 3) * HW8 + pix8 + (cc & 7)] = f2act(y[c]);
                 }
               }
             }
@@ -1168,6 +1182,7 @@ int launch_conv_gemm(const ConvGemmParams& p, int mode, cudaStream_t stream) {
   RIB_REQUIRE(p.MT == 1 || p.MT == 2, "conv_gemm: MT must be 1 or 2");
   RIB_REQUIRE(2 * p.MT * p.BN <= 512, "conv_gemm: accumulators exceed TMEM");
   RIB_REQUIRE(p.n_tiles >= 1, "conv_gemm: no N tiles");
+  RIB_REQUIRE(mode != EPI_FINAL || p.n_valid <= 4, "conv_gemm: EPI_FINAL writes at most 4 channels");
   RIB_REQUIRE(mode != EPI_SPADE || (p.BN == 2 * p.CT && p.CT % 16 == 0 && p.C % p.CT == 0),
               "conv_gemm: EPI_SPADE needs BN == 2*CT");
   const bool xf = p.xf_stats != nullptr;

@@ -410,6 +410,7 @@ struct PlanBuilder {
   std::vector<Op> ops;
   std::map<std::string, View> views;
   std::vector<std::pair<double*, size_t>> stats_bufs;
+  float* final_scratch = nullptr;  // stand-in for the caller's fp32 outputs while the auto-tuner times EPI_FINAL launches
   int rc = 0;
 
   PlanBuilder(Generator* g, void* base, int b) : G(g), ws(base), B(b), real(base != nullptr) {}
@@ -606,6 +607,9 @@ struct PlanBuilder {
     op.g = p;
     op.mode = EPI_FINAL;
     op.ext = ext;
+    op.layer = last_layer;
+    op.in0 = last_in0;
+    op.has_in1 = false;
     ops.push_back(op);
   }
 
@@ -733,7 +737,8 @@ bool same_tiling(const ConvGemmParams& a, const ConvGemmParams& b) {
 void autotune(PlanBuilder& pb, cudaStream_t stream) {
   std::lock_guard<std::mutex> lk(g_tune_mu);
   for (Op& op : pb.ops) {
-    if (op.kind != OP_GEMM || op.mode == EPI_FINAL || op.layer == nullptr) continue;
+    if (op.kind != OP_GEMM || op.layer == nullptr) continue;
+    if (op.mode == EPI_FINAL) op.g.out_f32 = pb.final_scratch;
     const std::string key = tune_key(op);
     auto it = g_tune_cache.find(key);
     if (it != g_tune_cache.end()) {
@@ -783,6 +788,8 @@ void autotune(PlanBuilder& pb, cudaStream_t stream) {
     g_tune_cache[key] = best_tune;
     op.g = best_p;
   }
+  for (Op& op : pb.ops)
+    if (op.kind == OP_GEMM && op.mode == EPI_FINAL) op.g.out_f32 = nullptr;   // bound to the caller's tensors per forward
   set_error("");  // candidates that did not fit left messages behind
 }
 
@@ -1069,6 +1076,7 @@ static int build_plan(Generator* G, int B, int H, int W, void* wsbase, size_t* b
     r = o;
   }
   pb.conv_final("mask.conv_mask", r, ACT_SIGMOID, EXT_OUT_MASK, nullptr, 0);
+  pb.final_scratch = static_cast<float*>(pb.ws.take((size_t)B * 4 * H * W * sizeof(float)));
 
   if (pb.rc) return pb.rc;
   *bytes_out = align_up(pb.ws.off, 1024);

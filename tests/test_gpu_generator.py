@@ -122,6 +122,26 @@ def test_generator_default_resolution_and_batch_independence(dev, gen, arch, syn
     assert p >= PSNR_MIN_DB, 'fused PSNR %.2f dB at 320x480' % p
 
 
+@pytest.mark.parametrize('b,size', [(2, 256), (1, 1024)], ids=['B2x256', 'B1x1024'])
+def test_generator_resolution_sweep(dev, gen, arch, synth_sd, b, size):
+    """BASELINE configs[4] (resolution sweep 256-1024 px): parity of the whole forward against the fp32 oracle at the
+    sweep's end points (the plan, the tiling and the auto-tuner's choices all depend on the shape)."""
+    j = synth_joints(b, size, size, seed=11)
+    label = torch.from_numpy(np.stack([ro.label([(a[0], a[1]) for a in j[t]], [a[2] for a in j[t]], size, size)
+                                       for t in range(b)]))
+    fake, prev = synth_image(b, size, size, seed=12), synth_image(b, size, size, seed=13)
+    with torch.no_grad():
+        img, mask = gen(label.to(dev), None, fake.to(dev), prev.to(dev))
+        ref_img, ref_mask = go.generator_forward(synth_sd, arch, label, fake, prev)
+    fuse, ref_fuse = go.composite(img.cpu(), mask.cpu(), fake), go.composite(ref_img, ref_mask, fake)
+    p = go.psnr(fuse, ref_fuse)
+    _log('%dx%d B=%d: fused PSNR %.2f dB vs oracle; max|d img| %.4f max|d mask| %.4f' % (
+        size, size, b, p, (img.cpu() - ref_img).abs().max().item(), (mask.cpu() - ref_mask).abs().max().item()))
+    assert torch.isfinite(img).all() and torch.isfinite(mask).all()
+    assert p >= PSNR_MIN_DB, 'fused PSNR %.2f dB at %dx%d' % (p, size, size)
+    assert (mask.cpu() - ref_mask).abs().max().item() <= MAXABS_MASK
+
+
 def test_generator_rejects_bad_shapes(dev, gen):
     x = torch.zeros(1, 22, 40, 40, device=dev)      # not a multiple of 16
     im = torch.zeros(1, 3, 40, 40, device=dev)

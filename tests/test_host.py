@@ -70,3 +70,21 @@ def test_synth_is_deterministic():
     a, b = synth_joints(4, 64, 96, seed=3), synth_joints(4, 64, 96, seed=3)
     assert (a == b).all() and a.shape == (4, 19, 3)
     assert ((a[..., :2] % 1.0) != 0).all()    # generic floats, never grid-aligned
+
+
+def test_tune_table_import_export_roundtrip():
+    """The tuning table is plain text (key, mt, policy); import parses without a GPU and export returns it."""
+    import ctypes as C
+    from rib import _lib
+    n = _lib.lib.rib_tune_import(b'unit-test-shape-a\t2\t1\nunit-test-shape-b\t0\t0\nmalformed line\nunit-test-bad\t7\t9\n')
+    assert n == 2
+    buf = C.create_string_buffer(1 << 20)
+    assert _lib.lib.rib_tune_export(buf, len(buf)) == 0
+    lines = buf.value.decode().splitlines()
+    assert 'unit-test-shape-a\t2\t1' in lines and 'unit-test-shape-b\t0\t0' in lines
+    assert not any(l.startswith('unit-test-bad') for l in lines)
+    # the shipped table parses completely
+    import os
+    if os.path.isfile(_lib.TUNE_TABLE):
+        text = open(_lib.TUNE_TABLE, 'rb').read()
+        assert _lib.lib.rib_tune_import(text + b'\0') == len(text.strip().splitlines())
