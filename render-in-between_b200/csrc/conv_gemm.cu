@@ -974,7 +974,7 @@ static constexpr size_t kBigResident = (size_t)148 * 1024;    // ... that still 
 int choose_bkc(int cin0, int cin1, int taps, int BN, int stride) {
   const size_t b_all = ((size_t)cin0 * taps + cin1) * BN * 2;
   int cap;
-  if (b_all <= kSmallResident) cap = stride == 2 ? 32 : 64;       // stride 2 keeps four parity tiles per slot
+  if (b_all <= kSmallResident) cap = stride == 2 ? 16 : 64;       // stride 2 keeps four parity tiles per slot
   else if (b_all <= kBigResident) cap = stride == 2 ? 16 : 64;    // big resident weights: small halo slots
   else cap = stride == 2 ? 16 : 32;                               // streamed: a slot holds the halo tile(s) AND 9 weight sub-tiles
   int bk = cin0 < cap ? cin0 : cap;
@@ -1066,7 +1066,8 @@ int conv_gemm_configure(ConvGemmParams* p, int B, int Hout, int Wout, int cin0, 
     if (!mt_forced && fixed + 2 * (size_t)p->a_slot_bytes > kSmemMax) set_geometry(1);
     RIB_REQUIRE(fixed + 2 * (size_t)p->a_slot_bytes <= kSmemMax, "conv_gemm: resident weights do not fit");
     int ring = (int)((kSmemMax - fixed) / p->a_slot_bytes);
-    p->a_ring = ring > 4 ? 4 : ring;
+    const int ring_cap = (tune != nullptr && tune->ring >= 2 && tune->ring <= 8) ? tune->ring : 4;
+    p->a_ring = ring > ring_cap ? ring_cap : ring;
   } else {
     // a ring slot holds the halo tile(s) of a channel group AND that group's weight sub-tiles (one barrier round trip
     // per group); two stacked sub-tiles halve the weight traffic per pixel (measured: also for stride 2, whose four

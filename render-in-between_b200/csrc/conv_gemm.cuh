@@ -128,8 +128,10 @@ int choose_bkc(int cin0, int cin1, int taps, int BN, int stride);
 //   mt      M=128 sub-tiles stacked per super-tile (1 or 2)
 //   policy  1 = resident weights, ~100 KB CTAs (several per SM); 2 = resident weights, one CTA per SM, deep halo ring;
 //           3 = weights streamed with the halo tiles
+//   ring    policy 2 only: cap of the halo ring (default 4, at most 8); deeper rings help one-CTA-per-SM layers whose
+//           pipeline has the extra transform stage
 struct ConvTune {
-  int mt = 0, policy = 0;
+  int mt = 0, policy = 0, ring = 0;
 };
 // Fills the tiling / pipeline fields of p (everything except tensor maps and epilogue pointers).  Returns non-zero
 // when the requested tuning does not fit the layer.

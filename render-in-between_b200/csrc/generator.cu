@@ -742,7 +742,7 @@ void autotune(PlanBuilder& pb, cudaStream_t stream) {
     const std::string key = tune_key(op);
     auto it = g_tune_cache.find(key);
     if (it != g_tune_cache.end()) {
-      if (it->second.mt != 0 || it->second.policy != 0) {
+      if (it->second.mt != 0 || it->second.policy != 0 || it->second.ring != 0) {
         ConvGemmParams q;
         if (pb.retile(op, it->second, &q) == 0) op.g = q;
       }
@@ -758,11 +758,13 @@ void autotune(PlanBuilder& pb, cudaStream_t stream) {
              op.g.b_resident, t_def * 1e3f);
     std::string log = line;
     if (t_def > 0.f) {
-      for (int policy = 1; policy <= 3; ++policy)
-        for (int mt = 1; mt <= 2; ++mt) {
+      for (int cand = 0; cand < 8; ++cand) {
+        {
+          const int policy = cand < 6 ? cand / 2 + 1 : 2, mt = cand % 2 + 1;
           ConvTune t;
           t.mt = mt;
           t.policy = policy;
+          t.ring = cand < 6 ? 0 : 8;   // the last two candidates: one CTA per SM with a ring of up to 8 slots
           ConvGemmParams q;
           if (pb.retile(op, t, &q) != 0) continue;
           bool dup = false;
@@ -778,12 +780,13 @@ void autotune(PlanBuilder& pb, cudaStream_t stream) {
             best_p = q;
           }
         }
+      }
     }
     if (best_t >= 0.97f * t_def) {  // not worth leaving the default (and keeps the choice stable run to run)
       best_tune = ConvTune();
       best_p = op.g;
     }
-    snprintf(line, sizeof(line), " -> p%d MT%d", best_tune.policy, best_tune.mt);
+    snprintf(line, sizeof(line), " -> p%d MT%d r%d", best_tune.policy, best_tune.mt, best_tune.ring);
     g_tune_log += log + line + "\n";
     g_tune_cache[key] = best_tune;
     op.g = best_p;
@@ -800,7 +803,9 @@ void autotune(PlanBuilder& pb, cudaStream_t stream) {
 int generator_tune_export(char* buf, long long cap) {
   std::lock_guard<std::mutex> lk(g_tune_mu);
   std::string out;
-  for (const auto& kv : g_tune_cache) out += kv.first + "\t" + std::to_string(kv.second.mt) + "\t" + std::to_string(kv.second.policy) + "\n";
+  for (const auto& kv : g_tune_cache)
+    out += kv.first + "\t" + std::to_string(kv.second.mt) + "\t" + std::to_string(kv.second.policy) + "\t" +
+           std::to_string(kv.second.ring) + "\n";
   if ((long long)out.size() + 1 > cap) return -1;
   memcpy(buf, out.c_str(), out.size() + 1);
   return 0;
@@ -818,8 +823,10 @@ int generator_tune_import(const char* text) {
     if (t2 == std::string::npos) continue;
     ConvTune t;
     t.mt = atoi(line.substr(t1 + 1, t2 - t1 - 1).c_str());
-    t.policy = atoi(line.substr(t2 + 1).c_str());
-    if (t.mt < 0 || t.mt > 2 || t.policy < 0 || t.policy > 3) continue;
+    t.policy = atoi(line.substr(t2 + 1).c_str());           // (stops at the next tab)
+    const size_t t3 = line.find('\t', t2 + 1);
+    t.ring = t3 == std::string::npos ? 0 : atoi(line.substr(t3 + 1).c_str());
+    if (t.mt < 0 || t.mt > 2 || t.policy < 0 || t.policy > 3 || t.ring < 0 || t.ring > 8) continue;
     g_tune_cache[line.substr(0, t1)] = t;
     ++n;
   }

@@ -81,7 +81,7 @@ def test_tune_table_import_export_roundtrip():
     buf = C.create_string_buffer(1 << 20)
     assert _lib.lib.rib_tune_export(buf, len(buf)) == 0
     lines = buf.value.decode().splitlines()
-    assert 'unit-test-shape-a\t2\t1' in lines and 'unit-test-shape-b\t0\t0' in lines
+    assert 'unit-test-shape-a\t2\t1\t0' in lines and 'unit-test-shape-b\t0\t0\t0' in lines
     assert not any(l.startswith('unit-test-bad') for l in lines)
     # the shipped table parses completely
     import os
