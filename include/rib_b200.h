@@ -157,6 +157,16 @@ long long rib_conv_test_scratch_bytes(int Cin, int Cout, int k);
 int rib_conv_test(const void* x, const float* w, const float* bias, void* out, double* stats, int B, int Hin, int Win,
                   int Cin, int Cout, int k, int stride, int act, void* scratch, void* stream);
 
+/* Same with the two in-kernel fusions of the mask network:
+ *   subpix = 1   conv3x3(nearest_x2(x)) in its sub-pixel form (k = 3, stride 1): `out` is the parity-planar
+ *                [B][Cout/8][py][px][Hin][Win][8] map of the (2 Hin, 2 Win) result
+ *   xf_stats     f64 [B][Cin][2] (sum, sum of squares of x per image and channel), xf_w / xf_b f32 [Cin] (may be NULL):
+ *                x is a RAW map and the kernel applies lrelu?(instance_norm_affine(x)) to its halo tiles in shared
+ *                memory before the MMAs (xf_act = 1: LeakyReLU 0.2) */
+int rib_conv_test_ex(const void* x, const float* w, const float* bias, void* out, double* stats, int B, int Hin, int Win,
+                     int Cin, int Cout, int k, int stride, int act, int subpix, const double* xf_stats, const float* xf_w,
+                     const float* xf_b, int xf_act, void* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -177,4 +177,14 @@ int rib_conv_test(const void* x, const float* w, const float* bias, void* out, d
   RIB_GUARD_END
 }
 
+int rib_conv_test_ex(const void* x, const float* w, const float* bias, void* out, double* stats, int B, int Hin, int Win,
+                     int Cin, int Cout, int k, int stride, int act, int subpix, const double* xf_stats, const float* xf_w,
+                     const float* xf_b, int xf_act, void* scratch, void* stream) {
+  RIB_GUARD_BEGIN
+  RIB_REQUIRE(x && w && out && scratch, "rib_conv_test_ex: null argument");
+  return conv_test_ex(x, w, bias, out, stats, B, Hin, Win, Cin, Cout, k, stride, act, subpix, xf_stats, xf_w, xf_b, xf_act,
+                      scratch, (cudaStream_t)stream);
+  RIB_GUARD_END
+}
+
 }  // extern "C"

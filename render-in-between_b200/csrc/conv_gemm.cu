@@ -5,8 +5,10 @@
 // quarter = warp_idx & 3); group g drains every kEpiGroups-th tile of the CTA.  Two groups (one per accumulator
 // buffer) were measured: no gain for the one-CTA-per-SM layers (they are MMA / TMA bound) and a loss for the
 // small layers (fewer CTAs per SM), so one group is built.
-// Barriers: full/empty per ring slot (TMA <-> MMA), tmem_full/tmem_empty per accumulator buffer
-// (MMA <-> epilogue), one barrier for the resident weights.
+// Kernels built with the A-operand transform (XF, see ConvGemmParams::xf_*) carry eight more warps that rewrite every
+// halo tile in place between its TMA load and the MMAs (instance-norm affine + LeakyReLU of the producer's raw output).
+// Barriers: full/empty per ring slot (TMA <-> MMA; XF: TMA -> transform via full, transform -> MMA via ready),
+// tmem_full/tmem_empty per accumulator buffer (MMA <-> epilogue), one barrier for the resident weights.
 #include "conv_gemm.cuh"
 
 #include <atomic>

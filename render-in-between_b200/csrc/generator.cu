@@ -1260,44 +1260,60 @@ int generator_debug_tensor(Generator* G, const char* name, const void** ptr, int
 
 // ---- stand-alone conv for unit tests ----------------------------------------------------------
 long long conv_test_scratch_bytes(int Cin, int Cout, int k) {
-  return (long long)(align_up((size_t)Cout * Cin * k * k * sizeof(act_t), 256) + align_up((size_t)Cout * 4, 256) + 1024);
+  // (sized for the sub-pixel form as well: 4 parities x 4 taps)
+  const size_t kk = (size_t)std::max(k * k, 16);
+  return (long long)(align_up((size_t)Cout * Cin * kk * sizeof(act_t), 256) + align_up((size_t)Cout * 4 * 4, 256) + 1024);
 }
 
 int conv_test(const void* x, const float* w, const float* bias, void* out, double* stats, int B, int Hin, int Win,
               int Cin, int Cout, int k, int stride, int act, void* scratch, cudaStream_t stream) {
+  return conv_test_ex(x, w, bias, out, stats, B, Hin, Win, Cin, Cout, k, stride, act, 0, nullptr, nullptr, nullptr, 0,
+                      scratch, stream);
+}
+
+int conv_test_ex(const void* x, const float* w, const float* bias, void* out, double* stats, int B, int Hin, int Win,
+                 int Cin, int Cout, int k, int stride, int act, int subpix, const double* xf_stats, const float* xf_w,
+                 const float* xf_b, int xf_act, void* scratch, cudaStream_t stream) {
   RIB_REQUIRE(Cin % 16 == 0 && Cout % 16 == 0, "conv_test: channels must be multiples of 16");
   RIB_REQUIRE((k == 1 || k == 3) && (stride == 1 || stride == 2), "conv_test: unsupported kernel/stride");
   RIB_REQUIRE(Cin <= 64 || Cin % 64 == 0, "conv_test: Cin must be 16, 32, 64 or a multiple of 64");
+  RIB_REQUIRE(!subpix || (k == 3 && stride == 1 && xf_stats == nullptr && act == 0), "conv_test: bad sub-pixel conv");
   Generator G;  // a throw-away holder for one layer
   GemmLayer L;
   L.name = "test";
-  L.n_valid = L.n_pad = Cout;
+  L.n_valid = Cout;
+  L.n_pad = subpix ? 4 * Cout : Cout;
   L.cin0 = Cin;
-  L.taps = k * k;
+  L.taps = subpix ? 4 : k * k;
   L.cin1 = 0;
-  L.ktotal = Cin * k * k;
+  L.ktotal = Cin * L.taps;
   L.BN = std::min(Cout, 128);
   L.stride = stride;
-  L.bkc = choose_bkc(Cin, 0, k * k, L.BN, stride);
+  L.bkc = choose_bkc(Cin, 0, L.taps, L.BN, stride);
   uint8_t* sp = static_cast<uint8_t*>(scratch);
   sp = reinterpret_cast<uint8_t*>(align_up((size_t)(uintptr_t)sp, 256));
   L.w = reinterpret_cast<act_t*>(sp);
-  L.bias = reinterpret_cast<float*>(sp + align_up((size_t)Cout * L.ktotal * sizeof(act_t), 256));
+  L.bias = reinterpret_cast<float*>(sp + align_up((size_t)L.n_pad * L.ktotal * sizeof(act_t), 256));
   G.layers["test"] = L;
-  RIB_CHECK_CUDA(cudaMemsetAsync(L.bias, 0, (size_t)Cout * 4, stream));
-  PackWeightParams pp;
-  memset(&pp, 0, sizeof(pp));
-  pp.w = w;
-  pp.bias = bias;
-  pp.Cout = Cout;
-  pp.Cin = Cin;
-  pp.taps = k * k;
-  pp.dst = L.w;
-  pp.bias_dst = L.bias;
-  pp.ktotal = L.ktotal;
-  pp.bkc = L.bkc;
-  int rc = launch_pack_weight(pp, stream);
-  if (rc) return rc;
+  RIB_CHECK_CUDA(cudaMemsetAsync(L.bias, 0, (size_t)L.n_pad * 4, stream));
+  for (int par = 0; par < (subpix ? 4 : 1); ++par) {
+    PackWeightParams pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.w = w;
+    pp.bias = bias;
+    pp.Cout = Cout;
+    pp.Cin = Cin;
+    pp.taps = k * k;
+    pp.dst = L.w;
+    pp.bias_dst = L.bias;
+    pp.ktotal = L.ktotal;
+    pp.bkc = L.bkc;
+    pp.row_off = par * Cout;
+    pp.subpix = subpix ? 1 : 0;
+    pp.subpix_parity = par;
+    int rc = launch_pack_weight(pp, stream);
+    if (rc) return rc;
+  }
   PlanBuilder pb(&G, scratch, B);  // non-null base => builds real tensor maps; no allocation is made
   View in;
   in.p = static_cast<act_t*>(const_cast<void*>(x));
@@ -1309,10 +1325,20 @@ int conv_test(const void* x, const float* w, const float* bias, void* out, doubl
   View o;
   o.p = static_cast<act_t*>(out);
   o.B = B;
-  o.H = Hin / stride;
-  o.W = Win / stride;
+  o.H = subpix ? 2 * Hin : Hin / stride;
+  o.W = subpix ? 2 * Win : Win / stride;
   o.C = o.Ctot = Cout;
-  pb.conv_store("test", in, nullptr, stride, o, stats, act, nullptr);
+  if (subpix) {
+    o.parity = true;
+    pb.conv_subpix("test", in, o, stats);
+  } else {
+    PlanBuilder::Xf xf;
+    xf.stats = xf_stats;
+    xf.w = xf_w;
+    xf.b = xf_b;
+    xf.act = xf_act;
+    pb.conv_store("test", in, nullptr, stride, o, stats, act, nullptr, nullptr, xf_stats ? &xf : nullptr);
+  }
   if (pb.rc) return pb.rc;
   return launch_conv_gemm(pb.ops[0].g, EPI_STORE, stream);
 }

@@ -23,6 +23,9 @@ int generator_tune_import(const char* text);
 long long conv_test_scratch_bytes(int Cin, int Cout, int k);
 int conv_test(const void* x, const float* w, const float* bias, void* out, double* stats, int B, int Hin, int Win,
               int Cin, int Cout, int k, int stride, int act, void* scratch, cudaStream_t stream);
+int conv_test_ex(const void* x, const float* w, const float* bias, void* out, double* stats, int B, int Hin, int Win,
+                 int Cin, int Cout, int k, int stride, int act, int subpix, const double* xf_stats, const float* xf_w,
+                 const float* xf_b, int xf_act, void* scratch, cudaStream_t stream);
 long long misc_launch_count();
 void count_misc_launch(int n);
 

@@ -16,7 +16,7 @@ SYMBOLS = [
     'rib_generator_create', 'rib_generator_destroy', 'rib_generator_workspace_bytes', 'rib_generator_bind', 'rib_generator_forward',
     'rib_debug_set_simt', 'rib_debug_get_simt', 'rib_generator_debug_tensor', 'rib_generator_plan_text', 'rib_act_is_fp16',
     'rib_conv_test_scratch_bytes', 'rib_conv_test', 'rib_profile_enable', 'rib_profile_collect', 'rib_profile_collect_launches',
-    'rib_tune_log', 'rib_tune_export', 'rib_tune_import',
+    'rib_tune_log', 'rib_tune_export', 'rib_tune_import', 'rib_conv_test_ex',
 ]
 
 
@@ -83,6 +83,8 @@ def _load():
     lib.rib_conv_test_scratch_bytes.argtypes = [i32, i32, i32]
     lib.rib_conv_test.restype = i32
     lib.rib_conv_test.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp]
+    lib.rib_conv_test_ex.restype = i32
+    lib.rib_conv_test_ex.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp]
     return lib
 
 

@@ -178,3 +178,80 @@ def test_conv_gemm_lrelu_epilogue(dev):
     ref = F.leaky_relu(F.conv2d(x.to(dt).float(), wt.to(dt).float(), bias, padding=1), 0.2)
     out, _ = _run_conv(dev, x, wt, bias, 3, 1, act=1, want_stats=False, simt=False)
     assert bool(((out - ref).abs() <= 2.0 ** -7 * ref.abs() + 2e-3).all())
+
+
+# ---------------------------------------------------------------- in-kernel fusions of the mask network
+def _run_conv_ex(dev, x_planar, w, bias, b, h, wd, cin, cout, stride, subpix, xf, out_shape, want_stats, simt):
+    from rib._lib import check, lib
+    dt = _act_dtype()
+    out = torch.zeros(*out_shape, dtype=dt, device=dev)
+    stats = torch.zeros(b, cout, 2, dtype=torch.float64, device=dev) if want_stats else None
+    scratch = torch.empty(lib.rib_conv_test_scratch_bytes(cin, cout, 3) + 1024, dtype=torch.uint8, device=dev)
+    wd_, bd_ = w.contiguous().to(dev), bias.contiguous().to(dev)
+    xs, xw, xb = (t.contiguous().to(dev) for t in xf) if xf is not None else (None, None, None)
+    lib.rib_debug_set_simt(1 if simt else 0)
+    try:
+        check(lib.rib_conv_test_ex(x_planar.data_ptr(), wd_.data_ptr(), bd_.data_ptr(), out.data_ptr(),
+                                   stats.data_ptr() if want_stats else None, b, h, wd, cin, cout, 3, stride, 0,
+                                   1 if subpix else 0, xs.data_ptr() if xf is not None else None,
+                                   xw.data_ptr() if xf is not None else None, xb.data_ptr() if xf is not None else None,
+                                   1, scratch.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+              'rib_conv_test_ex')
+        torch.cuda.synchronize()
+    finally:
+        lib.rib_debug_set_simt(0)
+    return out.float().cpu(), (stats.cpu() if want_stats else None)
+
+
+@pytest.mark.parametrize('simt', [True, False], ids=['simt', 'tcgen05'])
+@pytest.mark.parametrize('case', [(1, 16, 16, 16, 16), (2, 64, 32, 32, 32), (1, 128, 64, 16, 24), (1, 256, 128, 16, 16)],
+                         ids=lambda c: 'B%d_%dto%d_%dx%d' % c)
+def test_subpixel_conv_matches_upsample_conv(dev, case, simt):
+    """conv3x3(nearest_x2(x)) == the four 2x2 parity convs on the low-resolution map (generator.py:478-481)."""
+    b, cin, cout, h, w = case
+    dt = _act_dtype()
+    g = torch.Generator().manual_seed(cin + cout + h)
+    x = torch.randn(b, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    ref = F.conv2d(F.interpolate(x.to(dt).float(), scale_factor=2), wt, bias, padding=1)
+    out_pp, stats = _run_conv_ex(dev, to_planar(x, dt).to(dev), wt, bias, b, h, w, cin, cout, 1, True, None,
+                                 (b, cout // 8, 2, 2, h, w, 8), True, simt)
+    # parity-planar [b][plane][py][px][y][x][e] -> NCHW at twice the size
+    out = out_pp.permute(0, 1, 6, 4, 2, 5, 3).reshape(b, cout, 2 * h, 2 * w)
+    err = (out - ref).abs()
+    tol = 2.0 ** -6 * ref.abs() + 6e-3     # summed taps are rounded to 16 bits once (the reference keeps fp32 weights)
+    assert bool((err <= tol).all()), 'max err %.4g (ref %.4g)' % (err.max().item(), ref.flatten()[err.argmax()].item())
+    s_ref = torch.stack([ref.double().sum(dim=(2, 3)), (ref.double() ** 2).sum(dim=(2, 3))], dim=2)
+    assert torch.allclose(stats, s_ref, rtol=1e-2, atol=0.2), (stats - s_ref).abs().max().item()
+
+
+@pytest.mark.parametrize('simt', [True, False], ids=['simt', 'tcgen05'])
+@pytest.mark.parametrize('case', [(2, 32, 64, 32, 32, 2), (1, 64, 128, 32, 48, 2), (2, 128, 128, 16, 16, 2), (1, 64, 64, 20, 28, 1),
+                                  (3, 256, 128, 16, 16, 1)], ids=lambda c: 'B%d_%dto%d_%dx%d_s%d' % c)
+def test_transform_conv_matches_norm_act_conv(dev, case, simt):
+    """conv(lrelu(instance_norm_affine(x))) with the N-A applied to the halo tiles in shared memory (conv.py:56-69,
+    order C-N-A of the producer) == the separate normalisation pass followed by the conv; zero padding stays zero."""
+    b, cin, cout, h, w, stride = case
+    dt = _act_dtype()
+    g = torch.Generator().manual_seed(cin * 7 + cout + h + stride)
+    x = (torch.randn(b, cin, h, w, generator=g) * 1.7 + 0.4).to(dt).float()
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    aw, ab = torch.rand(cin, generator=g) + 0.5, torch.randn(cin, generator=g) * 0.2
+    xd = x.double()
+    stats = torch.stack([xd.sum(dim=(2, 3)), (xd ** 2).sum(dim=(2, 3))], dim=2)           # [b, cin, 2]
+    mean = stats[..., 0] / (h * w)
+    var = (stats[..., 1] / (h * w) - mean ** 2).clamp_min(0)
+    rstd = 1.0 / torch.sqrt(var + 1e-5)
+    scale = (aw.double() * rstd).float()[:, :, None, None]
+    shift = (ab.double() - mean * aw.double() * rstd).float()[:, :, None, None]
+    xn = F.leaky_relu(x * scale + shift, 0.2).to(dt).float()
+    ref = F.conv2d(xn, wt.to(dt).float(), bias, stride=stride, padding=1)
+    xin = (to_parity_planar(x, dt) if stride == 2 else to_planar(x, dt)).to(dev)
+    out, _ = _run_conv_ex(dev, xin, wt, bias, b, h, w, cin, cout, stride, False, (stats, aw, ab),
+                          (b, cout // 8, h // stride, w // stride, 8), False, simt)
+    out = from_planar(out)
+    err = (out - ref).abs()
+    tol = 2.0 ** -7 * ref.abs() + 4e-3
+    assert bool((err <= tol).all()), 'max err %.4g (ref %.4g)' % (err.max().item(), ref.flatten()[err.argmax()].item())
