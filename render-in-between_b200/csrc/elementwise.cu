@@ -428,11 +428,12 @@ __global__ void warp_kernel(const float* __restrict__ src, const float* __restri
   const int y = hw / W, x = hw - y * W;
   const float fx = __ldg(flow + n * flow_bs + hw);
   const float fy = __ldg(flow + n * flow_bs + (size_t)HW + hw);
-  // same float sequence as building the normalised grid and un-normalising it in grid_sample
+  // same float sequence as building the normalised grid and un-normalising it in grid_sample (the division by 2 is
+  // written as an exact multiplication by 0.5)
   const float gx = __fsub_rn(__fmul_rn(__fadd_rn((float)x, fx), sx), 1.0f);
   const float gy = __fsub_rn(__fmul_rn(__fadd_rn((float)y, fy), sy), 1.0f);
-  float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.0f), 2.0f), (float)(W - 1));
-  float iy = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.0f), 2.0f), (float)(H - 1));
+  float ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.0f), 0.5f), (float)(W - 1));
+  float iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.0f), 0.5f), (float)(H - 1));
   ix = fminf(fmaxf(ix, 0.f), (float)(W - 1));
   iy = fminf(fmaxf(iy, 0.f), (float)(H - 1));
   const float x0f = floorf(ix), y0f = floorf(iy);
@@ -451,8 +452,9 @@ __global__ void warp_kernel(const float* __restrict__ src, const float* __restri
 
 // Four consecutive pixels of a row per thread (W % 4 == 0): 16-byte flow loads and output stores, 16 gathers in flight.
 // Per pixel the float sequence is the one of warp_kernel.
+template <int CT>   // CT > 0: channel count known at compile time (all gathers of a thread are issued together)
 __global__ void warp4_kernel(const float* __restrict__ src, const float* __restrict__ flow, float* __restrict__ out,
-                             int C, int H, int W, float sx, float sy, size_t total4, long long src_bs, long long flow_bs,
+                             int Crt, int H, int W, float sx, float sy, size_t total4, long long src_bs, long long flow_bs,
                              long long out_bs) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over B*H*W/4
   if (i >= total4) return;
@@ -469,8 +471,8 @@ __global__ void warp4_kernel(const float* __restrict__ src, const float* __restr
   for (int p = 0; p < 4; ++p) {
     const float gx = __fsub_rn(__fmul_rn(__fadd_rn((float)(xb + p), fxs[p]), sx), 1.0f);
     const float gy = __fsub_rn(__fmul_rn(__fadd_rn((float)y, fys[p]), sy), 1.0f);
-    float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.0f), 2.0f), (float)(W - 1));
-    float iy = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.0f), 2.0f), (float)(H - 1));
+    float ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.0f), 0.5f), (float)(W - 1));
+    float iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.0f), 0.5f), (float)(H - 1));
     ix = fminf(fmaxf(ix, 0.f), (float)(W - 1));
     iy = fminf(fmaxf(iy, 0.f), (float)(H - 1));
     const float x0f = floorf(ix), y0f = floorf(iy);
@@ -481,6 +483,8 @@ __global__ void warp4_kernel(const float* __restrict__ src, const float* __restr
     dx1[p] = x0 + 1 < W ? 1 : -1;   // -1: neighbour outside the image (its weight is an exact 0 then; term skipped)
     dy1[p] = y0 + 1 < H ? W : -1;
   }
+  const int C = CT > 0 ? CT : Crt;
+#pragma unroll
   for (int c = 0; c < C; ++c) {
     const float* s = src + n * src_bs + (size_t)c * HW;
     float acc[4];
@@ -507,8 +511,12 @@ int launch_warp(const float* src, const float* flow, float* out, int B, int C, i
   if (W % 4 == 0 && flow_bstride % 4 == 0 && out_bstride % 4 == 0 &&
       (((uintptr_t)flow | (uintptr_t)out) & 15) == 0) {
     const size_t total4 = total / 4;
-    warp4_kernel<<<(unsigned)((total4 + threads - 1) / threads), threads, 0, s>>>(src, flow, out, C, H, W, sx, sy, total4,
-                                                                                  src_bstride, flow_bstride, out_bstride);
+    if (C == 3)
+      warp4_kernel<3><<<(unsigned)((total4 + threads - 1) / threads), threads, 0, s>>>(src, flow, out, C, H, W, sx, sy, total4,
+                                                                                       src_bstride, flow_bstride, out_bstride);
+    else
+      warp4_kernel<0><<<(unsigned)((total4 + threads - 1) / threads), threads, 0, s>>>(src, flow, out, C, H, W, sx, sy, total4,
+                                                                                       src_bstride, flow_bstride, out_bstride);
     RIB_CHECK_CUDA(cudaGetLastError());
     return 0;
   }

@@ -122,10 +122,10 @@ def test_generator_default_resolution_and_batch_independence(dev, gen, arch, syn
     assert p >= PSNR_MIN_DB, 'fused PSNR %.2f dB at 320x480' % p
 
 
-@pytest.mark.parametrize('b,size', [(2, 256), (1, 1024)], ids=['B2x256', 'B1x1024'])
+@pytest.mark.parametrize('b,size', [(16, 256), (1, 1024)], ids=['B16x256', 'B1x1024'])
 def test_generator_resolution_sweep(dev, gen, arch, synth_sd, b, size):
-    """BASELINE configs[4] (resolution sweep 256-1024 px): parity of the whole forward against the fp32 oracle at the
-    sweep's end points (the plan, the tiling and the auto-tuner's choices all depend on the shape)."""
+    """BASELINE configs[1] (single-frame forward, 256x256, batch 16) and configs[4] (resolution sweep 256-1024 px):
+    parity of the whole forward against the fp32 oracle at the sweep's end points (the plan, the tiling and the auto-tuner's choices all depend on the shape)."""
     j = synth_joints(b, size, size, seed=11)
     label = torch.from_numpy(np.stack([ro.label([(a[0], a[1]) for a in j[t]], [a[2] for a in j[t]], size, size)
                                        for t in range(b)]))
