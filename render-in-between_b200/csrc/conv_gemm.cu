@@ -586,8 +586,11 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
         if (col < p.n_valid) {
           const float t1 = ((s_auxg[c] + s_auxg[2 * BN + c]) + s_auxg[4 * BN + c]) + s_auxg[6 * BN + c];
           const float t2 = ((s_auxg[BN + c] + s_auxg[3 * BN + c]) + s_auxg[5 * BN + c]) + s_auxg[7 * BN + c];
-          atomicAdd(&p.stats[((size_t)n_img * p.stats_ld + col) * 2 + 0], (double)t1);
-          atomicAdd(&p.stats[((size_t)n_img * p.stats_ld + col) * 2 + 1], (double)t2);
+          double* st = (p.seg_cols && col >= p.seg_cols)
+                           ? p.stats_b + ((size_t)n_img * p.stats_b_ld + (col - p.seg_cols)) * 2
+                           : p.stats + ((size_t)n_img * p.stats_ld + col) * 2;
+          atomicAdd(st, (double)t1);
+          atomicAdd(st + 1, (double)t2);
         }
       }
       epi_bar(eg);
@@ -675,6 +678,13 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
             obase = p.out.p + (size_t)n * p.out.bstride + (size_t)((ntile * BN) >> 3) * HW8 +
                     (size_t)((oy & 1) * 2 + (ox & 1)) * (HW8 >> 2) + ((size_t)(oy >> 1) * (p.W >> 1) + (ox >> 1)) * 8;
           // parity-planar copy for a stride-2 consumer: [plane][py][px][H/2][W/2][8]
+          // merged convs: base of the second output for this pixel (chunks at and after seg_cols go there)
+          act_t* obase_b = nullptr;
+          if (p.seg_cols)
+            obase_b = p.out_b.p + (size_t)n * p.out_b.bstride +
+                      (p.out_b_parity ? (size_t)((oy & 1) * 2 + (ox & 1)) * (HW8 >> 2) + ((size_t)(oy >> 1) * (p.W >> 1) + (ox >> 1)) * 8
+                                      : pix8);
+          const int nch_eff = p.seg_cols ? (p.n_valid + 15) >> 4 : NCH;   // merged convs: the padding columns are skipped
           act_t* obase2 = nullptr;
           if (p.has_out2)
             obase2 = p.out2.p + (size_t)n * p.out2.bstride + (size_t)((ntile * BN) >> 3) * HW8 +
@@ -685,6 +695,7 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
           if (!SIMT) tmem_ld16_issue(trow, r[0]);
 #pragma unroll
           for (int j = 0; j < NCH; ++j) {
+            if (j >= nch_eff) break;
             uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
             if (p.has_res && valid) {
               r0 = *reinterpret_cast<const uint4*>(rbase + (size_t)(2 * j) * HW8);
@@ -695,7 +706,7 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
               simt_chunk(p, n, oy, ox, ntile * BN + j * 16, v, par);
             } else {
               tmem_ld16_wait(r[j & 1]);
-              if (j + 1 < NCH) tmem_ld16_issue(trow + (uint32_t)((j + 1) * 16), r[(j + 1) & 1]);
+              if (j + 1 < nch_eff) tmem_ld16_issue(trow + (uint32_t)((j + 1) * 16), r[(j + 1) & 1]);
 #pragma unroll
               for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(r[j & 1][c]);
             }
@@ -753,8 +764,10 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
               }
 #pragma unroll
               for (int c = 0; c < 8; ++c) o[c] = pack2(v[2 * c], v[2 * c + 1]);
-              *reinterpret_cast<uint4*>(obase + (size_t)(2 * j) * oplane) = make_uint4(o[0], o[1], o[2], o[3]);
-              *reinterpret_cast<uint4*>(obase + (size_t)(2 * j + 1) * oplane) = make_uint4(o[4], o[5], o[6], o[7]);
+              const bool segb = p.seg_cols && j * 16 >= p.seg_cols;   // uniform
+              act_t* ob = segb ? obase_b + (size_t)(2 * j - (p.seg_cols >> 3)) * HW8 : obase + (size_t)(2 * j) * oplane;
+              *reinterpret_cast<uint4*>(ob) = make_uint4(o[0], o[1], o[2], o[3]);
+              *reinterpret_cast<uint4*>(ob + (segb ? HW8 : oplane)) = make_uint4(o[4], o[5], o[6], o[7]);
               if (p.has_out2) {
                 *reinterpret_cast<uint4*>(obase2 + (size_t)(2 * j) * HW8) = make_uint4(o[0], o[1], o[2], o[3]);
                 *reinterpret_cast<uint4*>(obase2 + (size_t)(2 * j + 1) * HW8) = make_uint4(o[4], o[5], o[6], o[7]);
@@ -1186,6 +1199,10 @@ int launch_conv_gemm(const ConvGemmParams& p, int mode, cudaStream_t stream) {
   RIB_REQUIRE(2 * p.MT * p.BN <= 512, "conv_gemm: accumulators exceed TMEM");
   RIB_REQUIRE(p.n_tiles >= 1, "conv_gemm: no N tiles");
   RIB_REQUIRE(mode != EPI_FINAL || p.n_valid <= 4, "conv_gemm: EPI_FINAL writes at most 4 channels");
+  RIB_REQUIRE(p.seg_cols == 0 || (mode == EPI_STORE && p.n_tiles == 1 && p.seg_cols % 16 == 0 && p.n_valid % 16 == 0 &&
+                                  p.seg_cols < p.n_valid && !p.has_res && !p.has_out2 && !p.subpix && !p.out_parity &&
+                                  p.BN > RIB_REGSTATS_MAXBN),
+              "conv_gemm: bad merged-conv launch");
   RIB_REQUIRE(mode != EPI_SPADE || (p.BN == 2 * p.CT && p.CT % 16 == 0 && p.C % p.CT == 0),
               "conv_gemm: EPI_SPADE needs BN == 2*CT");
   const bool xf = p.xf_stats != nullptr;

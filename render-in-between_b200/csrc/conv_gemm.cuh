@@ -94,6 +94,11 @@ struct alignas(64) ConvGemmParams {
   PlanarRef out;
   PlanarRef res; int has_res;
   PlanarRef out2; int has_out2;  // optional second copy of the output in parity-planar layout (feeds a stride-2 conv)
+  // Two convs over the same input merged along N (one N tile): columns [0, seg_cols) are the first conv (out, stats),
+  // [seg_cols, n_valid) the second (out_b, stats_b).  Both multiples of 16; 0 = single output.
+  int seg_cols;
+  PlanarRef out_b; int out_b_parity;
+  double* stats_b; int stats_b_ld;
   double* stats;       // [B][stats_ld][2] (sum, sum of squares; this launch's channel 0 first) or null
   int stats_ld;        // channels per image of the statistics buffer (>= n_valid: several producers may share one)
   int out_parity;      // 1: `out` is parity-planar [plane][py][px][H/2][W/2][8] (its only consumer is a stride-2 conv)

@@ -220,9 +220,21 @@ int generator_create(const rib_gen_config* cfg, const rib_tensor* tensors, int n
     add_layer(G, ln, emb_ch(c, i + 1), emb_ch(c, i + 1), emb_ch(c, i), 9, 0, 0, 2);
     jobs.push_back({ln, "ref_embedding.down_" + std::to_string(i) + ".layers.conv", true, emb_ch(c, i + 1), emb_ch(c, i), 9, 0, emb_ch(c, i), 0, 0, 0, false});
   }
-  // down_first
-  add_layer(G, "down_first", c.nf, c.nf, lab_pad, 9, 0);
-  jobs.push_back({"down_first", "down_first.layers.conv", false, c.nf, c.label_nc, 9, 0, lab_pad, 0, 0, 0, false});
+  // down_first and the mask net's down_lbl.0 are both 3x3 convs over the label: one GEMM with their output channels side
+  // by side (N = nf + mask_nf) reads the label once and doubles the columns per tcgen05.mma, which is what bounds these
+  // narrow full-resolution layers.  RIB_MERGE_LABEL=0 keeps them apart.
+  static const bool merge_env = !(getenv("RIB_MERGE_LABEL") != nullptr && atoi(getenv("RIB_MERGE_LABEL")) == 0);
+  const bool merge_label = merge_env && c.nf + c.mask_nf <= 128;
+  if (merge_label) {
+    int bn = 16;
+    while (bn < c.nf + c.mask_nf) bn <<= 1;
+    add_layer(G, "label3x3", c.nf + c.mask_nf, bn, lab_pad, 9, 0, bn);
+    jobs.push_back({"label3x3", "down_first.layers.conv", false, c.nf, c.label_nc, 9, 0, lab_pad, 0, 0, 0, false});
+    jobs.push_back({"label3x3", "flow_network_temp.down_lbl.0.layers.conv", true, c.mask_nf, c.label_nc, 9, 0, lab_pad, c.nf, 0, 0, false});
+  } else {
+    add_layer(G, "down_first", c.nf, c.nf, lab_pad, 9, 0);
+    jobs.push_back({"down_first", "down_first.layers.conv", false, c.nf, c.label_nc, 9, 0, lab_pad, 0, 0, 0, false});
+  }
   // SPADE res-blocks
   for (const BlockDef& b : res_blocks(c)) {
     const int cond = emb_ch(c, b.lvl);
@@ -247,8 +259,10 @@ int generator_create(const rib_gen_config* cfg, const rib_tensor* tensors, int n
   for (int br = 0; br < 2; ++br) {
     const std::string bn = br == 0 ? "down_lbl" : "down_img";
     const int cin = br == 0 ? c.label_nc : 3 * c.img_nc, cpad = br == 0 ? lab_pad : mask_in_pad;
-    add_layer(G, "mask." + bn + ".0", c.mask_nf, c.mask_nf, cpad, 9, 0);
-    jobs.push_back({"mask." + bn + ".0", f + bn + ".0.layers.conv", true, c.mask_nf, cin, 9, 0, cpad, 0, 0, 0, false});
+    if (!(br == 0 && merge_label)) {
+      add_layer(G, "mask." + bn + ".0", c.mask_nf, c.mask_nf, cpad, 9, 0);
+      jobs.push_back({"mask." + bn + ".0", f + bn + ".0.layers.conv", true, c.mask_nf, cin, 9, 0, cpad, 0, 0, 0, false});
+    }
     for (int i = 0; i < c.mask_down; ++i) {
       std::string ln = "mask." + bn + "." + std::to_string(i + 1);
       add_layer(G, ln, mask_nfilt(c, i + 1), mask_nfilt(c, i + 1), mask_nfilt(c, i), 9, 0, 0, 2);
@@ -557,6 +571,27 @@ struct PlanBuilder {
     p.act = act;
     p.has_res = res ? 1 : 0;
     if (res) p.res = res->ref();
+    push_gemm(p, EPI_STORE, lname);
+  }
+
+  // Two convs over in0 merged along N: columns [0, a.C) -> a (+ stats_a), the rest -> b (+ stats_b); no activation.
+  void conv_store_merged(const std::string& lname, const View& in0, const View& a, double* stats_a, const View& b,
+                         double* stats_b) {
+    const GemmLayer& L = G->layers.at(lname);
+    if (a.C + b.C != L.n_valid || a.H != b.H || a.W != b.W || a.parity) {
+      set_error("plan: bad merged conv " + lname);
+      rc = -4;
+    }
+    ConvGemmParams p = gemm_common(L, in0, nullptr, 1, a.H, a.W, L.BN);
+    p.out = a.ref();
+    p.stats = stats_a;
+    p.stats_ld = a.C;
+    p.seg_cols = a.C;
+    p.out_b = b.ref();
+    p.out_b_parity = b.parity ? 1 : 0;
+    p.stats_b = stats_b;
+    p.stats_b_ld = b.C;
+    p.act = ACT_NONE;
     push_gemm(p, EPI_STORE, lname);
   }
 
@@ -937,7 +972,16 @@ static int build_plan(Generator* G, int B, int H, int W, void* wsbase, size_t* b
   }
   // -- main branch --
   View x = pb.alloc("down_first", H, W, c.nf);
-  pb.conv_store("down_first", lab, nullptr, 1, x, st_x0, ACT_NONE, nullptr);
+  const bool merge_label = G->layers.count("label3x3") != 0;
+  static const int xf_mode = getenv("RIB_XF") ? atoi(getenv("RIB_XF")) : 1;
+  View lbl0_raw;   // merged launch: the mask net's down_lbl.0 raw output comes out of the same GEMM
+  if (merge_label) {
+    lbl0_raw = pb.alloc("mask.down_lbl.0.raw", H, W, c.mask_nf);
+    if (c.mask_down > 0 && xf_mode >= 1) lbl0_raw.parity = true;
+    pb.conv_store_merged("label3x3", lab, x, st_x0, lbl0_raw, mst["down_lbl0"]);
+  } else {
+    pb.conv_store("down_first", lab, nullptr, 1, x, st_x0, ACT_NONE, nullptr);
+  }
   const double* xst = st_x0;
   bool x_ups = false;
   int lvl_h = H, lvl_w = W;  // resolution at which the current block runs
@@ -1003,7 +1047,6 @@ static int build_plan(Generator* G, int B, int H, int W, void* wsbase, size_t* b
   // level and the res_flow blocks keep the separate in_apply pass.
   // RIB_XF = 0: separate in_apply everywhere; 1 (default): transform in the stride-2 down convs; 2: also in the
   // res_flow convs (the statistics of both branches' last level then share one buffer in cat order).
-  static const int xf_mode = getenv("RIB_XF") ? atoi(getenv("RIB_XF")) : 1;
   View cat = pb.alloc("mask.cat", H >> c.mask_down, W >> c.mask_down, 2 * mch);
   for (int br = 0; br < 2; ++br) {
     const std::string bn = br == 0 ? "down_lbl" : "down_img";
@@ -1015,11 +1058,13 @@ static int build_plan(Generator* G, int B, int H, int W, void* wsbase, size_t* b
       const std::string pre = f + bn + "." + std::to_string(i) + ".layers.norm";
       const bool lastl = i == c.mask_down;
       const bool raw_in_cat = lastl && xf_mode >= 2;
-      View raw = raw_in_cat ? PlanBuilder::slice(cat, br * mch, mch) : pb.alloc(nm + ".raw", h, w, ch);
-      if (!lastl && xf_mode >= 1) raw.parity = true;  // consumed only by the next (stride-2) conv
+      const bool merged = merge_label && br == 0 && i == 0;   // already computed with down_first
+      View raw = merged ? lbl0_raw : (raw_in_cat ? PlanBuilder::slice(cat, br * mch, mch) : pb.alloc(nm + ".raw", h, w, ch));
+      if (!merged && !lastl && xf_mode >= 1) raw.parity = true;  // consumed only by the next (stride-2) conv
       double* st = raw_in_cat ? st_cat + (size_t)br * mch * 2 : mst[bn + std::to_string(i)];
-      pb.conv_store(nm, cur, nullptr, i == 0 ? 1 : 2, raw, st, ACT_NONE, nullptr, nullptr,
-                    (i == 0 || xf_mode < 1) ? nullptr : &xf_prev, raw_in_cat ? 2 * mch : 0);
+      if (!merged)
+        pb.conv_store(nm, cur, nullptr, i == 0 ? 1 : 2, raw, st, ACT_NONE, nullptr, nullptr,
+                      (i == 0 || xf_mode < 1) ? nullptr : &xf_prev, raw_in_cat ? 2 * mch : 0);
       xf_prev.stats = st;
       xf_prev.w = G->in_affine.at(pre + ".weight");
       xf_prev.b = G->in_affine.at(pre + ".bias");
