@@ -49,7 +49,8 @@ def alg_bytes(d):
     elif d['mode'] == 2:
         wr = px * d['nvalid'] * 4
     else:
-        wr = px * d['N'] * 2
+        # plain store: the real output columns (a sub-pixel conv's N = 4 x Cout are all real; merged convs pad N)
+        wr = px * (d['N'] if d['taps'] == 4 else d['nvalid']) * 2
     return rd + wr + d['N'] * d['K'] * 2
 
 
