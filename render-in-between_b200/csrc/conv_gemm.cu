@@ -196,7 +196,9 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
 
   constexpr int NCH = BN / 16;                         // 16-column chunks of the N tile
-  constexpr int CT = BN / 2;                           // EPI_SPADE: channels per tile ([gamma | beta])
+  constexpr bool kSpade = MODE == EPI_SPADE || MODE == EPI_SPADE2;
+  constexpr int NQ = MODE == EPI_SPADE2 ? 2 : 1;       // SPADE outputs per tile ([gamma | beta] pairs side by side)
+  constexpr int CT = BN / (2 * NQ);                    // SPADE: channels per tile
   const int G = p.stages0 + p.stages1;                 // channel groups (halo tiles) per output tile
   const int n_bt = p.stages0 * p.ntaps + p.stages1;    // weight sub-tiles per output tile
   // ring of group slots: [halo tile(s) | (streamed mode) the group's weight sub-tiles]; then the resident weights
@@ -618,7 +620,7 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
 
       if (n != cur_n) {  // uniform over the 128 epilogue threads
         if (MODE == EPI_STORE && want_stats && cur_n >= 0) flush_stats(cur_n);
-        if (MODE == EPI_SPADE) {
+        if (kSpade) {
           const int tiles_per_q = p.C / CT;
           const int c0 = (ntile % tiles_per_q) * CT;
           const double cnt = (double)p.Hx * (double)p.Wx;
@@ -640,7 +642,7 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
 
       // EPI_SPADE: the x values of a sub-tile are fetched one sub-tile ahead (the first one before waiting for
       // the accumulator), so that their DRAM latency overlaps the MMAs / the previous sub-tile's arithmetic
-      constexpr int NXC = MODE == EPI_SPADE ? CT / 16 : 1;
+      constexpr int NXC = kSpade ? CT / 16 : 1;
       uint4 xcur[NXC][2], xnext[NXC][2];
       auto load_x = [&](int m, uint4 (*dst)[2]) {
         const int oy = oy0 + m * p.th + ty, ox = ox0 + tx;
@@ -659,7 +661,7 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
           }
         }
       };
-      if (MODE == EPI_SPADE) load_x(0, xcur);
+      if (kSpade) load_x(0, xcur);
       if (!SIMT) {
         mbar_wait(smem_u32(&tmem_full_bar[buf]), use & 1u);
         tc_fence_after();
@@ -774,56 +776,69 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
               }
             }
           }
-        } else if (MODE == EPI_SPADE) {
+        } else if (kSpade) {
           constexpr int NCS = CT / 16;
           const int tiles_per_q = p.C / CT;
-          const int qq = ntile / tiles_per_q;
-          const int c0 = (ntile - qq * tiles_per_q) * CT;
-          act_t* orow = p.outq[qq].p + (size_t)n * p.outq[qq].bstride + (size_t)(c0 >> 3) * HW8 + pix8;
-          const float sl = p.actq[qq] == ACT_LRELU ? 0.2f : 1.0f;
+          const int q0 = NQ == 1 ? ntile / tiles_per_q : 0;              // first output of this tile
+          const int c0 = (ntile - q0 * tiles_per_q) * CT;
           uint32_t rg[16], rb[16];
           if (m + 1 < p.MT) load_x(m + 1, xnext);
 #pragma unroll
           for (int j = 0; j < NCS; ++j) {
             const uint4 x0 = xcur[j][0], x1 = xcur[j][1];
-            float g[16], b[16];
-            if (SIMT) {
-              simt_chunk(p, n, oy, ox, ntile * BN + j * 16, g);
-              simt_chunk(p, n, oy, ox, ntile * BN + CT + j * 16, b);
-            } else {
-              tmem_ld16_issue(trow + (uint32_t)(j * 16), rg);
-              tmem_ld16_issue(trow + (uint32_t)(CT + j * 16), rb);
-              tmem_ld16_wait(rg);
-              tmem_ld16_wait(rb);
+            const uint32_t xu[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+            float xn[16];   // (x - mean) * rstd, shared by the outputs of the tile
 #pragma unroll
-              for (int c = 0; c < 16; ++c) {
-                g[c] = __uint_as_float(rg[c]);
-                b[c] = __uint_as_float(rb[c]);
-              }
+            for (int c4 = 0; c4 < 4; ++c4) {
+              const int cb = j * 16 + c4 * 4;
+              const float4 rs = *reinterpret_cast<const float4*>(s_auxg + cb);        // rstd
+              const float4 ms = *reinterpret_cast<const float4*>(s_auxg + CT + cb);   // -mean * rstd
+              float xa, xb, xc, xd;
+              unpack2(xu[c4 * 2], xa, xb);
+              unpack2(xu[c4 * 2 + 1], xc, xd);
+              xn[c4 * 4 + 0] = fmaf(xa, rs.x, ms.x);
+              xn[c4 * 4 + 1] = fmaf(xb, rs.y, ms.y);
+              xn[c4 * 4 + 2] = fmaf(xc, rs.z, ms.z);
+              xn[c4 * 4 + 3] = fmaf(xd, rs.w, ms.w);
             }
-            if (valid) {
-              const uint32_t xu[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-              float y[16];
 #pragma unroll
-              for (int c4 = 0; c4 < 4; ++c4) {
-                const int cb = j * 16 + c4 * 4;
-                const float4 rs = *reinterpret_cast<const float4*>(s_auxg + cb);        // rstd
-                const float4 ms = *reinterpret_cast<const float4*>(s_auxg + CT + cb);   // -mean * rstd
-                const float4 bg = *reinterpret_cast<const float4*>(s_bias + cb);       // gamma bias + 1
-                const float4 bb = *reinterpret_cast<const float4*>(s_bias + CT + cb);  // beta bias
-                float xa, xb, xc, xd;
-                unpack2(xu[c4 * 2], xa, xb);
-                unpack2(xu[c4 * 2 + 1], xc, xd);
-                y[c4 * 4 + 0] = fmaf(fmaf(xa, rs.x, ms.x), g[c4 * 4 + 0] + bg.x, b[c4 * 4 + 0] + bb.x);
-                y[c4 * 4 + 1] = fmaf(fmaf(xb, rs.y, ms.y), g[c4 * 4 + 1] + bg.y, b[c4 * 4 + 1] + bb.y);
-                y[c4 * 4 + 2] = fmaf(fmaf(xc, rs.z, ms.z), g[c4 * 4 + 2] + bg.z, b[c4 * 4 + 2] + bb.z);
-                y[c4 * 4 + 3] = fmaf(fmaf(xd, rs.w, ms.w), g[c4 * 4 + 3] + bg.w, b[c4 * 4 + 3] + bb.w);
+            for (int qi = 0; qi < NQ; ++qi) {
+              const int qq = q0 + qi;
+              const int colg = qi * 2 * CT + j * 16, colb = colg + CT;       // gamma / beta columns inside the tile
+              float g[16], b[16];
+              if (SIMT) {
+                simt_chunk(p, n, oy, ox, ntile * BN + colg, g);
+                simt_chunk(p, n, oy, ox, ntile * BN + colb, b);
+              } else {
+                tmem_ld16_issue(trow + (uint32_t)colg, rg);
+                tmem_ld16_issue(trow + (uint32_t)colb, rb);
+                tmem_ld16_wait(rg);
+                tmem_ld16_wait(rb);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                  g[c] = __uint_as_float(rg[c]);
+                  b[c] = __uint_as_float(rb[c]);
+                }
               }
-              uint32_t o[8];
+              if (valid) {
+                float y[16];
 #pragma unroll
-              for (int c = 0; c < 8; ++c) o[c] = pack2(fmaxf(y[2 * c], sl * y[2 * c]), fmaxf(y[2 * c + 1], sl * y[2 * c + 1]));
-              *reinterpret_cast<uint4*>(orow + (size_t)(2 * j) * HW8) = make_uint4(o[0], o[1], o[2], o[3]);
-              *reinterpret_cast<uint4*>(orow + (size_t)(2 * j + 1) * HW8) = make_uint4(o[4], o[5], o[6], o[7]);
+                for (int c4 = 0; c4 < 4; ++c4) {
+                  const float4 bg = *reinterpret_cast<const float4*>(s_bias + colg + c4 * 4);  // gamma bias + 1
+                  const float4 bb = *reinterpret_cast<const float4*>(s_bias + colb + c4 * 4);  // beta bias
+                  y[c4 * 4 + 0] = fmaf(xn[c4 * 4 + 0], g[c4 * 4 + 0] + bg.x, b[c4 * 4 + 0] + bb.x);
+                  y[c4 * 4 + 1] = fmaf(xn[c4 * 4 + 1], g[c4 * 4 + 1] + bg.y, b[c4 * 4 + 1] + bb.y);
+                  y[c4 * 4 + 2] = fmaf(xn[c4 * 4 + 2], g[c4 * 4 + 2] + bg.z, b[c4 * 4 + 2] + bb.z);
+                  y[c4 * 4 + 3] = fmaf(xn[c4 * 4 + 3], g[c4 * 4 + 3] + bg.w, b[c4 * 4 + 3] + bb.w);
+                }
+                const float sl = p.actq[qq] == ACT_LRELU ? 0.2f : 1.0f;
+                act_t* orow = p.outq[qq].p + (size_t)n * p.outq[qq].bstride + (size_t)(c0 >> 3) * HW8 + pix8;
+                uint32_t o[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) o[c] = pack2(fmaxf(y[2 * c], sl * y[2 * c]), fmaxf(y[2 * c + 1], sl * y[2 * c + 1]));
+                *reinterpret_cast<uint4*>(orow + (size_t)(2 * j) * HW8) = make_uint4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<uint4*>(orow + (size_t)(2 * j + 1) * HW8) = make_uint4(o[4], o[5], o[6], o[7]);
+              }
             }
           }
 #pragma unroll
@@ -1186,6 +1201,11 @@ static ConvKernel pick_kernel(int mode, int BN, bool xf) {
       case 64: return conv_gemm_kernel<EPI_SPADE, 64, SIMT, false>;
       case 128: return conv_gemm_kernel<EPI_SPADE, 128, SIMT, false>;
     }
+  } else if (mode == EPI_SPADE2) {
+    switch (BN) {
+      case 64: return conv_gemm_kernel<EPI_SPADE2, 64, SIMT, false>;
+      case 128: return conv_gemm_kernel<EPI_SPADE2, 128, SIMT, false>;
+    }
   } else if (mode == EPI_FINAL && BN == 16) {
     return conv_gemm_kernel<EPI_FINAL, 16, SIMT, false>;
   }
@@ -1205,6 +1225,8 @@ int launch_conv_gemm(const ConvGemmParams& p, int mode, cudaStream_t stream) {
               "conv_gemm: bad merged-conv launch");
   RIB_REQUIRE(mode != EPI_SPADE || (p.BN == 2 * p.CT && p.CT % 16 == 0 && p.C % p.CT == 0),
               "conv_gemm: EPI_SPADE needs BN == 2*CT");
+  RIB_REQUIRE(mode != EPI_SPADE2 || (p.BN == 4 * p.CT && p.CT % 16 == 0 && p.C % p.CT == 0 && p.n_tiles == p.C / p.CT),
+              "conv_gemm: EPI_SPADE2 needs BN == 4*CT and one tile per CT channels");
   const bool xf = p.xf_stats != nullptr;
   RIB_REQUIRE(!xf || (p.stages1 == 0 && p.subpix == 0), "conv_gemm: the A-operand transform needs a single source");
   RIB_REQUIRE(!p.out_parity || (p.H % 2 == 0 && p.W % 2 == 0 && !p.subpix), "conv_gemm: bad parity-planar output");

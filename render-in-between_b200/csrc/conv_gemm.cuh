@@ -29,13 +29,16 @@
 //              pixel (2y+py, 2x+px) only sees the 2x2 low-resolution neighbourhood {y-1+py, y+py} x {x-1+px, x+px} with
 //              the 3x3 weights summed per source pixel, so the up-sampled map is never written or read and the MACs
 //              drop by 9/4
+//   EPI_SPADE2 the same for the two SPADE layers of a res-block that modulate the same x over the same cond map
+//              (conv_block_0 and conv_block_s): an N tile holds [gamma0|beta0|gamma1|beta1] of CT = BN/4 channels, so cond
+//              and x are read once for both outputs and every MMA carries twice the columns
 //   EPI_FINAL  bias -> tanh / sigmoid -> fp32 NCHW (+ optional 16-bit planar copy)  generator.py:228, :484-485
 #pragma once
 #include "common.cuh"
 
 namespace rib {
 
-enum { EPI_STORE = 0, EPI_SPADE = 1, EPI_FINAL = 2 };
+enum { EPI_STORE = 0, EPI_SPADE = 1, EPI_FINAL = 2, EPI_SPADE2 = 3 };
 enum { ACT_NONE = 0, ACT_LRELU = 1, ACT_TANH = 2, ACT_SIGMOID = 3 };
 
 static constexpr int kTileW = 8;    // output pixels per tile row  (= one 8-row UMMA core-matrix group)

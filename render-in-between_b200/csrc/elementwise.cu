@@ -556,7 +556,8 @@ int launch_sn_sigma_inv(const float* w, const float* u, const float* v, int Cout
 __device__ __forceinline__ int pack_row(const PackWeightParams& p, int co) {
   if (p.spade_C == 0) return p.row_off + co;
   const int half = co / p.spade_C, c = co - half * p.spade_C;
-  return p.row_off + (c / p.spade_CT) * 2 * p.spade_CT + half * p.spade_CT + c % p.spade_CT;
+  const int nq = p.spade_nq > 1 ? p.spade_nq : 1;
+  return p.row_off + (c / p.spade_CT) * 2 * nq * p.spade_CT + p.spade_q * 2 * p.spade_CT + half * p.spade_CT + c % p.spade_CT;
 }
 
 __global__ void pack_weight_subpix_kernel(const PackWeightParams p) {

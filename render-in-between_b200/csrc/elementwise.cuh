@@ -74,6 +74,9 @@ struct PackWeightParams {
   act_t* dst; float* bias_dst;
   int ktotal, koff, bkc, row_off;
   int spade_C, spade_CT;  // 0 for plain convs
+  int spade_nq, spade_q;  // SPADE outputs sharing an N tile (0/1: one) and this conv's index among them: with nq outputs a
+                          // tile is [gamma_0|beta_0|...|gamma_{nq-1}|beta_{nq-1}] of CT channels each,
+                          // row = row_off + (c / CT) * 2 * nq * CT + q * 2 * CT + half * CT + c % CT
   int bias_accumulate;    // add into bias_dst instead of overwriting (fused shortcut)
   // Sub-pixel form of "nearest x2 -> conv3x3" (taps == 9 in the source): emit the 2x2 kernel of output parity
   // (py, px) = (subpix_parity >> 1, subpix_parity & 1), K order (channel group, tap (a, b), channel) with 4 taps:

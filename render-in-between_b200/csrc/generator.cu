@@ -175,9 +175,15 @@ struct PackJob {  // one reference conv placed inside a GEMM layer
   int cout, cin, taps, koff, cin_pad /* padded input channels (informational) */, row_off, spade_C, spade_CT;
   bool bias_acc;
   int subpix = 0, parity = 0;  // sub-pixel form of a conv that follows nearest x2 (see PackWeightParams)
+  int spade_nq = 1, spade_q = 0;  // SPADE outputs sharing an N tile / this conv's index among them
 };
 
-int spade_ct(int C) { return std::min(C, 64); }
+// Channels per SPADE tile: BN = 2 * nq * CT <= 128.  RIB_SPADE2=0 keeps the two shortcut-block outputs in separate tiles.
+bool spade_pairs() {
+  static const bool on = !(getenv("RIB_SPADE2") != nullptr && atoi(getenv("RIB_SPADE2")) == 0);
+  return on;
+}
+int spade_ct(int C, int nq_tile = 1) { return std::min(C, nq_tile == 2 ? 32 : 64); }
 
 // BN = 0 selects the plain-store default min(n_pad, 128).
 void add_layer(Generator* G, const std::string& name, int n_valid, int n_pad, int cin0_pad, int taps, int cin1,
@@ -239,10 +245,14 @@ int generator_create(const rib_gen_config* cfg, const rib_tensor* tensors, int n
   for (const BlockDef& b : res_blocks(c)) {
     const int cond = emb_ch(c, b.lvl);
     const int nq = b.shortcut ? 2 : 1;
-    add_layer(G, b.name + ".spadeA", nq * 2 * b.cin, nq * 2 * b.cin, cond, 1, 0, 2 * spade_ct(b.cin));
-    jobs.push_back({b.name + ".spadeA", b.name + ".conv_block_0.layers.norm.mlps.0.0.layers.conv", false, 2 * b.cin, cond, 1, 0, cond, 0, b.cin, spade_ct(b.cin), false});
+    // conv_block_0 and conv_block_s modulate the same x over the same cond map: their [gamma|beta] columns share N
+    // tiles (EPI_SPADE2), so cond and x are read once for both outputs
+    const int nqt = (nq == 2 && spade_pairs()) ? 2 : 1;
+    const int ctA = spade_ct(b.cin, nqt);
+    add_layer(G, b.name + ".spadeA", nq * 2 * b.cin, nq * 2 * b.cin, cond, 1, 0, 2 * nqt * ctA);
+    jobs.push_back({b.name + ".spadeA", b.name + ".conv_block_0.layers.norm.mlps.0.0.layers.conv", false, 2 * b.cin, cond, 1, 0, cond, 0, b.cin, ctA, false, 0, 0, nqt, 0});
     if (b.shortcut)
-      jobs.push_back({b.name + ".spadeA", b.name + ".conv_block_s.layers.norm.mlps.0.0.layers.conv", false, 2 * b.cin, cond, 1, 0, cond, 2 * b.cin, b.cin, spade_ct(b.cin), false});
+      jobs.push_back({b.name + ".spadeA", b.name + ".conv_block_s.layers.norm.mlps.0.0.layers.conv", false, 2 * b.cin, cond, 1, 0, cond, nqt == 2 ? 0 : 2 * b.cin, b.cin, ctA, false, 0, 0, nqt, nqt == 2 ? 1 : 0});
     add_layer(G, b.name + ".conv0", b.hid, b.hid, b.cin, 9, 0);
     jobs.push_back({b.name + ".conv0", b.name + ".conv_block_0.layers.conv", true, b.hid, b.cin, 9, 0, b.cin, 0, 0, 0, false});
     add_layer(G, b.name + ".spadeB", 2 * b.hid, 2 * b.hid, cond, 1, 0, 2 * spade_ct(b.hid));
@@ -367,6 +377,8 @@ int generator_create(const rib_gen_config* cfg, const rib_tensor* tensors, int n
     pp.bias_accumulate = pj.bias_acc ? 1 : 0;
     pp.subpix = pj.subpix;
     pp.subpix_parity = pj.parity;
+    pp.spade_nq = pj.spade_nq;
+    pp.spade_q = pj.spade_q;
     rc = launch_pack_weight(pp, stream);
     if (rc) return fail(rc);
   }
@@ -613,8 +625,9 @@ struct PlanBuilder {
   void spade(const std::string& lname, const View& cond, const View& x, const double* xstats, bool ups, int nq,
              const View* outs, const int* acts) {
     const GemmLayer& L = G->layers.at(lname);
-    const int CT = spade_ct(x.C);
-    ConvGemmParams p = gemm_common(L, cond, nullptr, 1, cond.H, cond.W, 2 * CT);
+    const int nqt = (nq == 2 && spade_pairs()) ? 2 : 1;
+    const int CT = spade_ct(x.C, nqt);
+    ConvGemmParams p = gemm_common(L, cond, nullptr, 1, cond.H, cond.W, 2 * nqt * CT);
     p.x = x.ref();
     p.Hx = x.H;
     p.Wx = x.W;
@@ -626,7 +639,7 @@ struct PlanBuilder {
       p.outq[q] = outs[q].ref();
       p.actq[q] = acts[q];
     }
-    push_gemm(p, EPI_SPADE, lname);
+    push_gemm(p, nqt == 2 ? EPI_SPADE2 : EPI_SPADE, lname);
   }
 
   void conv_final(const std::string& lname, const View& in0, int act, int ext, const View* copy, int copy_coff) {
@@ -741,7 +754,7 @@ std::string tune_key(const Op& op) {
   char buf[256];
   snprintf(buf, sizeof(buf), "m%d B%d H%d W%d c%d+%d t%d s%d BN%d N%d r%d o%d st%d u%d q%d par%d", op.mode, p.B, p.H, p.W,
            L.cin0, L.cin1, L.taps, L.stride, p.BN, L.n_pad, p.has_res, p.has_out2, p.stats != nullptr, p.ups,
-           op.mode == EPI_SPADE ? p.n_tiles * p.BN / (2 * p.C) : 0, p.s2_parity + 2 * (p.xf_stats != nullptr) + 4 * p.out_parity);
+           (op.mode == EPI_SPADE || op.mode == EPI_SPADE2) ? p.n_tiles * p.BN / (2 * p.C) : 0, p.s2_parity + 2 * (p.xf_stats != nullptr) + 4 * p.out_parity);
   return buf;
 }
 

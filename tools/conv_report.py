@@ -41,7 +41,7 @@ def alg_bytes(d):
     px = d['B'] * d['H'] * d['W']
     s = d['stride']
     rd = px * s * s * d['cin0'] * 2 + px * d['cin1'] * 2
-    if d['mode'] == 1:      # SPADE: reads x (C = N/2 per quantity... N = nq*2*C) and writes nq maps of C
+    if d['mode'] in (1, 3):      # SPADE: reads x (C = N/2 per quantity... N = nq*2*C) and writes nq maps of C
         c_total = d['N'] // 2
         rd += px * c_total * 2 * 0 + px * (d['N'] // 2) * 2 * 0   # x is re-read per quantity; counted below
         wr = px * (d['N'] // 2) * 2
