@@ -9,8 +9,15 @@ Pinned against the reference by tests/golden/keypoints_cases.json (oracle/make_g
 `scale_keypoints` is the key-point half of `A.Resize` as the evaluator uses it (PGNR/models/evaluator.py:18-26, :218-220):
 x * W / w0, y * H / h0.  albumentations is not installed in the build container, so this one line is restated from its
 documented behaviour (parity unpinned).
+
+`save_frames` is the output side: the uint8 HWC frames that `rib.composite` / `ClipRenderer` already
+produce on the GPU (tensor2images semantics, PGNR/utils/utils.py:122-147) are written as PNGs named after the DAIN inputs,
+exactly what `Image.fromarray(tensor2images(fuse)).save(name)` writes per frame (PGNR/models/evaluator.py:265-266), but
+encoded by a thread pool (zlib releases the GIL) instead of one frame at a time between generator calls.
 """
 import json
+import os
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -66,3 +73,28 @@ def clip_joints(json_paths, src_hw, dst_hw):
     """[T, 19, 3] joint array of a clip (one OpenPose file per frame) at the model resolution: the `joints` argument of
     ClipRenderer.render (evaluator.py:213-220 for every frame)."""
     return np.stack([scale_keypoints(read_keypoints(p), src_hw, dst_hw) for p in json_paths])
+
+
+def frame_names(dain_paths, frames_dir):
+    """The reference's output names (evaluator.py:265): basename of the DAIN frame with a .png extension."""
+    return [os.path.join(frames_dir, os.path.basename(p))[:-4] + '.png' for p in dain_paths]
+
+
+def save_frames(frames_u8, paths, workers=8):
+    """frames_u8: uint8 [T, H, W, 3] (numpy array or CPU torch tensor, e.g. ClipRenderer.render(...)['u8'].cpu());
+    paths: T file names.  Writes lossless PNGs with PIL, `workers` frames at a time; returns the paths."""
+    from PIL import Image
+    arr = frames_u8.numpy() if hasattr(frames_u8, 'numpy') else np.asarray(frames_u8)
+    if arr.dtype != np.uint8 or arr.ndim != 4 or arr.shape[-1] != 3:
+        raise ValueError('save_frames expects uint8 [T, H, W, 3]')
+    if len(paths) != arr.shape[0]:
+        raise ValueError('need one path per frame')
+
+    def one(i):
+        Image.fromarray(arr[i]).save(paths[i])
+        return paths[i]
+
+    if workers <= 1:
+        return [one(i) for i in range(len(paths))]
+    with ThreadPoolExecutor(max_workers=workers) as ex:
+        return list(ex.map(one, range(len(paths))))

@@ -60,3 +60,25 @@ def test_scale_and_clip_joints(golden_dir, tmp_path):
         paths.append(str(p))
     j = rio.clip_joints(paths, (480, 640), (512, 512))
     assert j.shape == (3, 19, 3) and j.dtype == np.float64 and np.array_equal(j[1], s)
+
+
+def test_save_frames_roundtrip_and_reference_bytes(tmp_path):
+    """PNG is lossless: what save_frames writes decodes to the same pixels as the reference's per-frame
+    Image.fromarray(...).save(...) (evaluator.py:265-266), under the reference's file names."""
+    from PIL import Image
+    rng = np.random.default_rng(0)
+    frames = rng.integers(0, 256, size=(5, 48, 64, 3), dtype=np.uint8)
+    dain = ['/data/clip/DAIN/%05d.png' % i for i in range(5)]
+    names = rio.frame_names(dain, str(tmp_path))
+    assert names[3] == os.path.join(str(tmp_path), '00003.png')
+    out = rio.save_frames(frames, names, workers=4)
+    assert out == names
+    for i, n in enumerate(names):
+        assert np.array_equal(np.asarray(Image.open(n)), frames[i])
+    ref = tmp_path / 'ref.png'
+    Image.fromarray(frames[2]).save(str(ref))
+    assert ref.read_bytes() == open(names[2], 'rb').read()
+    import torch
+    rio.save_frames(torch.from_numpy(frames[:2]), names[:2], workers=1)
+    with pytest.raises(ValueError):
+        rio.save_frames(frames.astype(np.float32), names)
