@@ -135,6 +135,10 @@ int rib_generator_debug_tensor(rib_generator* g, const char* name, const void** 
 /* Text description (one line per planned kernel launch, in launch order) of the plan built by the last
  * rib_generator_forward: layer name, tiling, algorithmic FLOPs.  Joined with ncu launch lists by tools/. */
 int rib_generator_plan_text(rib_generator* g, char* buf, long long cap);
+/* The launch plan rib_generator_forward would build for (B, H, W), WITHOUT a GPU: validates the configuration of every
+ * layer for the shape (tile geometry, shared-memory budget, TMEM columns), applies the imported tuning table, and writes
+ * the plan text (as rib_generator_plan_text; buf may be NULL) and the workspace size.  Nothing is allocated or launched. */
+int rib_plan_dry_run(const rib_gen_config* cfg, int B, int H, int W, long long* ws_bytes, char* buf, long long cap);
 /* The plan-time auto-tuner's log: one line per tuned launch shape of this process (candidate tilings with their
  * measured device times and the choice).  RIB_AUTOTUNE=0 in the environment disables the tuner. */
 int rib_tune_log(char* buf, long long cap);

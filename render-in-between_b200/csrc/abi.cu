@@ -136,6 +136,12 @@ int rib_generator_plan_text(rib_generator* g, char* buf, long long cap) {
   RIB_GUARD_END
 }
 
+int rib_plan_dry_run(const rib_gen_config* cfg, int B, int H, int W, long long* ws_bytes, char* buf, long long cap) {
+  RIB_GUARD_BEGIN
+  return generator_plan_dry_run(cfg, B, H, W, ws_bytes, buf, cap);
+  RIB_GUARD_END
+}
+
 int rib_tune_log(char* buf, long long cap) {
   RIB_GUARD_BEGIN
   RIB_REQUIRE(buf && cap > 0, "rib_tune_log: bad argument");

@@ -204,18 +204,10 @@ void add_layer(Generator* G, const std::string& name, int n_valid, int n_pad, in
 
 }  // namespace
 
-int generator_create(const rib_gen_config* cfg, const rib_tensor* tensors, int n, cudaStream_t stream,
-                     Generator** out) {
-  RIB_REQUIRE(cfg && tensors && out, "generator_create: null argument");
-  const rib_gen_config& c = *cfg;
-  RIB_REQUIRE(c.nf % 16 == 0 && c.emb_nf % 16 == 0 && c.mask_nf % 16 == 0, "channel counts must be multiples of 16");
-  RIB_REQUIRE(c.label_nc <= 32 && c.img_nc == 3, "unsupported input channel counts");
-  Source src;
-  for (int i = 0; i < n; ++i) src.t[tensors[i].name] = {tensors[i].data, tensors[i].numel};
-
-  Generator* G = new Generator();
-  G->cfg = c;
-  std::vector<PackJob> jobs;
+// The GEMM layers of the generator and the reference convs packed into each (no device memory involved: also used by
+// the CPU dry run of the launch plan).
+static void define_layers(Generator* G, std::vector<PackJob>& jobs) {
+  const rib_gen_config& c = G->cfg;
   const int lab_pad = 32, emb_in_pad = 16, mask_in_pad = 16;
 
   // ref_embedding
@@ -304,6 +296,23 @@ int generator_create(const rib_gen_config* cfg, const rib_tensor* tensors, int n
   }
   add_layer(G, "mask.conv_mask", 1, 16, c.mask_nf, 9, 0);
   jobs.push_back({"mask.conv_mask", f + "conv_mask.0.layers.conv", false, 1, c.mask_nf, 9, 0, c.mask_nf, 0, 0, 0, false});
+}
+
+int generator_create(const rib_gen_config* cfg, const rib_tensor* tensors, int n, cudaStream_t stream,
+                     Generator** out) {
+  RIB_REQUIRE(cfg && tensors && out, "generator_create: null argument");
+  const rib_gen_config& c = *cfg;
+  RIB_REQUIRE(c.nf % 16 == 0 && c.emb_nf % 16 == 0 && c.mask_nf % 16 == 0, "channel counts must be multiples of 16");
+  RIB_REQUIRE(c.label_nc <= 32 && c.img_nc == 3, "unsupported input channel counts");
+  Source src;
+  for (int i = 0; i < n; ++i) src.t[tensors[i].name] = {tensors[i].data, tensors[i].numel};
+
+  Generator* G = new Generator();
+  G->cfg = c;
+  std::vector<PackJob> jobs;
+  define_layers(G, jobs);
+  const std::string f = "flow_network_temp.";
+  const int mch = mask_nfilt(c, c.mask_down);
 
   // arena: packed weights + biases + one sigma scalar per job
   size_t off = 0;
@@ -440,6 +449,9 @@ struct PlanBuilder {
   int rc = 0;
 
   PlanBuilder(Generator* g, void* base, int b) : G(g), ws(base), B(b), real(base != nullptr) {}
+  // CPU dry run: views get (never dereferenced) non-null addresses so that every "is this pointer set" decision of the
+  // plan, and with it the tuning-table key of each launch, is the one of a real plan; no tensor maps are built.
+  PlanBuilder(Generator* g, int b, bool /*dry*/) : G(g), ws(reinterpret_cast<void*>((uintptr_t)1 << 30)), B(b), real(false) {}
 
   View alloc(const std::string& name, int H, int W, int C) {
     View v;
@@ -532,7 +544,7 @@ struct PlanBuilder {
     const GemmLayer& L = *op.layer;
     int r = conv_gemm_configure(&p, B, p.H, p.W, L.cin0, L.cin1, L.taps, L.stride, p.BN, L.n_pad, &t);
     if (r || p.BKc != L.bkc) return r ? r : -4;
-    r = make_maps(&p, L, op.in0, op.has_in1 ? &op.in1 : nullptr);
+    if (real) r = make_maps(&p, L, op.in0, op.has_in1 ? &op.in1 : nullptr);   // (the CPU dry run has no tensors to map)
     if (r) return r;
     *out = p;
     return 0;
@@ -881,6 +893,19 @@ int generator_tune_import(const char* text) {
   return n;
 }
 
+// CPU dry run: the tilings of the imported tuning table without any timing (cache hits only).
+static void apply_tune_table(PlanBuilder& pb) {
+  std::lock_guard<std::mutex> lk(g_tune_mu);
+  for (Op& op : pb.ops) {
+    if (op.kind != OP_GEMM || op.layer == nullptr) continue;
+    auto it = g_tune_cache.find(tune_key(op));
+    if (it == g_tune_cache.end() || (it->second.mt == 0 && it->second.policy == 0 && it->second.ring == 0)) continue;
+    ConvGemmParams q;
+    if (pb.retile(op, it->second, &q) == 0) op.g = q;
+  }
+  set_error("");
+}
+
 int generator_tune_log(char* buf, long long cap) {
   std::lock_guard<std::mutex> lk(g_tune_mu);
   if ((long long)g_tune_log.size() + 1 > cap) return -1;
@@ -888,13 +913,14 @@ int generator_tune_log(char* buf, long long cap) {
   return 0;
 }
 
-static int build_plan(Generator* G, int B, int H, int W, void* wsbase, size_t* bytes_out, cudaStream_t stream) {
+static int build_plan(Generator* G, int B, int H, int W, void* wsbase, size_t* bytes_out, cudaStream_t stream,
+                      std::vector<Op>* dry_ops = nullptr) {
   const rib_gen_config& c = G->cfg;
   RIB_REQUIRE(B >= 1 && H >= 16 && W >= 16, "forward: bad batch or image size");
   const int max_down = std::max(std::max(c.n_down, c.emb_down), c.mask_down);
   RIB_REQUIRE(H % (1 << max_down) == 0 && W % (1 << max_down) == 0,
               "forward: H and W must be multiples of " + std::to_string(1 << max_down));
-  PlanBuilder pb(G, wsbase, B);
+  PlanBuilder pb = (wsbase == nullptr && dry_ops != nullptr) ? PlanBuilder(G, B, true) : PlanBuilder(G, wsbase, B);
   const std::string f = "flow_network_temp.";
 
   // statistics arena first (zeroed by one memset per forward)
@@ -1145,6 +1171,10 @@ static int build_plan(Generator* G, int B, int H, int W, void* wsbase, size_t* b
 
   if (pb.rc) return pb.rc;
   *bytes_out = align_up(pb.ws.off, 1024);
+  if (dry_ops != nullptr && wsbase == nullptr) {
+    if (autotune_enabled()) apply_tune_table(pb);
+    dry_ops->swap(pb.ops);
+  }
   if (wsbase) {
     if (!g_debug_simt && autotune_enabled()) autotune(pb, stream);
     G->ops.swap(pb.ops);
@@ -1255,10 +1285,50 @@ int generator_forward(Generator* G, int B, int H, int W, const float* label, con
 }
 
 // One text line per planned launch: kind, layer, tiling and the algorithmic work, in launch order.
-int generator_plan_text(Generator* G, char* buf, long long cap) {
+static int plan_text_of(const std::vector<Op>& ops, char* buf, long long cap);
+
+int generator_plan_text(Generator* G, char* buf, long long cap) { return plan_text_of(G->ops, buf, cap); }
+
+// Launch plan for (B, H, W) without a GPU: layer table, tiling (default heuristics + imported tuning table), shared-memory
+// and workspace sizes.  Validates every layer's configuration for the shape; nothing is launched or allocated.
+int generator_plan_dry_run(const rib_gen_config* cfg, int B, int H, int W, long long* ws_bytes, char* buf, long long cap) {
+  RIB_REQUIRE(cfg != nullptr, "plan_dry_run: null config");
+  const rib_gen_config& c = *cfg;
+  RIB_REQUIRE(c.nf % 16 == 0 && c.emb_nf % 16 == 0 && c.mask_nf % 16 == 0, "channel counts must be multiples of 16");
+  RIB_REQUIRE(c.label_nc <= 32 && c.img_nc == 3, "unsupported input channel counts");
+  Generator G;
+  G.cfg = c;
+  std::vector<PackJob> jobs;
+  define_layers(&G, jobs);
+  {  // the instance-norm affine tables of the mask network: names only
+    const std::string f = "flow_network_temp.";
+    auto reg = [&](const std::string& prefix) {
+      G.in_affine[prefix + ".weight"] = nullptr;
+      G.in_affine[prefix + ".bias"] = nullptr;
+    };
+    for (int br = 0; br < 2; ++br)
+      for (int i = 0; i <= c.mask_down; ++i)
+        reg(f + (br == 0 ? "down_lbl." : "down_img.") + std::to_string(i) + ".layers.norm");
+    for (int i = 0; i < c.mask_res; ++i) {
+      reg(f + "res_flow." + std::to_string(i) + ".conv_block_0.layers.norm");
+      reg(f + "res_flow." + std::to_string(i) + ".conv_block_1.layers.norm");
+      if (i == 0) reg(f + "res_flow.0.conv_block_s.layers.norm");
+    }
+    for (int k = 0; k < c.mask_down; ++k) reg(f + "up_flow." + std::to_string(2 * k + 1) + ".layers.norm");
+  }
+  size_t bytes = 0;
+  std::vector<Op> ops;
+  int rc = build_plan(&G, B, H, W, nullptr, &bytes, nullptr, &ops);
+  if (rc) return rc;
+  if (ws_bytes) *ws_bytes = (long long)bytes;
+  if (buf == nullptr) return 0;
+  return plan_text_of(ops, buf, cap);
+}
+
+static int plan_text_of(const std::vector<Op>& ops, char* buf, long long cap) {
   std::string out;
   char line[512];
-  for (const Op& op : G->ops) {
+  for (const Op& op : ops) {
     switch (op.kind) {
       case OP_MEMSET:
         snprintf(line, sizeof(line), "memset bytes=%zu\n", op.ms_bytes);

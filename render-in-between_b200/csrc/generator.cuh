@@ -17,6 +17,7 @@ int generator_forward(Generator* g, int B, int H, int W, const float* label, con
 int generator_bind(Generator* g, int B, int H, int W, void* ws, long long ws_bytes, void** label_planar);
 int generator_debug_tensor(Generator* g, const char* name, const void** ptr, int* B, int* H, int* W, int* C, int* ld);
 int generator_plan_text(Generator* g, char* buf, long long cap);
+int generator_plan_dry_run(const rib_gen_config* cfg, int B, int H, int W, long long* ws_bytes, char* buf, long long cap);
 int generator_tune_log(char* buf, long long cap);
 int generator_tune_export(char* buf, long long cap);
 int generator_tune_import(const char* text);

@@ -161,6 +161,17 @@ class Generator(nn.Module):
         check(lib.rib_generator_plan_text(self._handle, buf, len(buf)), 'rib_generator_plan_text')
         return buf.value.decode()
 
+    def plan_dry_run(self, b, h, w):
+        """(workspace bytes, plan text) of the launch plan for a (b, h, w) batch, computed WITHOUT a GPU: every layer's
+        tiling is validated for the shape (tile geometry, shared-memory and TMEM budgets, imported tuning table)."""
+        a = self.arch
+        cfg = GenConfig(a.label_nc, a.img_nc, a.nf, a.maxf, a.n_down, a.n_res, a.emb_nf, a.emb_max, a.emb_down,
+                        a.mask_nf, a.mask_max, a.mask_down, a.mask_res)
+        need = C.c_longlong()
+        buf = C.create_string_buffer(1 << 16)
+        check(lib.rib_plan_dry_run(C.byref(cfg), b, h, w, C.byref(need), buf, len(buf)), 'rib_plan_dry_run')
+        return need.value, buf.value.decode()
+
     @staticmethod
     def tune_log():
         """The auto-tuner's candidates / timings / choices for every launch shape tuned in this process."""
