@@ -8,6 +8,12 @@
  * by the caller unless stated otherwise; every call is asynchronous on `stream` (a cudaStream_t
  * passed as void*), allocates no device memory (except rib_generator_create) and returns 0 on
  * success or a negative code, with the message available from rib_last_error().  No CPU fallback.
+ *
+ * Environment switches read by the library (all optional; defaults are the measured-best settings):
+ *   RIB_AUTOTUNE=0      no plan-time timing of candidate tilings (static heuristics + imported table only)
+ *   RIB_XF=0|1|2        scope of the in-kernel instance-norm transform of the mask network (default 1)
+ *   RIB_MERGE_LABEL=0   down_first and down_lbl.0 as two launches instead of one GEMM over the label
+ *   RIB_SPADE2=0        the two SPADE layers of a shortcut res-block in separate N tiles
  */
 #ifndef RIB_B200_H_
 #define RIB_B200_H_
