@@ -88,22 +88,30 @@ class ClockSampler:
         self.f.flush()
         rows = [r.strip().split(', ') for r in open(self.f.name).read().strip().splitlines() if r.strip()]
         os.unlink(self.f.name)
-        sm, reasons = [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for r in rows:
-            if len(r) < 9:
-                continue
-            ts = self._epoch(r[0])
-            if t0 is not None and ts is not None and not (t0 - 0.05 <= ts <= t1 + 0.05):
-                continue
-            try:
-                sm.append(float(r[1]))
-                out['sm_max_mhz'] = float(r[2])
-            except ValueError:
-                continue
-            for n, v in zip(names, r[5:9]):
-                if v.strip().lower().startswith('active'):
-                    reasons.add(n)
+
+        def collect(windowed):
+            sm, reasons = [], set()
+            for r in rows:
+                if len(r) < 9:
+                    continue
+                ts = self._epoch(r[0])
+                if windowed and t0 is not None and ts is not None and not (t0 - 0.05 <= ts <= t1 + 0.05):
+                    continue
+                try:
+                    sm.append(float(r[1]))
+                    out['sm_max_mhz'] = float(r[2])
+                except ValueError:
+                    continue
+                for n, v in zip(names, r[5:9]):
+                    if v.strip().lower().startswith('active'):
+                        reasons.add(n)
+            return sm, reasons
+
+        sm, reasons = collect(True)
+        if not sm:      # nothing fell into the window (clock skew between nvidia-smi and this process): use every sample
+            sm, reasons = collect(False)
+            out['window'] = 'whole run (no sample inside the timed region)'
         if sm:
             out['sm_mhz'] = float(np.median(sm))
             out['samples'] = len(sm)
