@@ -21,6 +21,12 @@ namespace rib {
 static constexpr int kEpiGroups = 1;                       // epilogue groups (4 warps each), one per TMEM accumulator buffer
 static constexpr int kThreads = 64 + 128 * kEpiGroups;
 static constexpr int kNumSms = 148;
+// Accumulator buffers in TMEM per CTA.  Two everywhere in the shipped build; -DRIB_ACC4_MAXBN=16|32 builds the narrow
+// tiles with four (the MMA lane may then run three tiles ahead of the epilogue) for the A/B runs of tools/gpu_ab.sh.
+#ifndef RIB_ACC4_MAXBN
+#define RIB_ACC4_MAXBN 0
+#endif
+__host__ __device__ constexpr int acc_bufs(int BN) { return BN <= RIB_ACC4_MAXBN ? 4 : 2; }
 static constexpr int kXfThreads = 256;                     // transform warps of the XF kernels (after the epilogue warps)
 
 // Geometry of tap t of a stage: which halo tile of the slot it reads and the pixel offset of its
@@ -210,9 +216,10 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + p.a_ring;
   uint64_t* a_ready = a_empty + p.a_ring;        // XF only: halo tile transformed, MMA may read it
-  uint64_t* tmem_full_bar = a_ready + (XF ? p.a_ring : 0);  // [2]
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [2]
-  uint64_t* bres_bar = tmem_empty_bar + 2;
+  constexpr int NB = acc_bufs(BN);                                       // accumulator buffers
+  uint64_t* tmem_full_bar = a_ready + (XF ? p.a_ring : 0);  // [NB]
+  uint64_t* tmem_empty_bar = tmem_full_bar + NB;  // [NB]
+  uint64_t* bres_bar = tmem_empty_bar + NB;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bres_bar + 1);
   float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr + 4) + 15) & ~(uintptr_t)15);  // [BN], 16-byte aligned
   float* s_aux = s_bias + BN;                              // per epilogue group: STORE [4 warps][2*BN] stats; SPADE [2*CT] rstd, -mean*rstd
@@ -236,7 +243,7 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
   const int t_end = (int)(total_tiles * (cta_m + 1) / cta_groups);
   const int acc_cols = p.MT * BN;  // TMEM columns of one accumulator buffer
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < 2 * acc_cols) tmem_cols <<= 1;
+  while ((int)tmem_cols < NB * acc_cols) tmem_cols <<= 1;
 
   if (!SIMT) {
     if (warp == 0 && lane == 0) {
@@ -247,7 +254,7 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
         mbar_init(smem_u32(&a_empty[i]), 1);
         if (XF) mbar_init(smem_u32(&a_ready[i]), kXfThreads / 32);
       }
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < NB; ++i) {
         mbar_init(smem_u32(&tmem_full_bar[i]), 1);
         mbar_init(smem_u32(&tmem_empty_bar[i]), 4);
       }
@@ -380,8 +387,8 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
       uint32_t a_phase = 0;
       int it = 0;
       for (int mt = t_begin; mt < t_end; ++mt, ++it) {
-        const int buf = it & 1;
-        const uint32_t use = (uint32_t)(it >> 1);
+        const int buf = (int)((unsigned)it % (unsigned)NB);
+        const uint32_t use = (uint32_t)it / (uint32_t)NB;
         mbar_wait(tempty0 + 8u * buf, (use & 1u) ^ 1u);  // epilogue has drained this buffer
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)(buf * acc_cols);
@@ -614,8 +621,8 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
     };
     it = eg;
     for (int mt = t_first; mt < t_end; mt += kEpiGroups, it += kEpiGroups) {
-      const int buf = it & 1;
-      const uint32_t use = (uint32_t)(it >> 1);
+      const int buf = (int)((unsigned)it % (unsigned)NB);
+      const uint32_t use = (uint32_t)it / (uint32_t)NB;
       const int oy0 = tile_y * p.th * p.MT, ox0 = tile_x * p.tw;
 
       if (n != cur_n) {  // uniform over the 128 epilogue threads
@@ -1125,7 +1132,7 @@ size_t conv_gemm_smem_bytes(const ConvGemmParams& p) {
                  (size_t)(p.b_resident ? n_bt : 0) * p.b_tap_bytes;
   size_t stat = p.stats != nullptr ? kStatStageBytes : 0;
   const bool xf = p.xf_stats != nullptr;
-  size_t bars = (size_t)((xf ? 3 : 2) * p.a_ring + 5) * 8 + 32;
+  size_t bars = (size_t)((xf ? 3 : 2) * p.a_ring + 2 * acc_bufs(p.BN) + 1) * 8 + 32;
   size_t scratch = (size_t)p.BN * 4 * (1 + 8 * kEpiGroups) + 64 + 64 + (xf ? (size_t)2 * p.stages0 * p.BKc * 4 : 0);
   return 1024 + tiles + stat + bars + scratch;
 }
@@ -1216,7 +1223,7 @@ int launch_conv_gemm(const ConvGemmParams& p, int mode, cudaStream_t stream) {
   RIB_REQUIRE(p.BKc == 16 || p.BKc == 32 || p.BKc == 64, "conv_gemm: BKc must be 16/32/64");
   RIB_REQUIRE(p.a_ring >= 2 && p.a_ring <= 8, "conv_gemm: bad ring depth");
   RIB_REQUIRE(p.MT == 1 || p.MT == 2, "conv_gemm: MT must be 1 or 2");
-  RIB_REQUIRE(2 * p.MT * p.BN <= 512, "conv_gemm: accumulators exceed TMEM");
+  RIB_REQUIRE(acc_bufs(p.BN) * p.MT * p.BN <= 512, "conv_gemm: accumulators exceed TMEM");
   RIB_REQUIRE(p.n_tiles >= 1, "conv_gemm: no N tiles");
   RIB_REQUIRE(mode != EPI_FINAL || p.n_valid <= 4, "conv_gemm: EPI_FINAL writes at most 4 channels");
   RIB_REQUIRE(p.seg_cols == 0 || (mode == EPI_STORE && p.n_tiles == 1 && p.seg_cols % 16 == 0 && p.n_valid % 16 == 0 &&
@@ -1247,7 +1254,7 @@ int launch_conv_gemm(const ConvGemmParams& p, int mode, cudaStream_t stream) {
   }
   // persistent grid: as many CTAs as fit on the chip, a multiple of n_tiles
   int tmem_cols = 32;
-  while (tmem_cols < 2 * p.MT * p.BN) tmem_cols <<= 1;
+  while (tmem_cols < acc_bufs(p.BN) * p.MT * p.BN) tmem_cols <<= 1;
   int occ = 1;
   const int threads = kThreads + (xf ? kXfThreads : 0);
   int rc = ctas_per_sm((const void*)fn, smem, tmem_cols, threads, &occ);
