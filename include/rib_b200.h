@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RIB_ABI_VERSION 3
+#define RIB_ABI_VERSION 4
 
 /* Message of the last failing call on this host thread ("" if none). */
 const char* rib_last_error(void);
@@ -71,6 +71,16 @@ int rib_composite(const float* img, const float* mask, const float* dain, float*
                   int H, int W, long long img_bstride, long long out_f32_bstride, long long out_u8_bstride,
                   void* stream);
 
+/* ---- decoded frame -> network input ----------------------------------------------------------
+ * Replaces dataset.to_tensor_norm (datasets/HSM_auto_dataset.py:73-75: transforms.ToTensor + Normalize(0.5, 0.5))
+ * as applied to the key frames and the DAIN frames in models/evaluator.py:223-224:
+ * out = (float32(v) / 255 - 0.5) / 0.5, bit-exact.  Lets a caller upload 8-bit frames (what a PNG decode
+ * yields) instead of fp32 tensors.
+ *   frames u8 [B][H][W][3]; out f32 [B][3][H][W]; *_bstride: elements between frames (0 = dense).
+ */
+int rib_frames_from_u8(const uint8_t* frames, float* out, int B, int H, int W, long long in_bstride,
+                       long long out_bstride, void* stream);
+
 /* ---- A2: generator ---------------------------------------------------------------------------
  * Replaces models.generator.Generator (models/generator.py:35-302), LabelEmbedder (:306-410) and
  * MaskGenerator (:415-510) in eval mode.
@@ -107,7 +117,7 @@ long long rib_generator_workspace_bytes(rib_generator* g, int B, int H, int W);
  * that rasterises on the GPU lets rib_rasterize write `label_planar` there and then passes label = NULL to
  * rib_generator_forward, which skips the fp32 -> 16-bit repack of the label (same values, one pass less). */
 int rib_generator_bind(rib_generator* g, int B, int H, int W, void* workspace, long long workspace_bytes,
-                       void** label_planar);
+                       void** label_planar, void* stream);
 
 /* Generator.forward(label, label_prev, img_fake, img_prev) -> (img_final, mask)
  * (models/generator.py:181-234; label_prev is dead in the reference and is not taken).
@@ -161,7 +171,8 @@ int rib_act_is_fp16(void);
  *        parity-planar layout [B][Cin/8][py][px][Hin/2][Win/2][8] that a stride-2 layer's producer writes
  *   w    f32 [Cout][Cin][k][k], bias f32 [Cout] (may be NULL), k in {1,3}, stride in {1,2}, pad k/2
  *   out  16-bit chunk-planar [B][Cout/8][Hout][Wout][8] (Cout 16/32/64 or a multiple of 128), act: 0 none, 1 leaky-relu 0.2
- *   stats f64 [B][Cout][2] (may be NULL; accumulated into)
+ *   stats [B][Cout][2] 64-bit slots (may be NULL; accumulated into): fixed-point integers, sum * 2^32 and sum of
+ *         squares * 2^24 (integer atomics make the totals independent of CTA arrival order: bit-reproducible)
  *   scratch: device buffer of at least rib_conv_test_scratch_bytes() bytes */
 long long rib_conv_test_scratch_bytes(int Cin, int Cout, int k);
 int rib_conv_test(const void* x, const float* w, const float* bias, void* out, double* stats, int B, int Hin, int Win,
@@ -170,7 +181,7 @@ int rib_conv_test(const void* x, const float* w, const float* bias, void* out, d
 /* Same with the two in-kernel fusions of the mask network:
  *   subpix = 1   conv3x3(nearest_x2(x)) in its sub-pixel form (k = 3, stride 1): `out` is the parity-planar
  *                [B][Cout/8][py][px][Hin][Win][8] map of the (2 Hin, 2 Win) result
- *   xf_stats     f64 [B][Cin][2] (sum, sum of squares of x per image and channel), xf_w / xf_b f32 [Cin] (may be NULL):
+ *   xf_stats     [B][Cin][2] 64-bit fixed-point slots as above (sum, sum of squares of x per image and channel), xf_w / xf_b f32 [Cin] (may be NULL):
  *                x is a RAW map and the kernel applies lrelu?(instance_norm_affine(x)) to its halo tiles in shared
  *                memory before the MMAs (xf_act = 1: LeakyReLU 0.2) */
 int rib_conv_test_ex(const void* x, const float* w, const float* bias, void* out, double* stats, int B, int Hin, int Win,

@@ -71,6 +71,16 @@ int rib_composite(const float* img, const float* mask, const float* dain, float*
   RIB_GUARD_END
 }
 
+int rib_frames_from_u8(const uint8_t* frames, float* out, int B, int H, int W, long long in_bstride,
+                       long long out_bstride, void* stream) {
+  RIB_GUARD_BEGIN
+  RIB_REQUIRE(frames && out && B > 0 && H > 0 && W > 0, "rib_frames_from_u8: bad argument");
+  int rc = launch_frames_from_u8(frames, out, B, H, W, in_bstride, out_bstride, (cudaStream_t)stream);
+  if (!rc) count_misc_launch(1);
+  return rc;
+  RIB_GUARD_END
+}
+
 int rib_generator_create(const rib_gen_config* cfg, const rib_tensor* tensors, int n_tensors, void* stream,
                          rib_generator** out) {
   RIB_GUARD_BEGIN
@@ -88,10 +98,11 @@ long long rib_generator_workspace_bytes(rib_generator* g, int B, int H, int W) {
 }
 
 int rib_generator_bind(rib_generator* g, int B, int H, int W, void* workspace, long long workspace_bytes,
-                       void** label_planar) {
+                       void** label_planar, void* stream) {
   RIB_GUARD_BEGIN
   RIB_REQUIRE(g && workspace, "rib_generator_bind: null argument");
-  return generator_bind(reinterpret_cast<Generator*>(g), B, H, W, workspace, workspace_bytes, label_planar);
+  return generator_bind(reinterpret_cast<Generator*>(g), B, H, W, workspace, workspace_bytes, label_planar,
+                        (cudaStream_t)stream);
   RIB_GUARD_END
 }
 

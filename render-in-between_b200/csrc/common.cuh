@@ -274,4 +274,24 @@ static inline uint32_t make_idesc_f16(int m, int n) {
 
 __device__ __forceinline__ float lrelu02(float v) { return v > 0.f ? v : 0.2f * v; }
 
+// ---------------------------------------------------------------------------------------------
+// Instance-norm statistics slots: [B][C][2] 64-bit words = (sum, sum of squares) per image and channel, accumulated
+// by many CTAs with atomics.  The words are FIXED-POINT integers (sum * 2^32, sum of squares * 2^24): integer addition
+// is associative, so the totals do not depend on the order in which CTAs arrive and the forward is bit-reproducible
+// run to run and across GPUs.  Every partial is an fp32 sum whose ulp is far above the 2^-32 / 2^-24 quantum;
+// the range is |sum| < 2.1e9 and sum of squares < 5.5e11 per (image, channel).
+// ---------------------------------------------------------------------------------------------
+#define RIB_STAT_SCALE1 4294967296.0
+#define RIB_STAT_SCALE2 16777216.0
+__device__ __forceinline__ void stat_add(double* slot, int which, float partial) {
+  const long long q = __double2ll_rn((double)partial * (which ? RIB_STAT_SCALE2 : RIB_STAT_SCALE1));
+  atomicAdd(reinterpret_cast<unsigned long long*>(slot) + which, (unsigned long long)q);
+}
+__device__ __forceinline__ double stat_sum(const double* slot) {
+  return (double)(*reinterpret_cast<const long long*>(slot)) * (1.0 / RIB_STAT_SCALE1);
+}
+__device__ __forceinline__ double stat_sumsq(const double* slot) {
+  return (double)(*(reinterpret_cast<const long long*>(slot) + 1)) * (1.0 / RIB_STAT_SCALE2);
+}
+
 }  // namespace rib

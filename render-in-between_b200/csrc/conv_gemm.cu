@@ -20,7 +20,6 @@ namespace rib {
 
 static constexpr int kEpiGroups = 1;                       // epilogue groups (4 warps each), one per TMEM accumulator buffer
 static constexpr int kThreads = 64 + 128 * kEpiGroups;
-static constexpr int kNumSms = 148;
 // Accumulator buffers in TMEM per CTA.  Two everywhere in the shipped build; -DRIB_ACC4_MAXBN=16|32 builds the narrow
 // tiles with four (the MMA lane may then run three tiles ahead of the epilogue) for the A/B runs of tools/gpu_ab.sh.
 #ifndef RIB_ACC4_MAXBN
@@ -124,7 +123,7 @@ __device__ void simt_chunk(const ConvGemmParams& p, int n, int oy, int ox, int c
       float av = act2f(*ap);
       if (p.xf_stats != nullptr) {  // A-operand transform, same arithmetic as the transform warps (result rounded to 16 bits)
         const double cnt = (double)p.Hin * (double)p.Win;
-        const double s1 = p.xf_stats[((size_t)n * cin0 + ci) * 2], s2 = p.xf_stats[((size_t)n * cin0 + ci) * 2 + 1];
+        const double s1 = stat_sum(p.xf_stats + ((size_t)n * cin0 + ci) * 2), s2 = stat_sumsq(p.xf_stats + ((size_t)n * cin0 + ci) * 2);
         const double mean = s1 / cnt;
         double var = s2 / cnt - mean * mean;
         var = var < 0.0 ? 0.0 : var;
@@ -449,7 +448,7 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
         if (n != cur_n) {  // uniform over the four warps
           asm volatile("bar.sync 8, %0;" ::"n"(kXfThreads) : "memory");   // nobody still reads the previous image's coefficients
           for (int c = threadIdx.x - (kThreads); c < cin0; c += kXfThreads) {
-            const double s1 = p.xf_stats[((size_t)n * cin0 + c) * 2], s2 = p.xf_stats[((size_t)n * cin0 + c) * 2 + 1];
+            const double s1 = stat_sum(p.xf_stats + ((size_t)n * cin0 + c) * 2), s2 = stat_sumsq(p.xf_stats + ((size_t)n * cin0 + c) * 2);
             const double mean = s1 / cnt;
             double var = s2 / cnt - mean * mean;
             var = var < 0.0 ? 0.0 : var;
@@ -562,7 +561,7 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
     int it = 0;
 
     // Deterministic: every warp parks its column sums in its own slot, then one thread per column adds the
-    // four slots in a fixed order and issues the fp64 atomics (whose rounding is far below fp32 resolution).
+    // four slots in a fixed order and issues the fixed-point integer atomics (order-independent, see stat_add).
     auto flush_stats = [&](int n_img) {
       float* slot = s_auxg + ((warp - 2) & 3) * 2 * BN;
       if (kRegStats) {
@@ -598,8 +597,8 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
           double* st = (p.seg_cols && col >= p.seg_cols)
                            ? p.stats_b + ((size_t)n_img * p.stats_b_ld + (col - p.seg_cols)) * 2
                            : p.stats + ((size_t)n_img * p.stats_ld + col) * 2;
-          atomicAdd(st, (double)t1);
-          atomicAdd(st + 1, (double)t2);
+          stat_add(st, 0, t1);
+          stat_add(st, 1, t2);
         }
       }
       epi_bar(eg);
@@ -633,8 +632,8 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
           const double cnt = (double)p.Hx * (double)p.Wx;
           epi_bar(eg);
           for (int c = e; c < CT; c += 128) {
-            const double s = p.xstats[((size_t)n * p.C + c0 + c) * 2 + 0];
-            const double ss = p.xstats[((size_t)n * p.C + c0 + c) * 2 + 1];
+            const double s = stat_sum(p.xstats + ((size_t)n * p.C + c0 + c) * 2);
+            const double ss = stat_sumsq(p.xstats + ((size_t)n * p.C + c0 + c) * 2);
             const double mean = s / cnt;
             double var = ss / cnt - mean * mean;
             var = var < 0.0 ? 0.0 : var;
@@ -698,7 +697,11 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
           if (p.has_out2)
             obase2 = p.out2.p + (size_t)n * p.out2.bstride + (size_t)((ntile * BN) >> 3) * HW8 +
                      (size_t)((oy & 1) * 2 + (ox & 1)) * (HW8 >> 2) + ((size_t)(oy >> 1) * (p.W >> 1) + (ox >> 1)) * 8;
-          const act_t* rbase = p.has_res ? p.res.p + (size_t)n * p.res.bstride + (size_t)((ntile * BN) >> 3) * HW8 + pix8
+          // identity shortcut (residual.py:146-151); res_ups: the shortcut is the nearest x2 up-sampling of a half-size map
+          // (generator.py:248-249 followed by a block whose input and output widths are equal)
+          const size_t rHW8 = p.res_ups ? HW8 >> 2 : HW8;
+          const act_t* rbase = p.has_res ? p.res.p + (size_t)n * p.res.bstride + (size_t)((ntile * BN) >> 3) * rHW8 +
+                                               (p.res_ups ? ((size_t)(oy >> 1) * (p.W >> 1) + (ox >> 1)) * 8 : pix8)
                                          : nullptr;
           uint32_t r[2][16];
           if (!SIMT) tmem_ld16_issue(trow, r[0]);
@@ -707,8 +710,8 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
             if (j >= nch_eff) break;
             uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
             if (p.has_res && valid) {
-              r0 = *reinterpret_cast<const uint4*>(rbase + (size_t)(2 * j) * HW8);
-              r1 = *reinterpret_cast<const uint4*>(rbase + (size_t)(2 * j + 1) * HW8);
+              r0 = *reinterpret_cast<const uint4*>(rbase + (size_t)(2 * j) * rHW8);
+              r1 = *reinterpret_cast<const uint4*>(rbase + (size_t)(2 * j + 1) * rHW8);
             }
             float v[16];
             if (SIMT) {
@@ -1185,6 +1188,21 @@ static int ctas_per_sm(const void* fn, size_t smem, int tmem_cols, int threads, 
 
 typedef void (*ConvKernel)(const ConvGemmParams);
 
+// SM count of a device (queried once per device; the persistent grids are sized from it).
+int device_sm_count(int dev) {
+  static std::mutex mu;
+  static std::vector<int> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  if (dev < 0) return 0;
+  if ((int)cache.size() <= dev) cache.resize(dev + 1, 0);
+  if (cache[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    cache[dev] = n;
+  }
+  return cache[dev];
+}
+
 template <bool SIMT>
 static ConvKernel pick_kernel(int mode, int BN, bool xf) {
   if (xf) {  // the A-operand transform is built for the layers that use it: plain-store convs with 64 / 128 columns
@@ -1237,19 +1255,24 @@ int launch_conv_gemm(const ConvGemmParams& p, int mode, cudaStream_t stream) {
   const bool xf = p.xf_stats != nullptr;
   RIB_REQUIRE(!xf || (p.stages1 == 0 && p.subpix == 0), "conv_gemm: the A-operand transform needs a single source");
   RIB_REQUIRE(!p.out_parity || (p.H % 2 == 0 && p.W % 2 == 0 && !p.subpix), "conv_gemm: bad parity-planar output");
+  RIB_REQUIRE(!p.res_ups || (p.has_res && p.H % 2 == 0 && p.W % 2 == 0 && !p.subpix && !p.out_parity),
+              "conv_gemm: bad up-sampled residual");
   ConvKernel fn = p.debug_simt ? pick_kernel<true>(mode, p.BN, xf) : pick_kernel<false>(mode, p.BN, xf);
   RIB_REQUIRE(fn != nullptr, "conv_gemm: no kernel for this (epilogue, BN)");
   const size_t smem = conv_gemm_smem_bytes(p);
   RIB_REQUIRE(smem <= 227 * 1024, "conv_gemm: shared memory budget exceeded");
+  int dev = 0;
+  RIB_CHECK_CUDA(cudaGetDevice(&dev));
   {
+    // the opt-in is per device (context), not per process: key the cache by (device, kernel)
     static std::mutex mu;
-    static std::vector<const void*> done;
+    static std::vector<std::pair<int, const void*>> done;
     std::lock_guard<std::mutex> lk(mu);
     bool seen = false;
-    for (const void* f : done) seen = seen || f == (const void*)fn;
+    for (const auto& f : done) seen = seen || (f.first == dev && f.second == (const void*)fn);
     if (!seen) {
       RIB_CHECK_CUDA(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      done.push_back((const void*)fn);
+      done.push_back({dev, (const void*)fn});
     }
   }
   // persistent grid: as many CTAs as fit on the chip, a multiple of n_tiles
@@ -1260,7 +1283,9 @@ int launch_conv_gemm(const ConvGemmParams& p, int mode, cudaStream_t stream) {
   int rc = ctas_per_sm((const void*)fn, smem, tmem_cols, threads, &occ);
   if (rc) return rc;
   const long long m_tiles = (long long)p.tiles_x * p.tiles_y * p.B;
-  long long groups = ((long long)kNumSms * occ) / p.n_tiles;
+  const int n_sms = device_sm_count(dev);
+  RIB_REQUIRE(n_sms > 0, "conv_gemm: cannot query the SM count");
+  long long groups = ((long long)n_sms * occ) / p.n_tiles;
   if (groups < 1) groups = 1;
   if (groups > m_tiles) groups = m_tiles;
   dim3 grid((unsigned)(groups * p.n_tiles));

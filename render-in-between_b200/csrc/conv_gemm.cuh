@@ -96,6 +96,7 @@ struct alignas(64) ConvGemmParams {
   // EPI_STORE
   PlanarRef out;
   PlanarRef res; int has_res;
+  int res_ups;                   // 1: `res` is a (H/2, W/2) map read through a nearest x2 up-sampling
   PlanarRef out2; int has_out2;  // optional second copy of the output in parity-planar layout (feeds a stride-2 conv)
   // Two convs over the same input merged along N (one N tile): columns [0, seg_cols) are the first conv (out, stats),
   // [seg_cols, n_valid) the second (out_b, stats_b).  Both multiples of 16; 0 = single output.
@@ -147,6 +148,7 @@ int conv_gemm_configure(ConvGemmParams* p, int B, int Hout, int Wout, int cin0, 
                         int BN, int n_pad, const ConvTune* tune = nullptr);
 size_t conv_gemm_smem_bytes(const ConvGemmParams& p);
 int launch_conv_gemm(const ConvGemmParams& p, int mode, cudaStream_t stream);
+int device_sm_count(int dev);   // multiprocessors of device `dev` (cached)
 long long conv_gemm_launch_count();
 void conv_gemm_profile_enable(int on);
 int conv_gemm_profile_collect(double* total_ms, long long* launches, float* per_launch_ms, long long cap);

@@ -92,7 +92,7 @@ int launch_pack_images(const float* fake, const float* prev, act_t* emb, long lo
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void in_coeffs(const double* stats, const float* w, const float* b, int n, int C, int c,
                                           double cnt, float eps, float* scale, float* shift) {
-  const double s = stats[((size_t)n * C + c) * 2], ss = stats[((size_t)n * C + c) * 2 + 1];
+  const double s = stat_sum(stats + ((size_t)n * C + c) * 2), ss = stat_sumsq(stats + ((size_t)n * C + c) * 2);
   const double mean = s / cnt;
   double var = ss / cnt - mean * mean;
   var = var < 0.0 ? 0.0 : var;
@@ -229,6 +229,14 @@ __global__ void in_apply_unparity_kernel(const InApplyParams p) {
   }
 }
 
+// SM count of the current device (grid sizing of the bandwidth kernels); 148 only if the query fails.
+static unsigned sm_count_current() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148u;
+  const int n = device_sm_count(dev);
+  return n > 0 ? (unsigned)n : 148u;
+}
+
 int launch_in_apply(const InApplyParams& p, cudaStream_t s) {
   RIB_REQUIRE(p.C % 8 == 0, "in_apply: channels must be a multiple of 8");
   if (p.in_parity) {
@@ -236,7 +244,7 @@ int launch_in_apply(const InApplyParams& p, cudaStream_t s) {
                 "in_apply: the parity-planar input form is single-term, same-size, normal output");
     const size_t npair = (size_t)p.H * (p.W / 2) * (p.C / 8);
     unsigned gx = (unsigned)((npair + 255) / 256);
-    unsigned want = (148u * 8u + (unsigned)p.B - 1u) / (unsigned)p.B;
+    unsigned want = (sm_count_current() * 8u + (unsigned)p.B - 1u) / (unsigned)p.B;
     if (gx > want) gx = want;
     in_apply_unparity_kernel<<<dim3(gx, (unsigned)p.B), 256, 2 * p.C * sizeof(float), s>>>(p);
     RIB_CHECK_CUDA(cudaGetLastError());
@@ -247,7 +255,7 @@ int launch_in_apply(const InApplyParams& p, cudaStream_t s) {
   // every block first derives the normalisation coefficients of its image (fp64 divide + sqrt per channel),
   // so blocks are kept few and fat: about 8 resident blocks per SM over the whole batch
   unsigned gx = (unsigned)((nvec + threads - 1) / threads);
-  unsigned want = (148u * 8u + (unsigned)p.B - 1u) / (unsigned)p.B;
+  unsigned want = (sm_count_current() * 8u + (unsigned)p.B - 1u) / (unsigned)p.B;
   if (want < 1u) want = 1u;
   if (gx > want) gx = want;
   dim3 grid(gx, (unsigned)p.B);
@@ -326,7 +334,7 @@ __global__ void avgpool3s2_kernel(const act_t* __restrict__ src, long long src_b
 #pragma unroll
       for (int w = 0; w < 8; ++w) t += s_red[w][threadIdx.x];
       const int c = pl * 8 + (threadIdx.x & 7);
-      atomicAdd(&stats[((size_t)n * C + c) * 2 + (threadIdx.x >> 3)], (double)t);
+      stat_add(&stats[((size_t)n * C + c) * 2], threadIdx.x >> 3, t);
     }
   }
 }
@@ -410,6 +418,47 @@ int launch_composite(const float* img, const float* mask, const float* dain, flo
   const int threads = 256;
   composite_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(
       img, mask, dain, out_f32, out_u8, HW / 4, HW, total, img_bstride, f32_bstride, u8_bstride);
+  RIB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Decoded frame -> network input: uint8 HWC -> fp32 CHW in [-1, 1]
+// (transforms.ToTensor + Normalize(0.5, 0.5): float32(v) / 255, then (t - 0.5) / 0.5, separate roundings;
+//  HSM_auto_dataset.py:73-75, used by evaluator.py:223-224).  Four pixels per thread.
+// ---------------------------------------------------------------------------------------------
+__global__ void frames_from_u8_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, int HW4, int HW,
+                                      size_t total, long long in_bs, long long out_bs) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over B * HW/4
+  if (i >= total) return;
+  const size_t n = i / HW4, q = i - n * HW4;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(in + n * in_bs + q * 12);
+  const uint32_t w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
+  const uint8_t px[12] = {(uint8_t)w0, (uint8_t)(w0 >> 8), (uint8_t)(w0 >> 16), (uint8_t)(w0 >> 24),
+                          (uint8_t)w1, (uint8_t)(w1 >> 8), (uint8_t)(w1 >> 16), (uint8_t)(w1 >> 24),
+                          (uint8_t)w2, (uint8_t)(w2 >> 8), (uint8_t)(w2 >> 16), (uint8_t)(w2 >> 24)};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      v[k] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)px[3 * k + c], 255.0f), 0.5f), 0.5f);
+    reinterpret_cast<float4*>(out + n * out_bs + (size_t)c * HW)[q] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+int launch_frames_from_u8(const uint8_t* in, float* out, int B, int H, int W, long long in_bstride,
+                          long long out_bstride, cudaStream_t s) {
+  RIB_REQUIRE((H * W) % 4 == 0, "frames_from_u8: H*W must be a multiple of 4");
+  const int HW = H * W;
+  if (in_bstride == 0) in_bstride = 3LL * HW;
+  if (out_bstride == 0) out_bstride = 3LL * HW;
+  RIB_REQUIRE(in_bstride % 4 == 0 && out_bstride % 4 == 0 && ((uintptr_t)in & 3) == 0 && ((uintptr_t)out & 15) == 0,
+              "frames_from_u8: strides / pointers must be 4-element aligned");
+  const size_t total = (size_t)B * (HW / 4);
+  const int threads = 256;
+  frames_from_u8_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(in, out, HW / 4, HW, total,
+                                                                                         in_bstride, out_bstride);
   RIB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -529,14 +578,28 @@ int launch_warp(const float* src, const float* flow, float* out, int B, int C, i
 // ---------------------------------------------------------------------------------------------
 // Weight folding / packing (runs once at model creation)
 // ---------------------------------------------------------------------------------------------
-__global__ void sn_sigma_inv_kernel(const float* __restrict__ w, const float* __restrict__ u,
-                                    const float* __restrict__ v, int Cout, int K, float* sigma_inv) {
+// sigma = u^T W v (weight_norm.py:84-85 -> torch spectral_norm, eval mode).  One block per output row computes
+// u[r] * dot(W[r, :], v) in fp64 (fixed-order tree), a second single-block pass adds the rows in a fixed order.
+__global__ void sn_sigma_rows_kernel(const float* __restrict__ w, const float* __restrict__ u,
+                                     const float* __restrict__ v, int K, double* __restrict__ partial) {
+  __shared__ double s_part[256];
+  const int r = blockIdx.x;
+  const float* wr = w + (size_t)r * K;
+  double acc = 0.0;
+  for (int c = threadIdx.x; c < K; c += blockDim.x) acc += (double)wr[c] * (double)v[c];
+  s_part[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) s_part[threadIdx.x] += s_part[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[r] = (double)u[r] * s_part[0];
+}
+
+__global__ void sn_sigma_final_kernel(const double* __restrict__ partial, int Cout, float* sigma_inv) {
   __shared__ double s_part[256];
   double acc = 0.0;
-  for (size_t i = threadIdx.x; i < (size_t)Cout * K; i += blockDim.x) {
-    const int r = (int)(i / K), c = (int)(i - (size_t)r * K);
-    acc += (double)u[r] * (double)w[i] * (double)v[c];
-  }
+  for (int r = threadIdx.x; r < Cout; r += blockDim.x) acc += partial[r];
   s_part[threadIdx.x] = acc;
   __syncthreads();
   for (int s = 128; s > 0; s >>= 1) {
@@ -546,9 +609,13 @@ __global__ void sn_sigma_inv_kernel(const float* __restrict__ w, const float* __
   if (threadIdx.x == 0) sigma_inv[0] = (float)(1.0 / s_part[0]);
 }
 
+// `scratch`: at least Cout doubles, re-used by consecutive calls on the same stream.
 int launch_sn_sigma_inv(const float* w, const float* u, const float* v, int Cout, int K, float* sigma_inv,
-                        cudaStream_t s) {
-  sn_sigma_inv_kernel<<<1, 256, 0, s>>>(w, u, v, Cout, K, sigma_inv);
+                        double* scratch, cudaStream_t s) {
+  RIB_REQUIRE(scratch != nullptr && Cout >= 1, "sn_sigma_inv: bad arguments");
+  sn_sigma_rows_kernel<<<Cout, 256, 0, s>>>(w, u, v, K, scratch);
+  RIB_CHECK_CUDA(cudaGetLastError());
+  sn_sigma_final_kernel<<<1, 256, 0, s>>>(scratch, Cout, sigma_inv);
   RIB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

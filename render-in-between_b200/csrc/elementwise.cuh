@@ -4,6 +4,9 @@
 
 namespace rib {
 
+int device_sm_count(int dev);   // conv_gemm.cu
+
+
 // All 16-bit activation maps are chunk-planar: [B][Ctot/8][H][W][8] (see conv_gemm.cuh).  A map (or a
 // channel slice of one that starts on a multiple of 8) is passed as the pointer to its first plane
 // plus `bstride`, the element distance between images (= Ctot/8 * H * W * 8).
@@ -55,12 +58,14 @@ int launch_composite(const float* img, const float* mask, const float* dain, flo
                      int H, int W, long long img_bstride, long long f32_bstride, long long u8_bstride, cudaStream_t s);
 
 // out = bilinear sample of src at (x + flow_x, y + flow_y), border padding, align_corners=True.
+int launch_frames_from_u8(const uint8_t* in, float* out, int B, int H, int W, long long in_bstride,
+                          long long out_bstride, cudaStream_t s);
 int launch_warp(const float* src, const float* flow, float* out, int B, int C, int H, int W, long long src_bstride,
                 long long flow_bstride, long long out_bstride, cudaStream_t s);
 
 // sigma_inv[0] = 1 / (u . (W v)),  W = [Cout, K] fp32 (torch.nn.utils.spectral_norm, eval mode).
 int launch_sn_sigma_inv(const float* w, const float* u, const float* v, int Cout, int K, float* sigma_inv,
-                        cudaStream_t s);
+                        double* scratch, cudaStream_t s);
 
 // Repack a conv weight [Cout][Cin][taps] fp32 into the K-major 16-bit GEMM operand:
 //   dst[row(co) * ktotal + koff + ((ci / bkc) * taps + tap) * bkc + ci % bkc] = w[co][ci][tap] * (sigma_inv ? *sigma_inv : 1)

@@ -331,6 +331,11 @@ int generator_create(const rib_gen_config* cfg, const rib_tensor* tensors, int n
   off = align_up(off, 256);
   const size_t cat_off = off;
   off += (size_t)4 * mask_nfilt(c, c.mask_down) * sizeof(float);
+  off = align_up(off, 256);
+  const size_t sn_scratch_off = off;   // per-row partial sums of the spectral-norm sigma (re-used by every conv)
+  int max_cout = 1;
+  for (const PackJob& pj : jobs) max_cout = std::max(max_cout, pj.cout);
+  off += (size_t)max_cout * sizeof(double);
   G->arena_bytes = off;
   cudaError_t ce = cudaMalloc(&G->arena, G->arena_bytes);
   if (ce != cudaSuccess) {
@@ -362,7 +367,8 @@ int generator_create(const rib_gen_config* cfg, const rib_tensor* tensors, int n
       const float* u = src.get(pj.prefix + ".weight_u", pj.cout, &err);
       const float* v = src.get(pj.prefix + ".weight_v", (long long)pj.cin * pj.taps, &err);
       if (!err) {
-        rc = launch_sn_sigma_inv(w, u, v, pj.cout, pj.cin * pj.taps, sigmas + j, stream);
+        rc = launch_sn_sigma_inv(w, u, v, pj.cout, pj.cin * pj.taps, sigmas + j,
+                                 reinterpret_cast<double*>(G->arena + sn_scratch_off), stream);
         if (rc) return fail(rc);
         sig = sigmas + j;
       }
@@ -577,7 +583,7 @@ struct PlanBuilder {
   // when this layer's statistics are a slice of a wider one (0 = its own).
   void conv_store(const std::string& lname, const View& in0, const View* in1, int stride, const View& out,
                   double* stats, int act, const View* res, const View* out2 = nullptr, const Xf* xf = nullptr,
-                  int stats_ld = 0) {
+                  int stats_ld = 0, bool res_ups = false) {
     const GemmLayer& L = G->layers.at(lname);
     ConvGemmParams p = gemm_common(L, in0, in1, stride, out.H, out.W, L.BN);
     p.out = out.ref();
@@ -594,7 +600,15 @@ struct PlanBuilder {
     p.stats = stats;
     p.act = act;
     p.has_res = res ? 1 : 0;
-    if (res) p.res = res->ref();
+    if (res) {
+      p.res = res->ref();
+      p.res_ups = res_ups ? 1 : 0;
+      const int rh = res_ups ? out.H / 2 : out.H, rw = res_ups ? out.W / 2 : out.W;
+      if (res->H != rh || res->W != rw || res->C != out.C || res->parity) {
+        set_error("plan: residual shape mismatch in " + lname);
+        rc = -4;
+      }
+    }
     push_gemm(p, EPI_STORE, lname);
   }
 
@@ -765,7 +779,7 @@ std::string tune_key(const Op& op) {
   const GemmLayer& L = *op.layer;
   char buf[256];
   snprintf(buf, sizeof(buf), "m%d B%d H%d W%d c%d+%d t%d s%d BN%d N%d r%d o%d st%d u%d q%d par%d", op.mode, p.B, p.H, p.W,
-           L.cin0, L.cin1, L.taps, L.stride, p.BN, L.n_pad, p.has_res, p.has_out2, p.stats != nullptr, p.ups,
+           L.cin0, L.cin1, L.taps, L.stride, p.BN, L.n_pad, p.has_res + 2 * p.res_ups, p.has_out2, p.stats != nullptr, p.ups,
            (op.mode == EPI_SPADE || op.mode == EPI_SPADE2) ? p.n_tiles * p.BN / (2 * p.C) : 0, p.s2_parity + 2 * (p.xf_stats != nullptr) + 4 * p.out_parity);
   return buf;
 }
@@ -1055,7 +1069,7 @@ static int build_plan(Generator* G, int B, int H, int W, void* wsbase, size_t* b
     double* ost = (last || pooled_next) ? nullptr : bst[bi].out;
     // up_0 feeds conv_img through a LeakyReLU (conv_img order 'AC', generator.py:114-116)
     pb.conv_store(b.name + ".conv1", a1, b.shortcut ? &as : nullptr, 1, o, ost, last ? ACT_LRELU : ACT_NONE,
-                  b.shortcut ? nullptr : &x);
+                  b.shortcut ? nullptr : &x, nullptr, nullptr, 0, !b.shortcut && x_ups);
     if (pooled_next) {  // AvgPool2d(3, 2, 1)  generator.py:207-208
       lvl_h /= 2;
       lvl_w /= 2;
@@ -1205,10 +1219,13 @@ long long misc_launch_count() { return g_misc_launches.load(); }
 void count_misc_launch(int n) { g_misc_launches.fetch_add(n); }
 
 // Builds (or re-uses) the launch plan for (B, H, W) on this workspace.
-static int ensure_plan(Generator* G, int B, int H, int W, void* ws, long long ws_bytes, cudaStream_t stream) {
+static int ensure_plan(Generator* G, int B, int H, int W, void* ws, long long ws_bytes, cudaStream_t stream,
+                       bool* rebuilt = nullptr) {
   RIB_REQUIRE(G && ws, "forward: null argument");
   RIB_REQUIRE(((uintptr_t)ws & 1023) == 0, "forward: workspace must be 1024-byte aligned");
+  if (rebuilt) *rebuilt = false;
   if (G->pB != B || G->pH != H || G->pW != W || G->pws != ws || G->plan_simt != (g_debug_simt != 0)) {
+    if (rebuilt) *rebuilt = true;
     size_t need = 0;
     int rc = build_plan(G, B, H, W, nullptr, &need, nullptr);
     if (rc) return rc;
@@ -1220,8 +1237,10 @@ static int ensure_plan(Generator* G, int B, int H, int W, void* ws, long long ws
   return 0;
 }
 
-int generator_bind(Generator* G, int B, int H, int W, void* ws, long long ws_bytes, void** label_planar) {
-  int rc = ensure_plan(G, B, H, W, ws, ws_bytes, nullptr);
+int generator_bind(Generator* G, int B, int H, int W, void* ws, long long ws_bytes, void** label_planar,
+                   cudaStream_t stream) {
+  // (the auto-tuner's timing launches write into the workspace: they run on the caller's stream)
+  int rc = ensure_plan(G, B, H, W, ws, ws_bytes, stream);
   if (rc) return rc;
   if (label_planar) *label_planar = G->debug_views.at("label").p;
   return 0;
@@ -1231,8 +1250,13 @@ int generator_forward(Generator* G, int B, int H, int W, const float* label, con
                       const float* img_prev, float* out_img, float* out_mask, void* ws, long long ws_bytes,
                       cudaStream_t stream) {
   RIB_REQUIRE(G && img_fake && img_prev && out_img && out_mask && ws, "forward: null argument");
-  int prc = ensure_plan(G, B, H, W, ws, ws_bytes, stream);
+  bool rebuilt = false;
+  int prc = ensure_plan(G, B, H, W, ws, ws_bytes, stream, &rebuilt);
   if (prc) return prc;
+  // label == NULL means "the caller rasterised into the buffer rib_generator_bind returned": that buffer only exists
+  // if the plan for this exact (B, H, W, workspace) was already in place
+  RIB_REQUIRE(label != nullptr || !rebuilt,
+              "forward: label is NULL but no plan was bound to this (B, H, W, workspace); call rib_generator_bind first");
   if (G->zero_pending) {
     for (const Generator::ZeroPlane& z : G->zero_once)
       RIB_CHECK_CUDA(cudaMemset2DAsync(z.ptr, z.pitch, 0, z.width, (size_t)z.rows, stream));

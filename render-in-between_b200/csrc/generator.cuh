@@ -14,7 +14,8 @@ long long generator_workspace_bytes(Generator* g, int B, int H, int W);
 int generator_forward(Generator* g, int B, int H, int W, const float* label, const float* img_fake,
                       const float* img_prev, float* out_img, float* out_mask, void* ws, long long ws_bytes,
                       cudaStream_t stream);
-int generator_bind(Generator* g, int B, int H, int W, void* ws, long long ws_bytes, void** label_planar);
+int generator_bind(Generator* g, int B, int H, int W, void* ws, long long ws_bytes, void** label_planar,
+                   cudaStream_t stream);
 int generator_debug_tensor(Generator* g, const char* name, const void** ptr, int* B, int* H, int* W, int* C, int* ld);
 int generator_plan_text(Generator* g, char* buf, long long cap);
 int generator_plan_dry_run(const rib_gen_config* cfg, int B, int H, int W, long long* ws_bytes, char* buf, long long cap);

@@ -16,7 +16,7 @@ def __getattr__(name):
     if name in ('Generator',):
         from .generator import Generator
         return Generator
-    if name in ('rasterize', 'warp', 'composite', 'gaussian_taps'):
+    if name in ('rasterize', 'warp', 'composite', 'gaussian_taps', 'frames_from_u8'):
         from . import ops
         return getattr(ops, name)
     if name in ('ClipRenderer',):

@@ -24,9 +24,11 @@ class ClipRenderer:
         return (num_keyframes - 1) * sample_rate + 1            # evaluator.py:191
 
     def render(self, key_frames, joints, backgrounds=None, flows=None, want_u8=True, want_mask=False, want_fuse=True):
-        """key_frames [K,3,H,W] f32, joints [T,19,3] f64, and either backgrounds [T,3,H,W] f32 (the
-        pre-computed DAIN frames of the reference) or flows [T,2,H,W] f32 from which the background of
-        frame i is resampled out of the preceding key frame (stage A3).  All CUDA tensors.
+        """key_frames [K,3,H,W] f32 in [-1,1] or [K,H,W,3] uint8 (decoded images; normalised on the GPU exactly like
+        dataset.to_tensor_norm), joints [T,19,3] f64, and either backgrounds (the pre-computed DAIN frames of the
+        reference: [T,3,H,W] f32, or [T-K,3,H,W] f32 holding only the generated frames in frame order) or flows
+        ([T,2,H,W] or [T-K,2,H,W] f32) from which the background of frame i is resampled out of the preceding key
+        frame (stage A3).  All CUDA tensors.
         Returns dict(fuse [T,3,H,W] f32 | None, u8 [T,H,W,3] uint8 | None, mask [T,1,H,W] | None).
 
         Only the labels of generated frames are rasterised: a key frame's label is consumed by the reference
@@ -34,6 +36,8 @@ class ClipRenderer:
         rasterises straight into the generator's input buffer and blends straight into frames s, s+r, ... of
         the clip, so no frame is gathered, scattered or converted twice."""
         r = self.rate
+        if key_frames.dtype == torch.uint8:
+            key_frames = ops.frames_from_u8(key_frames)
         k, _, h, w = key_frames.shape
         t = self.seq_len(k, r)
         if joints.shape[0] != t:
@@ -42,12 +46,21 @@ class ClipRenderer:
             raise ValueError('pass exactly one of backgrounds / flows')
         if not (want_u8 or want_fuse):
             raise ValueError('nothing to return')
+        per_frame = backgrounds if backgrounds is not None else flows
+        if per_frame.shape[0] not in (t, t - k):
+            raise ValueError('backgrounds / flows must cover all %d frames or the %d generated ones' % (t, t - k))
+        gen_only = per_frame.shape[0] == t - k          # rows = generated frames only: frame k*r+s -> row k*(r-1)+s-1
+
+        def of_step(x, s):
+            return x[s - 1::r - 1] if gen_only else x[s::r]
+
         dev = key_frames.device
         key_frames = key_frames.contiguous()
         fuse = torch.empty(t, 3, h, w, dtype=torch.float32, device=dev) if want_fuse else None
         u8 = torch.empty(t, h, w, 3, dtype=torch.uint8, device=dev) if want_u8 else None
         mask_out = torch.zeros(t, 1, h, w, dtype=torch.float32, device=dev) if want_mask else None
-        # key frames pass through (:240-244)
+        # key frames pass through (:240-244).  Their output frame is tensor2images(to_tensor_norm(v)), which truncates
+        # and is NOT v for 63 of the 256 levels, so uint8 key frames take the same path as fp32 ones.
         ops.composite(key_frames, None, None, out=fuse[0::r] if want_fuse else None, out_u8=u8[0::r] if want_u8 else None)
         b = k - 1
         prev = key_frames[:b]                                      # fuse[i-1] of step 1 is the key frame
@@ -55,9 +68,9 @@ class ClipRenderer:
             lab_addr = self.gen.bind(b, h, w, dev)
             ops.rasterize(joints[s::r].contiguous(), h, w, planar_out=lab_addr, want_label=False)
             if backgrounds is not None:
-                dain = backgrounds[s::r].contiguous()
+                dain = of_step(backgrounds, s).contiguous()
             else:
-                dain = ops.warp(key_frames[:b], flows[s::r])
+                dain = ops.warp(key_frames[:b], of_step(flows, s))
             pred, m = self.gen.forward_bound(b, h, w, dain, prev)
             need_f32 = want_fuse or s + 1 < r                      # the next AR step reads this step's frames
             step_out = None

@@ -123,8 +123,8 @@ class Generator(nn.Module):
         _, ws_ptr, ws_bytes = self._workspace(b, h, w, device)
         out = C.c_void_p()
         with torch.cuda.device(device):
-            check(lib.rib_generator_bind(self._handle, b, h, w, C.c_void_p(ws_ptr), ws_bytes, C.byref(out)),
-                  'rib_generator_bind')
+            check(lib.rib_generator_bind(self._handle, b, h, w, C.c_void_p(ws_ptr), ws_bytes, C.byref(out),
+                                         C.c_void_p(torch.cuda.current_stream().cuda_stream)), 'rib_generator_bind')
         return out.value
 
     def forward_bound(self, b, h, w, img_fake, img_prev):

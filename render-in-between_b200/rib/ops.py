@@ -84,6 +84,25 @@ def _frames(t, name, tail):
     return t, (t.stride(0) if t.shape[0] > 1 else 0)
 
 
+def frames_from_u8(frames, out=None):
+    """uint8 [B,H,W,3] CUDA frames (a decoded PNG) -> float32 [B,3,H,W] in [-1,1]: dataset.to_tensor_norm
+    (PGNR/datasets/HSM_auto_dataset.py:73-75) on the GPU, bit-exact.  `frames` / `out` may be strided along dim 0."""
+    if not (isinstance(frames, torch.Tensor) and frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 4
+            and frames.shape[3] == 3):
+        raise ValueError('frames must be a CUDA uint8 tensor [B, H, W, 3]')
+    b, h, w, _ = frames.shape
+    if b > 0 and not frames[0].is_contiguous():
+        frames = frames.contiguous()
+    if out is None:
+        out = torch.empty(b, 3, h, w, dtype=torch.float32, device=frames.device)
+    elif not (out.is_cuda and out.dtype == torch.float32 and tuple(out.shape) == (b, 3, h, w) and out[0].is_contiguous()):
+        raise ValueError('frames_from_u8: bad out tensor')
+    with torch.cuda.device(frames.device):
+        check(lib.rib_frames_from_u8(frames.data_ptr(), out.data_ptr(), b, h, w, frames.stride(0) if b > 1 else 0,
+                                     out.stride(0) if b > 1 else 0, _stream()), 'rib_frames_from_u8')
+    return out
+
+
 def warp(src, flow):
     """Bilinear resample of src [B,C,H,W] by flow [B,2,H,W] (pixels), border padding (stage A3).
     Both inputs may be strided along the frame dimension (e.g. flows[s::r])."""

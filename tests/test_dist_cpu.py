@@ -25,10 +25,16 @@ def _worker(rank, world, port, n_total, q):
     lo, hi = shard_range(n_total, rank, world)
     local = torch.arange(lo, hi, dtype=torch.uint8).view(-1, 1, 1, 1).repeat(1, 4, 6, 3)
     out = gather_frames(local, n_total, dst=0)
+    # the asynchronous form into a caller-owned buffer (what bench.py uses): same frames, same buffer
+    buf = torch.full((n_total, 4, 6, 3), 255, dtype=torch.uint8) if rank == 0 else None
+    pending = gather_frames(local + 100, n_total, dst=0, out=buf, async_op=True)
+    out2 = pending.wait()
     if rank == 0:
+        assert out2 is buf and out.shape == (n_total, 4, 6, 3)
+        assert torch.equal(out2, out + 100)
         q.put(out[:, 0, 0, 0].tolist())
     else:
-        assert out is None
+        assert out is None and out2 is None
     dist.destroy_process_group()
 
 

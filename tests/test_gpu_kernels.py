@@ -107,6 +107,17 @@ def _act_dtype():
     return torch.float16 if lib.rib_act_is_fp16() else torch.bfloat16
 
 
+def _decode_stats(t):
+    """Statistics slots are fixed-point integers (sum * 2^32, sum of squares * 2^24; csrc/common.cuh stat_add)."""
+    q = t.view(torch.int64).double()
+    return torch.stack([q[..., 0] / 2.0 ** 32, q[..., 1] / 2.0 ** 24], dim=-1)
+
+
+def _encode_stats(t):
+    q = torch.stack([torch.round(t[..., 0] * 2.0 ** 32), torch.round(t[..., 1] * 2.0 ** 24)], dim=-1)
+    return q.to(torch.int64).view(torch.float64)
+
+
 def _run_conv(dev, x_nchw, w, bias, k, stride, act, want_stats, simt):
     from rib._lib import check, lib
     dt = _act_dtype()
@@ -126,7 +137,7 @@ def _run_conv(dev, x_nchw, w, bias, k, stride, act, want_stats, simt):
         torch.cuda.synchronize()
     finally:
         lib.rib_debug_set_simt(0)
-    return from_planar(out.float().cpu()), (stats.cpu() if want_stats else None)
+    return from_planar(out.float().cpu()), (_decode_stats(stats.cpu()) if want_stats else None)
 
 
 CONV_CASES = [
@@ -200,7 +211,7 @@ def _run_conv_ex(dev, x_planar, w, bias, b, h, wd, cin, cout, stride, subpix, xf
         torch.cuda.synchronize()
     finally:
         lib.rib_debug_set_simt(0)
-    return out.float().cpu(), (stats.cpu() if want_stats else None)
+    return out.float().cpu(), (_decode_stats(stats.cpu()) if want_stats else None)
 
 
 @pytest.mark.parametrize('simt', [True, False], ids=['simt', 'tcgen05'])
@@ -264,9 +275,26 @@ def test_transform_conv_matches_norm_act_conv(dev, case, simt):
     xn = F.leaky_relu(x * scale + shift, 0.2).to(dt).float()
     ref = F.conv2d(xn, wt.to(dt).float(), bias, stride=stride, padding=1)
     xin = (to_parity_planar(x, dt) if stride == 2 else to_planar(x, dt)).to(dev)
-    out, _ = _run_conv_ex(dev, xin, wt, bias, b, h, w, cin, cout, stride, False, (stats, aw, ab),
+    out, _ = _run_conv_ex(dev, xin, wt, bias, b, h, w, cin, cout, stride, False, (_encode_stats(stats), aw, ab),
                           (b, cout // 8, h // stride, w // stride, 8), False, simt)
     out = from_planar(out)
     err = (out - ref).abs()
     tol = 2.0 ** -7 * ref.abs() + 4e-3
     assert bool((err <= tol).all()), 'max err %.4g (ref %.4g)' % (err.max().item(), ref.flatten()[err.argmax()].item())
+
+
+def test_frames_from_u8_matches_to_tensor_norm(dev):
+    """uint8 HWC -> fp32 CHW == transforms.ToTensor + Normalize(0.5, 0.5) (HSM_auto_dataset.py:73-75), bit-exact,
+    dense and strided; and the clip renderer gives the same frames for uint8 and fp32 key frames."""
+    import rib
+    g = torch.Generator().manual_seed(9)
+    b, h, w = 5, 32, 48
+    u8 = torch.randint(0, 256, (b, h, w, 3), generator=g, dtype=torch.uint8)
+    u8[0, 0, :, 0] = torch.arange(48, dtype=torch.uint8)
+    u8[0, 1, :, 1] = torch.arange(208, 256, dtype=torch.uint8)
+    ref = (u8.permute(0, 3, 1, 2).float().div(255) - 0.5) / 0.5
+    out = rib.frames_from_u8(u8.to(dev))
+    assert torch.equal(out.cpu(), ref)
+    clip = torch.zeros(2 * b, 3, h, w, device=dev)
+    rib.frames_from_u8(u8.to(dev)[::2], out=clip[1::2][:3])
+    assert torch.equal(clip[1::2][:3].cpu(), ref[::2]) and (clip[0::2] == 0).all()
