@@ -127,6 +127,23 @@ def make_clip(seed):
     return key, joints, flows
 
 
+def to_u8_frames(x):
+    """fp32 [N,3,H,W] in [-1,1] -> uint8 [N,H,W,3] (rounded): what a decoded PNG key frame looks like."""
+    return ((x * 0.5 + 0.5).clamp(0, 1) * 255.0).round().to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+
+
+def make_clip_lean(seed, n_key=N_KEY, rate=RATE):
+    """The upload of one clip as a pipeline would hold it on the host: uint8 HWC key frames (decoded images), joints
+    for every frame (19x3 doubles each) and flows for the GENERATED frames only, in frame order."""
+    from rib.synth import synth_flow, synth_image, synth_joints
+    t = (n_key - 1) * rate + 1
+    key_u8 = to_u8_frames(synth_image(n_key, H, W, seed=seed))
+    joints = torch.from_numpy(synth_joints(t, H, W, seed=seed))
+    flows = synth_flow(t, H, W, seed=seed)
+    gen_rows = [i for i in range(t) if i % rate]
+    return key_u8, joints, flows[gen_rows].contiguous()
+
+
 # --------------------------------------------------------------------------------------------
 # CPU baseline (the oracle "port"; the unmodified reference when /root/reference is importable)
 # --------------------------------------------------------------------------------------------
@@ -216,8 +233,164 @@ def workload_config(n_gpus):
                         '512x512, rasterise + flow warp + generator + mask blend; one clip per GPU per step',
             'height': H, 'width': W, 'frames_per_clip': T, 'generated_frames_per_clip': GEN_FRAMES,
             'sample_rate': RATE, 'clips_per_step': n_gpus, 'generator_batch': GEN_FRAMES,
+            'inputs': 'uint8 key frames (decoded images), joints, flows of the generated frames',
             'l2': 'per-step working set (~20 GB of activations) exceeds the 126 MB L2; no flush needed',
-            'parallelism': 'clips sharded across GPUs, no collective in the forward, NCCL all_gather of uint8 frames'}
+            'parallelism': 'clips sharded across GPUs, no collective in the forward, asynchronous NCCL gather of the '
+                           'uint8 frames onto rank 0 (grouped send/recv, overlaps the next clip)'}
+
+
+# --------------------------------------------------------------------------------------------
+# Same-box bar: the reference generator's dataflow (the functional fp32
+# restatement in oracle/, which test_oracle_vs_reference pins bit-for-bit to the reference nn.Module) executed by
+# stock PyTorch / cuDNN on the same B200.  A baseline leg: nothing here is on the product path.
+# --------------------------------------------------------------------------------------------
+def aten_baseline(dev, gen, batch, iters=3):
+    from oracle import generator_oracle as go
+    from rib.arch import Arch
+    from rib.config import default_gen_cfg
+    from rib.synth import synth_image, synth_state_dict
+    arch = Arch(default_gen_cfg())
+    sd = {k: v.to(dev) for k, v in synth_state_dict(arch, seed=0, power_iters=5).items()}
+    label = torch.rand(batch, 22, H, W, device=dev) * 2 - 1
+    fake, prev = synth_image(batch, H, W, seed=1).to(dev), synth_image(batch, H, W, seed=2).to(dev)
+    out = {'batch': batch, 'height': H, 'width': W, 'iters': iters,
+           'what': 'oracle/generator_oracle.generator_forward (== reference Generator.forward) run by ATen/cuDNN on cuda'}
+
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.benchmark = True
+    try:
+        with torch.no_grad():
+            torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+            out['generator_ms_fp32'] = timed(lambda: go.generator_forward(sd, arch, label, fake, prev))
+            torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = True
+            out['generator_ms_tf32'] = timed(lambda: go.generator_forward(sd, arch, label, fake, prev))
+            cl = torch.channels_last
+            sd_cl = {k: (v.contiguous(memory_format=cl) if v.dim() == 4 else v) for k, v in sd.items()}
+            lab_cl, fake_cl, prev_cl = (t.contiguous(memory_format=cl) for t in (label, fake, prev))
+
+            def bf16():
+                with torch.autocast('cuda', dtype=torch.bfloat16):
+                    go.generator_forward(sd_cl, arch, lab_cl, fake_cl, prev_cl)
+            out['generator_ms_bf16_autocast_channels_last'] = timed(bf16)
+            out['generator_ms_ours'] = timed(lambda: gen(label, None, fake, prev))
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = old
+    best = min(out['generator_ms_fp32'], out['generator_ms_tf32'], out['generator_ms_bf16_autocast_channels_last'])
+    out['generator_frames_per_s'] = {k[len('generator_ms_'):]: batch / (v * 1e-3) for k, v in out.items()
+                                     if k.startswith('generator_ms_')}
+    out['ours_vs_best_aten'] = best / out['generator_ms_ours']
+    out['ours_vs_fp32_aten'] = out['generator_ms_fp32'] / out['generator_ms_ours']
+    del sd, sd_cl
+    torch.cuda.empty_cache()
+    return out
+
+
+# --------------------------------------------------------------------------------------------
+# BASELINE configs[3]: 4x interpolation of 256 synthetic clips sharded across the ranks (strong scaling), end to end:
+# every clip is uploaded from pinned host memory, rendered (3 dependent AR passes of batch 16), downloaded, and
+# gathered onto rank 0 asynchronously.
+# --------------------------------------------------------------------------------------------
+C4_CLIPS, C4_KEY, C4_RATE = 256, 17, 4
+C4_T = (C4_KEY - 1) * C4_RATE + 1
+
+
+def run_c4(gen, dev, rank, world, n_clips=C4_CLIPS):
+    import torch.distributed as dist
+    from rib.clip import ClipRenderer
+    from rib.dist import gather_frames, shard_range
+    assert n_clips % world == 0, 'configs[3] shards 256 clips evenly over 1/2/4/8 GPUs'
+    renderer = ClipRenderer(gen, sample_rate=C4_RATE)
+    lo, hi = shard_range(n_clips, rank, world)
+    mine = hi - lo
+    pool = [tuple(t.pin_memory() for t in make_clip_lean(1000 + rank * 2 + j, C4_KEY, C4_RATE)) for j in range(2)]
+    dbuf = [tuple(torch.empty_like(t, device=dev) for t in pool[0]) for _ in range(2)]
+    hosts = [torch.empty(C4_T, H, W, 3, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    big = None
+    if world > 1 and rank == 0:     # [clip index inside a shard][rank][frame]: 13 GB of uint8 frames for 256 clips
+        big = torch.empty(mine, world * C4_T, H, W, 3, dtype=torch.uint8, device=dev)
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream()
+
+    def run(count):
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_free = [torch.cuda.Event() for _ in range(2)]
+        ev_done = [torch.cuda.Event() for _ in range(2)]
+        ev_out = [torch.cuda.Event() for _ in range(2)]
+        pend = []
+
+        def upload(i):
+            b = i & 1
+            with torch.cuda.stream(s_in):
+                if i >= 2:
+                    s_in.wait_event(ev_free[b])
+                else:
+                    s_in.wait_stream(main)
+                for dst, src in zip(dbuf[b], pool[i & 1]):
+                    dst.copy_(src, non_blocking=True)
+                ev_in[b].record(s_in)
+
+        upload(0)
+        for i in range(count):
+            b = i & 1
+            if i + 1 < count:
+                upload(i + 1)
+            main.wait_event(ev_in[b])
+            k, j, f = dbuf[b]
+            out = renderer.render(k, j, flows=f, want_u8=True, want_fuse=False)
+            ev_free[b].record(main)
+            if world > 1:
+                pend.append(gather_frames(out['u8'], world * C4_T, out=big[i] if rank == 0 else None, async_op=True))
+            ev_done[b].record(main)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_done[b])
+                if i >= 2:
+                    s_out.wait_event(ev_out[b])
+                hosts[b].copy_(out['u8'], non_blocking=True)
+                out['u8'].record_stream(s_out)
+                ev_out[b].record(s_out)
+        for p in pend:
+            p.wait()
+        main.wait_stream(s_out)
+        main.wait_stream(s_in)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    run(min(2, mine))                  # warm-up: builds the batch-16 plan, touches every buffer
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run(mine)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    gen_frames = n_clips * (C4_T - C4_KEY)
+    del big
+    return {'workload': 'BASELINE configs[3]: 4x interpolation of %d synthetic 65-frame clips (17 key + 48 generated, 3 '
+                        'dependent AR passes of batch 16) at 512x512, clips sharded contiguously over the ranks' % n_clips,
+            'value': gen_frames / (ms * 1e-3), 'unit': 'frames/s', 'scaling': 'strong', 'n_gpus': world, 'clips': n_clips,
+            'generated_frames': gen_frames, 'ms_total': ms,
+            'includes': 'per-clip H2D from pinned memory (uint8 keys, joints, flows of generated frames), per-clip D2H '
+                        'of the uint8 frames, asynchronous NCCL gather of every clip onto rank 0',
+            'h2d_bytes_per_clip': int(sum(t.numel() * t.element_size() for t in pool[0])),
+            'd2h_bytes_per_clip': int(hosts[0].numel())}
 
 
 # --------------------------------------------------------------------------------------------
@@ -228,6 +401,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-aten', action='store_true', help='skip the same-box ATen/cuDNN generator timing')
+    ap.add_argument('--no-c4', action='store_true', help='skip the configs[3] (4x, 256 clips, strong scaling) pass')
+    ap.add_argument('--c4-clips', type=int, default=C4_CLIPS)
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', '0'))
@@ -264,34 +440,33 @@ def main():
     gen = gen.to(dev).eval()
     renderer = ClipRenderer(gen, sample_rate=RATE)
 
-    key_h, joints_h, flows_h = make_clip(seed=rank)
-    key_h, joints_h, flows_h = key_h.pin_memory(), joints_h.pin_memory(), flows_h.pin_memory()
+    key_h, joints_h, flows_h = (t.pin_memory() for t in make_clip_lean(rank))
     key_d, joints_d, flows_d = key_h.to(dev), joints_h.to(dev), flows_h.to(dev)
+    gather_out = None
+    if world > 1 and rank == 0:
+        gather_out = [torch.empty(world * T, H, W, 3, dtype=torch.uint8, device=dev) for _ in range(2)]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident():
-        out = renderer.render(key_d, joints_d, flows=flows_d, want_u8=True, want_fuse=False)
-        if world > 1:
-            gather_frames(out['u8'], world * T)
-        return out
-
-    # End-to-end pipeline: every step uploads ITS inputs from pinned host memory and downloads ITS uint8 frames,
-    # all inside the timed region; uploads of step i+1 and downloads of step i-1 run on their own streams so that
-    # they overlap the kernels of step i (double-buffered inputs, stream-ordered events, no host syncs in the loop).
     s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     in_bufs = [(torch.empty_like(key_d), torch.empty_like(joints_d), torch.empty_like(flows_d)) for _ in range(2)]
     u8_hosts = [torch.empty(T, H, W, 3, dtype=torch.uint8).pin_memory() for _ in range(2)]
 
-    def run_e2e(steps):
+    def run_steps(steps, e2e):
+        """`steps` clips back to back.  Resident mode: inputs are already in HBM, outputs stay there.  End-to-end mode:
+        every step uploads ITS inputs from pinned host memory and downloads ITS uint8 frames inside the timed region;
+        uploads of step i+1 and downloads of step i-1 run on their own streams so that they overlap the kernels of step
+        i (double-buffered, stream-ordered events, no host syncs in the loop).  With several ranks every clip's frames
+        are gathered onto rank 0 by an asynchronous grouped send/recv that overlaps the next clip."""
         main = torch.cuda.current_stream()
         ev_in = [torch.cuda.Event() for _ in range(2)]
         ev_free = [torch.cuda.Event() for _ in range(2)]
         ev_done = [torch.cuda.Event() for _ in range(2)]
         ev_out = [torch.cuda.Event() for _ in range(2)]
+        pend = []
 
         def upload(i):
             b = i & 1
@@ -304,37 +479,44 @@ def main():
                     dst.copy_(src, non_blocking=True)
                 ev_in[b].record(s_in)
 
-        upload(0)
+        if e2e:
+            upload(0)
         for i in range(steps):
             b = i & 1
-            if i + 1 < steps:
-                upload(i + 1)
-            main.wait_event(ev_in[b])
-            k, j, f = in_bufs[b]
+            if e2e:
+                if i + 1 < steps:
+                    upload(i + 1)
+                main.wait_event(ev_in[b])
+                k, j, f = in_bufs[b]
+            else:
+                k, j, f = key_d, joints_d, flows_d
             out = renderer.render(k, j, flows=f, want_u8=True, want_fuse=False)
+            if e2e:
+                ev_free[b].record(main)
             if world > 1:
-                gather_frames(out['u8'], world * T)
-            ev_free[b].record(main)
-            ev_done[b].record(main)
-            with torch.cuda.stream(s_out):
-                s_out.wait_event(ev_done[b])
                 if i >= 2:
-                    s_out.wait_event(ev_out[b])
-                u8_hosts[b].copy_(out['u8'], non_blocking=True)
-                out['u8'].record_stream(s_out)
-                ev_out[b].record(s_out)
-        main.wait_stream(s_out)                          # the caller holds every frame on the host
-        main.wait_stream(s_in)
+                    pend[i - 2].wait()                   # its receive buffer is re-used now
+                pend.append(gather_frames(out['u8'], world * T, out=gather_out[b] if rank == 0 else None, async_op=True))
+            if e2e:
+                ev_done[b].record(main)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_done[b])
+                    if i >= 2:
+                        s_out.wait_event(ev_out[b])
+                    u8_hosts[b].copy_(out['u8'], non_blocking=True)
+                    out['u8'].record_stream(s_out)
+                    ev_out[b].record(s_out)
+        for p in pend[-2:]:
+            p.wait()
+        if e2e:
+            main.wait_stream(s_out)                      # the caller holds every frame on the host
+            main.wait_stream(s_in)
 
-    def step_e2e():
-        run_e2e(1)
-
-    def timed(fn, steps):
+    def timed(steps, e2e):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
-            fn()
+        run_steps(steps, e2e)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -346,59 +528,60 @@ def main():
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
-        for _ in range(args.warmup):
-            step_resident()
+        run_steps(args.warmup, False)
         l0 = lib.rib_kernel_launch_count()
         w0 = time.time()
-        ms = timed(step_resident, args.steps)
+        ms = timed(args.steps, False)
         w1 = time.time()
         launches = lib.rib_kernel_launch_count() - l0
         clocks = sampler.stop(w0, w1) if rank == 0 else None
-        for _ in range(2):
-            step_e2e()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        run_e2e(args.steps)
-        e1.record()
-        barrier()
-        ms_t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(ms_t.item())
+        run_steps(2, True)
+        ms_e2e = timed(args.steps, True)
         # roofline pass: the same steps with every implicit-GEMM launch bracketed by CUDA events
         lib.rib_profile_enable(1)
         barrier()
-        for _ in range(args.steps):
-            step_resident()
+        run_steps(args.steps, False)
         barrier()
         conv_ms, conv_n = C.c_double(), C.c_longlong()
         lib.rib_profile_collect(C.byref(conv_ms), C.byref(conv_n))
         lib.rib_profile_enable(0)
+        aten = None
+        if rank == 0 and world == 1 and not args.no_aten:
+            aten = aten_baseline(dev, gen, GEN_FRAMES)
+        c4 = None
+        if not args.no_c4:
+            c4 = run_c4(gen, dev, rank, world, args.c4_clips)
 
     frames = GEN_FRAMES * world * args.steps
     value = frames / (ms * 1e-3)
     e2e_value = frames / (ms_e2e * 1e-3)
     tc_peak, hbm_peak, peak_src = peaks()
     conv_flop_per_step = CONV_FLOP_PER_FRAME * GEN_FRAMES
-    # DRAM traffic of the implicit-GEMM launches: from the committed ncu launch list of this same command
+    launches_per_step = conv_n.value / max(args.steps, 1)
+    conv_ms_per_step = conv_ms.value / max(args.steps, 1)
+    # DRAM traffic of the implicit-GEMM launches: from the committed ncu launch list of this same command.  The file
+    # records how many conv launches a step had when it was captured; a different count means the kernels changed
+    # since, and the figure is withheld rather than quoted stale.
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, 'profiles', 'conv_gemm_traffic.json')
     if os.path.isfile(tpath):
         tj = json.load(open(tpath))
-        traffic, traffic_src = tj.get('dram_bytes_per_launch'), tj.get('source')
-    launches_per_step = conv_n.value / max(args.steps, 1)
-    conv_ms_per_step = conv_ms.value / max(args.steps, 1)
+        if round(tj.get('launches_per_step', -1)) == round(launches_per_step):
+            traffic, traffic_src = tj.get('dram_bytes_per_launch'), tj.get('source')
+        else:
+            traffic_src = 'withheld: %s was captured with %s conv launches per step, this run has %d' % (
+                os.path.basename(tpath), tj.get('launches_per_step'), round(launches_per_step))
     achieved = conv_flop_per_step / (conv_ms_per_step * 1e-3) / 1e12
+    h2d = int(sum(t.numel() * t.element_size() for t in (key_h, joints_h, flows_h)))
     line = {
         'metric': 'rendered frames/s (raster+warp+gen+blend)', 'value': value, 'unit': 'frames/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'fp16' if lib.rib_act_is_fp16() else 'bf16', 'data': 'synthetic',
         'config': workload_config(world),
-        'e2e': {'value': e2e_value, 'unit': 'frames/s',
-                'h2d_bytes_per_step': int(key_h.numel() * 4 + joints_h.numel() * 8 + flows_h.numel() * 4),
-                'd2h_bytes_per_step': int(u8_hosts[0].numel()), 'ms_per_step': ms_e2e / args.steps},
+        'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d * world,
+                'd2h_bytes_per_step': int(u8_hosts[0].numel()) * world, 'ms_per_step': ms_e2e / args.steps,
+                'note': 'bytes are summed over the %d rank(s); every rank moves its own clip' % world},
         'gpu_launches': int(launches),
         'clocks': clocks,
         'roofline': {
@@ -411,6 +594,8 @@ def main():
             'traffic_source': traffic_src,
             'note': 'achieved = 883.5 kFLOP/pixel x 512x512 x 32 frames / summed CUDA-event time of all conv_gemm '
                     'launches of a step (events on the launching stream, separate pass of the same steps)'},
+        'aten_baseline': aten,
+        'c4': c4,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         fps, kind, cores = cpu_frames_per_s(3, seed=0, warm=1)

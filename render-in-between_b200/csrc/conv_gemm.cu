@@ -167,7 +167,7 @@ struct IssueCtx {
 //   a_lo      low descriptor word of the halo tile in this ring slot (tap offset not yet added)
 //   b_lo      low descriptor word of the group's first weight sub-tile
 //   tap       per-tap A offsets (16-byte units);  mk[m * KK + kk] = m * m_step + kk * a_kk_step
-template <int NT, int KK, int MT>
+template <int NT, int KK, int MT, bool PAIR>
 __device__ __forceinline__ void issue_group(const IssueCtx& c, uint32_t a_lo, const uint32_t* tap, const uint32_t* mk,
                                             uint32_t b_lo, uint32_t d0, uint32_t acc_first) {
 #pragma unroll
@@ -179,23 +179,61 @@ __device__ __forceinline__ void issue_group(const IssueCtx& c, uint32_t a_lo, co
 #pragma unroll
       for (int kk = 0; kk < KK; ++kk) {
         const uint32_t acc = (t == 0 && kk == 0) ? acc_first : 1u;
-        umma_f16(d0 + (uint32_t)m * c.bn, ((uint64_t)c.a_hi << 32) | (uint64_t)(a_t + mk[m * KK + kk]),
-                 ((uint64_t)c.b_hi << 32) | (uint64_t)(b_t + 2u * (uint32_t)kk), c.idesc, acc);
+        const uint64_t ad = ((uint64_t)c.a_hi << 32) | (uint64_t)(a_t + mk[m * KK + kk]);
+        const uint64_t bd = ((uint64_t)c.b_hi << 32) | (uint64_t)(b_t + 2u * (uint32_t)kk);
+        if (PAIR) umma_f16_pair(d0 + (uint32_t)m * c.bn, ad, bd, c.idesc, acc);
+        else umma_f16(d0 + (uint32_t)m * c.bn, ad, bd, c.idesc, acc);
       }
     }
   }
 }
 
+// Sub-pixel conv with several output parities per CTA: parity q runs its four taps (their A offsets come from the
+// table in shared memory: tapq[q * 4 + t]) against rows [q * bnp, (q + 1) * bnp) of every weight sub-tile and
+// accumulates into columns [q * bnp, (q + 1) * bnp) of the tile.  The halo tile is read from HBM / L2 once for all of them.
 template <int KK, int MT>
-__device__ __forceinline__ void issue_group_nt(int nt, const IssueCtx& c, uint32_t a_lo, const uint32_t* tap,
-                                               const uint32_t* mk, uint32_t b_lo, uint32_t d0, uint32_t acc_first) {
-  if (nt == 9) issue_group<9, KK, MT>(c, a_lo, tap, mk, b_lo, d0, acc_first);
-  else if (nt == 4) issue_group<4, KK, MT>(c, a_lo, tap, mk, b_lo, d0, acc_first);
-  else issue_group<1, KK, MT>(c, a_lo, tap, mk, b_lo, d0, acc_first);
+__device__ __forceinline__ void issue_group_subpix(int ppc, const IssueCtx& c, uint32_t a_lo, uint32_t tapq_addr,
+                                                   const uint32_t* mk, uint32_t b_lo, uint32_t d0, uint32_t acc_first,
+                                                   uint32_t bq16, uint32_t bnp) {
+#pragma unroll 1
+  for (int q = 0; q < ppc; ++q) {
+    uint32_t tap[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) tap[t] = ld_shared_u32(tapq_addr + (uint32_t)(q * 4 + t) * 4u);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const uint32_t a_t = a_lo + tap[t];
+      const uint32_t b_t = b_lo + (uint32_t)t * c.b_tap16 + (uint32_t)q * bq16;
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+#pragma unroll
+        for (int kk = 0; kk < KK; ++kk) {
+          const uint32_t acc = (t == 0 && kk == 0) ? acc_first : 1u;
+          umma_f16(d0 + (uint32_t)m * c.bn + (uint32_t)q * bnp, ((uint64_t)c.a_hi << 32) | (uint64_t)(a_t + mk[m * KK + kk]),
+                   ((uint64_t)c.b_hi << 32) | (uint64_t)(b_t + 2u * (uint32_t)kk), c.idesc, acc);
+        }
+      }
+    }
+  }
 }
 
-template <int MODE, int BN, bool SIMT, bool XF>
-__global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF) ? 1 : (kEpiGroups == 1 ? (BN <= 32 ? 3 : 2) : (BN <= 32 ? 2 : 1))) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+template <int KK, int MT, bool PAIR>
+__device__ __forceinline__ void issue_group_nt(int nt, const IssueCtx& c, uint32_t a_lo, const uint32_t* tap,
+                                               const uint32_t* mk, uint32_t b_lo, uint32_t d0, uint32_t acc_first) {
+  if (nt == 9) issue_group<9, KK, MT, PAIR>(c, a_lo, tap, mk, b_lo, d0, acc_first);
+  else if (nt == 4) issue_group<4, KK, MT, PAIR>(c, a_lo, tap, mk, b_lo, d0, acc_first);
+  else issue_group<1, KK, MT, PAIR>(c, a_lo, tap, mk, b_lo, d0, acc_first);
+}
+
+// PAIR: the CTA is one half of a CTA pair (cluster of two on the SMs of one TPC).  The pair computes two adjacent
+// super-tiles of the same N tile with tcgen05.mma.cta_group::2 (M = 256: 128 pixels from each CTA's shared memory, the
+// N = BN weight rows split half / half between the two CTAs' shared memory), issued by the leader (cluster rank 0).
+// Each CTA therefore stages only half of every weight sub-tile: half the L2 -> SM weight traffic and half the weight
+// reads from shared memory per MMA.  Barriers: both producers arrive (with their byte counts) on the LEADER's full
+// barrier; the leader's tcgen05.commit is multicast to the empty / accumulator-full barriers of both CTAs; the
+// epilogue warps of both CTAs arrive on the leader's accumulator-empty barrier.
+template <int MODE, int BN, bool SIMT, bool XF, bool PAIR>
+__global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF || PAIR) ? 1 : (kEpiGroups == 1 ? (BN <= 32 ? 3 : 2) : (BN <= 32 ? 2 : 1))) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -222,24 +260,33 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bres_bar + 1);
   float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr + 4) + 15) & ~(uintptr_t)15);  // [BN], 16-byte aligned
   float* s_aux = s_bias + BN;                              // per epilogue group: STORE [4 warps][2*BN] stats; SPADE [2*CT] rstd, -mean*rstd
-  uint32_t* s_tapoff = reinterpret_cast<uint32_t*>(s_aux + kEpiGroups * 8 * BN);  // [10] A start offset (16-byte units) of tap t; [9]: 1x1 second source
-  float* s_xf = reinterpret_cast<float*>(s_tapoff + 12);   // XF: [2][cin0] scale, shift of the current image
+  uint32_t* s_tapoff = reinterpret_cast<uint32_t*>(s_aux + kEpiGroups * 8 * BN);  // [16] A start offset (16-byte units) of tap t (sub-pixel conv: [parity q][tap]); [16]: 1x1 second source
+  float* s_xf = reinterpret_cast<float*>(s_tapoff + 20);   // XF: [2][cin0] scale, shift of the current image
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int ntile = blockIdx.x % p.n_tiles;
-  // sub-pixel conv: the N tiles of output parity `par` cover channels [ncol0, ncol0 + BN) of that parity's map
-  const int tiles_per_par = p.subpix ? p.n_tiles >> 2 : p.n_tiles;
-  const int par = ntile / tiles_per_par;
-  const int ncol0 = (ntile - par * tiles_per_par) * BN;
-  const int cta_m = blockIdx.x / p.n_tiles;
-  const int cta_groups = gridDim.x / p.n_tiles;
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;   // 0 = the pair's leader
+  const int cta_lin = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // pair index / CTA index
+  const int n_ctas = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int tstride = PAIR ? 2 : 1;                            // super-tiles advanced per iteration
+  const int ntile = cta_lin % p.n_tiles;
+  // sub-pixel conv: an N tile covers ppc consecutive output parities (from `par`) x channels [ncol0, ncol0 + BN / ppc)
+  const int ppc = p.subpix ? p.ppc : 1;
+  const int bnp = BN / ppc;                                                      // columns per parity
+  const int tiles_per_pg = p.subpix ? p.n_tiles / (4 / ppc) : p.n_tiles;
+  const int pgrp = ntile / tiles_per_pg;
+  const int par = pgrp * ppc;
+  const int ncol0 = (ntile - pgrp * tiles_per_pg) * bnp;
+  const int cta_m = cta_lin / p.n_tiles;
+  const int cta_groups = n_ctas / p.n_tiles;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const long long total_tiles = (long long)tiles_per_img * p.B;
   // contiguous range of super-tiles: neighbouring tiles share halo rows in L2 and an image's statistics
   // are flushed by few CTAs
-  const int t_begin = (int)(total_tiles * cta_m / cta_groups);
-  const int t_end = (int)(total_tiles * (cta_m + 1) / cta_groups);
+  // (a pair walks pairs of adjacent super-tiles: 2 i + rank; the host only pairs layers with an even tile count)
+  const long long units = PAIR ? total_tiles >> 1 : total_tiles;
+  const int t_begin = (int)(units * cta_m / cta_groups) * tstride + (int)cta_rank;
+  const int t_end = (int)(units * (cta_m + 1) / cta_groups) * tstride;
   const int acc_cols = p.MT * BN;  // TMEM columns of one accumulator buffer
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < NB * acc_cols) tmem_cols <<= 1;
@@ -249,32 +296,39 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
       prefetch_tmap(&p.amap[0]);
       prefetch_tmap(&p.bmap);
       for (int i = 0; i < p.a_ring; ++i) {
-        mbar_init(smem_u32(&a_full[i]), 1);
+        mbar_init(smem_u32(&a_full[i]), PAIR ? 2 : 1);       // pair: one arrival (+ bytes) per CTA, on the leader's barrier
         mbar_init(smem_u32(&a_empty[i]), 1);
         if (XF) mbar_init(smem_u32(&a_ready[i]), kXfThreads / 32);
       }
       for (int i = 0; i < NB; ++i) {
         mbar_init(smem_u32(&tmem_full_bar[i]), 1);
-        mbar_init(smem_u32(&tmem_empty_bar[i]), 4);
+        mbar_init(smem_u32(&tmem_empty_bar[i]), PAIR ? 8 : 4);   // pair: the epilogue warps of both CTAs
       }
       mbar_init(smem_u32(bres_bar), 1);
       fence_barrier_init();
     }
     if (warp == 1) {
-      tmem_alloc(smem_u32(tmem_ptr), tmem_cols);
-      tmem_relinquish();
+      if (PAIR) {
+        tmem_alloc_pair(smem_u32(tmem_ptr), tmem_cols);
+        tmem_relinquish_pair();
+      } else {
+        tmem_alloc(smem_u32(tmem_ptr), tmem_cols);
+        tmem_relinquish();
+      }
     }
   }
   if (warp >= 2 && warp < 6) {
     const int e = threadIdx.x - 64;
-    if (e < 10) {
-      const TapGeom tg = tap_geom(p, e == 9, e == 9 ? 0 : e, par);
+    if (e < 17) {
+      // sub-pixel conv: entry q * 4 + t = tap t of output parity par + q; otherwise entry t = tap t, entry 16 = 1x1 source
+      const TapGeom tg = p.subpix ? tap_geom(p, false, e & 3, par + (e >> 2)) : tap_geom(p, e == 16, e == 16 ? 0 : (e < 9 ? e : 0), 0);
       s_tapoff[e] = (uint32_t)tg.tile * (p.a_tile_bytes >> 4) + (uint32_t)tg.poff;
     }
     for (int c = e; c < BN; c += 128) s_bias[c] = p.bias[ntile * BN + c];
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = SIMT ? 0u : *tmem_ptr;
 
@@ -289,9 +343,10 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
       const uint32_t g_slot_bytes = p.g_slot_bytes, a_tile_bytes = p.a_tile_bytes, a_tx_bytes = p.a_tx_bytes;
       const uint32_t b_tap_bytes = p.b_tap_bytes, b_off = p.b_off;
       const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
-      const uint32_t a_full0 = smem_u32(a_full), a_empty0 = smem_u32(a_empty);
+      // pair: completions are signalled on the leader's full barriers (shared::cluster addresses)
+      const uint32_t a_full0 = PAIR ? mapa_shared(smem_u32(a_full), 0u) : smem_u32(a_full), a_empty0 = smem_u32(a_empty);
       const int planes_per_group = BKc >> 3;
-      const int n_col0 = ntile * BN;
+      const int n_col0 = ntile * BN + (PAIR ? (int)cta_rank * (BN / 2) : 0);   // pair: this CTA stages half of the weight rows
       if (b_resident) {  // all weight sub-tiles of this N tile, once
         const uint32_t bb = smem_u32(bres_bar);
         mbar_arrive_expect_tx(bb, (uint32_t)n_bt * b_tap_bytes);
@@ -304,7 +359,7 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
       int rem0 = t_begin - n * tiles_per_img;
       int tile_y = rem0 / tiles_x, tile_x = rem0 - tile_y * tiles_x;
       const int tiles_y = p.tiles_y;
-      for (int mt = t_begin; mt < t_end; ++mt) {
+      for (int mt = t_begin; mt < t_end; mt += tstride) {
         const int oy0 = tile_y * p.th * MT, ox0 = tile_x * p.tw;
         for (int g = 0; g < G; ++g) {
           mbar_wait(a_empty0 + 8u * a_slot, a_phase ^ 1u);
@@ -314,8 +369,11 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
           const int cg = (src1 ? g - stages0 : g) * planes_per_group;  // first 8-channel plane of the group
           const int nt = src1 ? 1 : ntaps;
           // one barrier covers the halo tile and (streamed mode) every weight sub-tile of the group
-          mbar_arrive_expect_tx(fb, a_tx_bytes + (b_resident ? 0u : (uint32_t)nt * b_tap_bytes));
-          if (stride == 1) {
+          if (PAIR) mbar_arrive_expect_tx_cluster(fb, a_tx_bytes + (uint32_t)nt * b_tap_bytes);
+          else mbar_arrive_expect_tx(fb, a_tx_bytes + (b_resident ? 0u : (uint32_t)nt * b_tap_bytes));
+          if (PAIR) {
+            tma_load_4d_pair(a_dst, &p.amap[src1 ? 1 : 0], fb, (ox0 - halo) * 8, oy0 - halo, cg, n);
+          } else if (stride == 1) {
             tma_load_4d(a_dst, &p.amap[src1 ? 1 : 0], fb, (ox0 - halo) * 8, oy0 - halo, cg, n);
           } else {
             if (p.s2_parity) {
@@ -329,19 +387,23 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
           if (!b_resident) {
             const int i0 = src1 ? stages0 * ntaps + (g - stages0) : g * ntaps;
 #pragma unroll 1
-            for (int t = 0; t < nt; ++t)
-              tma_load_2d(a_dst + b_off + (uint32_t)t * b_tap_bytes, &p.bmap, fb, (i0 + t) * BKc, n_col0);
+            for (int t = 0; t < nt; ++t) {
+              if (PAIR) tma_load_2d_pair(a_dst + b_off + (uint32_t)t * b_tap_bytes, &p.bmap, fb, (i0 + t) * BKc, n_col0);
+              else tma_load_2d(a_dst + b_off + (uint32_t)t * b_tap_bytes, &p.bmap, fb, (i0 + t) * BKc, n_col0);
+            }
           }
           if (++a_slot == a_ring) {
             a_slot = 0;
             a_phase ^= 1u;
           }
         }
-        if (++tile_x == tiles_x) {
-          tile_x = 0;
-          if (++tile_y == tiles_y) {
-            tile_y = 0;
-            ++n;
+        for (int k = 0; k < tstride; ++k) {
+          if (++tile_x == tiles_x) {
+            tile_x = 0;
+            if (++tile_y == tiles_y) {
+              tile_y = 0;
+              ++n;
+            }
           }
         }
       }
@@ -350,7 +412,7 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     // One elected lane; the MMAs of a channel group are fully unrolled (issue_group).
-    if (!SIMT && elect_one()) {
+    if (!SIMT && (!PAIR || cta_rank == 0u) && elect_one()) {   // pair: only the leader issues (for both CTAs)
       const int ntaps = p.ntaps, stages0 = p.stages0, a_ring = p.a_ring, MT = p.MT;
       const bool b_resident = p.b_resident != 0;
       const uint32_t g_slot16 = p.g_slot_bytes >> 4, b_off16 = p.b_off >> 4;
@@ -375,7 +437,9 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
       uint32_t tap[9], mk[8];
 #pragma unroll
       for (int t = 0; t < 9; ++t) tap[t] = s_tapoff[t];
-      const uint32_t tap1 = s_tapoff[9];
+      const uint32_t tap1 = s_tapoff[16];
+      const uint32_t tapq_addr = smem_u32(s_tapoff);
+      const uint32_t bq16 = ((uint32_t)bnp * b_row_bytes) >> 4;   // 16-byte units between the parity row blocks of a weight sub-tile
 #pragma unroll
       for (int i = 0; i < 8; ++i) mk[i] = (uint32_t)(i / kk_steps) * m_step + (uint32_t)(i % kk_steps) * a_kk_step;
       if (b_resident) {
@@ -385,7 +449,7 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
       int a_slot = 0;
       uint32_t a_phase = 0;
       int it = 0;
-      for (int mt = t_begin; mt < t_end; ++mt, ++it) {
+      for (int mt = t_begin; mt < t_end; mt += tstride, ++it) {
         const int buf = (int)((unsigned)it % (unsigned)NB);
         const uint32_t use = (uint32_t)it / (uint32_t)NB;
         mbar_wait(tempty0 + 8u * buf, (use & 1u) ^ 1u);  // epilogue has drained this buffer
@@ -402,22 +466,35 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
           const uint32_t b_lo = b_lo_c + (b_resident ? sB16 + (uint32_t)i0 * c.b_tap16 : slot16 + b_off16);
           const uint32_t acc_first = g != 0 ? 1u : 0u;
           const uint32_t* tp = src1 ? &tap1 : tap;
-          if (MT == 1) {
-            if (kk_steps == 1) issue_group_nt<1, 1>(nt, c, a_lo, tp, mk, b_lo, d0, acc_first);
-            else if (kk_steps == 2) issue_group_nt<2, 1>(nt, c, a_lo, tp, mk, b_lo, d0, acc_first);
-            else issue_group_nt<4, 1>(nt, c, a_lo, tp, mk, b_lo, d0, acc_first);
+          if (!PAIR && ppc > 1) {
+            if (MT == 1) {
+              if (kk_steps == 1) issue_group_subpix<1, 1>(ppc, c, a_lo, tapq_addr, mk, b_lo, d0, acc_first, bq16, (uint32_t)bnp);
+              else if (kk_steps == 2) issue_group_subpix<2, 1>(ppc, c, a_lo, tapq_addr, mk, b_lo, d0, acc_first, bq16, (uint32_t)bnp);
+              else issue_group_subpix<4, 1>(ppc, c, a_lo, tapq_addr, mk, b_lo, d0, acc_first, bq16, (uint32_t)bnp);
+            } else {
+              if (kk_steps == 1) issue_group_subpix<1, 2>(ppc, c, a_lo, tapq_addr, mk, b_lo, d0, acc_first, bq16, (uint32_t)bnp);
+              else if (kk_steps == 2) issue_group_subpix<2, 2>(ppc, c, a_lo, tapq_addr, mk, b_lo, d0, acc_first, bq16, (uint32_t)bnp);
+              else issue_group_subpix<4, 2>(ppc, c, a_lo, tapq_addr, mk, b_lo, d0, acc_first, bq16, (uint32_t)bnp);
+            }
+          } else if (MT == 1) {
+            if (kk_steps == 1) issue_group_nt<1, 1, PAIR>(nt, c, a_lo, tp, mk, b_lo, d0, acc_first);
+            else if (kk_steps == 2) issue_group_nt<2, 1, PAIR>(nt, c, a_lo, tp, mk, b_lo, d0, acc_first);
+            else issue_group_nt<4, 1, PAIR>(nt, c, a_lo, tp, mk, b_lo, d0, acc_first);
           } else {
-            if (kk_steps == 1) issue_group_nt<1, 2>(nt, c, a_lo, tp, mk, b_lo, d0, acc_first);
-            else if (kk_steps == 2) issue_group_nt<2, 2>(nt, c, a_lo, tp, mk, b_lo, d0, acc_first);
-            else issue_group_nt<4, 2>(nt, c, a_lo, tp, mk, b_lo, d0, acc_first);
+            if (kk_steps == 1) issue_group_nt<1, 2, PAIR>(nt, c, a_lo, tp, mk, b_lo, d0, acc_first);
+            else if (kk_steps == 2) issue_group_nt<2, 2, PAIR>(nt, c, a_lo, tp, mk, b_lo, d0, acc_first);
+            else issue_group_nt<4, 2, PAIR>(nt, c, a_lo, tp, mk, b_lo, d0, acc_first);
           }
-          umma_commit(a_empty0 + 8u * a_slot);  // frees the slot (halo tile + streamed weights) once the MMAs have read it
+          // frees the slot (halo tile + streamed weights) once the MMAs have read it (pair: in both CTAs)
+          if (PAIR) umma_commit_pair(a_empty0 + 8u * a_slot, (uint16_t)3);
+          else umma_commit(a_empty0 + 8u * a_slot);
           if (++a_slot == a_ring) {
             a_slot = 0;
             a_phase ^= 1u;
           }
         }
-        umma_commit(tfull0 + 8u * buf);
+        if (PAIR) umma_commit_pair(tfull0 + 8u * buf, (uint16_t)3);
+        else umma_commit(tfull0 + 8u * buf);
       }
     }
     __syncwarp();
@@ -590,7 +667,7 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
       }
       epi_bar(eg);
       for (int c = e; c < BN; c += 128) {
-        const int col = ncol0 + c;
+        const int col = ncol0 + (ppc > 1 ? c % bnp : c);   // several parities of a sub-pixel tile feed the same channel
         if (col < p.n_valid) {
           const float t1 = ((s_auxg[c] + s_auxg[2 * BN + c]) + s_auxg[4 * BN + c]) + s_auxg[6 * BN + c];
           const float t2 = ((s_auxg[BN + c] + s_auxg[3 * BN + c]) + s_auxg[5 * BN + c]) + s_auxg[7 * BN + c];
@@ -619,7 +696,7 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
       }
     };
     it = eg;
-    for (int mt = t_first; mt < t_end; mt += kEpiGroups, it += kEpiGroups) {
+    for (int mt = t_first; mt < t_end; mt += kEpiGroups * tstride, it += kEpiGroups) {
       const int buf = (int)((unsigned)it % (unsigned)NB);
       const uint32_t use = (uint32_t)it / (uint32_t)NB;
       const int oy0 = tile_y * p.th * p.MT, ox0 = tile_x * p.tw;
@@ -715,7 +792,7 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
             }
             float v[16];
             if (SIMT) {
-              simt_chunk(p, n, oy, ox, ntile * BN + j * 16, v, par);
+              simt_chunk(p, n, oy, ox, ntile * BN + j * 16, v, par + (ppc > 1 ? (j * 16) / bnp : 0));
             } else {
               tmem_ld16_wait(r[j & 1]);
               if (j + 1 < nch_eff) tmem_ld16_issue(trow + (uint32_t)((j + 1) * 16), r[(j + 1) & 1]);
@@ -778,6 +855,10 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
               for (int c = 0; c < 8; ++c) o[c] = pack2(v[2 * c], v[2 * c + 1]);
               const bool segb = p.seg_cols && j * 16 >= p.seg_cols;   // uniform
               act_t* ob = segb ? obase_b + (size_t)(2 * j - (p.seg_cols >> 3)) * HW8 : obase + (size_t)(2 * j) * oplane;
+              if (ppc > 1) {   // chunk j = channels [16 jc, 16 jc + 16) of output parity par + q
+                const int q = (j * 16) / bnp, jc = j - q * (bnp >> 4);
+                ob = obase + (size_t)q * HW8 + (size_t)(2 * jc) * oplane;
+              }
               *reinterpret_cast<uint4*>(ob) = make_uint4(o[0], o[1], o[2], o[3]);
               *reinterpret_cast<uint4*>(ob + (segb ? HW8 : oplane)) = make_uint4(o[4], o[5], o[6], o[7]);
               if (p.has_out2) {
@@ -892,20 +973,24 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF)
       if (!SIMT) {  // hand the accumulator buffer back to the MMA issuer
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[buf]));
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty_bar[buf]), 0u));   // the leader's barrier
+          else mbar_arrive(smem_u32(&tmem_empty_bar[buf]));
+        }
       }
-#pragma unroll
-      for (int k = 0; k < kEpiGroups; ++k) advance_tile();
+      for (int k = 0; k < kEpiGroups * tstride; ++k) advance_tile();
     }
     if (MODE == EPI_STORE && want_stats && cur_n >= 0) flush_stats(cur_n);
     tc_fence_before();
   }
 
-  __syncthreads();
+  if (PAIR) cluster_sync_all();   // neither CTA leaves (or frees its tensor memory) while the peer may still touch it
+  else __syncthreads();
   if (!SIMT && warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, tmem_cols);
+    if (PAIR) tmem_dealloc_pair(tmem_base, tmem_cols);
+    else tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
@@ -1011,21 +1096,30 @@ static constexpr size_t kSmallResident = (size_t)72 * 1024;   // weights of an N
 static constexpr size_t kBigResident = (size_t)148 * 1024;    // ... that still fit beside two halo-tile slots (one CTA per SM)
 
 // Channels per group.  Also fixes the K order of the packed weights, so it may only depend on the layer shape.
+// RIB_STREAM_BKC: channels per ring slot of a stride-1 layer with streamed weights (32: two ~95 KB slots; 16: four ~48 KB
+// slots, i.e. finer-grained refills of the same shared memory).
+#ifndef RIB_STREAM_BKC
+#define RIB_STREAM_BKC 32
+#endif
 int choose_bkc(int cin0, int cin1, int taps, int BN, int stride) {
   const size_t b_all = ((size_t)cin0 * taps + cin1) * BN * 2;
   int cap;
   if (b_all <= kSmallResident) cap = stride == 2 ? 16 : 64;       // stride 2 keeps four parity tiles per slot
   else if (b_all <= kBigResident) cap = stride == 2 ? 16 : 64;    // big resident weights: small halo slots
-  else cap = stride == 2 ? 16 : 32;                               // streamed: a slot holds the halo tile(s) AND 9 weight sub-tiles
+  else cap = stride == 2 ? 16 : RIB_STREAM_BKC;                   // streamed: a slot holds the halo tile(s) AND 9 weight sub-tiles
   int bk = cin0 < cap ? cin0 : cap;
   if (cin1 > 0 && cin1 < bk) bk = cin1;
   return bk;
 }
 
 int conv_gemm_configure(ConvGemmParams* p, int B, int Hout, int Wout, int cin0, int cin1, int taps, int stride,
-                        int BN, int n_pad, const ConvTune* tune) {
+                        int BN, int n_pad, const ConvTune* tune, int ppc) {
   RIB_REQUIRE(taps == 1 || taps == 9 || taps == 4, "conv_gemm: 1x1, 3x3 or sub-pixel 2x2 only");
-  RIB_REQUIRE(taps != 4 || (stride == 1 && cin1 == 0 && (n_pad / BN) % 4 == 0), "conv_gemm: bad sub-pixel conv");
+  RIB_REQUIRE(ppc == 1 || ppc == 2 || ppc == 4, "conv_gemm: parities per CTA must be 1, 2 or 4");
+  RIB_REQUIRE(taps == 4 || ppc == 1, "conv_gemm: parities per CTA only apply to the sub-pixel conv");
+  RIB_REQUIRE(taps != 4 || (stride == 1 && cin1 == 0 && ((n_pad / BN) * ppc) % 4 == 0 && (BN / ppc) % 16 == 0 &&
+                            (ppc == 1 || n_pad == 4 * (BN / ppc))),
+              "conv_gemm: bad sub-pixel conv");
   RIB_REQUIRE(stride == 1 || (stride == 2 && taps == 9 && cin1 == 0), "conv_gemm: stride 2 needs a plain 3x3");
   RIB_REQUIRE(BN >= 16 && BN <= 128 && (BN & (BN - 1)) == 0 && n_pad % BN == 0, "conv_gemm: bad BN");
   const int bkc = choose_bkc(cin0, cin1, taps, BN, stride);
@@ -1043,6 +1137,7 @@ int conv_gemm_configure(ConvGemmParams* p, int B, int Hout, int Wout, int cin0, 
   p->stride = stride;
   p->halo = taps == 1 ? 0 : 1;
   p->subpix = taps == 4 ? 1 : 0;
+  p->ppc = ppc;
   p->b_tap_bytes = (uint32_t)(BN * bkc * 2);
   const int n_bt = p->stages0 * taps + p->stages1;
   const size_t b_all = (size_t)n_bt * p->b_tap_bytes;
@@ -1081,8 +1176,17 @@ int conv_gemm_configure(ConvGemmParams* p, int B, int Hout, int Wout, int cin0, 
   // halo tiles.  Defaults by weight size; a ConvTune (the plan-time auto-tuner, generator.cu) may override policy and MT.
   int policy = b_all <= kSmallResident ? 1 : (b_all <= kBigResident ? 2 : 3);
   if (tune != nullptr && tune->policy != 0) policy = tune->policy;
-  RIB_REQUIRE(policy >= 1 && policy <= 3 && (policy == 3 ? b_all > kSmallResident : b_all <= kBigResident),
+  if (tune == nullptr) {   // kernel tests select a policy for the stand-alone conv (read per call, never set by the product)
+    const char* force = getenv("RIB_TEST_POLICY");
+    if (force != nullptr && atoi(force) >= 1 && atoi(force) <= 4) policy = atoi(force);
+  }
+  RIB_REQUIRE(policy >= 1 && policy <= 4 && (policy >= 3 ? b_all > kSmallResident : b_all <= kBigResident),
               "conv_gemm: residency policy does not apply to this layer");
+  p->pair = policy == 4 ? 1 : 0;
+  if (policy == 4) {
+    RIB_REQUIRE(BN == 128 && stride == 1 && taps != 4 && cin1 == 0, "conv_gemm: CTA pairs need a plain stride-1 layer with BN = 128");
+    p->b_tap_bytes = (uint32_t)((BN / 2) * bkc * 2);   // each CTA of the pair stages half of the weight rows
+  }
   int mt = policy == 1 ? 1 : (can_mt2 ? 2 : 1);
   const bool mt_forced = tune != nullptr && tune->mt != 0;
   if (mt_forced) mt = tune->mt;
@@ -1111,7 +1215,7 @@ int conv_gemm_configure(ConvGemmParams* p, int B, int Hout, int Wout, int cin0, 
   } else {
     // a ring slot holds the halo tile(s) of a channel group AND that group's weight sub-tiles (one barrier round trip
     // per group); two stacked sub-tiles halve the weight traffic per pixel (measured: also for stride 2, whose four
-    // parity tiles otherwise make the layer L2-bound)
+    // parity tiles otherwise make the layer L2-bound).  CTA pairs (policy 4): same slots with half-height weight tiles.
     p->b_resident = 0;
     const size_t budget = kSmemMax - kStatStageBytes - kOverhead;
     for (;;) {
@@ -1123,9 +1227,11 @@ int conv_gemm_configure(ConvGemmParams* p, int B, int Hout, int Wout, int cin0, 
     }
     const int ring = (int)(budget / p->g_slot_bytes);
     RIB_REQUIRE(ring >= 2, "conv_gemm: streamed group slots do not fit");
-    p->a_ring = ring > 4 ? 4 : ring;
+    const int ring_cap = (tune != nullptr && tune->ring >= 2 && tune->ring <= 8) ? tune->ring : 4;
+    p->a_ring = ring > ring_cap ? ring_cap : ring;
+    if (policy == 4) RIB_REQUIRE(((long long)p->tiles_x * p->tiles_y * B) % 2 == 0, "conv_gemm: CTA pairs need an even number of super-tiles");
   }
-  p->idesc = make_idesc_f16(128, BN);
+  p->idesc = make_idesc_f16(p->pair ? 256 : 128, BN / ppc);
   return 0;
 }
 
@@ -1136,7 +1242,7 @@ size_t conv_gemm_smem_bytes(const ConvGemmParams& p) {
   size_t stat = p.stats != nullptr ? kStatStageBytes : 0;
   const bool xf = p.xf_stats != nullptr;
   size_t bars = (size_t)((xf ? 3 : 2) * p.a_ring + 2 * acc_bufs(p.BN) + 1) * 8 + 32;
-  size_t scratch = (size_t)p.BN * 4 * (1 + 8 * kEpiGroups) + 64 + 64 + (xf ? (size_t)2 * p.stages0 * p.BKc * 4 : 0);
+  size_t scratch = (size_t)p.BN * 4 * (1 + 8 * kEpiGroups) + 64 + 128 + (xf ? (size_t)2 * p.stages0 * p.BKc * 4 : 0);
   return 1024 + tiles + stat + bars + scratch;
 }
 
@@ -1204,35 +1310,39 @@ int device_sm_count(int dev) {
 }
 
 template <bool SIMT>
-static ConvKernel pick_kernel(int mode, int BN, bool xf) {
+static ConvKernel pick_kernel(int mode, int BN, bool xf, bool pair) {
+  if (pair) {   // CTA pairs: the streamed heavy 3x3 layers (plain store, 128 columns)
+    if (SIMT || xf || mode != EPI_STORE || BN != 128) return nullptr;
+    return conv_gemm_kernel<EPI_STORE, 128, false, false, true>;
+  }
   if (xf) {  // the A-operand transform is built for the layers that use it: plain-store convs with 64 / 128 columns
     if (mode != EPI_STORE) return nullptr;
     switch (BN) {
-      case 64: return conv_gemm_kernel<EPI_STORE, 64, SIMT, true>;
-      case 128: return conv_gemm_kernel<EPI_STORE, 128, SIMT, true>;
+      case 64: return conv_gemm_kernel<EPI_STORE, 64, SIMT, true, false>;
+      case 128: return conv_gemm_kernel<EPI_STORE, 128, SIMT, true, false>;
     }
     return nullptr;
   }
   if (mode == EPI_STORE) {
     switch (BN) {
-      case 16: return conv_gemm_kernel<EPI_STORE, 16, SIMT, false>;
-      case 32: return conv_gemm_kernel<EPI_STORE, 32, SIMT, false>;
-      case 64: return conv_gemm_kernel<EPI_STORE, 64, SIMT, false>;
-      case 128: return conv_gemm_kernel<EPI_STORE, 128, SIMT, false>;
+      case 16: return conv_gemm_kernel<EPI_STORE, 16, SIMT, false, false>;
+      case 32: return conv_gemm_kernel<EPI_STORE, 32, SIMT, false, false>;
+      case 64: return conv_gemm_kernel<EPI_STORE, 64, SIMT, false, false>;
+      case 128: return conv_gemm_kernel<EPI_STORE, 128, SIMT, false, false>;
     }
   } else if (mode == EPI_SPADE) {
     switch (BN) {
-      case 32: return conv_gemm_kernel<EPI_SPADE, 32, SIMT, false>;
-      case 64: return conv_gemm_kernel<EPI_SPADE, 64, SIMT, false>;
-      case 128: return conv_gemm_kernel<EPI_SPADE, 128, SIMT, false>;
+      case 32: return conv_gemm_kernel<EPI_SPADE, 32, SIMT, false, false>;
+      case 64: return conv_gemm_kernel<EPI_SPADE, 64, SIMT, false, false>;
+      case 128: return conv_gemm_kernel<EPI_SPADE, 128, SIMT, false, false>;
     }
   } else if (mode == EPI_SPADE2) {
     switch (BN) {
-      case 64: return conv_gemm_kernel<EPI_SPADE2, 64, SIMT, false>;
-      case 128: return conv_gemm_kernel<EPI_SPADE2, 128, SIMT, false>;
+      case 64: return conv_gemm_kernel<EPI_SPADE2, 64, SIMT, false, false>;
+      case 128: return conv_gemm_kernel<EPI_SPADE2, 128, SIMT, false, false>;
     }
   } else if (mode == EPI_FINAL && BN == 16) {
-    return conv_gemm_kernel<EPI_FINAL, 16, SIMT, false>;
+    return conv_gemm_kernel<EPI_FINAL, 16, SIMT, false, false>;
   }
   return nullptr;
 }
@@ -1257,7 +1367,11 @@ int launch_conv_gemm(const ConvGemmParams& p, int mode, cudaStream_t stream) {
   RIB_REQUIRE(!p.out_parity || (p.H % 2 == 0 && p.W % 2 == 0 && !p.subpix), "conv_gemm: bad parity-planar output");
   RIB_REQUIRE(!p.res_ups || (p.has_res && p.H % 2 == 0 && p.W % 2 == 0 && !p.subpix && !p.out_parity),
               "conv_gemm: bad up-sampled residual");
-  ConvKernel fn = p.debug_simt ? pick_kernel<true>(mode, p.BN, xf) : pick_kernel<false>(mode, p.BN, xf);
+  // (the bring-up FMA loop has no pair form: a paired layer falls back to single CTAs with the same shared-memory plan)
+  const bool pair = p.pair != 0 && !p.debug_simt;
+  RIB_REQUIRE(!p.pair || (!p.b_resident && p.stride == 1 && !p.subpix && p.stages1 == 0 && !xf),
+              "conv_gemm: CTA pairs need a streamed stride-1 single-source layer");
+  ConvKernel fn = p.debug_simt ? pick_kernel<true>(mode, p.BN, xf, false) : pick_kernel<false>(mode, p.BN, xf, pair);
   RIB_REQUIRE(fn != nullptr, "conv_gemm: no kernel for this (epilogue, BN)");
   const size_t smem = conv_gemm_smem_bytes(p);
   RIB_REQUIRE(smem <= 227 * 1024, "conv_gemm: shared memory budget exceeded");
@@ -1285,10 +1399,11 @@ int launch_conv_gemm(const ConvGemmParams& p, int mode, cudaStream_t stream) {
   const long long m_tiles = (long long)p.tiles_x * p.tiles_y * p.B;
   const int n_sms = device_sm_count(dev);
   RIB_REQUIRE(n_sms > 0, "conv_gemm: cannot query the SM count");
-  long long groups = ((long long)n_sms * occ) / p.n_tiles;
+  // pair: `groups` counts CTA pairs per N tile, each pair walks pairs of super-tiles
+  long long groups = pair ? ((long long)(n_sms / 2) * occ) / p.n_tiles : ((long long)n_sms * occ) / p.n_tiles;
   if (groups < 1) groups = 1;
-  if (groups > m_tiles) groups = m_tiles;
-  dim3 grid((unsigned)(groups * p.n_tiles));
+  if (groups > (pair ? m_tiles / 2 : m_tiles)) groups = pair ? m_tiles / 2 : m_tiles;
+  dim3 grid((unsigned)(groups * p.n_tiles * (pair ? 2 : 1)));
   dim3 block(threads);
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (g_profile) {
@@ -1296,7 +1411,23 @@ int launch_conv_gemm(const ConvGemmParams& p, int mode, cudaStream_t stream) {
     RIB_CHECK_CUDA(cudaEventCreate(&ev1));
     RIB_CHECK_CUDA(cudaEventRecord(ev0, stream));
   }
-  fn<<<grid, block, smem, stream>>>(p);
+  if (pair) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    RIB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fn, p));
+  } else {
+    fn<<<grid, block, smem, stream>>>(p);
+  }
   RIB_CHECK_CUDA(cudaGetLastError());
   if (g_profile) {
     RIB_CHECK_CUDA(cudaEventRecord(ev1, stream));

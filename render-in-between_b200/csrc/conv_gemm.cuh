@@ -65,9 +65,14 @@ struct alignas(64) ConvGemmParams {
   int subpix;           // 1: 3x3 conv on a nearest-x2 up-sampled map, folded into four 2x2 convs on the LOW-resolution map
                         //    (ntaps = 4; N tile -> output parity (py, px) = ntile / (n_tiles / 4); the output, twice the
                         //    size of H x W, is written parity-planar [plane][py][px][H][W][8])
+  int ppc;              // sub-pixel conv: output parities computed per CTA (1, 2 or 4).  With ppc > 1 an N tile is
+                        //    [parity par0 | par0 + 1 | ...] x (BN / ppc) output channels (= all channels of the layer): the
+                        //    low-resolution halo tile is loaded once for ppc parities, each parity runs its own four taps
+                        //    (N = BN / ppc per tcgen05.mma) into its own accumulator columns
   int s2_parity;        // stride 2: 1 = the input is a parity-planar map, 0 = strided parity views of a normal map
   int a_ring, b_ring;   // ring slots (one channel group each); b_ring is unused
   int b_resident;       // 1: all weight sub-tiles of this CTA's N tile stay in shared memory
+  int pair;             // 1: CTA pairs (cluster of 2, tcgen05 cta_group::2, M = 256): each CTA stages half of the weight rows
   int halo_w;           // pixels per halo-tile row
   uint32_t a_tile_bytes;  // one halo tile (one parity view for stride 2), padded to 128 bytes
   uint32_t a_slot_bytes;  // A bytes per ring slot (1 or 4 tiles)
@@ -136,7 +141,8 @@ int choose_bkc(int cin0, int cin1, int taps, int BN, int stride);
 // Tiling choices the plan-time auto-tuner may override (0 = the default heuristic):
 //   mt      M=128 sub-tiles stacked per super-tile (1 or 2)
 //   policy  1 = resident weights, ~100 KB CTAs (several per SM); 2 = resident weights, one CTA per SM, deep halo ring;
-//           3 = weights streamed with the halo tiles
+//           3 = weights streamed with the halo tiles; 4 = streamed, CTA pairs (cta_group::2): each CTA of a pair
+//           stages half of the weight rows of every sub-tile and the leader issues M = 256 MMAs for both
 //   ring    policy 2 only: cap of the halo ring (default 4, at most 8); deeper rings help one-CTA-per-SM layers whose
 //           pipeline has the extra transform stage
 struct ConvTune {
@@ -145,7 +151,7 @@ struct ConvTune {
 // Fills the tiling / pipeline fields of p (everything except tensor maps and epilogue pointers).  Returns non-zero
 // when the requested tuning does not fit the layer.
 int conv_gemm_configure(ConvGemmParams* p, int B, int Hout, int Wout, int cin0, int cin1, int taps, int stride,
-                        int BN, int n_pad, const ConvTune* tune = nullptr);
+                        int BN, int n_pad, const ConvTune* tune = nullptr, int ppc = 1);
 size_t conv_gemm_smem_bytes(const ConvGemmParams& p);
 int launch_conv_gemm(const ConvGemmParams& p, int mode, cudaStream_t stream);
 int device_sm_count(int dev);   // multiprocessors of device `dev` (cached)

@@ -44,6 +44,7 @@ struct GemmLayer {
   int n_pad = 0, n_valid = 0, ktotal = 0;
   int cin0 = 0, taps = 0, cin1 = 0;  // padded input channels of source 0, its taps, source 1 (1x1) channels
   int BN = 0, bkc = 0, stride = 1;   // N tile, channels per group (fixes the packed K order), conv stride
+  int ppc = 1;                       // sub-pixel conv: output parities per CTA (ConvGemmParams::ppc)
   act_t* w = nullptr;
   float* bias = nullptr;
   size_t w_off = 0, b_off = 0;
@@ -187,8 +188,9 @@ int spade_ct(int C, int nq_tile = 1) { return std::min(C, nq_tile == 2 ? 32 : 64
 
 // BN = 0 selects the plain-store default min(n_pad, 128).
 void add_layer(Generator* G, const std::string& name, int n_valid, int n_pad, int cin0_pad, int taps, int cin1,
-               int BN = 0, int stride = 1) {
+               int BN = 0, int stride = 1, int ppc = 1) {
   GemmLayer L;
+  L.ppc = ppc;
   L.BN = BN ? BN : std::min(n_pad, 128);
   L.stride = stride;
   L.bkc = choose_bkc(cin0_pad, cin1, taps, L.BN, stride);
@@ -290,7 +292,11 @@ static void define_layers(Generator* G, std::vector<PackJob>& jobs) {
     // nn.Upsample(2) -> conv3x3 (generator.py:478-481) runs as four 2x2 convs on the low-resolution map, one per output
     // parity: N = 4 x Cout, K = 4 x Cin
     const int co = mask_nfilt(c, i), ci = mask_nfilt(c, i + 1);
-    add_layer(G, ln, co, 4 * co, ci, 4, 0, std::min(co, 128));
+    // Narrow layers (Cout < 128) compute 128 / Cout output parities per CTA from one halo load (RIB_SUBPIX_PPC=1: one
+    // parity per CTA, the halo tile is then fetched once per parity)
+    static const bool ppc_env = !(getenv("RIB_SUBPIX_PPC") != nullptr && atoi(getenv("RIB_SUBPIX_PPC")) == 1);
+    const int ppc = (ppc_env && co < 128 && 128 % co == 0 && co % 16 == 0) ? std::min(4, 128 / co) : 1;
+    add_layer(G, ln, co, 4 * co, ci, 4, 0, std::min(co * ppc, 128), 1, ppc);
     for (int par = 0; par < 4; ++par)
       jobs.push_back({ln, f + "up_flow." + std::to_string(2 * k + 1) + ".layers.conv", true, co, ci, 9, 0, ci, par * co, 0, 0, false, 1, par});
   }
@@ -493,7 +499,7 @@ struct PlanBuilder {
       rc = -4;
       return p;
     }
-    int r = conv_gemm_configure(&p, B, Hout, Wout, L.cin0, L.cin1, L.taps, stride, BN, L.n_pad);
+    int r = conv_gemm_configure(&p, B, Hout, Wout, L.cin0, L.cin1, L.taps, stride, BN, L.n_pad, nullptr, L.ppc);
     if (r || p.BKc != L.bkc) {
       if (!r) set_error("plan: K ordering mismatch in " + L.name);
       rc = r ? r : -4;
@@ -540,7 +546,7 @@ struct PlanBuilder {
                          : make_tmap_act_s2_strided(&p->amap[py * 2 + px], in0.p, in0.C, in0.W, in0.H, B, in0.bstride(),
                                                     py, px, p->BKc, p->halo_w, halo_h);
     }
-    if (!r) r = make_tmap_w(&p->bmap, L.w, L.ktotal, L.n_pad, p->BKc, p->BN, L.taps);
+    if (!r) r = make_tmap_w(&p->bmap, L.w, L.ktotal, L.n_pad, p->BKc, p->pair ? p->BN / 2 : p->BN, L.taps);
     return r;
   }
 
@@ -548,7 +554,7 @@ struct PlanBuilder {
   int retile(const Op& op, const ConvTune& t, ConvGemmParams* out) {
     ConvGemmParams p = op.g;
     const GemmLayer& L = *op.layer;
-    int r = conv_gemm_configure(&p, B, p.H, p.W, L.cin0, L.cin1, L.taps, L.stride, p.BN, L.n_pad, &t);
+    int r = conv_gemm_configure(&p, B, p.H, p.W, L.cin0, L.cin1, L.taps, L.stride, p.BN, L.n_pad, &t, L.ppc);
     if (r || p.BKc != L.bkc) return r ? r : -4;
     if (real) r = make_maps(&p, L, op.in0, op.has_in1 ? &op.in1 : nullptr);   // (the CPU dry run has no tensors to map)
     if (r) return r;
@@ -805,7 +811,8 @@ float time_gemm(const ConvGemmParams& p, int mode, cudaStream_t s) {
 }
 
 bool same_tiling(const ConvGemmParams& a, const ConvGemmParams& b) {
-  return a.MT == b.MT && a.a_ring == b.a_ring && a.g_slot_bytes == b.g_slot_bytes && a.b_resident == b.b_resident;
+  return a.MT == b.MT && a.a_ring == b.a_ring && a.g_slot_bytes == b.g_slot_bytes && a.b_resident == b.b_resident &&
+         a.pair == b.pair;
 }
 
 void autotune(PlanBuilder& pb, cudaStream_t stream) {
@@ -830,15 +837,18 @@ void autotune(PlanBuilder& pb, cudaStream_t stream) {
     char line[160];
     snprintf(line, sizeof(line), "%-20s default MT%d ring%d res%d %.1f us |", op.name.c_str(), op.g.MT, op.g.a_ring,
              op.g.b_resident, t_def * 1e3f);
+    (void)0;
     std::string log = line;
     if (t_def > 0.f) {
-      for (int cand = 0; cand < 8; ++cand) {
+      static const bool pairs_on = !(getenv("RIB_PAIRS") != nullptr && atoi(getenv("RIB_PAIRS")) == 0);
+      for (int cand = 0; cand < (pairs_on ? 10 : 8); ++cand) {
         {
-          const int policy = cand < 6 ? cand / 2 + 1 : 2, mt = cand % 2 + 1;
+          // candidates 0-5: policies 1-3 x MT 1/2; 6-7: one CTA per SM with a ring of up to 8 slots; 8-9: CTA pairs
+          const int policy = cand < 6 ? cand / 2 + 1 : (cand < 8 ? 2 : 4), mt = cand % 2 + 1;
           ConvTune t;
           t.mt = mt;
           t.policy = policy;
-          t.ring = cand < 6 ? 0 : 8;   // the last two candidates: one CTA per SM with a ring of up to 8 slots
+          t.ring = (cand < 6 || cand >= 8) ? 0 : 8;
           ConvGemmParams q;
           if (pb.retile(op, t, &q) != 0) continue;
           bool dup = false;
@@ -900,7 +910,7 @@ int generator_tune_import(const char* text) {
     t.policy = atoi(line.substr(t2 + 1).c_str());           // (stops at the next tab)
     const size_t t3 = line.find('\t', t2 + 1);
     t.ring = t3 == std::string::npos ? 0 : atoi(line.substr(t3 + 1).c_str());
-    if (t.mt < 0 || t.mt > 2 || t.policy < 0 || t.policy > 3 || t.ring < 0 || t.ring > 8) continue;
+    if (t.mt < 0 || t.mt > 2 || t.policy < 0 || t.policy > 4 || t.ring < 0 || t.ring > 8) continue;
     g_tune_cache[line.substr(0, t1)] = t;
     ++n;
   }
@@ -1370,10 +1380,10 @@ static int plan_text_of(const std::vector<Op>& ops, char* buf, long long cap) {
         const long long M = (long long)p.B * p.H * p.W;
         snprintf(line, sizeof(line),
                  "gemm %s mode=%d B=%d H=%d W=%d N=%lld nvalid=%d K=%lld BN=%d BKc=%d MT=%d taps=%d stride=%d "
-                 "cin0=%d cin1=%d bres=%d aring=%d bring=%d smem=%zu flops=%.6g\n",
+                 "cin0=%d cin1=%d bres=%d aring=%d bring=%d smem=%zu flops=%.6g pair=%d ppc=%d\n",
                  op.name.c_str(), op.mode, p.B, p.H, p.W, N, p.n_valid, K, p.BN, p.BKc, p.MT, p.ntaps, p.stride,
                  p.stages0 * p.BKc, p.stages1 * p.BKc, p.b_resident, p.a_ring, p.b_ring, conv_gemm_smem_bytes(p),
-                 2.0 * (double)M * (double)N * (double)K);
+                 2.0 * (double)M * (double)N * (double)K, p.pair, p.subpix ? p.ppc : 1);
         break;
       }
       case OP_IN_APPLY:
@@ -1440,6 +1450,10 @@ int conv_test_ex(const void* x, const float* w, const float* bias, void* out, do
   L.cin1 = 0;
   L.ktotal = Cin * L.taps;
   L.BN = std::min(Cout, 128);
+  if (subpix && Cout < 128 && 128 % Cout == 0 && !(getenv("RIB_SUBPIX_PPC") != nullptr && atoi(getenv("RIB_SUBPIX_PPC")) == 1)) {
+    L.ppc = std::min(4, 128 / Cout);   // as the generator plans it: several output parities per CTA
+    L.BN = Cout * L.ppc;
+  }
   L.stride = stride;
   L.bkc = choose_bkc(Cin, 0, L.taps, L.BN, stride);
   uint8_t* sp = static_cast<uint8_t*>(scratch);

@@ -179,6 +179,37 @@ def test_conv_gemm_matches_conv2d(dev, case, simt):
     assert torch.allclose(stats, s_ref, rtol=2e-3, atol=2e-2), (stats - s_ref).abs().max().item()
 
 
+PAIR_CASES = [
+    # (B, Cin, Cout, H, W): stride-1 3x3 layers with streamed weights and 128-column tiles
+    (2, 256, 256, 32, 32),     # MT=2, two N tiles, 8 super-tiles
+    (3, 128, 128, 24, 40),     # MT=1 (H < 32), ragged tile rows / columns, 30 super-tiles
+    (4, 512, 256, 64, 64),     # the mask net's res_flow shape at a smaller batch: more pair-tiles than CTA pairs
+]
+
+
+@pytest.mark.parametrize('case', PAIR_CASES, ids=lambda c: 'B%d_%dto%d_%dx%d' % c)
+def test_conv_gemm_cta_pairs_match_conv2d(dev, case, monkeypatch):
+    """The CTA-pair form (cluster of two, tcgen05.mma.cta_group::2 with M = 256, each CTA staging half of the weight
+    rows; policy 4 of conv_gemm_configure) against conv2d, and bit-identical to the single-CTA kernel."""
+    b, cin, cout, h, w = case
+    dt = _act_dtype()
+    g = torch.Generator().manual_seed(cin + cout + h)
+    x = torch.randn(b, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    ref = F.conv2d(x.to(dt).float(), wt.to(dt).float(), bias, padding=1)
+    single, s_single = _run_conv(dev, x, wt, bias, 3, 1, act=0, want_stats=True, simt=False)
+    monkeypatch.setenv('RIB_TEST_POLICY', '4')
+    out, stats = _run_conv(dev, x, wt, bias, 3, 1, act=0, want_stats=True, simt=False)
+    monkeypatch.delenv('RIB_TEST_POLICY')
+    err = (out - ref).abs()
+    assert bool((err <= 2.0 ** -7 * ref.abs() + 2e-3).all()), 'max err %.4g' % err.max().item()
+    s_ref = torch.stack([ref.double().sum(dim=(2, 3)), (ref.double() ** 2).sum(dim=(2, 3))], dim=2)
+    assert torch.allclose(stats, s_ref, rtol=2e-3, atol=2e-2), (stats - s_ref).abs().max().item()
+    # same K order and the same fp32 accumulation per output element: the pair computes the same bits
+    assert torch.equal(out, single)
+
+
 def test_conv_gemm_lrelu_epilogue(dev):
     b, cin, cout, h, w = 1, 32, 32, 16, 16
     g = torch.Generator().manual_seed(1)

@@ -55,7 +55,7 @@ def test_plan_dry_run_rejects_bad_shapes(gen, b, h, w):
 
 def test_plan_dry_run_reproduces_the_measured_plan(gen):
     """The plan text committed from the GPU run (tuned tilings included) is reproduced field by field on the CPU."""
-    path = os.path.join(ROOT, 'profiles', 'r1l_plan_B32_512.txt')
+    path = os.path.join(ROOT, 'profiles', 'r2_plan_B32_512.txt')
     if not os.path.isfile(path):
         pytest.skip('no committed plan')
     want = _gemm_lines(open(path).read())

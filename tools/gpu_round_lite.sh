@@ -13,5 +13,5 @@ python bench.py > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err; echo 
 python tools/conv_bench.py --out gpurun_out/conv_events_$tag.txt
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,launch__registers_per_thread \
     --clock-control none -c 3000 --csv --log-file gpurun_out/launches_$tag.csv \
-    python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench_$tag.log 2>&1
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-aten --no-c4 > gpurun_out/ncu_bench_$tag.log 2>&1
 echo "ncu bench rc=$?"

@@ -31,8 +31,10 @@ def main(path, tag, steps):
     def short(d):
         m = re.search(r'rib::(\w+)', d['name'])
         return m.group(1) if m else d['name'][:40]
-    starts = [i for i, d in enumerate(allrows) if short(d) == 'composite_kernel' and
-              (i + 1 < len(allrows) and short(allrows[i + 1]) != 'composite_kernel')]
+    starts = [i for i, d in enumerate(allrows) if short(d) == 'frames_from_u8_kernel']   # r2+: uint8 key frames first
+    if not starts:
+        starts = [i for i, d in enumerate(allrows) if short(d) == 'composite_kernel' and
+                  (i + 1 < len(allrows) and short(allrows[i + 1]) != 'composite_kernel')]
     segs = [allrows[a:b] for a, b in zip(starts, starts[1:] + [len(allrows)])]
     from collections import Counter
     modal = Counter(len(x) for x in segs).most_common(1)[0][0]
@@ -47,7 +49,7 @@ def main(path, tag, steps):
         a['us'] += d.get('gpu__time_duration.sum', 0) / 1e3
         a['dram_read'] += d.get('dram__bytes_read.sum', 0)
         a['dram_write'] += d.get('dram__bytes_write.sum', 0)
-    once = ('sn_sigma_inv_kernel', 'pack_weight_kernel', 'pack_weight_subpix_kernel')   # model creation, not per step
+    once = ('sn_sigma_inv_kernel', 'sn_sigma_rows_kernel', 'sn_sigma_final_kernel', 'pack_weight_kernel', 'pack_weight_subpix_kernel')   # model creation, not per step
     out = {'source': os.path.basename(path), 'clean_steps_averaged': steps, 'launches_per_step': modal, 'per_step': {}, 'once': {}}
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1]['us']):
         if k in once:

@@ -6,7 +6,7 @@
 tag=$1; b=${2:-32}; s=${3:-512}
 mkdir -p gpurun_out
 ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section WarpStateStats --section LaunchStats \
-    --section Occupancy --section SchedulerStats --clock-control none -k regex:conv_gemm -c 100 \
+    --section Occupancy --section SchedulerStats --clock-control none --profile-from-start off -k regex:conv_gemm -c 100 \
     -o gpurun_out/conv_$tag -f python tools/profile_forward.py --batch $b --size $s --iters 1 > gpurun_out/ncu_$tag.log 2>&1
 tail -2 gpurun_out/ncu_$tag.log
 ncu -i gpurun_out/conv_$tag.ncu-rep --page raw --csv > gpurun_out/conv_$tag.csv 2>/dev/null

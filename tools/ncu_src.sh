@@ -5,7 +5,7 @@
 tag=$1; shift
 mkdir -p gpurun_out
 for s in "$@"; do
-  ncu --set full --import-source on --clock-control none -k regex:conv_gemm -s $s -c 1 -f -o gpurun_out/src_${tag}_$s \
+  ncu --set full --import-source on --clock-control none --profile-from-start off -k regex:conv_gemm -s $s -c 1 -f -o gpurun_out/src_${tag}_$s \
       python tools/profile_forward.py --batch 32 --size 512 --iters 1 > gpurun_out/ncu_src_${tag}_$s.log 2>&1
   ncu -i gpurun_out/src_${tag}_$s.ncu-rep --page raw --csv > gpurun_out/src_${tag}_$s.raw.csv 2>/dev/null
   ncu -i gpurun_out/src_${tag}_$s.ncu-rep --page source --csv > gpurun_out/src_${tag}_$s.source.csv 2>/dev/null

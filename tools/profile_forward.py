@@ -41,18 +41,28 @@ def main():
         flows = synth_flow(t, h, w, seed=0).to(dev)
         r = ClipRenderer(gen, sample_rate=rate)
         with torch.no_grad():
+            r.render(key, joints, flows=flows, want_u8=True, want_fuse=False)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
             for _ in range(a.iters):
                 out = r.render(key, joints, flows=flows, want_u8=True, want_fuse=False)
-        torch.cuda.synchronize()
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
         print('ok clip', int(out['u8'].sum()))
         return
     label = rib.rasterize(torch.from_numpy(synth_joints(b, h, w, seed=3)).to(dev), h, w)
     fake, prev = synth_image(b, h, w, seed=1).to(dev), synth_image(b, h, w, seed=2).to(dev)
     with torch.no_grad():
+        # one untimed forward first (plan build, auto-tuner candidates); with `ncu --profile-from-start off` only the
+        # forwards after cudaProfilerStart are seen, so `-s <i>` is the index of a launch in the plan
+        gen(label, None, fake, prev)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
         for _ in range(a.iters):
             img, mask = gen(label, None, fake, prev)
             rib.composite(img, mask, fake)
-    torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
     with open(os.path.join(ROOT, 'gpurun_out', 'plan_B%d_%d.txt' % (b, h)), 'w') as f:
         f.write(gen.plan_text())
