@@ -81,6 +81,16 @@ int rib_composite(const float* img, const float* mask, const float* dain, float*
 int rib_frames_from_u8(const uint8_t* frames, float* out, int B, int H, int W, long long in_bstride,
                        long long out_bstride, void* stream);
 
+/* Replaces the image half of the evaluator's A.Resize(height, width, interpolation=cv2.INTER_CUBIC)
+ * (models/evaluator.py:18-26, applied to every key frame and DAIN frame at :218-220), i.e.
+ * cv2.resize(img, (W, H), interpolation=cv2.INTER_CUBIC) on a uint8 HWC image: OpenCV's separable 4-tap cubic
+ * convolution (A = -0.75) in its floating-point form, bit-identical to oracle/resize_oracle.py, which is pinned to
+ * cv2 4.13 (IPP) within one level on <= 0.05 % of the pixels.  Equal sizes copy the frame, like cv2.
+ *   frames u8 [B][h][w][3] -> out u8 [B][H][W][3]; *_bstride: bytes between frames (0 = dense).
+ */
+int rib_resize_cubic_u8(const uint8_t* frames, uint8_t* out, int B, int h, int w, int H, int W, long long in_bstride,
+                        long long out_bstride, void* stream);
+
 /* ---- A2: generator ---------------------------------------------------------------------------
  * Replaces models.generator.Generator (models/generator.py:35-302), LabelEmbedder (:306-410) and
  * MaskGenerator (:415-510) in eval mode.

@@ -104,7 +104,8 @@ def _install_stubs():
                 for t in self.tlist:
                     h0, w0 = image.shape[:2]
                     image = cv2.resize(image, (t.w, t.h), interpolation=t.interp)
-                    kp = [(x * t.w / w0, y * t.h / h0) for (x, y) in kp]
+                    # albumentations' Resize.apply_to_keypoint: scale_x = width / cols, then x * scale_x
+                    kp = [(x * (t.w / w0), y * (t.h / h0)) for (x, y) in kp]
                 return {'image': image, 'keypoints': kp}
 
         mod('albumentations', Resize=Resize, KeypointParams=KeypointParams, Compose=Compose,

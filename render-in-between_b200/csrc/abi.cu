@@ -71,6 +71,16 @@ int rib_composite(const float* img, const float* mask, const float* dain, float*
   RIB_GUARD_END
 }
 
+int rib_resize_cubic_u8(const uint8_t* frames, uint8_t* out, int B, int h, int w, int H, int W, long long in_bstride,
+                        long long out_bstride, void* stream) {
+  RIB_GUARD_BEGIN
+  RIB_REQUIRE(frames && out, "rib_resize_cubic_u8: null argument");
+  int rc = launch_resize_cubic_u8(frames, out, B, h, w, H, W, in_bstride, out_bstride, (cudaStream_t)stream);
+  if (!rc) count_misc_launch(1);
+  return rc;
+  RIB_GUARD_END
+}
+
 int rib_frames_from_u8(const uint8_t* frames, float* out, int B, int H, int W, long long in_bstride,
                        long long out_bstride, void* stream) {
   RIB_GUARD_BEGIN

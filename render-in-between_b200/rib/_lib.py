@@ -17,7 +17,7 @@ SYMBOLS = [
     'rib_debug_set_simt', 'rib_debug_get_simt', 'rib_generator_debug_tensor', 'rib_generator_plan_text', 'rib_act_is_fp16',
     'rib_conv_test_scratch_bytes', 'rib_conv_test', 'rib_profile_enable', 'rib_profile_collect', 'rib_profile_collect_launches',
     'rib_tune_log', 'rib_tune_export', 'rib_tune_import', 'rib_conv_test_ex',
-    'rib_plan_dry_run', 'rib_frames_from_u8',
+    'rib_plan_dry_run', 'rib_frames_from_u8', 'rib_resize_cubic_u8',
 ]
 
 
@@ -50,6 +50,8 @@ def _load():
     lib.rib_warp.argtypes = [vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, vp]
     lib.rib_composite.restype = i32
     lib.rib_composite.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i64, i64, i64, vp]
+    lib.rib_resize_cubic_u8.restype = i32
+    lib.rib_resize_cubic_u8.argtypes = [vp, vp, i32, i32, i32, i32, i32, i64, i64, vp]
     lib.rib_frames_from_u8.restype = i32
     lib.rib_frames_from_u8.argtypes = [vp, vp, i32, i32, i32, i64, i64, vp]
     lib.rib_generator_create.restype = i32

@@ -84,6 +84,21 @@ def _frames(t, name, tail):
     return t, (t.stride(0) if t.shape[0] > 1 else 0)
 
 
+def resize_cubic_u8(frames, height, width):
+    """uint8 [B,h,w,3] CUDA frames -> uint8 [B,height,width,3]: cv2.resize(..., interpolation=cv2.INTER_CUBIC), the
+    image half of the evaluator's A.Resize (PGNR/models/evaluator.py:18-26, :218-220), on the GPU."""
+    if not (isinstance(frames, torch.Tensor) and frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 4
+            and frames.shape[3] == 3):
+        raise ValueError('frames must be a CUDA uint8 tensor [B, h, w, 3]')
+    frames = frames.contiguous()
+    b, h, w, _ = frames.shape
+    out = torch.empty(b, height, width, 3, dtype=torch.uint8, device=frames.device)
+    with torch.cuda.device(frames.device):
+        check(lib.rib_resize_cubic_u8(frames.data_ptr(), out.data_ptr(), b, h, w, height, width, 0, 0, _stream()),
+              'rib_resize_cubic_u8')
+    return out
+
+
 def frames_from_u8(frames, out=None):
     """uint8 [B,H,W,3] CUDA frames (a decoded PNG) -> float32 [B,3,H,W] in [-1,1]: dataset.to_tensor_norm
     (PGNR/datasets/HSM_auto_dataset.py:73-75) on the GPU, bit-exact.  `frames` / `out` may be strided along dim 0."""

@@ -82,3 +82,16 @@ def test_save_frames_roundtrip_and_reference_bytes(tmp_path):
     rio.save_frames(torch.from_numpy(frames[:2]), names[:2], workers=1)
     with pytest.raises(ValueError):
         rio.save_frames(frames.astype(np.float32), names)
+
+
+def test_clip_layout_follows_the_reference_formula():
+    """sample rate and sequence length from the file counts, evaluator.py:187-191 (surplus poses are ignored)."""
+    from rib.folder import clip_layout
+    assert clip_layout(3, 5) == (2, 5)
+    assert clip_layout(33, 65) == (2, 65)
+    assert clip_layout(17, 65) == (4, 65)
+    assert clip_layout(3, 6) == (2, 5)          # 2 ** int(log2(5 / 2)) = 2
+    assert clip_layout(2, 9) == (8, 9)
+    import pytest
+    with pytest.raises(ValueError):
+        clip_layout(1, 5)
