@@ -18,7 +18,23 @@
 
 namespace rib {
 
-static constexpr int kEpiGroups = 1;                       // epilogue groups (4 warps each), one per TMEM accumulator buffer
+// Epilogue groups (4 warps each), one per TMEM accumulator buffer.  -DRIB_EPI_GROUPS=2 builds the two-group form (group g
+// drains the tiles of accumulator buffer g) for the A/B runs; -DRIB_EPI2_MINB_WIDE=2 then keeps two such CTAs per SM for
+// the wide tiles as well (96 registers per thread).
+#ifndef RIB_EPI_GROUPS
+#define RIB_EPI_GROUPS 1
+#endif
+#ifndef RIB_EPI2_MINB_WIDE
+#define RIB_EPI2_MINB_WIDE 1
+#endif
+// Resident CTAs per SM the narrow-tile kernels (BN <= 32) are compiled for: 3 caps them at 96 registers per thread (with
+// spills in the epilogue), 2 lets them use 168.
+// Measured (profiles/r2g): two CTAs per SM without spills beat three with them by 0.5 ms per forward
+// (mask.up.2 579 -> 326 us, mask.down_img.0 429 -> 251 us).
+#ifndef RIB_SMALL_MINB
+#define RIB_SMALL_MINB 2
+#endif
+static constexpr int kEpiGroups = RIB_EPI_GROUPS;
 static constexpr int kThreads = 64 + 128 * kEpiGroups;
 // Accumulator buffers in TMEM per CTA.  Two everywhere in the shipped build; -DRIB_ACC4_MAXBN=16|32 builds the narrow
 // tiles with four (the MMA lane may then run three tiles ahead of the epilogue) for the A/B runs of tools/gpu_ab.sh.
@@ -26,7 +42,10 @@ static constexpr int kThreads = 64 + 128 * kEpiGroups;
 #define RIB_ACC4_MAXBN 0
 #endif
 __host__ __device__ constexpr int acc_bufs(int BN) { return BN <= RIB_ACC4_MAXBN ? 4 : 2; }
-static constexpr int kXfThreads = 256;                     // transform warps of the XF kernels (after the epilogue warps)
+#ifndef RIB_XF_THREADS
+#define RIB_XF_THREADS 256
+#endif
+static constexpr int kXfThreads = RIB_XF_THREADS;          // transform warps of the XF kernels (after the epilogue warps)
 
 // Geometry of tap t of a stage: which halo tile of the slot it reads and the pixel offset of its
 // top-left corner inside that tile.
@@ -225,6 +244,137 @@ __device__ __forceinline__ void issue_group_nt(int nt, const IssueCtx& c, uint32
   else issue_group<1, KK, MT, PAIR>(c, a_lo, tap, mk, b_lo, d0, acc_first);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Specialised EPI_STORE epilogue of one M = 128 sub-tile.  The generic code in the kernel decides everything per 16-column
+// chunk at run time (statistics? residual? activation? second output? merged outputs? ragged tile?) and executes about
+// 110 instructions per chunk for a plain bias + LeakyReLU + store layer, 45 of them branches, predicated-off loads and
+// selects (profiles/r2b source capture of emb_0).  The layers of the generator only use six combinations, so the kernel
+// picks one of these instantiations once per launch; ALLVALID (decided per sub-tile with one vote) drops the per-lane
+// masking of ragged tiles.  The arithmetic, its order and the statistics are those of the generic path.
+// ---------------------------------------------------------------------------------------------
+enum { EF_STATS = 1, EF_RES = 2, EF_LRELU = 4, EF_OUT2 = 8, EF_SEG = 16 };
+
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+#ifndef RIB_REGSTATS_MAXBN
+#define RIB_REGSTATS_MAXBN 16
+#endif
+
+struct EpiFastArgs {
+  uint32_t trow;          // tensor-memory address of this thread's lane quarter, column 0 of the sub-tile
+  act_t* obase;           // first output: plane 0 of this thread's pixel; planes are `oplane` elements apart
+  size_t oplane;
+  act_t* obase_b;         // EF_SEG: second output (chunks >= seg_chunk), planes HW8 apart
+  int seg_chunk, nch_eff;
+  act_t* obase2;          // EF_OUT2: parity-planar copy, planes HW8 apart
+  size_t HW8;
+  const act_t* rbase;     // EF_RES: residual, planes rHW8 apart
+  size_t rHW8;
+  float* sbuf;            // EF_STATS: this warp's transposition buffer
+  int lane;
+};
+
+template <int BN, int EF, bool ALLVALID>
+__device__ __forceinline__ void epi_store_fast(const EpiFastArgs& a, bool valid, float (&acc1)[BN / 16], float (&acc2)[BN / 16],
+                                               float* ps1, float* ps2) {
+  constexpr int NCH = BN / 16;
+  constexpr bool STATS = (EF & EF_STATS) != 0, RES = (EF & EF_RES) != 0, LRELU = (EF & EF_LRELU) != 0;
+  constexpr bool OUT2 = (EF & EF_OUT2) != 0, SEG = (EF & EF_SEG) != 0;
+  constexpr bool kReg = STATS && BN <= RIB_REGSTATS_MAXBN;
+  const bool ok = ALLVALID || valid;
+  const int st_col = a.lane & 15, st_half = a.lane >> 4;
+  // The accumulator columns of chunk j + 1 are fetched while chunk j is processed (measured, profiles/r2e: fetching two
+  // or four chunks ahead is slower: 13.75 -> 13.85 / 14.5 ms per forward).  The bias is already in the accumulator: the
+  // MMA lane opens every tile with a K = 16 MMA of a ones tile against the bias rows (see the kernel), so there is
+  // neither a shared-memory load nor an add per value here.
+  uint32_t r[2][16];
+  tmem_ld16_issue(a.trow, r[0]);
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) {
+    if (SEG && j >= a.nch_eff) break;   // merged convs: the padding columns are skipped
+    uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+    if (RES && ok) {
+      r0 = *reinterpret_cast<const uint4*>(a.rbase + (size_t)(2 * j) * a.rHW8);
+      r1 = *reinterpret_cast<const uint4*>(a.rbase + (size_t)(2 * j + 1) * a.rHW8);
+    }
+    tmem_ld16_wait(r[j & 1]);
+    if (j + 1 < NCH && (!SEG || j + 1 < a.nch_eff)) tmem_ld16_issue(a.trow + (uint32_t)((j + 1) * 16), r[(j + 1) & 1]);
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(r[j & 1][c]);
+    if (RES) {
+      const uint32_t ru[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float x0, x1;
+        unpack2(ru[c], x0, x1);
+        v[2 * c] += x0;
+        v[2 * c + 1] += x1;
+      }
+    }
+    if (STATS) {
+      if (kReg) {   // running sums of this thread's pixel row (combined over the lanes when the image changes)
+        if (ok) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            ps1[kReg ? j * 16 + c : 0] += v[c];
+            ps2[kReg ? j * 16 + c : 0] = fmaf(v[c], v[c], ps2[kReg ? j * 16 + c : 0]);
+          }
+        }
+      } else {      // transpose through shared memory: rows = pixels of this warp, then per-lane column sums
+        float4* srow = reinterpret_cast<float4*>(a.sbuf + a.lane * kStatPitch);
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4)
+          srow[c4] = ok ? make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncwarp();
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int row = (i >> 2) * 8 + st_half * 4 + (i & 3);
+          const float xv = a.sbuf[row * kStatPitch + st_col];
+          s1 += xv;
+          s2 = fmaf(xv, xv, s2);
+        }
+        acc1[j] += s1;
+        acc2[j] += s2;
+        __syncwarp();
+      }
+    }
+    if (LRELU) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c) v[c] = fmaxf(v[c], 0.2f * v[c]);
+    }
+    uint32_t o[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) o[c] = pack2(v[2 * c], v[2 * c + 1]);
+    if (ok) {
+      act_t* ob = a.obase + (size_t)(2 * j) * a.oplane;
+      size_t pl = a.oplane;
+      if (SEG && j >= a.seg_chunk) {
+        ob = a.obase_b + (size_t)(2 * (j - a.seg_chunk)) * a.HW8;
+        pl = a.HW8;
+      }
+      *reinterpret_cast<uint4*>(ob) = make_uint4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<uint4*>(ob + pl) = make_uint4(o[4], o[5], o[6], o[7]);
+      if (OUT2) {
+        *reinterpret_cast<uint4*>(a.obase2 + (size_t)(2 * j) * a.HW8) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4*>(a.obase2 + (size_t)(2 * j + 1) * a.HW8) = make_uint4(o[4], o[5], o[6], o[7]);
+      }
+    }
+  }
+}
+
+template <int BN, int EF>
+__device__ __forceinline__ void epi_store_fast_v(const EpiFastArgs& a, bool valid, float (&acc1)[BN / 16], float (&acc2)[BN / 16],
+                                                 float* ps1, float* ps2) {
+  if (__all_sync(0xffffffffu, valid)) epi_store_fast<BN, EF, true>(a, valid, acc1, acc2, ps1, ps2);
+  else epi_store_fast<BN, EF, false>(a, valid, acc1, acc2, ps1, ps2);
+}
+
 // PAIR: the CTA is one half of a CTA pair (cluster of two on the SMs of one TPC).  The pair computes two adjacent
 // super-tiles of the same N tile with tcgen05.mma.cta_group::2 (M = 256: 128 pixels from each CTA's shared memory, the
 // N = BN weight rows split half / half between the two CTAs' shared memory), issued by the leader (cluster rank 0).
@@ -233,7 +383,7 @@ __device__ __forceinline__ void issue_group_nt(int nt, const IssueCtx& c, uint32
 // barrier; the leader's tcgen05.commit is multicast to the empty / accumulator-full barriers of both CTAs; the
 // epilogue warps of both CTAs arrive on the leader's accumulator-empty barrier.
 template <int MODE, int BN, bool SIMT, bool XF, bool PAIR>
-__global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF || PAIR) ? 1 : (kEpiGroups == 1 ? (BN <= 32 ? 3 : 2) : (BN <= 32 ? 2 : 1))) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+__global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF || PAIR) ? 1 : (kEpiGroups == 1 ? (BN <= 32 ? RIB_SMALL_MINB : 2) : (BN <= 32 ? 2 : RIB_EPI2_MINB_WIDE))) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -261,7 +411,13 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF 
   float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr + 4) + 15) & ~(uintptr_t)15);  // [BN], 16-byte aligned
   float* s_aux = s_bias + BN;                              // per epilogue group: STORE [4 warps][2*BN] stats; SPADE [2*CT] rstd, -mean*rstd
   uint32_t* s_tapoff = reinterpret_cast<uint32_t*>(s_aux + kEpiGroups * 8 * BN);  // [16] A start offset (16-byte units) of tap t (sub-pixel conv: [parity q][tap]); [16]: 1x1 second source
-  float* s_xf = reinterpret_cast<float*>(s_tapoff + 20);   // XF: [2][cin0] scale, shift of the current image
+  // Bias through the tensor core: a K = 16 MMA of a "ones" A tile (1.0 in k = 0 and k = 1 of every row; one 128-byte core
+  // matrix per 8-channel plane, addressed by all sixteen row groups: SBO = 0) against a bias B tile (row n: k = 0 the 16-bit
+  // rounding of bias[n], k = 1 the 16-bit rounding of the remainder) opens the accumulation of every sub-tile, so the
+  // epilogues neither load nor add the bias (4 shared loads + 16 adds per 16 columns per thread before).
+  uint8_t* s_ones = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(s_tapoff + 20) + 127) & ~(uintptr_t)127);  // 256 B
+  uint8_t* s_btile = s_ones + 256;                         // [BN / 8][2 k-halves][8 rows][16 B] un-swizzled K-major, BN * 32 bytes
+  float* s_xf = reinterpret_cast<float*>(s_btile + BN * 32);   // XF: [2][cin0] scale, shift of the current image
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -324,7 +480,23 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF 
       const TapGeom tg = p.subpix ? tap_geom(p, false, e & 3, par + (e >> 2)) : tap_geom(p, e == 16, e == 16 ? 0 : (e < 9 ? e : 0), 0);
       s_tapoff[e] = (uint32_t)tg.tile * (p.a_tile_bytes >> 4) + (uint32_t)tg.poff;
     }
-    for (int c = e; c < BN; c += 128) s_bias[c] = p.bias[ntile * BN + c];
+    // (sub-pixel convs with several parities per CTA issue N = BN / ppc MMAs per parity and keep the epilogue add)
+    const bool bias_mma = !SIMT && ppc == 1;
+    for (int c = e; c < BN; c += 128) s_bias[c] = bias_mma ? 0.f : p.bias[ntile * BN + c];
+    if (bias_mma) {
+      // ones tile: 2 core matrices x 8 rows x 8 elements; rows of plane 0 are {1, 1, 0, 0, 0, 0, 0, 0}
+      reinterpret_cast<act_t*>(s_ones)[e] = (e < 64 && (e & 7) < 2) ? f2act(1.0f) : f2act(0.0f);
+      const int nb = PAIR ? BN / 2 : BN, n0 = ntile * BN + (PAIR ? (int)cta_rank * (BN / 2) : 0);
+      for (int nrow = e; nrow < nb; nrow += 128) {
+        const float b = p.bias[n0 + nrow];
+        const act_t hi = f2act(b), lo = f2act(b - act2f(hi));
+        uint32_t w0 = (uint32_t)(*reinterpret_cast<const uint16_t*>(&hi)) | ((uint32_t)(*reinterpret_cast<const uint16_t*>(&lo)) << 16);
+        uint4* row = reinterpret_cast<uint4*>(s_btile + (nrow >> 3) * 256 + (nrow & 7) * 16);
+        row[0] = make_uint4(w0, 0u, 0u, 0u);   // k = 0..7
+        row[8] = make_uint4(0u, 0u, 0u, 0u);   // k = 8..15 (the second core matrix, 128 bytes on)
+      }
+      fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's shared-memory reads
+    }
   }
   tc_fence_before();
   if (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
@@ -371,14 +543,16 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF 
           // one barrier covers the halo tile and (streamed mode) every weight sub-tile of the group
           if (PAIR) mbar_arrive_expect_tx_cluster(fb, a_tx_bytes + (uint32_t)nt * b_tap_bytes);
           else mbar_arrive_expect_tx(fb, a_tx_bytes + (b_resident ? 0u : (uint32_t)nt * b_tap_bytes));
-          if (PAIR) {
-            tma_load_4d_pair(a_dst, &p.amap[src1 ? 1 : 0], fb, (ox0 - halo) * 8, oy0 - halo, cg, n);
-          } else if (stride == 1) {
-            tma_load_4d(a_dst, &p.amap[src1 ? 1 : 0], fb, (ox0 - halo) * 8, oy0 - halo, cg, n);
+          if (stride == 1) {
+            if (PAIR) tma_load_4d_pair(a_dst, &p.amap[src1 ? 1 : 0], fb, (ox0 - halo) * 8, oy0 - halo, cg, n);
+            else tma_load_4d(a_dst, &p.amap[src1 ? 1 : 0], fb, (ox0 - halo) * 8, oy0 - halo, cg, n);
           } else {
             if (p.s2_parity) {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) tma_load_4d(a_dst + q * a_tile_bytes, &p.amap[q], fb, (ox0 - 1) * 8, oy0 - 1, cg, n);
+              for (int q = 0; q < 4; ++q) {
+                if (PAIR) tma_load_4d_pair(a_dst + q * a_tile_bytes, &p.amap[q], fb, (ox0 - 1) * 8, oy0 - 1, cg, n);
+                else tma_load_4d(a_dst + q * a_tile_bytes, &p.amap[q], fb, (ox0 - 1) * 8, oy0 - 1, cg, n);
+              }
             } else {
 #pragma unroll
               for (int q = 0; q < 4; ++q) tma_load_5d(a_dst + q * a_tile_bytes, &p.amap[q], fb, 0, ox0 - 1, oy0 - 1, cg, n);
@@ -446,6 +620,11 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF 
         mbar_wait(smem_u32(bres_bar), 0u);
         tc_fence_after();
       }
+      const bool bias_mma = ppc == 1;
+      // un-swizzled K-major descriptors (make_nosw_desc): ones tile LBO = 128, SBO = 0; bias tile LBO = 128, SBO = 256
+      const uint64_t ones_desc = ((uint64_t)(1u << 14) << 32) | (uint64_t)(((smem_u32(s_ones) >> 4) & 0x3fffu) | ((128u >> 4) << 16));
+      const uint64_t bias_desc = ((uint64_t)((256u >> 4) | (1u << 14)) << 32) |
+                                 (uint64_t)(((smem_u32(s_btile) >> 4) & 0x3fffu) | ((128u >> 4) << 16));
       int a_slot = 0;
       uint32_t a_phase = 0;
       int it = 0;
@@ -455,6 +634,12 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF 
         mbar_wait(tempty0 + 8u * buf, (use & 1u) ^ 1u);  // epilogue has drained this buffer
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)(buf * acc_cols);
+        if (bias_mma) {   // D = ones x bias^T: every row of the tile starts at bias[n] (hi + lo parts)
+          for (int m = 0; m < MT; ++m) {
+            if (PAIR) umma_f16_pair(d0 + (uint32_t)m * c.bn, ones_desc, bias_desc, c.idesc, 0u);
+            else umma_f16(d0 + (uint32_t)m * c.bn, ones_desc, bias_desc, c.idesc, 0u);
+          }
+        }
         for (int g = 0; g < G; ++g) {
           mbar_wait(a_full0 + 8u * a_slot, a_phase);
           tc_fence_after();
@@ -464,7 +649,7 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF 
           const uint32_t slot16 = sA16 + (uint32_t)a_slot * g_slot16;
           const uint32_t a_lo = a_lo_c + slot16;
           const uint32_t b_lo = b_lo_c + (b_resident ? sB16 + (uint32_t)i0 * c.b_tap16 : slot16 + b_off16);
-          const uint32_t acc_first = g != 0 ? 1u : 0u;
+          const uint32_t acc_first = (g != 0 || bias_mma) ? 1u : 0u;
           const uint32_t* tp = src1 ? &tap1 : tap;
           if (!PAIR && ppc > 1) {
             if (MT == 1) {
@@ -626,9 +811,6 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF 
     // The narrowest tiles (BN = 16) are bound by the epilogue's instruction latency, not by the tensor pipe: there every
     // thread keeps the running sums of its own pixel row in registers (two FMAs per value, no shuffle, no shared
     // memory) and the 32 lanes are combined only when the image changes.
-    #ifndef RIB_REGSTATS_MAXBN
-#define RIB_REGSTATS_MAXBN 16
-#endif
     constexpr bool kRegStats = MODE == EPI_STORE && BN <= RIB_REGSTATS_MAXBN;
     constexpr int kRegN = kRegStats ? BN : 1;
     float ps1[kRegN], ps2[kRegN];
@@ -681,8 +863,21 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF 
       epi_bar(eg);
     };
 
+    // EPI_STORE: which specialised epilogue serves this launch (-1: the generic code below)
+    int epi_fast = -1;
+    if (MODE == EPI_STORE && !SIMT && ppc == 1 && (p.act == ACT_NONE || p.act == ACT_LRELU)) {
+      const int ef = (want_stats ? EF_STATS : 0) | (p.has_res ? EF_RES : 0) | (p.act == ACT_LRELU ? EF_LRELU : 0) |
+                     (p.has_out2 ? EF_OUT2 : 0) | (p.seg_cols ? EF_SEG : 0);
+      if (ef == 0 || ef == EF_LRELU || ef == (EF_LRELU | EF_OUT2) || ef == EF_STATS || ef == (EF_STATS | EF_RES) ||
+          ef == (EF_STATS | EF_SEG))
+        epi_fast = ef;
+    }
+#ifdef RIB_NO_FAST_EPI
+    epi_fast = -1;
+#endif
+
     // group eg takes tiles t_begin + eg, t_begin + eg + 2, ...; tile coordinates advance incrementally
-    const int t_first = t_begin + eg;
+    const int t_first = t_begin + eg * tstride;
     int n = t_first / tiles_per_img;
     int tile_y = (t_first - n * tiles_per_img) / p.tiles_x;
     int tile_x = (t_first - n * tiles_per_img) - tile_y * p.tiles_x;
@@ -780,6 +975,32 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF 
           const act_t* rbase = p.has_res ? p.res.p + (size_t)n * p.res.bstride + (size_t)((ntile * BN) >> 3) * rHW8 +
                                                (p.res_ups ? ((size_t)(oy >> 1) * (p.W >> 1) + (ox >> 1)) * 8 : pix8)
                                          : nullptr;
+          if (epi_fast >= 0) {
+            EpiFastArgs fa;
+            fa.trow = trow;
+            fa.obase = obase;
+            fa.oplane = oplane;
+            fa.obase_b = obase_b;
+            fa.seg_chunk = p.seg_cols >> 4;
+            fa.nch_eff = nch_eff;
+            fa.obase2 = obase2;
+            fa.HW8 = HW8;
+            fa.rbase = rbase;
+            fa.rHW8 = rHW8;
+            fa.sbuf = sbuf;
+            fa.lane = lane;
+            float* q1 = ps1;
+            float* q2 = ps2;
+            switch (epi_fast) {
+              case 0: epi_store_fast_v<BN, 0>(fa, valid, acc1, acc2, q1, q2); break;
+              case EF_LRELU: epi_store_fast_v<BN, EF_LRELU>(fa, valid, acc1, acc2, q1, q2); break;
+              case EF_LRELU | EF_OUT2: epi_store_fast_v<BN, EF_LRELU | EF_OUT2>(fa, valid, acc1, acc2, q1, q2); break;
+              case EF_STATS: epi_store_fast_v<BN, EF_STATS>(fa, valid, acc1, acc2, q1, q2); break;
+              case EF_STATS | EF_RES: epi_store_fast_v<BN, EF_STATS | EF_RES>(fa, valid, acc1, acc2, q1, q2); break;
+              default: epi_store_fast_v<BN, EF_STATS | EF_SEG>(fa, valid, acc1, acc2, q1, q2); break;
+            }
+            continue;   // next sub-tile
+          }
           uint32_t r[2][16];
           if (!SIMT) tmem_ld16_issue(trow, r[0]);
 #pragma unroll
@@ -915,12 +1136,19 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF 
                 float y[16];
 #pragma unroll
                 for (int c4 = 0; c4 < 4; ++c4) {
-                  const float4 bg = *reinterpret_cast<const float4*>(s_bias + colg + c4 * 4);  // gamma bias + 1
-                  const float4 bb = *reinterpret_cast<const float4*>(s_bias + colb + c4 * 4);  // beta bias
-                  y[c4 * 4 + 0] = fmaf(xn[c4 * 4 + 0], g[c4 * 4 + 0] + bg.x, b[c4 * 4 + 0] + bb.x);
-                  y[c4 * 4 + 1] = fmaf(xn[c4 * 4 + 1], g[c4 * 4 + 1] + bg.y, b[c4 * 4 + 1] + bb.y);
-                  y[c4 * 4 + 2] = fmaf(xn[c4 * 4 + 2], g[c4 * 4 + 2] + bg.z, b[c4 * 4 + 2] + bb.z);
-                  y[c4 * 4 + 3] = fmaf(xn[c4 * 4 + 3], g[c4 * 4 + 3] + bg.w, b[c4 * 4 + 3] + bb.w);
+                  if (SIMT) {   // bring-up loop: the biases (gamma's includes the "+ 1") are added here
+                    const float4 bg = *reinterpret_cast<const float4*>(s_bias + colg + c4 * 4);
+                    const float4 bb = *reinterpret_cast<const float4*>(s_bias + colb + c4 * 4);
+                    y[c4 * 4 + 0] = fmaf(xn[c4 * 4 + 0], g[c4 * 4 + 0] + bg.x, b[c4 * 4 + 0] + bb.x);
+                    y[c4 * 4 + 1] = fmaf(xn[c4 * 4 + 1], g[c4 * 4 + 1] + bg.y, b[c4 * 4 + 1] + bb.y);
+                    y[c4 * 4 + 2] = fmaf(xn[c4 * 4 + 2], g[c4 * 4 + 2] + bg.z, b[c4 * 4 + 2] + bb.z);
+                    y[c4 * 4 + 3] = fmaf(xn[c4 * 4 + 3], g[c4 * 4 + 3] + bg.w, b[c4 * 4 + 3] + bb.w);
+                  } else {      // tcgen05 path: 1 + gamma and beta arrive complete from the bias MMA
+                    y[c4 * 4 + 0] = fmaf(xn[c4 * 4 + 0], g[c4 * 4 + 0], b[c4 * 4 + 0]);
+                    y[c4 * 4 + 1] = fmaf(xn[c4 * 4 + 1], g[c4 * 4 + 1], b[c4 * 4 + 1]);
+                    y[c4 * 4 + 2] = fmaf(xn[c4 * 4 + 2], g[c4 * 4 + 2], b[c4 * 4 + 2]);
+                    y[c4 * 4 + 3] = fmaf(xn[c4 * 4 + 3], g[c4 * 4 + 3], b[c4 * 4 + 3]);
+                  }
                 }
                 const float sl = p.actq[qq] == ACT_LRELU ? 0.2f : 1.0f;
                 act_t* orow = p.outq[qq].p + (size_t)n * p.outq[qq].bstride + (size_t)(c0 >> 3) * HW8 + pix8;
@@ -945,7 +1173,7 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF 
             // (kept small on purpose: the 16-way unrolled form of this block thrashed the instruction cache)
             float y[4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) y[c] = v[c] + s_bias[c];
+            for (int c = 0; c < 4; ++c) y[c] = SIMT ? v[c] + s_bias[c] : v[c];   // (tcgen05 path: bias MMA)
             if (p.act == ACT_TANH) {
 #pragma unroll
               for (int c = 0; c < 4; ++c) y[c] = tanhf(y[c]);
@@ -1184,7 +1412,7 @@ int conv_gemm_configure(ConvGemmParams* p, int B, int Hout, int Wout, int cin0, 
               "conv_gemm: residency policy does not apply to this layer");
   p->pair = policy == 4 ? 1 : 0;
   if (policy == 4) {
-    RIB_REQUIRE(BN == 128 && stride == 1 && taps != 4 && cin1 == 0, "conv_gemm: CTA pairs need a plain stride-1 layer with BN = 128");
+    RIB_REQUIRE(BN == 128 && taps != 4 && (cin1 == 0 || stride == 1), "conv_gemm: CTA pairs need a plain layer with BN = 128");
     p->b_tap_bytes = (uint32_t)((BN / 2) * bkc * 2);   // each CTA of the pair stages half of the weight rows
   }
   int mt = policy == 1 ? 1 : (can_mt2 ? 2 : 1);
@@ -1242,7 +1470,8 @@ size_t conv_gemm_smem_bytes(const ConvGemmParams& p) {
   size_t stat = p.stats != nullptr ? kStatStageBytes : 0;
   const bool xf = p.xf_stats != nullptr;
   size_t bars = (size_t)((xf ? 3 : 2) * p.a_ring + 2 * acc_bufs(p.BN) + 1) * 8 + 32;
-  size_t scratch = (size_t)p.BN * 4 * (1 + 8 * kEpiGroups) + 64 + 128 + (xf ? (size_t)2 * p.stages0 * p.BKc * 4 : 0);
+  size_t scratch = (size_t)p.BN * 4 * (1 + 8 * kEpiGroups) + 64 + 128 + (xf ? (size_t)2 * p.stages0 * p.BKc * 4 : 0) +
+                   128 + 256 + (size_t)p.BN * 32;   // ones tile + bias tile of the bias MMA (128-byte aligned)
   return 1024 + tiles + stat + bars + scratch;
 }
 
@@ -1369,8 +1598,8 @@ int launch_conv_gemm(const ConvGemmParams& p, int mode, cudaStream_t stream) {
               "conv_gemm: bad up-sampled residual");
   // (the bring-up FMA loop has no pair form: a paired layer falls back to single CTAs with the same shared-memory plan)
   const bool pair = p.pair != 0 && !p.debug_simt;
-  RIB_REQUIRE(!p.pair || (!p.b_resident && p.stride == 1 && !p.subpix && p.stages1 == 0 && !xf),
-              "conv_gemm: CTA pairs need a streamed stride-1 single-source layer");
+  RIB_REQUIRE(!p.pair || (!p.b_resident && (p.stride == 1 || (p.s2_parity && p.stages1 == 0)) && !p.subpix && !xf),
+              "conv_gemm: CTA pairs need a streamed layer (stride 2: parity-planar single source, no transform)");
   ConvKernel fn = p.debug_simt ? pick_kernel<true>(mode, p.BN, xf, false) : pick_kernel<false>(mode, p.BN, xf, pair);
   RIB_REQUIRE(fn != nullptr, "conv_gemm: no kernel for this (epilogue, BN)");
   const size_t smem = conv_gemm_smem_bytes(p);

@@ -292,10 +292,11 @@ static void define_layers(Generator* G, std::vector<PackJob>& jobs) {
     // nn.Upsample(2) -> conv3x3 (generator.py:478-481) runs as four 2x2 convs on the low-resolution map, one per output
     // parity: N = 4 x Cout, K = 4 x Cin
     const int co = mask_nfilt(c, i), ci = mask_nfilt(c, i + 1);
-    // Narrow layers (Cout < 128) compute 128 / Cout output parities per CTA from one halo load (RIB_SUBPIX_PPC=1: one
-    // parity per CTA, the halo tile is then fetched once per parity)
-    static const bool ppc_env = !(getenv("RIB_SUBPIX_PPC") != nullptr && atoi(getenv("RIB_SUBPIX_PPC")) == 1);
-    const int ppc = (ppc_env && co < 128 && 128 % co == 0 && co % 16 == 0) ? std::min(4, 128 / co) : 1;
+    // Narrow layers (Cout < 128) can compute 128 / Cout output parities per CTA from one halo load.
+    // Measured (profiles/r2b): with today's epilogue the wider tiles lose more CTAs per SM (fewer epilogue warps) than the
+    // shared halo load saves (mask.up.1 191 -> 259 us, up.2 432 -> 463 us), so the form is opt-in: RIB_SUBPIX_PPC=4.
+    static const int ppc_env = getenv("RIB_SUBPIX_PPC") != nullptr ? atoi(getenv("RIB_SUBPIX_PPC")) : 1;
+    const int ppc = (ppc_env > 1 && co < 128 && 128 % co == 0 && co % 16 == 0) ? std::min(std::min(4, ppc_env), 128 / co) : 1;
     add_layer(G, ln, co, 4 * co, ci, 4, 0, std::min(co * ppc, 128), 1, ppc);
     for (int par = 0; par < 4; ++par)
       jobs.push_back({ln, f + "up_flow." + std::to_string(2 * k + 1) + ".layers.conv", true, co, ci, 9, 0, ci, par * co, 0, 0, false, 1, par});
@@ -1450,8 +1451,8 @@ int conv_test_ex(const void* x, const float* w, const float* bias, void* out, do
   L.cin1 = 0;
   L.ktotal = Cin * L.taps;
   L.BN = std::min(Cout, 128);
-  if (subpix && Cout < 128 && 128 % Cout == 0 && !(getenv("RIB_SUBPIX_PPC") != nullptr && atoi(getenv("RIB_SUBPIX_PPC")) == 1)) {
-    L.ppc = std::min(4, 128 / Cout);   // as the generator plans it: several output parities per CTA
+  if (subpix && Cout < 128 && 128 % Cout == 0 && getenv("RIB_TEST_PPC") != nullptr && atoi(getenv("RIB_TEST_PPC")) > 1) {
+    L.ppc = std::min(std::min(4, atoi(getenv("RIB_TEST_PPC"))), 128 / Cout);   // several output parities per CTA (kernel tests)
     L.BN = Cout * L.ppc;
   }
   L.stride = stride;

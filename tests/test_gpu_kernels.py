@@ -180,27 +180,28 @@ def test_conv_gemm_matches_conv2d(dev, case, simt):
 
 
 PAIR_CASES = [
-    # (B, Cin, Cout, H, W): stride-1 3x3 layers with streamed weights and 128-column tiles
-    (2, 256, 256, 32, 32),     # MT=2, two N tiles, 8 super-tiles
-    (3, 128, 128, 24, 40),     # MT=1 (H < 32), ragged tile rows / columns, 30 super-tiles
-    (4, 512, 256, 64, 64),     # the mask net's res_flow shape at a smaller batch: more pair-tiles than CTA pairs
+    # (B, Cin, Cout, H, W, stride): 3x3 layers with streamed weights and 128-column tiles (H, W = input size)
+    (2, 256, 256, 32, 32, 1),     # MT=2, two N tiles, 8 super-tiles
+    (3, 128, 128, 24, 40, 1),     # MT=1 (H < 32), ragged tile rows / columns, 30 super-tiles
+    (4, 512, 256, 64, 64, 1),     # the mask net's res_flow shape at a smaller batch: more pair-tiles than CTA pairs
+    (2, 256, 512, 64, 64, 2),     # stride 2 from a parity-planar input (the embedder's emb_3 shape), four N tiles
 ]
 
 
-@pytest.mark.parametrize('case', PAIR_CASES, ids=lambda c: 'B%d_%dto%d_%dx%d' % c)
+@pytest.mark.parametrize('case', PAIR_CASES, ids=lambda c: 'B%d_%dto%d_%dx%d_s%d' % c)
 def test_conv_gemm_cta_pairs_match_conv2d(dev, case, monkeypatch):
     """The CTA-pair form (cluster of two, tcgen05.mma.cta_group::2 with M = 256, each CTA staging half of the weight
     rows; policy 4 of conv_gemm_configure) against conv2d, and bit-identical to the single-CTA kernel."""
-    b, cin, cout, h, w = case
+    b, cin, cout, h, w, stride = case
     dt = _act_dtype()
     g = torch.Generator().manual_seed(cin + cout + h)
     x = torch.randn(b, cin, h, w, generator=g)
     wt = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
     bias = torch.randn(cout, generator=g) * 0.1
-    ref = F.conv2d(x.to(dt).float(), wt.to(dt).float(), bias, padding=1)
-    single, s_single = _run_conv(dev, x, wt, bias, 3, 1, act=0, want_stats=True, simt=False)
+    ref = F.conv2d(x.to(dt).float(), wt.to(dt).float(), bias, stride=stride, padding=1)
+    single, s_single = _run_conv(dev, x, wt, bias, 3, stride, act=0, want_stats=True, simt=False)
     monkeypatch.setenv('RIB_TEST_POLICY', '4')
-    out, stats = _run_conv(dev, x, wt, bias, 3, 1, act=0, want_stats=True, simt=False)
+    out, stats = _run_conv(dev, x, wt, bias, 3, stride, act=0, want_stats=True, simt=False)
     monkeypatch.delenv('RIB_TEST_POLICY')
     err = (out - ref).abs()
     assert bool((err <= 2.0 ** -7 * ref.abs() + 2e-3).all()), 'max err %.4g' % err.max().item()
@@ -245,11 +246,14 @@ def _run_conv_ex(dev, x_planar, w, bias, b, h, wd, cin, cout, stride, subpix, xf
     return out.float().cpu(), (_decode_stats(stats.cpu()) if want_stats else None)
 
 
+@pytest.mark.parametrize('ppc', [1, 4], ids=['ppc1', 'ppc4'])
 @pytest.mark.parametrize('simt', [True, False], ids=['simt', 'tcgen05'])
 @pytest.mark.parametrize('case', [(1, 16, 16, 16, 16), (2, 64, 32, 32, 32), (1, 128, 64, 16, 24), (1, 256, 128, 16, 16)],
                          ids=lambda c: 'B%d_%dto%d_%dx%d' % c)
-def test_subpixel_conv_matches_upsample_conv(dev, case, simt):
-    """conv3x3(nearest_x2(x)) == the four 2x2 parity convs on the low-resolution map (generator.py:478-481)."""
+def test_subpixel_conv_matches_upsample_conv(dev, case, simt, ppc, monkeypatch):
+    """conv3x3(nearest_x2(x)) == the four 2x2 parity convs on the low-resolution map (generator.py:478-481); ppc4: the
+    form that computes up to four output parities per CTA from one halo load."""
+    monkeypatch.setenv('RIB_TEST_PPC', str(ppc))
     b, cin, cout, h, w = case
     dt = _act_dtype()
     g = torch.Generator().manual_seed(cin + cout + h)

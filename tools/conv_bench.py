@@ -52,8 +52,19 @@ def main():
             assert n.value == len(names), (n.value, len(names))
             for i in range(len(names)):
                 acc[i] += buf[i] * 1e3 / a.iters
+        # the whole forward as the caller sees it (launch gaps and the non-conv kernels included): CUDA events around
+        # `iters` back-to-back forwards without the per-launch instrumentation
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(a.iters):
+            gen(label, None, fake, prev)
+        e1.record()
+        torch.cuda.synchronize()
+        wall_us = e0.elapsed_time(e1) * 1e3 / a.iters
     lines = ['%-24s %9.1f' % (nm, us) for nm, us in zip(names, acc)]
     lines.append('%-24s %9.1f' % ('total', sum(acc)))
+    lines.append('%-24s %9.1f' % ('forward_wall', wall_us))
     txt = '\n'.join(lines)
     print(txt.splitlines()[-1], 'lib', os.environ.get('RIB_LIB', 'default'))
     if a.out:

@@ -13,6 +13,8 @@ for size in 256 512 1024; do
 import json, os, sys
 b, size, path = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
 us = float([l for l in open(path) if l.startswith('total')][0].split()[1])
+wall = [l for l in open(path) if l.startswith('forward_wall')]
+wall = float(wall[0].split()[1]) if wall else float('nan')
 flop = 883.5e3 * size * size * b
 peak = 1390.7
 try:
@@ -20,8 +22,9 @@ try:
 except OSError:
     pass
 tf = flop / (us * 1e-6) / 1e12
-print('B=%-3d %4dx%-4d conv %9.1f us/forward  %7.1f frames/s  %7.1f TFLOP/s  %.3f of the sustained tensor peak' % (
-    b, size, size, us, b / (us * 1e-6), tf, tf / peak))
+print('B=%-3d %4dx%-4d conv kernels %9.1f us/forward  %7.1f TFLOP/s  %.3f of the sustained tensor peak | whole forward '
+      '(wall, incl. launch gaps and non-conv kernels) %9.1f us  %7.1f frames/s' % (
+          b, size, size, us, tf, tf / peak, wall, b / (wall * 1e-6)))
 PY
   done
 done
