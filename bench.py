@@ -39,6 +39,15 @@ FLOP_PER_PIXEL = 883.5e3                    # 2*MAC of the 96 convs, SURVEY.md ย
 CONV_FLOP_PER_FRAME = FLOP_PER_PIXEL * H * W
 
 
+def protect_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner did, from the C side),
+    so file descriptor 1 is pointed at stderr for the whole run and the line goes to the saved descriptor."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, 'w')
+
+
 def peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.isfile(path):
@@ -202,7 +211,7 @@ def cpu_frames_per_s(n_frames, seed=0, warm=1):
     return len(frames[warm:]) / dt, kind, torch.get_num_threads()
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, out):
     """`--impl reference`: the reference's CPU implementation of the path on the host cores."""
     if rank != 0:
         return
@@ -225,7 +234,8 @@ def run_reference(args, rank, world):
                          'sample': '%d generated frames per step of the 512x512 clip, batch 1, all host threads' % n_frames},
         'e2e': {'value': value, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=out)
+    out.flush()
 
 
 def workload_config(n_gpus):
@@ -409,9 +419,10 @@ def main():
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    out = protect_stdout()
 
     if args.impl == 'reference':
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, out)
         return
 
     import torch.distributed as dist
@@ -524,7 +535,28 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    def reproducibility_check():
+        """SURVEY.md ยง8e "Check": N-GPU output identical to 1-GPU output.  Every rank renders the SAME clip (seed 4242)
+        twice and the uint8 frames are reduced to a 64-bit checksum; the checksums of all ranks (and of the two runs)
+        must agree bit for bit - instance-norm statistics are accumulated with order-independent integer atomics and
+        every rank runs the shipped tuning table, so a clip's frames do not depend on which GPU of the job renders it."""
+        k, j, f = (t.to(dev) for t in make_clip_lean(4242))
+        sums = []
+        for _ in range(2):
+            u8 = renderer.render(k, j, flows=f, want_u8=True, want_fuse=False)['u8']
+            w = torch.arange(1, u8.numel() + 1, device=dev, dtype=torch.int64) % 65521
+            sums.append(int((u8.view(-1).to(torch.int64) * w).sum().item()))
+        mine = torch.tensor(sums, device=dev, dtype=torch.int64)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(allr, mine)
+        else:
+            allr = [mine]
+        vals = sorted({int(v) for t in allr for v in t.tolist()})
+        return {'clip_checksum': vals[0], 'ranks': world, 'runs_per_rank': 2, 'bit_identical': len(vals) == 1}
+
     with torch.no_grad():
+        repro = reproducibility_check()
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
@@ -596,6 +628,7 @@ def main():
                     'launches of a step (events on the launching stream, separate pass of the same steps)'},
         'aten_baseline': aten,
         'c4': c4,
+        'reproducibility': repro,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         fps, kind, cores = cpu_frames_per_s(3, seed=0, warm=1)
@@ -604,7 +637,8 @@ def main():
     else:
         line['cpu_baseline'] = None
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), file=out)
+        out.flush()
     if world > 1:
         dist.destroy_process_group()
 
