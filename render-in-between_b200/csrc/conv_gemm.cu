@@ -460,7 +460,7 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF 
         mbar_init(smem_u32(&tmem_full_bar[i]), 1);
         mbar_init(smem_u32(&tmem_empty_bar[i]), PAIR ? 8 : 4);   // pair: the epilogue warps of both CTAs
       }
-      mbar_init(smem_u32(bres_bar), 1);
+      mbar_init(smem_u32(bres_bar), PAIR ? 2 : 1);   // pair: both CTAs' weight halves are counted on the leader's barrier
       fence_barrier_init();
     }
     if (warp == 1) {
@@ -519,10 +519,14 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF 
       const uint32_t a_full0 = PAIR ? mapa_shared(smem_u32(a_full), 0u) : smem_u32(a_full), a_empty0 = smem_u32(a_empty);
       const int planes_per_group = BKc >> 3;
       const int n_col0 = ntile * BN + (PAIR ? (int)cta_rank * (BN / 2) : 0);   // pair: this CTA stages half of the weight rows
-      if (b_resident) {  // all weight sub-tiles of this N tile, once
-        const uint32_t bb = smem_u32(bres_bar);
-        mbar_arrive_expect_tx(bb, (uint32_t)n_bt * b_tap_bytes);
-        for (int i = 0; i < n_bt; ++i) tma_load_2d(sB_addr + (uint32_t)i * b_tap_bytes, &p.bmap, bb, i * BKc, n_col0);
+      if (b_resident) {  // all weight sub-tiles of this N tile (pair: this CTA's half of their rows), once
+        const uint32_t bb = PAIR ? mapa_shared(smem_u32(bres_bar), 0u) : smem_u32(bres_bar);
+        if (PAIR) mbar_arrive_expect_tx_cluster(bb, (uint32_t)n_bt * b_tap_bytes);
+        else mbar_arrive_expect_tx(bb, (uint32_t)n_bt * b_tap_bytes);
+        for (int i = 0; i < n_bt; ++i) {
+          if (PAIR) tma_load_2d_pair(sB_addr + (uint32_t)i * b_tap_bytes, &p.bmap, bb, i * BKc, n_col0);
+          else tma_load_2d(sB_addr + (uint32_t)i * b_tap_bytes, &p.bmap, bb, i * BKc, n_col0);
+        }
       }
       int a_slot = 0;
       uint32_t a_phase = 0;
@@ -531,7 +535,8 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF 
       int rem0 = t_begin - n * tiles_per_img;
       int tile_y = rem0 / tiles_x, tile_x = rem0 - tile_y * tiles_x;
       const int tiles_y = p.tiles_y;
-      for (int mt = t_begin; mt < t_end; mt += tstride) {
+      // (gather mode: the halo tiles are brought in by the extra warps, the weights are resident: nothing left to do)
+      for (int mt = (XF && p.a_gather) ? t_end : t_begin; mt < t_end; mt += tstride) {
         const int oy0 = tile_y * p.th * MT, ox0 = tile_x * p.tw;
         for (int g = 0; g < G; ++g) {
           mbar_wait(a_empty0 + 8u * a_slot, a_phase ^ 1u);
@@ -541,7 +546,7 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF 
           const int cg = (src1 ? g - stages0 : g) * planes_per_group;  // first 8-channel plane of the group
           const int nt = src1 ? 1 : ntaps;
           // one barrier covers the halo tile and (streamed mode) every weight sub-tile of the group
-          if (PAIR) mbar_arrive_expect_tx_cluster(fb, a_tx_bytes + (uint32_t)nt * b_tap_bytes);
+          if (PAIR) mbar_arrive_expect_tx_cluster(fb, a_tx_bytes + (b_resident ? 0u : (uint32_t)nt * b_tap_bytes));
           else mbar_arrive_expect_tx(fb, a_tx_bytes + (b_resident ? 0u : (uint32_t)nt * b_tap_bytes));
           if (stride == 1) {
             if (PAIR) tma_load_4d_pair(a_dst, &p.amap[src1 ? 1 : 0], fb, (ox0 - halo) * 8, oy0 - halo, cg, n);
@@ -555,7 +560,10 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF 
               }
             } else {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) tma_load_5d(a_dst + q * a_tile_bytes, &p.amap[q], fb, 0, ox0 - 1, oy0 - 1, cg, n);
+              for (int q = 0; q < 4; ++q) {
+                if (PAIR) tma_load_5d_pair(a_dst + q * a_tile_bytes, &p.amap[q], fb, 0, ox0 - 1, oy0 - 1, cg, n);
+                else tma_load_5d(a_dst + q * a_tile_bytes, &p.amap[q], fb, 0, ox0 - 1, oy0 - 1, cg, n);
+              }
             }
           }
           if (!b_resident) {
@@ -687,7 +695,82 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF 
     // ===================== A-operand transform =====================
     // Four warps rewrite every halo tile in place: x -> lrelu?(x * scale[c] + shift[c]) for in-image pixels (padding
     // stays zero), one 8-channel plane per warp at a time with its 16 coefficients in registers.
-    if (!SIMT) {
+    if (!SIMT && p.a_gather) {
+      // ----- stride-2 gather: parity tile (py, px) of a channel group = input pixels (2 Y + py, 2 X + px) of a NORMAL
+      // planar map.  Every thread owns a fixed set of 16-byte vectors of the slot (same for every tile), copies them with
+      // cp.async (zero fill outside the image = the conv's zero padding) one ring slot ahead of the one it publishes.
+      const int tid = (int)threadIdx.x - kThreads;
+      const int stages0 = p.stages0, a_ring = p.a_ring, MT = p.MT, tiles_x = p.tiles_x, tiles_y = p.tiles_y;
+      const int planes = p.BKc >> 3, hw = p.halo_w, npix = (int)(p.lbo >> 4);
+      const int per_tile = planes * npix, nvec = 4 * per_tile;
+      const size_t plane_el = (size_t)p.Hin * p.Win * 8;
+      constexpr int kMaxVec = 12;
+      uint32_t doff[kMaxVec];   // byte offset inside the slot
+      int dyx[kMaxVec];         // (2 hy + py) << 16 | (2 hx + px): input offset from the pixel 2 * (tile origin - 1)
+      int plv[kMaxVec];         // 8-channel plane inside the group, -1 = no vector
+#pragma unroll
+      for (int k = 0; k < kMaxVec; ++k) {
+        const int v = tid + k * kXfThreads;
+        plv[k] = -1;
+        doff[k] = 0u;
+        dyx[k] = 0;
+        if (v < nvec) {
+          const int q = v / per_tile, r = v - q * per_tile, pl = r / npix, pix = r - pl * npix;
+          const int hy = pix / hw, hx = pix - hy * hw;
+          plv[k] = pl;
+          doff[k] = (uint32_t)q * p.a_tile_bytes + (uint32_t)pl * p.lbo + (uint32_t)pix * 16u;
+          dyx[k] = ((2 * hy + (q >> 1)) << 16) | (2 * hx + (q & 1));
+        }
+      }
+      const uint32_t sA_addr = smem_u32(sA), a_empty0 = smem_u32(a_empty), a_ready0 = smem_u32(a_ready);
+      int a_slot = 0, pend_slot = -1;
+      uint32_t a_phase = 0;
+      int n = t_begin / tiles_per_img;
+      int rem0 = t_begin - n * tiles_per_img;
+      int tile_y = rem0 / tiles_x, tile_x = rem0 - tile_y * tiles_x;
+      for (int mt = t_begin; mt < t_end; ++mt) {
+        const int iy0 = 2 * (tile_y * p.th * MT - 1), ix0 = 2 * (tile_x * p.tw - 1);
+        for (int g = 0; g < stages0; ++g) {
+          mbar_wait(a_empty0 + 8u * a_slot, a_phase ^ 1u);
+          const act_t* src_g = p.src0.p + (size_t)n * p.src0.bstride + (size_t)(g * planes) * plane_el;
+          const uint32_t dst0 = sA_addr + (uint32_t)a_slot * p.g_slot_bytes;
+#pragma unroll
+          for (int k = 0; k < kMaxVec; ++k) {
+            if (plv[k] >= 0) {
+              const int iy = iy0 + (dyx[k] >> 16), ix = ix0 + (dyx[k] & 0xffff);
+              const bool ok = (unsigned)iy < (unsigned)p.Hin && (unsigned)ix < (unsigned)p.Win;
+              const act_t* src = src_g + (size_t)plv[k] * plane_el + ((size_t)(ok ? iy : 0) * p.Win + (ok ? ix : 0)) * 8;
+              cp_async_16(dst0 + doff[k], src, ok ? 16u : 0u);
+            }
+          }
+          cp_async_commit();
+          if (pend_slot >= 0) {   // the previous slot's copies have landed: publish it to the MMA lane
+            cp_async_wait_group<1>();
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_ready0 + 8u * pend_slot);
+          }
+          pend_slot = a_slot;
+          if (++a_slot == a_ring) {
+            a_slot = 0;
+            a_phase ^= 1u;
+          }
+        }
+        if (++tile_x == tiles_x) {
+          tile_x = 0;
+          if (++tile_y == tiles_y) {
+            tile_y = 0;
+            ++n;
+          }
+        }
+      }
+      if (pend_slot >= 0) {
+        cp_async_wait_group<0>();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_ready0 + 8u * pend_slot);
+      }
+    } else if (!SIMT) {
       const int xw = warp - (2 + 4 * kEpiGroups);
       const int stages0 = p.stages0, a_ring = p.a_ring, BKc = p.BKc, MT = p.MT, tiles_x = p.tiles_x, tiles_y = p.tiles_y;
       const int planes = BKc >> 3, ntile_a = p.stride == 2 ? 4 : 1;
@@ -1406,12 +1489,14 @@ int conv_gemm_configure(ConvGemmParams* p, int B, int Hout, int Wout, int cin0, 
   if (tune != nullptr && tune->policy != 0) policy = tune->policy;
   if (tune == nullptr) {   // kernel tests select a policy for the stand-alone conv (read per call, never set by the product)
     const char* force = getenv("RIB_TEST_POLICY");
-    if (force != nullptr && atoi(force) >= 1 && atoi(force) <= 4) policy = atoi(force);
+    if (force != nullptr && atoi(force) >= 1 && atoi(force) <= 5) policy = atoi(force);
   }
-  RIB_REQUIRE(policy >= 1 && policy <= 4 && (policy >= 3 ? b_all > kSmallResident : b_all <= kBigResident),
+  RIB_REQUIRE(policy >= 1 && policy <= 5 &&
+                  (policy == 5 ? (b_all > kSmallResident && b_all / 2 <= kBigResident)
+                               : (policy >= 3 ? b_all > kSmallResident : b_all <= kBigResident)),
               "conv_gemm: residency policy does not apply to this layer");
-  p->pair = policy == 4 ? 1 : 0;
-  if (policy == 4) {
+  p->pair = policy >= 4 ? 1 : 0;
+  if (policy >= 4) {
     RIB_REQUIRE(BN == 128 && taps != 4 && (cin1 == 0 || stride == 1), "conv_gemm: CTA pairs need a plain layer with BN = 128");
     p->b_tap_bytes = (uint32_t)((BN / 2) * bkc * 2);   // each CTA of the pair stages half of the weight rows
   }
@@ -1431,15 +1516,18 @@ int conv_gemm_configure(ConvGemmParams* p, int B, int Hout, int Wout, int cin0, 
     p->a_ring = ring;
     RIB_REQUIRE(b_all + kStatStageBytes + kOverhead + (size_t)ring * p->a_slot_bytes <= kSmemMax,
                 "conv_gemm: halo ring does not fit beside the resident weights");
-  } else if (policy == 2) {
+  } else if (policy == 2 || policy == 5) {
+    // (policy 5: CTA pairs with RESIDENT weights - each CTA keeps its half of the N tile's rows, so layers whose whole
+    //  weight tile leaves room for two or three halo slots get a ring of up to eight)
     p->b_resident = 1;
-    const size_t fixed = b_all + kStatStageBytes + kOverhead;
+    const size_t fixed = (policy == 5 ? b_all / 2 : b_all) + kStatStageBytes + kOverhead;
     set_geometry(mt);
     if (!mt_forced && fixed + 2 * (size_t)p->a_slot_bytes > kSmemMax) set_geometry(1);
     RIB_REQUIRE(fixed + 2 * (size_t)p->a_slot_bytes <= kSmemMax, "conv_gemm: resident weights do not fit");
     int ring = (int)((kSmemMax - fixed) / p->a_slot_bytes);
-    const int ring_cap = (tune != nullptr && tune->ring >= 2 && tune->ring <= 8) ? tune->ring : 4;
+    const int ring_cap = (tune != nullptr && tune->ring >= 2 && tune->ring <= 8) ? tune->ring : (policy == 5 ? 8 : 4);
     p->a_ring = ring > ring_cap ? ring_cap : ring;
+    if (policy == 5) RIB_REQUIRE(((long long)p->tiles_x * p->tiles_y * B) % 2 == 0, "conv_gemm: CTA pairs need an even number of super-tiles");
   } else {
     // a ring slot holds the halo tile(s) of a channel group AND that group's weight sub-tiles (one barrier round trip
     // per group); two stacked sub-tiles halve the weight traffic per pixel (measured: also for stride 2, whose four
@@ -1468,7 +1556,7 @@ size_t conv_gemm_smem_bytes(const ConvGemmParams& p) {
   size_t tiles = (((size_t)p.a_ring * p.g_slot_bytes + 1023) & ~(size_t)1023) +
                  (size_t)(p.b_resident ? n_bt : 0) * p.b_tap_bytes;
   size_t stat = p.stats != nullptr ? kStatStageBytes : 0;
-  const bool xf = p.xf_stats != nullptr;
+  const bool xf = p.xf_stats != nullptr || p.a_gather;
   size_t bars = (size_t)((xf ? 3 : 2) * p.a_ring + 2 * acc_bufs(p.BN) + 1) * 8 + 32;
   size_t scratch = (size_t)p.BN * 4 * (1 + 8 * kEpiGroups) + 64 + 128 + (xf ? (size_t)2 * p.stages0 * p.BKc * 4 : 0) +
                    128 + 256 + (size_t)p.BN * 32;   // ones tile + bias tile of the bias MMA (128-byte aligned)
@@ -1591,15 +1679,18 @@ int launch_conv_gemm(const ConvGemmParams& p, int mode, cudaStream_t stream) {
               "conv_gemm: EPI_SPADE needs BN == 2*CT");
   RIB_REQUIRE(mode != EPI_SPADE2 || (p.BN == 4 * p.CT && p.CT % 16 == 0 && p.C % p.CT == 0 && p.n_tiles == p.C / p.CT),
               "conv_gemm: EPI_SPADE2 needs BN == 4*CT and one tile per CT channels");
-  const bool xf = p.xf_stats != nullptr;
+  const bool xf = p.xf_stats != nullptr || p.a_gather;
   RIB_REQUIRE(!xf || (p.stages1 == 0 && p.subpix == 0), "conv_gemm: the A-operand transform needs a single source");
+  RIB_REQUIRE(!p.a_gather || (p.xf_stats == nullptr && p.stride == 2 && !p.s2_parity && p.b_resident && !p.pair &&
+                              4 * (p.BKc / 8) * (int)(p.lbo >> 4) <= 12 * kXfThreads),
+              "conv_gemm: the stride-2 gather needs a normal-layout input, resident weights and at most 12 vectors per thread");
   RIB_REQUIRE(!p.out_parity || (p.H % 2 == 0 && p.W % 2 == 0 && !p.subpix), "conv_gemm: bad parity-planar output");
   RIB_REQUIRE(!p.res_ups || (p.has_res && p.H % 2 == 0 && p.W % 2 == 0 && !p.subpix && !p.out_parity),
               "conv_gemm: bad up-sampled residual");
   // (the bring-up FMA loop has no pair form: a paired layer falls back to single CTAs with the same shared-memory plan)
   const bool pair = p.pair != 0 && !p.debug_simt;
-  RIB_REQUIRE(!p.pair || (!p.b_resident && (p.stride == 1 || (p.s2_parity && p.stages1 == 0)) && !p.subpix && !xf),
-              "conv_gemm: CTA pairs need a streamed layer (stride 2: parity-planar single source, no transform)");
+  RIB_REQUIRE(!p.pair || ((p.stride == 1 || p.stages1 == 0) && !p.subpix && !xf),
+              "conv_gemm: CTA pairs: no sub-pixel form, no transform, stride 2 only with a single source");
   ConvKernel fn = p.debug_simt ? pick_kernel<true>(mode, p.BN, xf, false) : pick_kernel<false>(mode, p.BN, xf, pair);
   RIB_REQUIRE(fn != nullptr, "conv_gemm: no kernel for this (epilogue, BN)");
   const size_t smem = conv_gemm_smem_bytes(p);

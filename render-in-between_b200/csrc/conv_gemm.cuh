@@ -70,6 +70,9 @@ struct alignas(64) ConvGemmParams {
                         //    low-resolution halo tile is loaded once for ppc parities, each parity runs its own four taps
                         //    (N = BN / ppc per tcgen05.mma) into its own accumulator columns
   int s2_parity;        // stride 2: 1 = the input is a parity-planar map, 0 = strided parity views of a normal map
+  int a_gather;         // stride 2 from a NORMAL map: the kernel's eight extra warps (the XF build) gather the four parity
+                        //    tiles of every channel group with 16-byte cp.async copies instead of the strided TMA views, whose
+                        //    16-byte elements make the TMA unit the bottleneck (emb_1: 9 400 clk per tile, profiles/r2)
   int a_ring, b_ring;   // ring slots (one channel group each); b_ring is unused
   int b_resident;       // 1: all weight sub-tiles of this CTA's N tile stay in shared memory
   int pair;             // 1: CTA pairs (cluster of 2, tcgen05 cta_group::2, M = 256): each CTA stages half of the weight rows

@@ -557,6 +557,7 @@ struct PlanBuilder {
     const GemmLayer& L = *op.layer;
     int r = conv_gemm_configure(&p, B, p.H, p.W, L.cin0, L.cin1, L.taps, L.stride, p.BN, L.n_pad, &t, L.ppc);
     if (r || p.BKc != L.bkc) return r ? r : -4;
+    if (p.a_gather && (!p.b_resident || p.pair)) p.a_gather = 0;   // streamed weights / CTA pairs: the strided TMA views
     if (real) r = make_maps(&p, L, op.in0, op.has_in1 ? &op.in1 : nullptr);   // (the CPU dry run has no tensors to map)
     if (r) return r;
     *out = p;
@@ -604,6 +605,12 @@ struct PlanBuilder {
     }
     p.has_out2 = out2 ? 1 : 0;
     if (out2) p.out2 = out2->ref();
+    // stride 2 from a normal-layout map (emb_1 reads cond_0, which its stride-1 consumers need in normal layout): the
+    // kernel's extra warps gather the parity tiles with cp.async instead of 16-byte strided TMA elements
+    // (opt-in: measured slower than the TMA views, 684 vs 555 us for emb_1 - profiles/r2k - the layer is bound by the
+    //  bytes in flight, not by the TMA element rate)
+    static const bool gather_on = getenv("RIB_GATHER") != nullptr && atoi(getenv("RIB_GATHER")) == 1;
+    if (gather_on && stride == 2 && !in0.parity && !xf && p.b_resident && !p.pair && (L.BN == 64 || L.BN == 128)) p.a_gather = 1;
     p.stats = stats;
     p.act = act;
     p.has_res = res ? 1 : 0;
@@ -787,7 +794,7 @@ std::string tune_key(const Op& op) {
   char buf[256];
   snprintf(buf, sizeof(buf), "m%d B%d H%d W%d c%d+%d t%d s%d BN%d N%d r%d o%d st%d u%d q%d par%d", op.mode, p.B, p.H, p.W,
            L.cin0, L.cin1, L.taps, L.stride, p.BN, L.n_pad, p.has_res + 2 * p.res_ups, p.has_out2, p.stats != nullptr, p.ups,
-           (op.mode == EPI_SPADE || op.mode == EPI_SPADE2) ? p.n_tiles * p.BN / (2 * p.C) : 0, p.s2_parity + 2 * (p.xf_stats != nullptr) + 4 * p.out_parity);
+           (op.mode == EPI_SPADE || op.mode == EPI_SPADE2) ? p.n_tiles * p.BN / (2 * p.C) : 0, p.s2_parity + 2 * (p.xf_stats != nullptr) + 4 * p.out_parity + 8 * p.a_gather);
   return buf;
 }
 
@@ -842,10 +849,11 @@ void autotune(PlanBuilder& pb, cudaStream_t stream) {
     std::string log = line;
     if (t_def > 0.f) {
       static const bool pairs_on = !(getenv("RIB_PAIRS") != nullptr && atoi(getenv("RIB_PAIRS")) == 0);
-      for (int cand = 0; cand < (pairs_on ? 10 : 8); ++cand) {
+      for (int cand = 0; cand < (pairs_on ? 12 : 8); ++cand) {
         {
-          // candidates 0-5: policies 1-3 x MT 1/2; 6-7: one CTA per SM with a ring of up to 8 slots; 8-9: CTA pairs
-          const int policy = cand < 6 ? cand / 2 + 1 : (cand < 8 ? 2 : 4), mt = cand % 2 + 1;
+          // candidates 0-5: policies 1-3 x MT 1/2; 6-7: one CTA per SM with a ring of up to 8 slots; 8-9: CTA pairs with
+          // streamed weights; 10-11: CTA pairs with resident half-tiles of the weights
+          const int policy = cand < 6 ? cand / 2 + 1 : (cand < 8 ? 2 : (cand < 10 ? 4 : 5)), mt = cand % 2 + 1;
           ConvTune t;
           t.mt = mt;
           t.policy = policy;
@@ -911,7 +919,7 @@ int generator_tune_import(const char* text) {
     t.policy = atoi(line.substr(t2 + 1).c_str());           // (stops at the next tab)
     const size_t t3 = line.find('\t', t2 + 1);
     t.ring = t3 == std::string::npos ? 0 : atoi(line.substr(t3 + 1).c_str());
-    if (t.mt < 0 || t.mt > 2 || t.policy < 0 || t.policy > 4 || t.ring < 0 || t.ring > 8) continue;
+    if (t.mt < 0 || t.mt > 2 || t.policy < 0 || t.policy > 5 || t.ring < 0 || t.ring > 8) continue;
     g_tune_cache[line.substr(0, t1)] = t;
     ++n;
   }
@@ -1488,7 +1496,8 @@ int conv_test_ex(const void* x, const float* w, const float* bias, void* out, do
   in.H = Hin;
   in.W = Win;
   in.C = in.Ctot = Cin;
-  in.parity = stride == 2;
+  // (RIB_TEST_S2_NORMAL=1, kernel tests only: the stride-2 input is given in the normal layout, as emb_1 reads cond_0)
+  in.parity = stride == 2 && !(getenv("RIB_TEST_S2_NORMAL") != nullptr && atoi(getenv("RIB_TEST_S2_NORMAL")) == 1);
   View o;
   o.p = static_cast<act_t*>(out);
   o.B = B;

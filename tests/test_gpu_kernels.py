@@ -180,19 +180,22 @@ def test_conv_gemm_matches_conv2d(dev, case, simt):
 
 
 PAIR_CASES = [
-    # (B, Cin, Cout, H, W, stride): 3x3 layers with streamed weights and 128-column tiles (H, W = input size)
-    (2, 256, 256, 32, 32, 1),     # MT=2, two N tiles, 8 super-tiles
-    (3, 128, 128, 24, 40, 1),     # MT=1 (H < 32), ragged tile rows / columns, 30 super-tiles
-    (4, 512, 256, 64, 64, 1),     # the mask net's res_flow shape at a smaller batch: more pair-tiles than CTA pairs
-    (2, 256, 512, 64, 64, 2),     # stride 2 from a parity-planar input (the embedder's emb_3 shape), four N tiles
+    # (B, Cin, Cout, H, W, stride, policy): 3x3 layers with 128-column tiles (H, W = input size); policy 4 = streamed
+    # weights, 5 = each CTA keeps its half of the weight rows resident
+    (2, 256, 256, 32, 32, 1, 4),     # MT=2, two N tiles, 8 super-tiles
+    (3, 128, 128, 24, 40, 1, 4),     # MT=1 (H < 32), ragged tile rows / columns, 30 super-tiles
+    (4, 512, 256, 64, 64, 1, 4),     # the mask net's res_flow shape at a smaller batch: more pair-tiles than CTA pairs
+    (2, 256, 512, 64, 64, 2, 4),     # stride 2 from a parity-planar input (the embedder's emb_3 shape), four N tiles
+    (2, 64, 128, 64, 64, 2, 5),      # emb_1's shape: resident half-tiles of the weights, deep halo ring
+    (3, 64, 128, 24, 40, 1, 5),      # stride 1, ragged
 ]
 
 
-@pytest.mark.parametrize('case', PAIR_CASES, ids=lambda c: 'B%d_%dto%d_%dx%d_s%d' % c)
+@pytest.mark.parametrize('case', PAIR_CASES, ids=lambda c: 'B%d_%dto%d_%dx%d_s%d_p%d' % c)
 def test_conv_gemm_cta_pairs_match_conv2d(dev, case, monkeypatch):
     """The CTA-pair form (cluster of two, tcgen05.mma.cta_group::2 with M = 256, each CTA staging half of the weight
     rows; policy 4 of conv_gemm_configure) against conv2d, and bit-identical to the single-CTA kernel."""
-    b, cin, cout, h, w, stride = case
+    b, cin, cout, h, w, stride, policy = case
     dt = _act_dtype()
     g = torch.Generator().manual_seed(cin + cout + h)
     x = torch.randn(b, cin, h, w, generator=g)
@@ -200,7 +203,7 @@ def test_conv_gemm_cta_pairs_match_conv2d(dev, case, monkeypatch):
     bias = torch.randn(cout, generator=g) * 0.1
     ref = F.conv2d(x.to(dt).float(), wt.to(dt).float(), bias, stride=stride, padding=1)
     single, s_single = _run_conv(dev, x, wt, bias, 3, stride, act=0, want_stats=True, simt=False)
-    monkeypatch.setenv('RIB_TEST_POLICY', '4')
+    monkeypatch.setenv('RIB_TEST_POLICY', str(policy))
     out, stats = _run_conv(dev, x, wt, bias, 3, stride, act=0, want_stats=True, simt=False)
     monkeypatch.delenv('RIB_TEST_POLICY')
     err = (out - ref).abs()
@@ -209,6 +212,35 @@ def test_conv_gemm_cta_pairs_match_conv2d(dev, case, monkeypatch):
     assert torch.allclose(stats, s_ref, rtol=2e-3, atol=2e-2), (stats - s_ref).abs().max().item()
     # same K order and the same fp32 accumulation per output element: the pair computes the same bits
     assert torch.equal(out, single)
+
+
+@pytest.mark.parametrize('case', [(2, 64, 128, 32, 32, 0), (1, 32, 64, 24, 40, 0), (3, 64, 128, 128, 64, 0), (1, 128, 128, 16, 16, 0),
+                                  (2, 64, 128, 64, 64, 5), (1, 64, 128, 40, 24, 5)],
+                         ids=lambda c: 'B%d_%dto%d_%dx%d_p%d' % c)
+def test_conv_gemm_stride2_from_normal_layout(dev, case, monkeypatch):
+    """Stride-2 conv whose input is a NORMAL planar map (emb_1 reads cond_0 this way) through the strided TMA parity
+    views; with RIB_GATHER=1 in the environment of the process the kernel's extra warps gather the four parity tiles
+    with cp.async instead (ConvGemmParams::a_gather, opt-in: measured slower)."""
+    from rib._lib import check, lib
+    b, cin, cout, h, w, policy = case
+    if policy:     # 5: CTA pairs with resident half-tiles of the weights (5-D strided TMA views in their pair form)
+        monkeypatch.setenv('RIB_TEST_POLICY', str(policy))
+    dt = _act_dtype()
+    g = torch.Generator().manual_seed(cin * 3 + cout + h)
+    x = torch.randn(b, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    ref = F.leaky_relu(F.conv2d(x.to(dt).float(), wt.to(dt).float(), bias, stride=2, padding=1), 0.2)
+    monkeypatch.setenv('RIB_TEST_S2_NORMAL', '1')
+    out = torch.zeros(b, cout // 8, h // 2, w // 2, 8, dtype=dt, device=dev)
+    scratch = torch.empty(lib.rib_conv_test_scratch_bytes(cin, cout, 3) + 1024, dtype=torch.uint8, device=dev)
+    xd, wd_, bd_ = to_planar(x, dt).to(dev), wt.contiguous().to(dev), bias.contiguous().to(dev)
+    check(lib.rib_conv_test(xd.data_ptr(), wd_.data_ptr(), bd_.data_ptr(), out.data_ptr(), None, b, h, w, cin, cout, 3, 2, 1,
+                            scratch.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream)), 'rib_conv_test')
+    torch.cuda.synchronize()
+    got = from_planar(out.float().cpu())
+    err = (got - ref).abs()
+    assert bool((err <= 2.0 ** -7 * ref.abs() + 2e-3).all()), 'max err %.4g' % err.max().item()
 
 
 def test_conv_gemm_lrelu_epilogue(dev):
