@@ -77,9 +77,11 @@ int rib_composite(const float* img, const float* mask, const float* dain, float*
  * out = (float32(v) / 255 - 0.5) / 0.5, bit-exact.  Lets a caller upload 8-bit frames (what a PNG decode
  * yields) instead of fp32 tensors.
  *   frames u8 [B][H][W][3]; out f32 [B][3][H][W]; *_bstride: elements between frames (0 = dense).
+ *   out_u8 (may be NULL) u8 [B][H][W][3]: tensor2images(out) (utils/utils.py:122-147), the frame the evaluator saves
+ *   for a key frame (evaluator.py:240-244, :265-266); it truncates, so it differs from `frames` on 63 of the 256 levels.
  */
-int rib_frames_from_u8(const uint8_t* frames, float* out, int B, int H, int W, long long in_bstride,
-                       long long out_bstride, void* stream);
+int rib_frames_from_u8(const uint8_t* frames, float* out, uint8_t* out_u8, int B, int H, int W, long long in_bstride,
+                       long long out_bstride, long long out_u8_bstride, void* stream);
 
 /* Replaces the image half of the evaluator's A.Resize(height, width, interpolation=cv2.INTER_CUBIC)
  * (models/evaluator.py:18-26, applied to every key frame and DAIN frame at :218-220), i.e.

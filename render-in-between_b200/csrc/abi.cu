@@ -81,11 +81,11 @@ int rib_resize_cubic_u8(const uint8_t* frames, uint8_t* out, int B, int h, int w
   RIB_GUARD_END
 }
 
-int rib_frames_from_u8(const uint8_t* frames, float* out, int B, int H, int W, long long in_bstride,
-                       long long out_bstride, void* stream) {
+int rib_frames_from_u8(const uint8_t* frames, float* out, uint8_t* out_u8, int B, int H, int W, long long in_bstride,
+                       long long out_bstride, long long out_u8_bstride, void* stream) {
   RIB_GUARD_BEGIN
   RIB_REQUIRE(frames && out && B > 0 && H > 0 && W > 0, "rib_frames_from_u8: bad argument");
-  int rc = launch_frames_from_u8(frames, out, B, H, W, in_bstride, out_bstride, (cudaStream_t)stream);
+  int rc = launch_frames_from_u8(frames, out, out_u8, B, H, W, in_bstride, out_bstride, out_u8_bstride, (cudaStream_t)stream);
   if (!rc) count_misc_launch(1);
   return rc;
   RIB_GUARD_END

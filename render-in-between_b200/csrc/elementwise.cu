@@ -427,8 +427,10 @@ int launch_composite(const float* img, const float* mask, const float* dain, flo
 // (transforms.ToTensor + Normalize(0.5, 0.5): float32(v) / 255, then (t - 0.5) / 0.5, separate roundings;
 //  HSM_auto_dataset.py:73-75, used by evaluator.py:223-224).  Four pixels per thread.
 // ---------------------------------------------------------------------------------------------
-__global__ void frames_from_u8_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, int HW4, int HW,
-                                      size_t total, long long in_bs, long long out_bs) {
+// out_u8 (optional): the frame tensor2images(out) would give (utils/utils.py:122-147) - what the evaluator saves for a key
+// frame (evaluator.py:240-244, :265-266); it truncates, so it is NOT the input byte for 63 of the 256 levels.
+__global__ void frames_from_u8_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, uint8_t* __restrict__ out_u8,
+                                      int HW4, int HW, size_t total, long long in_bs, long long out_bs, long long u8_bs) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over B * HW/4
   if (i >= total) return;
   const size_t n = i / HW4, q = i - n * HW4;
@@ -437,28 +439,39 @@ __global__ void frames_from_u8_kernel(const uint8_t* __restrict__ in, float* __r
   const uint8_t px[12] = {(uint8_t)w0, (uint8_t)(w0 >> 8), (uint8_t)(w0 >> 16), (uint8_t)(w0 >> 24),
                           (uint8_t)w1, (uint8_t)(w1 >> 8), (uint8_t)(w1 >> 16), (uint8_t)(w1 >> 24),
                           (uint8_t)w2, (uint8_t)(w2 >> 8), (uint8_t)(w2 >> 16), (uint8_t)(w2 >> 24)};
+  uint8_t qx[12];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     float v[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
+    for (int k = 0; k < 4; ++k) {
       v[k] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)px[3 * k + c], 255.0f), 0.5f), 0.5f);
+      qx[3 * k + c] = to_u8(v[k]);
+    }
     reinterpret_cast<float4*>(out + n * out_bs + (size_t)c * HW)[q] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  if (out_u8 != nullptr) {
+    uint32_t* o = reinterpret_cast<uint32_t*>(out_u8 + n * u8_bs + q * 12);
+    o[0] = qx[0] | (qx[1] << 8) | (qx[2] << 16) | ((uint32_t)qx[3] << 24);
+    o[1] = qx[4] | (qx[5] << 8) | (qx[6] << 16) | ((uint32_t)qx[7] << 24);
+    o[2] = qx[8] | (qx[9] << 8) | (qx[10] << 16) | ((uint32_t)qx[11] << 24);
   }
 }
 
-int launch_frames_from_u8(const uint8_t* in, float* out, int B, int H, int W, long long in_bstride,
-                          long long out_bstride, cudaStream_t s) {
+int launch_frames_from_u8(const uint8_t* in, float* out, uint8_t* out_u8, int B, int H, int W, long long in_bstride,
+                          long long out_bstride, long long u8_bstride, cudaStream_t s) {
   RIB_REQUIRE((H * W) % 4 == 0, "frames_from_u8: H*W must be a multiple of 4");
   const int HW = H * W;
   if (in_bstride == 0) in_bstride = 3LL * HW;
   if (out_bstride == 0) out_bstride = 3LL * HW;
-  RIB_REQUIRE(in_bstride % 4 == 0 && out_bstride % 4 == 0 && ((uintptr_t)in & 3) == 0 && ((uintptr_t)out & 15) == 0,
+  if (u8_bstride == 0) u8_bstride = 3LL * HW;
+  RIB_REQUIRE(in_bstride % 4 == 0 && out_bstride % 4 == 0 && u8_bstride % 4 == 0 && ((uintptr_t)in & 3) == 0 &&
+                  ((uintptr_t)out & 15) == 0 && ((uintptr_t)out_u8 & 3) == 0,
               "frames_from_u8: strides / pointers must be 4-element aligned");
   const size_t total = (size_t)B * (HW / 4);
   const int threads = 256;
-  frames_from_u8_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(in, out, HW / 4, HW, total,
-                                                                                         in_bstride, out_bstride);
+  frames_from_u8_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(in, out, out_u8, HW / 4, HW, total,
+                                                                                         in_bstride, out_bstride, u8_bstride);
   RIB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

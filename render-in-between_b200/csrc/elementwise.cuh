@@ -60,8 +60,8 @@ int launch_composite(const float* img, const float* mask, const float* dain, flo
 // out = bilinear sample of src at (x + flow_x, y + flow_y), border padding, align_corners=True.
 int launch_resize_cubic_u8(const uint8_t* in, uint8_t* out, int B, int h, int w, int H, int W, long long in_bstride,
                            long long out_bstride, cudaStream_t s);
-int launch_frames_from_u8(const uint8_t* in, float* out, int B, int H, int W, long long in_bstride,
-                          long long out_bstride, cudaStream_t s);
+int launch_frames_from_u8(const uint8_t* in, float* out, uint8_t* out_u8, int B, int H, int W, long long in_bstride,
+                          long long out_bstride, long long u8_bstride, cudaStream_t s);
 int launch_warp(const float* src, const float* flow, float* out, int B, int C, int H, int W, long long src_bstride,
                 long long flow_bstride, long long out_bstride, cudaStream_t s);
 

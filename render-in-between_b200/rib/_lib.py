@@ -53,7 +53,7 @@ def _load():
     lib.rib_resize_cubic_u8.restype = i32
     lib.rib_resize_cubic_u8.argtypes = [vp, vp, i32, i32, i32, i32, i32, i64, i64, vp]
     lib.rib_frames_from_u8.restype = i32
-    lib.rib_frames_from_u8.argtypes = [vp, vp, i32, i32, i32, i64, i64, vp]
+    lib.rib_frames_from_u8.argtypes = [vp, vp, vp, i32, i32, i32, i64, i64, i64, vp]
     lib.rib_generator_create.restype = i32
     lib.rib_generator_create.argtypes = [C.POINTER(GenConfig), C.POINTER(Tensor), i32, vp, C.POINTER(vp)]
     lib.rib_generator_destroy.restype = None

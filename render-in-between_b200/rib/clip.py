@@ -36,9 +36,11 @@ class ClipRenderer:
         rasterises straight into the generator's input buffer and blends straight into frames s, s+r, ... of
         the clip, so no frame is gathered, scattered or converted twice."""
         r = self.rate
-        if key_frames.dtype == torch.uint8:
-            key_frames = ops.frames_from_u8(key_frames)
-        k, _, h, w = key_frames.shape
+        key_u8 = key_frames if key_frames.dtype == torch.uint8 else None     # decoded images: converted below
+        if key_u8 is not None:
+            k, h, w = key_u8.shape[0], key_u8.shape[1], key_u8.shape[2]
+        else:
+            k, _, h, w = key_frames.shape
         t = self.seq_len(k, r)
         if joints.shape[0] != t:
             raise ValueError('need %d joint sets for %d key frames at %dx' % (t, k, r))
@@ -54,14 +56,20 @@ class ClipRenderer:
         def of_step(x, s):
             return x[s - 1::r - 1] if gen_only else x[s::r]
 
-        dev = key_frames.device
-        key_frames = key_frames.contiguous()
+        dev = key_u8.device if key_u8 is not None else key_frames.device
         fuse = torch.empty(t, 3, h, w, dtype=torch.float32, device=dev) if want_fuse else None
         u8 = torch.empty(t, h, w, 3, dtype=torch.uint8, device=dev) if want_u8 else None
         mask_out = torch.zeros(t, 1, h, w, dtype=torch.float32, device=dev) if want_mask else None
         # key frames pass through (:240-244).  Their output frame is tensor2images(to_tensor_norm(v)), which truncates
-        # and is NOT v for 63 of the 256 levels, so uint8 key frames take the same path as fp32 ones.
-        ops.composite(key_frames, None, None, out=fuse[0::r] if want_fuse else None, out_u8=u8[0::r] if want_u8 else None)
+        # and is NOT v for 63 of the 256 levels: uint8 key frames are normalised and re-quantised in one pass.
+        if key_u8 is not None:
+            key_frames = ops.frames_from_u8(key_u8, out_u8=u8[0::r] if want_u8 else None)
+            if want_fuse:
+                fuse[0::r] = key_frames
+        else:
+            key_frames = key_frames.contiguous()
+            ops.composite(key_frames, None, None, out=fuse[0::r] if want_fuse else None,
+                          out_u8=u8[0::r] if want_u8 else None)
         b = k - 1
         prev = key_frames[:b]                                      # fuse[i-1] of step 1 is the key frame
         for s in range(1, r):

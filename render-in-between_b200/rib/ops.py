@@ -99,9 +99,11 @@ def resize_cubic_u8(frames, height, width):
     return out
 
 
-def frames_from_u8(frames, out=None):
+def frames_from_u8(frames, out=None, out_u8=None):
     """uint8 [B,H,W,3] CUDA frames (a decoded PNG) -> float32 [B,3,H,W] in [-1,1]: dataset.to_tensor_norm
-    (PGNR/datasets/HSM_auto_dataset.py:73-75) on the GPU, bit-exact.  `frames` / `out` may be strided along dim 0."""
+    (PGNR/datasets/HSM_auto_dataset.py:73-75) on the GPU, bit-exact.  `frames` / `out` may be strided along dim 0.
+    out_u8: optional uint8 [B,H,W,3] destination (may be strided along dim 0) for tensor2images(out), the bytes the
+    evaluator saves for a key frame (PGNR/models/evaluator.py:240-244, :265-266)."""
     if not (isinstance(frames, torch.Tensor) and frames.is_cuda and frames.dtype == torch.uint8 and frames.dim() == 4
             and frames.shape[3] == 3):
         raise ValueError('frames must be a CUDA uint8 tensor [B, H, W, 3]')
@@ -112,9 +114,14 @@ def frames_from_u8(frames, out=None):
         out = torch.empty(b, 3, h, w, dtype=torch.float32, device=frames.device)
     elif not (out.is_cuda and out.dtype == torch.float32 and tuple(out.shape) == (b, 3, h, w) and out[0].is_contiguous()):
         raise ValueError('frames_from_u8: bad out tensor')
+    if out_u8 is not None and not (out_u8.is_cuda and out_u8.dtype == torch.uint8 and tuple(out_u8.shape) == (b, h, w, 3)
+                                   and out_u8[0].is_contiguous()):
+        raise ValueError('frames_from_u8: bad out_u8 tensor')
     with torch.cuda.device(frames.device):
-        check(lib.rib_frames_from_u8(frames.data_ptr(), out.data_ptr(), b, h, w, frames.stride(0) if b > 1 else 0,
-                                     out.stride(0) if b > 1 else 0, _stream()), 'rib_frames_from_u8')
+        check(lib.rib_frames_from_u8(frames.data_ptr(), out.data_ptr(), out_u8.data_ptr() if out_u8 is not None else None,
+                                     b, h, w, frames.stride(0) if b > 1 else 0, out.stride(0) if b > 1 else 0,
+                                     (out_u8.stride(0) if b > 1 else 0) if out_u8 is not None else 0, _stream()),
+              'rib_frames_from_u8')
     return out
 
 
