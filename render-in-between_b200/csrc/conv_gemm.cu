@@ -1628,9 +1628,12 @@ int device_sm_count(int dev) {
 
 template <bool SIMT>
 static ConvKernel pick_kernel(int mode, int BN, bool xf, bool pair) {
-  if (pair) {   // CTA pairs: the streamed heavy 3x3 layers (plain store, 128 columns)
-    if (SIMT || xf || mode != EPI_STORE || BN != 128) return nullptr;
-    return conv_gemm_kernel<EPI_STORE, 128, false, false, true>;
+  if (pair) {   // CTA pairs: 128-column tiles of the heavy 3x3 layers and of the low-resolution SPADE layers
+    if (SIMT || xf || BN != 128) return nullptr;
+    if (mode == EPI_STORE) return conv_gemm_kernel<EPI_STORE, 128, false, false, true>;
+    if (mode == EPI_SPADE) return conv_gemm_kernel<EPI_SPADE, 128, false, false, true>;
+    if (mode == EPI_SPADE2) return conv_gemm_kernel<EPI_SPADE2, 128, false, false, true>;
+    return nullptr;
   }
   if (xf) {  // the A-operand transform is built for the layers that use it: plain-store convs with 64 / 128 columns
     if (mode != EPI_STORE) return nullptr;
