@@ -439,8 +439,10 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF 
   const long long total_tiles = (long long)tiles_per_img * p.B;
   // contiguous range of super-tiles: neighbouring tiles share halo rows in L2 and an image's statistics
   // are flushed by few CTAs
-  // (a pair walks pairs of adjacent super-tiles: 2 i + rank; the host only pairs layers with an even tile count)
-  const long long units = PAIR ? total_tiles >> 1 : total_tiles;
+  // (a pair walks pairs of adjacent super-tiles: 2 i + rank.  With an odd tile count the last pair's second tile lies
+  //  behind the last image: its TMA boxes are out of bounds (zero fill, bytes still counted), its MMAs run on zeros and
+  //  its epilogue stores nothing)
+  const long long units = PAIR ? (total_tiles + 1) >> 1 : total_tiles;
   const int t_begin = (int)(units * cta_m / cta_groups) * tstride + (int)cta_rank;
   const int t_end = (int)(units * (cta_m + 1) / cta_groups) * tstride;
   const int acc_cols = p.MT * BN;  // TMEM columns of one accumulator buffer
@@ -979,7 +981,7 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF 
       const uint32_t use = (uint32_t)it / (uint32_t)NB;
       const int oy0 = tile_y * p.th * p.MT, ox0 = tile_x * p.tw;
 
-      if (n != cur_n) {  // uniform over the 128 epilogue threads
+      if (n != cur_n && n < p.B) {  // uniform over the 128 epilogue threads (n == B: the dummy tile of an odd pair)
         if (MODE == EPI_STORE && want_stats && cur_n >= 0) flush_stats(cur_n);
         if (kSpade) {
           const int tiles_per_q = p.C / CT;
@@ -1003,11 +1005,15 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF 
 
       // EPI_SPADE: the x values of a sub-tile are fetched one sub-tile ahead (the first one before waiting for
       // the accumulator), so that their DRAM latency overlaps the MMAs / the previous sub-tile's arithmetic
-      constexpr int NXC = kSpade ? CT / 16 : 1;
+      // (tiles with more than 64 channels - the 256-column pair tiles - fetch x per 16-channel chunk, one chunk ahead:
+      //  they only serve the low-resolution levels, whose x maps are L2-resident)
+      constexpr bool kXChunked = kSpade && CT / 16 > 4;
+      constexpr int NXC = (kSpade && !kXChunked) ? CT / 16 : 1;
       uint4 xcur[NXC][2], xnext[NXC][2];
       auto load_x = [&](int m, uint4 (*dst)[2]) {
+        if (kXChunked) return;
         const int oy = oy0 + m * p.th + ty, ox = ox0 + tx;
-        const bool valid = (oy < p.H) && (ox < p.W);
+        const bool valid = (oy < p.H) && (ox < p.W) && (n < p.B);
         const int tiles_per_q = p.C / CT;
         const int c0 = (ntile % tiles_per_q) * CT;
         const int sy = p.ups ? (oy >> 1) : oy, sx = p.ups ? (ox >> 1) : ox;
@@ -1029,7 +1035,7 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF 
       }
       for (int m = 0; m < p.MT; ++m) {
         const int oy = oy0 + m * p.th + ty, ox = ox0 + tx;
-        const bool valid = (oy < p.H) && (ox < p.W);
+        const bool valid = (oy < p.H) && (ox < p.W) && (n < p.B);
         const size_t pix8 = ((size_t)oy * p.W + ox) * 8;
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * acc_cols + m * BN);
 
@@ -1178,9 +1184,33 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF 
           const int c0 = (ntile - q0 * tiles_per_q) * CT;
           uint32_t rg[16], rb[16];
           if (m + 1 < p.MT) load_x(m + 1, xnext);
+          // chunked form: this pixel's x row, planes 2 j and 2 j + 1 are fetched one chunk ahead
+          const size_t xHW8c = (size_t)p.Hx * p.Wx * 8;
+          const act_t* xrowc = nullptr;
+          uint4 xa0 = make_uint4(0, 0, 0, 0), xa1 = xa0;
+          if (kXChunked) {
+            const int sy = p.ups ? (oy >> 1) : oy, sx = p.ups ? (ox >> 1) : ox;
+            xrowc = p.x.p + (size_t)(valid ? n : 0) * p.x.bstride + (size_t)(c0 >> 3) * xHW8c +
+                    ((size_t)(valid ? sy : 0) * p.Wx + (valid ? sx : 0)) * 8;
+            if (valid) {
+              xa0 = *reinterpret_cast<const uint4*>(xrowc);
+              xa1 = *reinterpret_cast<const uint4*>(xrowc + xHW8c);
+            }
+          }
 #pragma unroll
           for (int j = 0; j < NCS; ++j) {
-            const uint4 x0 = xcur[j][0], x1 = xcur[j][1];
+            uint4 x0, x1;
+            if (kXChunked) {
+              x0 = xa0;
+              x1 = xa1;
+              if (j + 1 < NCS && valid) {
+                xa0 = *reinterpret_cast<const uint4*>(xrowc + (size_t)(2 * j + 2) * xHW8c);
+                xa1 = *reinterpret_cast<const uint4*>(xrowc + (size_t)(2 * j + 3) * xHW8c);
+              }
+            } else {
+              x0 = xcur[kXChunked ? 0 : j][0];
+              x1 = xcur[kXChunked ? 0 : j][1];
+            }
             const uint32_t xu[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
             float xn[16];   // (x - mean) * rstd, shared by the outputs of the tile
 #pragma unroll
@@ -1244,7 +1274,7 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF 
             }
           }
 #pragma unroll
-          for (int j = 0; j < NCS; ++j) {
+          for (int j = 0; j < NXC; ++j) {
             xcur[j][0] = xnext[j][0];
             xcur[j][1] = xnext[j][1];
           }
@@ -1415,7 +1445,8 @@ static constexpr size_t kBigResident = (size_t)148 * 1024;    // ... that still 
 int choose_bkc(int cin0, int cin1, int taps, int BN, int stride) {
   const size_t b_all = ((size_t)cin0 * taps + cin1) * BN * 2;
   int cap;
-  if (b_all <= kSmallResident) cap = stride == 2 ? 16 : 64;       // stride 2 keeps four parity tiles per slot
+  if (BN == 256) cap = 64;   // 256-column pair tiles (1x1 SPADE layers): each CTA keeps its 128 weight rows resident
+  else if (b_all <= kSmallResident) cap = stride == 2 ? 16 : 64;       // stride 2 keeps four parity tiles per slot
   else if (b_all <= kBigResident) cap = stride == 2 ? 16 : 64;    // big resident weights: small halo slots
   else cap = stride == 2 ? 16 : RIB_STREAM_BKC;                   // streamed: a slot holds the halo tile(s) AND 9 weight sub-tiles
   int bk = cin0 < cap ? cin0 : cap;
@@ -1432,7 +1463,8 @@ int conv_gemm_configure(ConvGemmParams* p, int B, int Hout, int Wout, int cin0, 
                             (ppc == 1 || n_pad == 4 * (BN / ppc))),
               "conv_gemm: bad sub-pixel conv");
   RIB_REQUIRE(stride == 1 || (stride == 2 && taps == 9 && cin1 == 0), "conv_gemm: stride 2 needs a plain 3x3");
-  RIB_REQUIRE(BN >= 16 && BN <= 128 && (BN & (BN - 1)) == 0 && n_pad % BN == 0, "conv_gemm: bad BN");
+  RIB_REQUIRE(BN >= 16 && BN <= 256 && (BN & (BN - 1)) == 0 && n_pad % BN == 0, "conv_gemm: bad BN");
+  RIB_REQUIRE(BN != 256 || (taps == 1 && cin1 == 0 && stride == 1), "conv_gemm: 256-column tiles are for 1x1 layers (CTA pairs)");
   const int bkc = choose_bkc(cin0, cin1, taps, BN, stride);
   RIB_REQUIRE((bkc == 16 || bkc == 32 || bkc == 64) && cin0 % bkc == 0 && cin1 % bkc == 0,
               "conv_gemm: channel counts must be 16, 32 or multiples of 64");
@@ -1491,19 +1523,20 @@ int conv_gemm_configure(ConvGemmParams* p, int B, int Hout, int Wout, int cin0, 
     const char* force = getenv("RIB_TEST_POLICY");
     if (force != nullptr && atoi(force) >= 1 && atoi(force) <= 5) policy = atoi(force);
   }
+  if (BN == 256) policy = 5;   // only exists as a CTA pair with resident half-tiles (two accumulators of 256 columns)
   RIB_REQUIRE(policy >= 1 && policy <= 5 &&
                   (policy == 5 ? (b_all > kSmallResident && b_all / 2 <= kBigResident)
                                : (policy >= 3 ? b_all > kSmallResident : b_all <= kBigResident)),
               "conv_gemm: residency policy does not apply to this layer");
   p->pair = policy >= 4 ? 1 : 0;
   if (policy >= 4) {
-    RIB_REQUIRE(BN == 128 && taps != 4 && (cin1 == 0 || stride == 1), "conv_gemm: CTA pairs need a plain layer with BN = 128");
+    RIB_REQUIRE((BN == 128 || BN == 256) && taps != 4 && (cin1 == 0 || stride == 1), "conv_gemm: CTA pairs need a plain layer with BN = 128 / 256");
     p->b_tap_bytes = (uint32_t)((BN / 2) * bkc * 2);   // each CTA of the pair stages half of the weight rows
   }
-  int mt = policy == 1 ? 1 : (can_mt2 ? 2 : 1);
+  int mt = (policy == 1 || BN == 256) ? 1 : (can_mt2 ? 2 : 1);
   const bool mt_forced = tune != nullptr && tune->mt != 0;
   if (mt_forced) mt = tune->mt;
-  RIB_REQUIRE(mt == 1 || (mt == 2 && can_mt2), "conv_gemm: cannot stack two sub-tiles here");
+  RIB_REQUIRE(mt == 1 || (mt == 2 && can_mt2 && BN != 256), "conv_gemm: cannot stack two sub-tiles here");
   if (policy == 1) {
     p->b_resident = 1;
     set_geometry(mt);
@@ -1527,7 +1560,6 @@ int conv_gemm_configure(ConvGemmParams* p, int B, int Hout, int Wout, int cin0, 
     int ring = (int)((kSmemMax - fixed) / p->a_slot_bytes);
     const int ring_cap = (tune != nullptr && tune->ring >= 2 && tune->ring <= 8) ? tune->ring : (policy == 5 ? 8 : 4);
     p->a_ring = ring > ring_cap ? ring_cap : ring;
-    if (policy == 5) RIB_REQUIRE(((long long)p->tiles_x * p->tiles_y * B) % 2 == 0, "conv_gemm: CTA pairs need an even number of super-tiles");
   } else {
     // a ring slot holds the halo tile(s) of a channel group AND that group's weight sub-tiles (one barrier round trip
     // per group); two stacked sub-tiles halve the weight traffic per pixel (measured: also for stride 2, whose four
@@ -1545,7 +1577,6 @@ int conv_gemm_configure(ConvGemmParams* p, int B, int Hout, int Wout, int cin0, 
     RIB_REQUIRE(ring >= 2, "conv_gemm: streamed group slots do not fit");
     const int ring_cap = (tune != nullptr && tune->ring >= 2 && tune->ring <= 8) ? tune->ring : 4;
     p->a_ring = ring > ring_cap ? ring_cap : ring;
-    if (policy == 4) RIB_REQUIRE(((long long)p->tiles_x * p->tiles_y * B) % 2 == 0, "conv_gemm: CTA pairs need an even number of super-tiles");
   }
   p->idesc = make_idesc_f16(p->pair ? 256 : 128, BN / ppc);
   return 0;
@@ -1629,7 +1660,13 @@ int device_sm_count(int dev) {
 template <bool SIMT>
 static ConvKernel pick_kernel(int mode, int BN, bool xf, bool pair) {
   if (pair) {   // CTA pairs: 128-column tiles of the heavy 3x3 layers and of the low-resolution SPADE layers
-    if (SIMT || xf || BN != 128) return nullptr;
+    if (SIMT || xf) return nullptr;
+    if (BN == 256) {   // 256-column tiles of the low-resolution SPADE layers: [gamma | beta] of 128 (SPADE2: 64 + 64) channels
+      if (mode == EPI_SPADE) return conv_gemm_kernel<EPI_SPADE, 256, false, false, true>;
+      if (mode == EPI_SPADE2) return conv_gemm_kernel<EPI_SPADE2, 256, false, false, true>;
+      return nullptr;
+    }
+    if (BN != 128) return nullptr;
     if (mode == EPI_STORE) return conv_gemm_kernel<EPI_STORE, 128, false, false, true>;
     if (mode == EPI_SPADE) return conv_gemm_kernel<EPI_SPADE, 128, false, false, true>;
     if (mode == EPI_SPADE2) return conv_gemm_kernel<EPI_SPADE2, 128, false, false, true>;
@@ -1655,11 +1692,13 @@ static ConvKernel pick_kernel(int mode, int BN, bool xf, bool pair) {
       case 32: return conv_gemm_kernel<EPI_SPADE, 32, SIMT, false, false>;
       case 64: return conv_gemm_kernel<EPI_SPADE, 64, SIMT, false, false>;
       case 128: return conv_gemm_kernel<EPI_SPADE, 128, SIMT, false, false>;
+      case 256: if (SIMT) return conv_gemm_kernel<EPI_SPADE, 256, true, false, false>; break;   // (tcgen05: pairs only)
     }
   } else if (mode == EPI_SPADE2) {
     switch (BN) {
       case 64: return conv_gemm_kernel<EPI_SPADE2, 64, SIMT, false, false>;
       case 128: return conv_gemm_kernel<EPI_SPADE2, 128, SIMT, false, false>;
+      case 256: if (SIMT) return conv_gemm_kernel<EPI_SPADE2, 256, true, false, false>; break;
     }
   } else if (mode == EPI_FINAL && BN == 16) {
     return conv_gemm_kernel<EPI_FINAL, 16, SIMT, false, false>;
@@ -1725,7 +1764,7 @@ int launch_conv_gemm(const ConvGemmParams& p, int mode, cudaStream_t stream) {
   // pair: `groups` counts CTA pairs per N tile, each pair walks pairs of super-tiles
   long long groups = pair ? ((long long)(n_sms / 2) * occ) / p.n_tiles : ((long long)n_sms * occ) / p.n_tiles;
   if (groups < 1) groups = 1;
-  if (groups > (pair ? m_tiles / 2 : m_tiles)) groups = pair ? m_tiles / 2 : m_tiles;
+  if (groups > (pair ? (m_tiles + 1) / 2 : m_tiles)) groups = pair ? (m_tiles + 1) / 2 : m_tiles;
   dim3 grid((unsigned)(groups * p.n_tiles * (pair ? 2 : 1)));
   dim3 block(threads);
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -184,7 +184,15 @@ bool spade_pairs() {
   static const bool on = !(getenv("RIB_SPADE2") != nullptr && atoi(getenv("RIB_SPADE2")) == 0);
   return on;
 }
-int spade_ct(int C, int nq_tile = 1) { return std::min(C, nq_tile == 2 ? 32 : 64); }
+// Low-resolution levels (cond maps with >= 256 channels, i.e. K >= 256): 256-column tiles run by CTA pairs, so that a
+// cond tile is read once for twice the columns and each CTA keeps only its 128 weight rows (RIB_SPADE256=0: 128 columns).
+int spade_ct(int C, int nq_tile = 1, int cond = 0) {
+  static const bool wide_on = !(getenv("RIB_SPADE256") != nullptr && atoi(getenv("RIB_SPADE256")) == 0);
+  // (only the paired-output tiles [gamma0|beta0|gamma_s|beta_s] x 64 channels: measured, profiles/r2o, the single-output
+  //  form with 128 channels per tile loses 16 us per layer to its chunk-wise x loads while the paired form gains 13-35)
+  if (wide_on && nq_tile == 2 && cond >= 256 && C >= 64 && C % 64 == 0) return 64;
+  return std::min(C, nq_tile == 2 ? 32 : 64);
+}
 
 // BN = 0 selects the plain-store default min(n_pad, 128).
 void add_layer(Generator* G, const std::string& name, int n_valid, int n_pad, int cin0_pad, int taps, int cin1,
@@ -242,15 +250,15 @@ static void define_layers(Generator* G, std::vector<PackJob>& jobs) {
     // conv_block_0 and conv_block_s modulate the same x over the same cond map: their [gamma|beta] columns share N
     // tiles (EPI_SPADE2), so cond and x are read once for both outputs
     const int nqt = (nq == 2 && spade_pairs()) ? 2 : 1;
-    const int ctA = spade_ct(b.cin, nqt);
+    const int ctA = spade_ct(b.cin, nqt, cond);
     add_layer(G, b.name + ".spadeA", nq * 2 * b.cin, nq * 2 * b.cin, cond, 1, 0, 2 * nqt * ctA);
     jobs.push_back({b.name + ".spadeA", b.name + ".conv_block_0.layers.norm.mlps.0.0.layers.conv", false, 2 * b.cin, cond, 1, 0, cond, 0, b.cin, ctA, false, 0, 0, nqt, 0});
     if (b.shortcut)
       jobs.push_back({b.name + ".spadeA", b.name + ".conv_block_s.layers.norm.mlps.0.0.layers.conv", false, 2 * b.cin, cond, 1, 0, cond, nqt == 2 ? 0 : 2 * b.cin, b.cin, ctA, false, 0, 0, nqt, nqt == 2 ? 1 : 0});
     add_layer(G, b.name + ".conv0", b.hid, b.hid, b.cin, 9, 0);
     jobs.push_back({b.name + ".conv0", b.name + ".conv_block_0.layers.conv", true, b.hid, b.cin, 9, 0, b.cin, 0, 0, 0, false});
-    add_layer(G, b.name + ".spadeB", 2 * b.hid, 2 * b.hid, cond, 1, 0, 2 * spade_ct(b.hid));
-    jobs.push_back({b.name + ".spadeB", b.name + ".conv_block_1.layers.norm.mlps.0.0.layers.conv", false, 2 * b.hid, cond, 1, 0, cond, 0, b.hid, spade_ct(b.hid), false});
+    add_layer(G, b.name + ".spadeB", 2 * b.hid, 2 * b.hid, cond, 1, 0, 2 * spade_ct(b.hid, 1, cond));
+    jobs.push_back({b.name + ".spadeB", b.name + ".conv_block_1.layers.norm.mlps.0.0.layers.conv", false, 2 * b.hid, cond, 1, 0, cond, 0, b.hid, spade_ct(b.hid, 1, cond), false});
     add_layer(G, b.name + ".conv1", b.cout, b.cout, b.hid, 9, b.shortcut ? b.cin : 0);
     jobs.push_back({b.name + ".conv1", b.name + ".conv_block_1.layers.conv", true, b.cout, b.hid, 9, 0, b.hid, 0, 0, 0, false});
     if (b.shortcut)
@@ -666,7 +674,7 @@ struct PlanBuilder {
              const View* outs, const int* acts) {
     const GemmLayer& L = G->layers.at(lname);
     const int nqt = (nq == 2 && spade_pairs()) ? 2 : 1;
-    const int CT = spade_ct(x.C, nqt);
+    const int CT = spade_ct(x.C, nqt, cond.C);
     ConvGemmParams p = gemm_common(L, cond, nullptr, 1, cond.H, cond.W, 2 * nqt * CT);
     p.x = x.ref();
     p.Hx = x.H;
