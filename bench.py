@@ -48,6 +48,25 @@ def protect_stdout():
     return os.fdopen(saved, 'w')
 
 
+def bind_to_gpu_numa_node(index):
+    """Pins this process to the CPUs NVML reports as local to GPU `index` BEFORE the pinned host buffers are allocated
+    (first touch puts them on that NUMA node): with 8 ranks every upload / download then crosses its own socket's PCIe
+    root instead of one node's memory controllers.  Best effort: any failure leaves the affinity alone."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [w * 64 + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return len(allowed)
+    except Exception:
+        pass
+    return 0
+
+
 def peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.isfile(path):
@@ -440,6 +459,7 @@ def main():
     assert lib.rib_debug_get_simt() == 0
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else 0
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')   # keep NCCL's version banner off stdout (one JSON line)
@@ -613,7 +633,8 @@ def main():
         'config': workload_config(world),
         'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': h2d * world,
                 'd2h_bytes_per_step': int(u8_hosts[0].numel()) * world, 'ms_per_step': ms_e2e / args.steps,
-                'note': 'bytes are summed over the %d rank(s); every rank moves its own clip' % world},
+                'note': 'bytes are summed over the %d rank(s); every rank moves its own clip' % world,
+                'host_affinity': ('rank pinned to the %d CPUs local to its GPU (NVML)' % numa_cpus) if numa_cpus else 'unchanged'},
         'gpu_launches': int(launches),
         'clocks': clocks,
         'roofline': {

@@ -14,6 +14,7 @@
  *   RIB_XF=0|1|2        scope of the in-kernel instance-norm transform of the mask network (default 1)
  *   RIB_MERGE_LABEL=0   down_first and down_lbl.0 as two launches instead of one GEMM over the label
  *   RIB_SPADE2=0        the two SPADE layers of a shortcut res-block in separate N tiles
+ *   RIB_PDL=0           plain stream order between kernels instead of programmatic dependent launch
  *   RIB_PAIRS=0         the auto-tuner does not try the CTA-pair (tcgen05 cta_group::2) forms
  *   RIB_SPADE256=0      128-column tiles for every SPADE layer (default: 256-column CTA-pair tiles at the low-resolution levels)
  *   RIB_SUBPIX_PPC=4    sub-pixel convs compute up to four output parities per CTA (measured slower, opt-in)

@@ -169,6 +169,35 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint
       : "memory");
 }
 
+// ---- Programmatic dependent launch: a kernel launched with programmaticStreamSerializationAllowed may start while the
+// previous kernel of the stream is still running; everything it does before pdl_wait() must not depend on (or disturb) that
+// kernel's memory, and pdl_wait() returns once the previous kernel has completed and its writes are visible.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+}  // namespace rib
+#include <cstdlib>
+#include <utility>
+namespace rib {
+// Launch of a kernel whose first statement is pdl_wait(): it may be scheduled while the previous kernel of the stream
+// drains (no launch gap, its blocks start as SMs free up); RIB_PDL=0 restores plain stream order.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     Args&&... args) {
+  static const bool pdl_on = !(getenv("RIB_PDL") != nullptr && atoi(getenv("RIB_PDL")) == 0);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_on ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 // ---- Ampere-style asynchronous 16-byte copies (per-thread addresses; src_bytes = 0 zero-fills the destination) ----
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");

@@ -505,6 +505,10 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF 
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = SIMT ? 0u : *tmem_ptr;
+  // Programmatic dependent launch: the next conv kernel of the stream may be scheduled from here on (its CTAs take an SM
+  // as soon as one of ours leaves and run their prologue - barrier init, tensor-memory allocation, bias tile, resident
+  // weights - while our other CTAs finish); its own pdl_wait() holds all its activation traffic back until we are done.
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -530,6 +534,7 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF 
           else tma_load_2d(sB_addr + (uint32_t)i * b_tap_bytes, &p.bmap, bb, i * BKc, n_col0);
         }
       }
+      pdl_wait();   // the weights above are constants; the activations below are the previous kernel's output
       int a_slot = 0;
       uint32_t a_phase = 0;
       // tile coordinates are advanced incrementally (no divisions in the loop)
@@ -697,6 +702,7 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF 
     // ===================== A-operand transform =====================
     // Four warps rewrite every halo tile in place: x -> lrelu?(x * scale[c] + shift[c]) for in-image pixels (padding
     // stays zero), one 8-channel plane per warp at a time with its 16 coefficients in registers.
+    pdl_wait();
     if (!SIMT && p.a_gather) {
       // ----- stride-2 gather: parity tile (py, px) of a channel group = input pixels (2 Y + py, 2 X + px) of a NORMAL
       // planar map.  Every thread owns a fixed set of 16-byte vectors of the slot (same for every tile), copies them with
@@ -878,6 +884,7 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF 
     }
   } else {
     // ===================== Epilogue =====================
+    pdl_wait();   // statistics, x, residuals and every store below belong to the stream-ordered part of the kernel
     const int q = warp & 3;
     const int eg = (warp - 2) >> 2;                     // epilogue group = accumulator buffer it drains
     const int e = (threadIdx.x - 64) & 127;             // thread index inside the group
@@ -1187,25 +1194,30 @@ __global__ void __launch_bounds__(kThreads + (XF ? kXfThreads : 0), (SIMT || XF 
           // chunked form: this pixel's x row, planes 2 j and 2 j + 1 are fetched one chunk ahead
           const size_t xHW8c = (size_t)p.Hx * p.Wx * 8;
           const act_t* xrowc = nullptr;
-          uint4 xa0 = make_uint4(0, 0, 0, 0), xa1 = xa0;
+          constexpr int kXD = 4;   // chunks of x in flight (a ring of registers): L2 latency >> one chunk's arithmetic
+          uint4 xring[kXChunked ? kXD : 1][2];
           if (kXChunked) {
             const int sy = p.ups ? (oy >> 1) : oy, sx = p.ups ? (ox >> 1) : ox;
             xrowc = p.x.p + (size_t)(valid ? n : 0) * p.x.bstride + (size_t)(c0 >> 3) * xHW8c +
                     ((size_t)(valid ? sy : 0) * p.Wx + (valid ? sx : 0)) * 8;
-            if (valid) {
-              xa0 = *reinterpret_cast<const uint4*>(xrowc);
-              xa1 = *reinterpret_cast<const uint4*>(xrowc + xHW8c);
+#pragma unroll
+            for (int k = 0; k < kXD; ++k) {
+              xring[kXChunked ? k : 0][0] = xring[kXChunked ? k : 0][1] = make_uint4(0, 0, 0, 0);
+              if (valid && k < NCS) {
+                xring[kXChunked ? k : 0][0] = *reinterpret_cast<const uint4*>(xrowc + (size_t)(2 * k) * xHW8c);
+                xring[kXChunked ? k : 0][1] = *reinterpret_cast<const uint4*>(xrowc + (size_t)(2 * k + 1) * xHW8c);
+              }
             }
           }
 #pragma unroll
           for (int j = 0; j < NCS; ++j) {
             uint4 x0, x1;
             if (kXChunked) {
-              x0 = xa0;
-              x1 = xa1;
-              if (j + 1 < NCS && valid) {
-                xa0 = *reinterpret_cast<const uint4*>(xrowc + (size_t)(2 * j + 2) * xHW8c);
-                xa1 = *reinterpret_cast<const uint4*>(xrowc + (size_t)(2 * j + 3) * xHW8c);
+              x0 = xring[kXChunked ? j % kXD : 0][0];
+              x1 = xring[kXChunked ? j % kXD : 0][1];
+              if (j + kXD < NCS && valid) {   // refill the slot with the chunk kXD ahead
+                xring[kXChunked ? j % kXD : 0][0] = *reinterpret_cast<const uint4*>(xrowc + (size_t)(2 * (j + kXD)) * xHW8c);
+                xring[kXChunked ? j % kXD : 0][1] = *reinterpret_cast<const uint4*>(xrowc + (size_t)(2 * (j + kXD) + 1) * xHW8c);
               }
             } else {
               x0 = xcur[kXChunked ? 0 : j][0];
@@ -1773,22 +1785,31 @@ int launch_conv_gemm(const ConvGemmParams& p, int mode, cudaStream_t stream) {
     RIB_CHECK_CUDA(cudaEventCreate(&ev1));
     RIB_CHECK_CUDA(cudaEventRecord(ev0, stream));
   }
-  if (pair) {
+  {
+    // RIB_PDL=0: plain stream order between the conv launches (A/B runs)
+    static const bool pdl_on = !(getenv("RIB_PDL") != nullptr && atoi(getenv("RIB_PDL")) == 0);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (pair) {
+      attr[na].id = cudaLaunchAttributeClusterDimension;
+      attr[na].val.clusterDim.x = 2;
+      attr[na].val.clusterDim.y = 1;
+      attr[na].val.clusterDim.z = 1;
+      ++na;
+    }
+    if (pdl_on && !p.debug_simt) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = na;
     RIB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, fn, p));
-  } else {
-    fn<<<grid, block, smem, stream>>>(p);
   }
   RIB_CHECK_CUDA(cudaGetLastError());
   if (g_profile) {

@@ -12,6 +12,7 @@ namespace rib {
 // ---------------------------------------------------------------------------------------------
 __global__ void pack_nchw_kernel(const PackSrc s0, const PackSrc s1, const PackSrc s2, act_t* __restrict__ dst,
                                  long long dst_bs, int c_off, int plane0, int nplanes, int HW, size_t total) {
+  pdl_wait();   // programmatic dependent launch: nothing above depends on the previous kernel
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over B * nplanes * HW
   if (i >= total) return;
   const int hw = (int)(i % HW);
@@ -45,7 +46,7 @@ int launch_pack_nchw(const PackSrc* srcs, int nsrc, act_t* dst, long long dst_bs
   const PackSrc s0 = srcs[0], s1 = nsrc > 1 ? srcs[1] : z, s2 = nsrc > 2 ? srcs[2] : z;
   const size_t total = (size_t)B * nplanes * H * W;
   const int threads = 256;
-  pack_nchw_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(s0, s1, s2, dst, dst_bstride, c_off,
+  launch_pdl(pack_nchw_kernel, dim3((unsigned)((total + threads - 1) / threads)), dim3(threads), 0, s, s0, s1, s2, dst, dst_bstride, c_off,
                                                                                    plane0, nplanes, H * W, total);
   RIB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -54,6 +55,7 @@ int launch_pack_nchw(const PackSrc* srcs, int nsrc, act_t* dst, long long dst_bs
 __global__ void pack_images_kernel(const float* __restrict__ fake, const float* __restrict__ prev,
                                    act_t* __restrict__ emb, long long emb_bs, act_t* __restrict__ msk, long long msk_bs,
                                    int HW, size_t total) {
+  pdl_wait();   // programmatic dependent launch: nothing above depends on the previous kernel
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over B * HW / 4
   if (i >= total) return;
   const int q4 = HW >> 2;
@@ -81,7 +83,7 @@ int launch_pack_images(const float* fake, const float* prev, act_t* emb, long lo
   RIB_REQUIRE((H * W) % 4 == 0, "pack_images: H*W must be a multiple of 4");
   RIB_REQUIRE((((uintptr_t)fake | (uintptr_t)prev) & 15) == 0, "pack_images: inputs must be 16-byte aligned");
   const size_t total = (size_t)B * (H * W / 4);
-  pack_images_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(fake, prev, emb, emb_bstride, mask, mask_bstride,
+  launch_pdl(pack_images_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, s, fake, prev, emb, emb_bstride, mask, mask_bstride,
                                                                      H * W, total);
   RIB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -103,6 +105,7 @@ __device__ __forceinline__ void in_coeffs(const double* stats, const float* w, c
 }
 
 __global__ void in_apply_kernel(const InApplyParams p) {
+  pdl_wait();   // programmatic dependent launch: nothing above depends on the previous kernel
   extern __shared__ float s_coef[];  // [4][C]: scale_a, shift_a, scale_b, shift_b
   const int n = blockIdx.y;
   const double cnt = (double)p.H * (double)p.W;
@@ -173,6 +176,7 @@ __global__ void in_apply_kernel(const InApplyParams p) {
 // Same operation for the parity-planar output of a sub-pixel conv: one thread reads the two x parities of an output
 // pixel pair (two coalesced streams) and writes 32 contiguous bytes of the normal map.
 __global__ void in_apply_unparity_kernel(const InApplyParams p) {
+  pdl_wait();   // programmatic dependent launch: nothing above depends on the previous kernel
   extern __shared__ float s_coef[];  // [2][C]: scale, shift
   const int n = blockIdx.y;
   const double cnt = (double)p.H * (double)p.W;
@@ -246,7 +250,7 @@ int launch_in_apply(const InApplyParams& p, cudaStream_t s) {
     unsigned gx = (unsigned)((npair + 255) / 256);
     unsigned want = (sm_count_current() * 8u + (unsigned)p.B - 1u) / (unsigned)p.B;
     if (gx > want) gx = want;
-    in_apply_unparity_kernel<<<dim3(gx, (unsigned)p.B), 256, 2 * p.C * sizeof(float), s>>>(p);
+    launch_pdl(in_apply_unparity_kernel, dim3(gx, (unsigned)p.B), dim3(256), 2 * p.C * sizeof(float), s, p);
     RIB_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
@@ -259,7 +263,7 @@ int launch_in_apply(const InApplyParams& p, cudaStream_t s) {
   if (want < 1u) want = 1u;
   if (gx > want) gx = want;
   dim3 grid(gx, (unsigned)p.B);
-  in_apply_kernel<<<grid, threads, 4 * p.C * sizeof(float), s>>>(p);
+  launch_pdl(in_apply_kernel, grid, dim3(threads), 4 * p.C * sizeof(float), s, p);
   RIB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -270,6 +274,7 @@ int launch_in_apply(const InApplyParams& p, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------
 __global__ void avgpool3s2_kernel(const act_t* __restrict__ src, long long src_bs, act_t* __restrict__ dst,
                                   long long dst_bs, double* __restrict__ stats, int H, int W, int C) {
+  pdl_wait();   // programmatic dependent launch: nothing above depends on the previous kernel
   __shared__ float s_red[8][16];  // one slot per warp: fixed-order (deterministic) block reduction
   const int pl = blockIdx.y, n = blockIdx.z;
   const int Ho = H / 2, Wo = W / 2;
@@ -347,7 +352,7 @@ int launch_avgpool3s2(const act_t* src, long long src_bs, act_t* dst, long long 
   unsigned gx = (unsigned)((npix + threads * 4 - 1) / (threads * 4));
   if (gx < 1) gx = 1;
   dim3 grid(gx, (unsigned)(C / 8), (unsigned)B);
-  avgpool3s2_kernel<<<grid, threads, 0, s>>>(src, src_bs, dst, dst_bs, stats, H, W, C);
+  launch_pdl(avgpool3s2_kernel, grid, dim3(threads), 0, s, src, src_bs, dst, dst_bs, stats, H, W, C);
   RIB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -365,6 +370,7 @@ __global__ void composite_kernel(const float* __restrict__ img, const float* __r
                                  const float* __restrict__ dain, float* __restrict__ out_f32,
                                  uint8_t* __restrict__ out_u8, int HW4, int HW, size_t total, long long img_bs,
                                  long long f32_bs, long long u8_bs) {
+  pdl_wait();   // programmatic dependent launch: nothing above depends on the previous kernel
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over B * HW/4
   if (i >= total) return;
   const size_t n = i / HW4, q = i - n * HW4;
@@ -416,8 +422,8 @@ int launch_composite(const float* img, const float* mask, const float* dain, flo
   RIB_REQUIRE(img_bstride % 4 == 0 && f32_bstride % 4 == 0 && u8_bstride % 4 == 0, "composite: strides must be multiples of 4");
   const size_t total = (size_t)B * (HW / 4);
   const int threads = 256;
-  composite_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(
-      img, mask, dain, out_f32, out_u8, HW / 4, HW, total, img_bstride, f32_bstride, u8_bstride);
+  launch_pdl(composite_kernel, dim3((unsigned)((total + threads - 1) / threads)), dim3(threads), 0, s,
+             img, mask, dain, out_f32, out_u8, HW / 4, HW, total, img_bstride, f32_bstride, u8_bstride);
   RIB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -602,6 +608,7 @@ template <int CT>   // CT > 0: channel count known at compile time (all gathers 
 __global__ void warp4_kernel(const float* __restrict__ src, const float* __restrict__ flow, float* __restrict__ out,
                              int Crt, int H, int W, float sx, float sy, size_t total4, long long src_bs, long long flow_bs,
                              long long out_bs) {
+  pdl_wait();   // programmatic dependent launch: nothing above depends on the previous kernel
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over B*H*W/4
   if (i >= total4) return;
   const int HW = H * W, HW4 = HW >> 2;
@@ -658,11 +665,11 @@ int launch_warp(const float* src, const float* flow, float* out, int B, int C, i
       (((uintptr_t)flow | (uintptr_t)out) & 15) == 0) {
     const size_t total4 = total / 4;
     if (C == 3)
-      warp4_kernel<3><<<(unsigned)((total4 + threads - 1) / threads), threads, 0, s>>>(src, flow, out, C, H, W, sx, sy, total4,
-                                                                                       src_bstride, flow_bstride, out_bstride);
+      launch_pdl(warp4_kernel<3>, dim3((unsigned)((total4 + threads - 1) / threads)), dim3(threads), 0, s, src, flow, out, C, H, W,
+                 sx, sy, total4, src_bstride, flow_bstride, out_bstride);
     else
-      warp4_kernel<0><<<(unsigned)((total4 + threads - 1) / threads), threads, 0, s>>>(src, flow, out, C, H, W, sx, sy, total4,
-                                                                                       src_bstride, flow_bstride, out_bstride);
+      launch_pdl(warp4_kernel<0>, dim3((unsigned)((total4 + threads - 1) / threads)), dim3(threads), 0, s, src, flow, out, C, H, W,
+                 sx, sy, total4, src_bstride, flow_bstride, out_bstride);
     RIB_CHECK_CUDA(cudaGetLastError());
     return 0;
   }

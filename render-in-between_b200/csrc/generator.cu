@@ -191,6 +191,8 @@ int spade_ct(int C, int nq_tile = 1, int cond = 0) {
   // (only the paired-output tiles [gamma0|beta0|gamma_s|beta_s] x 64 channels: measured, profiles/r2o, the single-output
   //  form with 128 channels per tile loses 16 us per layer to its chunk-wise x loads while the paired form gains 13-35)
   if (wide_on && nq_tile == 2 && cond >= 256 && C >= 64 && C % 64 == 0) return 64;
+  static const bool wide1_on = getenv("RIB_SPADE256_SINGLE") != nullptr && atoi(getenv("RIB_SPADE256_SINGLE")) == 1;
+  if (wide_on && wide1_on && nq_tile == 1 && cond >= 256 && C >= 128 && C % 128 == 0) return 128;
   return std::min(C, nq_tile == 2 ? 32 : 64);
 }
 
