@@ -125,9 +125,9 @@ def frames_from_u8(frames, out=None, out_u8=None):
     return out
 
 
-def warp(src, flow):
+def warp(src, flow, out=None):
     """Bilinear resample of src [B,C,H,W] by flow [B,2,H,W] (pixels), border padding (stage A3).
-    Both inputs may be strided along the frame dimension (e.g. flows[s::r])."""
+    Both inputs may be strided along the frame dimension (e.g. flows[s::r]); `out`: optional dense destination."""
     if src.dim() != 4:
         raise ValueError('src must be [B, C, H, W]')
     b, c, h, w = src.shape
@@ -135,7 +135,10 @@ def warp(src, flow):
     if tuple(flow.shape) != (b, 2, h, w):
         raise ValueError('flow must be [B, 2, H, W]')
     flow, flow_bs = _frames(flow, 'flow', (2, h, w))
-    out = torch.empty(b, c, h, w, dtype=torch.float32, device=src.device)
+    if out is None:
+        out = torch.empty(b, c, h, w, dtype=torch.float32, device=src.device)
+    elif not (out.is_cuda and out.dtype == torch.float32 and tuple(out.shape) == (b, c, h, w) and out.is_contiguous()):
+        raise ValueError('warp: bad out tensor')
     with torch.cuda.device(src.device):
         check(lib.rib_warp(src.data_ptr(), flow.data_ptr(), out.data_ptr(), b, c, h, w, src_bs, flow_bs, 0, _stream()),
               'rib_warp')
