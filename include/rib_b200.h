@@ -57,12 +57,13 @@ int rib_rasterize(const double* joints, int B, int H, int W, const double* gauss
 /* ---- A3: flow-based bilinear resampling ------------------------------------------------------
  * No call site in the reference tree; semantics of imaginaire's resample():
  * out = grid_sample(src, identity + flow, bilinear, padding_mode='border', align_corners=True).
- *   src f32 [B][C][H][W], flow f32 [B][2][H][W] (pixels; channel 0 = x), out f32 [B][C][H][W]
+ *   src f32 [B][C][H][W], flow [B][2][H][W] (pixels; channel 0 = x) as f32, or as IEEE half when flow_fp16 != 0
+ *   (converted exactly on load: halves the upload of a flow field), out f32 [B][C][H][W]
  *   *_bstride: elements between consecutive frames (0 = dense), so that every r-th frame of a clip can be
  *   addressed without a gather copy.
  */
-int rib_warp(const float* src, const float* flow, float* out, int B, int C, int H, int W, long long src_bstride,
-             long long flow_bstride, long long out_bstride, void* stream);
+int rib_warp(const float* src, const void* flow, int flow_fp16, float* out, int B, int C, int H, int W,
+             long long src_bstride, long long flow_bstride, long long out_bstride, void* stream);
 
 /* ---- A4: mask-blend composite ----------------------------------------------------------------
  * Replaces models/evaluator.py:256-258 (fuse = pred*mask + dain*(1-mask)) and, when out_u8 is not

@@ -48,11 +48,11 @@ int rib_rasterize(const double* joints, int B, int H, int W, const double* gauss
   RIB_GUARD_END
 }
 
-int rib_warp(const float* src, const float* flow, float* out, int B, int C, int H, int W, long long src_bstride,
-             long long flow_bstride, long long out_bstride, void* stream) {
+int rib_warp(const float* src, const void* flow, int flow_fp16, float* out, int B, int C, int H, int W,
+             long long src_bstride, long long flow_bstride, long long out_bstride, void* stream) {
   RIB_GUARD_BEGIN
   RIB_REQUIRE(src && flow && out && B > 0 && C > 0 && H > 0 && W > 0, "rib_warp: bad argument");
-  int rc = launch_warp(src, flow, out, B, C, H, W, src_bstride, flow_bstride, out_bstride, (cudaStream_t)stream);
+  int rc = launch_warp(src, flow, flow_fp16, out, B, C, H, W, src_bstride, flow_bstride, out_bstride, (cudaStream_t)stream);
   if (!rc) count_misc_launch(1);
   return rc;
   RIB_GUARD_END

@@ -604,8 +604,9 @@ __global__ void warp_kernel(const float* __restrict__ src, const float* __restri
 
 // Four consecutive pixels of a row per thread (W % 4 == 0): 16-byte flow loads and output stores, 16 gathers in flight.
 // Per pixel the float sequence is the one of warp_kernel.
-template <int CT>   // CT > 0: channel count known at compile time (all gathers of a thread are issued together)
-__global__ void warp4_kernel(const float* __restrict__ src, const float* __restrict__ flow, float* __restrict__ out,
+// FH: the flow is stored as IEEE half (exactly converted to fp32 on load; halves the upload of a flow field).
+template <int CT, bool FH>   // CT > 0: channel count known at compile time (all gathers of a thread are issued together)
+__global__ void warp4_kernel(const float* __restrict__ src, const void* __restrict__ flow_v, float* __restrict__ out,
                              int Crt, int H, int W, float sx, float sy, size_t total4, long long src_bs, long long flow_bs,
                              long long out_bs) {
   pdl_wait();   // programmatic dependent launch: nothing above depends on the previous kernel
@@ -615,9 +616,22 @@ __global__ void warp4_kernel(const float* __restrict__ src, const float* __restr
   const size_t n = i / HW4;
   const int hw = (int)(i - n * HW4) * 4;
   const int y = hw / W, xb = hw - y * W;
-  const float4 fx4 = __ldg(reinterpret_cast<const float4*>(flow + n * flow_bs + hw));
-  const float4 fy4 = __ldg(reinterpret_cast<const float4*>(flow + n * flow_bs + (size_t)HW + hw));
-  const float fxs[4] = {fx4.x, fx4.y, fx4.z, fx4.w}, fys[4] = {fy4.x, fy4.y, fy4.z, fy4.w};
+  float fxs[4], fys[4];
+  if (FH) {
+    const __half* flow = static_cast<const __half*>(flow_v);
+    const uint2 hx = __ldg(reinterpret_cast<const uint2*>(flow + n * flow_bs + hw));
+    const uint2 hy = __ldg(reinterpret_cast<const uint2*>(flow + n * flow_bs + (size_t)HW + hw));
+    const float2 x01 = __half22float2(*reinterpret_cast<const __half2*>(&hx.x)), x23 = __half22float2(*reinterpret_cast<const __half2*>(&hx.y));
+    const float2 y01 = __half22float2(*reinterpret_cast<const __half2*>(&hy.x)), y23 = __half22float2(*reinterpret_cast<const __half2*>(&hy.y));
+    fxs[0] = x01.x, fxs[1] = x01.y, fxs[2] = x23.x, fxs[3] = x23.y;
+    fys[0] = y01.x, fys[1] = y01.y, fys[2] = y23.x, fys[3] = y23.y;
+  } else {
+    const float* flow = static_cast<const float*>(flow_v);
+    const float4 fx4 = __ldg(reinterpret_cast<const float4*>(flow + n * flow_bs + hw));
+    const float4 fy4 = __ldg(reinterpret_cast<const float4*>(flow + n * flow_bs + (size_t)HW + hw));
+    fxs[0] = fx4.x, fxs[1] = fx4.y, fxs[2] = fx4.z, fxs[3] = fx4.w;
+    fys[0] = fy4.x, fys[1] = fy4.y, fys[2] = fy4.z, fys[3] = fy4.w;
+  }
   int o00[4], dx1[4], dy1[4];
   float wnw[4], wne[4], wsw[4], wse[4];
 #pragma unroll
@@ -653,23 +667,29 @@ __global__ void warp4_kernel(const float* __restrict__ src, const float* __restr
   }
 }
 
-int launch_warp(const float* src, const float* flow, float* out, int B, int C, int H, int W, long long src_bstride,
-                long long flow_bstride, long long out_bstride, cudaStream_t s) {
+int launch_warp(const float* src, const void* flow_v, int flow_fp16, float* out, int B, int C, int H, int W,
+                long long src_bstride, long long flow_bstride, long long out_bstride, cudaStream_t s) {
+  const float* flow = static_cast<const float*>(flow_v);
   const size_t total = (size_t)B * H * W;
   if (src_bstride == 0) src_bstride = (long long)C * H * W;
   if (flow_bstride == 0) flow_bstride = 2LL * H * W;
   if (out_bstride == 0) out_bstride = (long long)C * H * W;
   const int threads = 256;
   const float sx = (float)(2.0 / (double)(W > 1 ? W - 1 : 1)), sy = (float)(2.0 / (double)(H > 1 ? H - 1 : 1));
+  RIB_REQUIRE(!flow_fp16 || (W % 4 == 0 && flow_bstride % 4 == 0 && out_bstride % 4 == 0 &&
+                             ((uintptr_t)flow_v & 7) == 0 && ((uintptr_t)out & 15) == 0),
+              "warp: half-precision flows need W % 4 == 0 and aligned frames");
   if (W % 4 == 0 && flow_bstride % 4 == 0 && out_bstride % 4 == 0 &&
-      (((uintptr_t)flow | (uintptr_t)out) & 15) == 0) {
+      (((uintptr_t)flow_v & (flow_fp16 ? 7 : 15)) | ((uintptr_t)out & 15)) == 0) {
     const size_t total4 = total / 4;
-    if (C == 3)
-      launch_pdl(warp4_kernel<3>, dim3((unsigned)((total4 + threads - 1) / threads)), dim3(threads), 0, s, src, flow, out, C, H, W,
-                 sx, sy, total4, src_bstride, flow_bstride, out_bstride);
-    else
-      launch_pdl(warp4_kernel<0>, dim3((unsigned)((total4 + threads - 1) / threads)), dim3(threads), 0, s, src, flow, out, C, H, W,
-                 sx, sy, total4, src_bstride, flow_bstride, out_bstride);
+    const dim3 grid((unsigned)((total4 + threads - 1) / threads)), block(threads);
+    if (flow_fp16) {
+      if (C == 3) launch_pdl(warp4_kernel<3, true>, grid, block, 0, s, src, flow_v, out, C, H, W, sx, sy, total4, src_bstride, flow_bstride, out_bstride);
+      else launch_pdl(warp4_kernel<0, true>, grid, block, 0, s, src, flow_v, out, C, H, W, sx, sy, total4, src_bstride, flow_bstride, out_bstride);
+    } else {
+      if (C == 3) launch_pdl(warp4_kernel<3, false>, grid, block, 0, s, src, flow_v, out, C, H, W, sx, sy, total4, src_bstride, flow_bstride, out_bstride);
+      else launch_pdl(warp4_kernel<0, false>, grid, block, 0, s, src, flow_v, out, C, H, W, sx, sy, total4, src_bstride, flow_bstride, out_bstride);
+    }
     RIB_CHECK_CUDA(cudaGetLastError());
     return 0;
   }

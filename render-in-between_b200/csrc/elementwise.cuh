@@ -62,8 +62,8 @@ int launch_resize_cubic_u8(const uint8_t* in, uint8_t* out, int B, int h, int w,
                            long long out_bstride, cudaStream_t s);
 int launch_frames_from_u8(const uint8_t* in, float* out, uint8_t* out_u8, int B, int H, int W, long long in_bstride,
                           long long out_bstride, long long u8_bstride, cudaStream_t s);
-int launch_warp(const float* src, const float* flow, float* out, int B, int C, int H, int W, long long src_bstride,
-                long long flow_bstride, long long out_bstride, cudaStream_t s);
+int launch_warp(const float* src, const void* flow, int flow_fp16, float* out, int B, int C, int H, int W,
+                long long src_bstride, long long flow_bstride, long long out_bstride, cudaStream_t s);
 
 // sigma_inv[0] = 1 / (u . (W v)),  W = [Cout, K] fp32 (torch.nn.utils.spectral_norm, eval mode).
 int launch_sn_sigma_inv(const float* w, const float* u, const float* v, int Cout, int K, float* sigma_inv,

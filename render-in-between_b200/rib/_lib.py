@@ -47,7 +47,7 @@ def _load():
     lib.rib_rasterize_workspace_bytes.restype = i64
     lib.rib_rasterize_workspace_bytes.argtypes = [i32, i32, i32]
     lib.rib_warp.restype = i32
-    lib.rib_warp.argtypes = [vp, vp, vp, i32, i32, i32, i32, i64, i64, i64, vp]
+    lib.rib_warp.argtypes = [vp, vp, i32, vp, i32, i32, i32, i32, i64, i64, i64, vp]
     lib.rib_composite.restype = i32
     lib.rib_composite.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i64, i64, i64, vp]
     lib.rib_resize_cubic_u8.restype = i32

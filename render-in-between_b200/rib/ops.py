@@ -73,10 +73,10 @@ def rasterize(joints, height, width, skeleton_thres=HSM_RASTER['skeleton_thres']
     return label
 
 
-def _frames(t, name, tail):
+def _frames(t, name, tail, dtypes=(torch.float32,)):
     """A float32 CUDA tensor [B, *tail] whose frames are dense but may be strided along dim 0 (t[s::r] views)."""
-    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32):
-        raise ValueError('%s must be a CUDA float32 tensor' % name)
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype in dtypes):
+        raise ValueError('%s must be a CUDA %s tensor' % (name, ' / '.join(str(d) for d in dtypes)))
     if tuple(t.shape[1:]) != tuple(tail):
         raise ValueError('%s: shape mismatch' % name)
     if t.shape[0] > 0 and not t[0].is_contiguous():
@@ -127,21 +127,22 @@ def frames_from_u8(frames, out=None, out_u8=None):
 
 def warp(src, flow, out=None):
     """Bilinear resample of src [B,C,H,W] by flow [B,2,H,W] (pixels), border padding (stage A3).
-    Both inputs may be strided along the frame dimension (e.g. flows[s::r]); `out`: optional dense destination."""
+    Both inputs may be strided along the frame dimension (e.g. flows[s::r]); `out`: optional dense destination.
+    flow may be float16 (converted exactly on load): the result equals warp(src, flow.float())."""
     if src.dim() != 4:
         raise ValueError('src must be [B, C, H, W]')
     b, c, h, w = src.shape
     src, src_bs = _frames(src, 'src', (c, h, w))
     if tuple(flow.shape) != (b, 2, h, w):
         raise ValueError('flow must be [B, 2, H, W]')
-    flow, flow_bs = _frames(flow, 'flow', (2, h, w))
+    flow, flow_bs = _frames(flow, 'flow', (2, h, w), (torch.float32, torch.float16))
     if out is None:
         out = torch.empty(b, c, h, w, dtype=torch.float32, device=src.device)
     elif not (out.is_cuda and out.dtype == torch.float32 and tuple(out.shape) == (b, c, h, w) and out.is_contiguous()):
         raise ValueError('warp: bad out tensor')
     with torch.cuda.device(src.device):
-        check(lib.rib_warp(src.data_ptr(), flow.data_ptr(), out.data_ptr(), b, c, h, w, src_bs, flow_bs, 0, _stream()),
-              'rib_warp')
+        check(lib.rib_warp(src.data_ptr(), flow.data_ptr(), 1 if flow.dtype == torch.float16 else 0, out.data_ptr(), b, c, h, w,
+                           src_bs, flow_bs, 0, _stream()), 'rib_warp')
     return out
 
 

@@ -365,3 +365,15 @@ def test_frames_from_u8_matches_to_tensor_norm(dev):
     clip = torch.zeros(2 * b, 3, h, w, device=dev)
     rib.frames_from_u8(u8.to(dev)[::2], out=clip[1::2][:3])
     assert torch.equal(clip[1::2][:3].cpu(), ref[::2]) and (clip[0::2] == 0).all()
+
+
+def test_warp_accepts_half_precision_flows(dev):
+    """rib.warp with a float16 flow == rib.warp with that flow converted to float32 (exact conversion on load),
+    dense and strided."""
+    import rib
+    from rib.synth import synth_flow, synth_image
+    b, h, w = 4, 64, 96
+    src = synth_image(b, h, w, seed=3).to(dev)
+    flow16 = synth_flow(2 * b, h, w, seed=4).to(dev).half()
+    assert torch.equal(rib.warp(src, flow16[:b].contiguous()), rib.warp(src, flow16[:b].float()))
+    assert torch.equal(rib.warp(src, flow16[1::2]), rib.warp(src, flow16[1::2].float().contiguous()))
