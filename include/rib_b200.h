@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RIB_ABI_VERSION 4
+#define RIB_ABI_VERSION 5
 
 /* Message of the last failing call on this host thread ("" if none). */
 const char* rib_last_error(void);
@@ -205,6 +205,14 @@ int rib_conv_test(const void* x, const float* w, const float* bias, void* out, d
 int rib_conv_test_ex(const void* x, const float* w, const float* bias, void* out, double* stats, int B, int Hin, int Win,
                      int Cin, int Cout, int k, int stride, int act, int subpix, const double* xf_stats, const float* xf_w,
                      const float* xf_b, int xf_act, void* scratch, void* stream);
+
+/* Stand-alone launch of the generator's AvgPool2d(3, stride 2, padding 1) pass (generator.py:203-208: the down-sampling
+ * between the SPADE blocks of the encoder) for unit tests:
+ *   x     16-bit chunk-planar [B][C/8][H][W][8] (C a multiple of 8, H and W even)
+ *   out   16-bit chunk-planar [B][C/8][H/2][W/2][8]: the fp32 window sums divided by 9 (zero padding counts), one rounding
+ *   stats [B][C][2] 64-bit fixed-point slots as above (may be NULL; accumulated into): sum / sum of squares of the
+ *         un-rounded pooled values, the instance-norm statistics of the next block */
+int rib_avgpool_test(const void* x, void* out, double* stats, int B, int H, int W, int C, void* stream);
 
 #ifdef __cplusplus
 }

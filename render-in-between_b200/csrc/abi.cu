@@ -214,4 +214,12 @@ int rib_conv_test_ex(const void* x, const float* w, const float* bias, void* out
   RIB_GUARD_END
 }
 
+int rib_avgpool_test(const void* x, void* out, double* stats, int B, int H, int W, int C, void* stream) {
+  RIB_GUARD_BEGIN
+  RIB_REQUIRE(x && out && B > 0 && H > 0 && W > 0 && C > 0, "rib_avgpool_test: bad argument");
+  return launch_avgpool3s2(static_cast<const act_t*>(x), (long long)C * H * W, static_cast<act_t*>(out),
+                           (long long)C * (H / 2) * (W / 2), stats, B, H, W, C, (cudaStream_t)stream);
+  RIB_GUARD_END
+}
+
 }  // extern "C"

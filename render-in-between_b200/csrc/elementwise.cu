@@ -269,53 +269,84 @@ int launch_in_apply(const InApplyParams& p, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// AvgPool 3x3 s2 p1 + statistics.  Grid = (x-blocks, channel plane, image): every thread of a block
-// works on the same 8 channels, so the statistics reduce with warp shuffles.
+// AvgPool 3x3 s2 p1 + statistics.  Grid = (strip blocks, channel plane, image): every thread of a block works on the same
+// 8 channels, so the statistics reduce with warp shuffles.  A warp owns a strip of kPoolR output rows x 31 output columns:
+// lane l > 0 produces column 31 * cg + l - 1 and loads its two centre / right input columns (32 contiguous bytes per
+// row); the left input column is the right column of lane l - 1 (one shuffle per 32-bit word; lane 0 only serves as
+// lane 1's left neighbour).  The horizontal sum of an odd input row is shared by the two output rows that touch it, so
+// an output costs 2.25 row loads of 32 bytes instead of nine 16-byte loads.
 // ---------------------------------------------------------------------------------------------
-__global__ void avgpool3s2_kernel(const act_t* __restrict__ src, long long src_bs, act_t* __restrict__ dst,
-                                  long long dst_bs, double* __restrict__ stats, int H, int W, int C) {
+static constexpr int kPoolR = 4;       // output rows per thread
+static constexpr int kPoolCols = 31;   // output columns per warp
+
+__global__ void __launch_bounds__(256) avgpool3s2_kernel(const act_t* __restrict__ src, long long src_bs,
+                                                         act_t* __restrict__ dst, long long dst_bs,
+                                                         double* __restrict__ stats, int H, int W, int C) {
   pdl_wait();   // programmatic dependent launch: nothing above depends on the previous kernel
   __shared__ float s_red[8][16];  // one slot per warp: fixed-order (deterministic) block reduction
   const int pl = blockIdx.y, n = blockIdx.z;
   const int Ho = H / 2, Wo = W / 2;
-  const act_t* sp = src + (size_t)n * src_bs + (size_t)pl * H * W * 8;
-  act_t* dp = dst + (size_t)n * dst_bs + (size_t)pl * Ho * Wo * 8;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ncg = (Wo + kPoolCols - 1) / kPoolCols, nrg = (Ho + kPoolR - 1) / kPoolR;
+  const int strip = blockIdx.x * 8 + warp;
+  const uint4* sp = reinterpret_cast<const uint4*>(src + (size_t)n * src_bs + (size_t)pl * H * W * 8);
+  uint4* dp = reinterpret_cast<uint4*>(dst + (size_t)n * dst_bs + (size_t)pl * Ho * Wo * 8);
   float t1[8], t2[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) t1[k] = t2[k] = 0.f;
-  const int npix = Ho * Wo;
-  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += gridDim.x * blockDim.x) {
-    const int oy = pix / Wo, ox = pix - oy * Wo;
-    float acc[8];
+  if (strip < ncg * nrg) {   // warp-uniform
+    const int cg = strip % ncg, rg = strip / ncg;
+    const int ox = cg * kPoolCols + lane - 1;
+    const bool ld_ok = ox >= 0 && ox < Wo, out_ok = lane > 0 && ox < Wo;
+    const int oy0 = rg * kPoolR;
+    constexpr int NR = 2 * kPoolR + 1;   // input rows 2 * oy0 - 1 ... 2 * oy0 + 2 * kPoolR - 1
+    uint4 v[NR][2];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-#pragma unroll
-    for (int dy = -1; dy <= 1; ++dy) {
-      const int iy = 2 * oy + dy;
-      if (iy < 0 || iy >= H) continue;
-#pragma unroll
-      for (int dx = -1; dx <= 1; ++dx) {
-        const int ix = 2 * ox + dx;
-        if (ix < 0 || ix >= W) continue;
-        const uint4 v = *reinterpret_cast<const uint4*>(sp + ((size_t)iy * W + ix) * 8);
-        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float a, b;
-          unpack2(u[k], a, b);
-          acc[2 * k] += a;
-          acc[2 * k + 1] += b;
-        }
+    for (int r = 0; r < NR; ++r) {
+      const int iy = 2 * oy0 - 1 + r;
+      v[r][0] = v[r][1] = make_uint4(0u, 0u, 0u, 0u);
+      if (ld_ok && iy >= 0 && iy < H) {
+        const uint4* rp = sp + (size_t)iy * W + 2 * ox;
+        v[r][0] = rp[0];
+        v[r][1] = rp[1];
       }
     }
+    auto hsum = [&](int r, float* h) {   // input columns 2 ox - 1, 2 ox, 2 ox + 1 of row r, added left to right
+      const uint32_t c0[4] = {v[r][0].x, v[r][0].y, v[r][0].z, v[r][0].w};
+      const uint32_t c1[4] = {v[r][1].x, v[r][1].y, v[r][1].z, v[r][1].w};
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      acc[k] = acc[k] / 9.0f;
-      t1[k] += acc[k];
-      t2[k] += acc[k] * acc[k];
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t lw = __shfl_up_sync(0xffffffffu, c1[k], 1);
+        float la, lb, ca, cb, ra, rb;
+        unpack2(lw, la, lb);
+        unpack2(c0[k], ca, cb);
+        unpack2(c1[k], ra, rb);
+        h[2 * k] = (la + ca) + ra;
+        h[2 * k + 1] = (lb + cb) + rb;
+      }
+    };
+    float h0[8], h1[8], h2[8];
+    hsum(0, h0);
+#pragma unroll
+    for (int o = 0; o < kPoolR; ++o) {
+      hsum(2 * o + 1, h1);
+      hsum(2 * o + 2, h2);
+      const int oy = oy0 + o;
+      const bool ok = out_ok && oy < Ho;
+      float acc[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        acc[k] = ((h0[k] + h1[k]) + h2[k]) / 9.0f;
+        h0[k] = h2[k];
+        if (ok) {
+          t1[k] += acc[k];
+          t2[k] += acc[k] * acc[k];
+        }
+      }
+      if (ok)
+        dp[(size_t)oy * Wo + ox] =
+            make_uint4(pack2(acc[0], acc[1]), pack2(acc[2], acc[3]), pack2(acc[4], acc[5]), pack2(acc[6], acc[7]));
     }
-    *reinterpret_cast<uint4*>(dp + (size_t)pix * 8) =
-        make_uint4(pack2(acc[0], acc[1]), pack2(acc[2], acc[3]), pack2(acc[4], acc[5]), pack2(acc[6], acc[7]));
   }
   if (stats != nullptr) {
 #pragma unroll
@@ -326,11 +357,11 @@ __global__ void avgpool3s2_kernel(const act_t* __restrict__ src, long long src_b
         t2[k] += __shfl_xor_sync(0xffffffffu, t2[k], off);
       }
     }
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        s_red[threadIdx.x >> 5][k] = t1[k];
-        s_red[threadIdx.x >> 5][8 + k] = t2[k];
+        s_red[warp][k] = t1[k];
+        s_red[warp][8 + k] = t2[k];
       }
     }
     __syncthreads();
@@ -347,12 +378,10 @@ __global__ void avgpool3s2_kernel(const act_t* __restrict__ src, long long src_b
 int launch_avgpool3s2(const act_t* src, long long src_bs, act_t* dst, long long dst_bs, double* stats, int B, int H,
                       int W, int C, cudaStream_t s) {
   RIB_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "avgpool: bad shape");
-  const int npix = (H / 2) * (W / 2);
-  const int threads = 256;
-  unsigned gx = (unsigned)((npix + threads * 4 - 1) / (threads * 4));
-  if (gx < 1) gx = 1;
-  dim3 grid(gx, (unsigned)(C / 8), (unsigned)B);
-  launch_pdl(avgpool3s2_kernel, grid, dim3(threads), 0, s, src, src_bs, dst, dst_bs, stats, H, W, C);
+  const int Ho = H / 2, Wo = W / 2;
+  const int nstrips = ((Wo + kPoolCols - 1) / kPoolCols) * ((Ho + kPoolR - 1) / kPoolR);
+  dim3 grid((unsigned)((nstrips + 7) / 8), (unsigned)(C / 8), (unsigned)B);
+  launch_pdl(avgpool3s2_kernel, grid, dim3(256), 0, s, src, src_bs, dst, dst_bs, stats, H, W, C);
   RIB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -667,6 +696,78 @@ __global__ void warp4_kernel(const float* __restrict__ src, const void* __restri
   }
 }
 
+
+// One pixel per lane, four pixels (32 apart) per thread: the four neighbour gathers of a warp touch one or two cache lines
+// each (consecutive lanes read consecutive source pixels displaced by a smooth flow), where the four-consecutive-pixels
+// form above spreads every gather instruction over five lines and is bound by the L1 wavefront rate.  Needs
+// H * W % 128 == 0 (a group of 128 pixels never straddles two frames).  Same float sequence per pixel as warp_kernel.
+template <int CT, bool FH>
+__global__ void __launch_bounds__(256) warp_px_kernel(const float* __restrict__ src, const void* __restrict__ flow_v,
+                                                      float* __restrict__ out, int Crt, int H, int W, float sx, float sy,
+                                                      size_t ngroups, long long src_bs, long long flow_bs,
+                                                      long long out_bs) {
+  pdl_wait();   // programmatic dependent launch: nothing above depends on the previous kernel
+  const size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // group of 128 pixels (one warp)
+  if (g >= ngroups) return;
+  const int lane = threadIdx.x & 31;
+  const int HW = H * W, gpf = HW >> 7;
+  const size_t n = g / gpf;
+  const int hw0 = (int)(g - n * gpf) * 128 + lane;
+  float fxs[4], fys[4];
+  if (FH) {
+    const __half* flow = static_cast<const __half*>(flow_v) + n * flow_bs;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      fxs[p] = __half2float(flow[hw0 + 32 * p]);
+      fys[p] = __half2float(flow[(size_t)HW + hw0 + 32 * p]);
+    }
+  } else {
+    const float* flow = static_cast<const float*>(flow_v) + n * flow_bs;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      fxs[p] = __ldg(flow + hw0 + 32 * p);
+      fys[p] = __ldg(flow + (size_t)HW + hw0 + 32 * p);
+    }
+  }
+  int o00[4], dx1[4], dy1[4];
+  float wnw[4], wne[4], wsw[4], wse[4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int hw = hw0 + 32 * p;
+    const int y = hw / W, x = hw - y * W;
+    const float gx = __fsub_rn(__fmul_rn(__fadd_rn((float)x, fxs[p]), sx), 1.0f);
+    const float gy = __fsub_rn(__fmul_rn(__fadd_rn((float)y, fys[p]), sy), 1.0f);
+    float ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.0f), 0.5f), (float)(W - 1));
+    float iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.0f), 0.5f), (float)(H - 1));
+    ix = fminf(fmaxf(ix, 0.f), (float)(W - 1));
+    iy = fminf(fmaxf(iy, 0.f), (float)(H - 1));
+    const float x0f = floorf(ix), y0f = floorf(iy);
+    const int x0 = (int)x0f, y0 = (int)y0f;
+    const float tx = ix - x0f, ty = iy - y0f;
+    wnw[p] = (1.f - tx) * (1.f - ty), wne[p] = tx * (1.f - ty), wsw[p] = (1.f - tx) * ty, wse[p] = tx * ty;
+    o00[p] = y0 * W + x0;
+    dx1[p] = x0 + 1 < W ? 1 : -1;   // -1: neighbour outside the image (its weight is an exact 0 then; term skipped)
+    dy1[p] = y0 + 1 < H ? W : -1;
+  }
+  const int C = CT > 0 ? CT : Crt;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const float* s = src + n * src_bs + (size_t)c * HW;
+    float acc[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      float a = __ldg(s + o00[p]) * wnw[p];
+      if (dx1[p] > 0) a += __ldg(s + o00[p] + 1) * wne[p];
+      if (dy1[p] > 0) a += __ldg(s + o00[p] + W) * wsw[p];
+      if (dx1[p] > 0 && dy1[p] > 0) a += __ldg(s + o00[p] + W + 1) * wse[p];
+      acc[p] = a;
+    }
+    float* o = out + n * out_bs + (size_t)c * HW + hw0;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) o[32 * p] = acc[p];
+  }
+}
+
 int launch_warp(const float* src, const void* flow_v, int flow_fp16, float* out, int B, int C, int H, int W,
                 long long src_bstride, long long flow_bstride, long long out_bstride, cudaStream_t s) {
   const float* flow = static_cast<const float*>(flow_v);
@@ -679,6 +780,19 @@ int launch_warp(const float* src, const void* flow_v, int flow_fp16, float* out,
   RIB_REQUIRE(!flow_fp16 || (W % 4 == 0 && flow_bstride % 4 == 0 && out_bstride % 4 == 0 &&
                              ((uintptr_t)flow_v & 7) == 0 && ((uintptr_t)out & 15) == 0),
               "warp: half-precision flows need W % 4 == 0 and aligned frames");
+  if (((size_t)H * W) % 128 == 0) {
+    const size_t ngroups = total / 128;
+    const dim3 grid((unsigned)((ngroups * 32 + threads - 1) / threads)), block(threads);
+    if (flow_fp16) {
+      if (C == 3) launch_pdl(warp_px_kernel<3, true>, grid, block, 0, s, src, flow_v, out, C, H, W, sx, sy, ngroups, src_bstride, flow_bstride, out_bstride);
+      else launch_pdl(warp_px_kernel<0, true>, grid, block, 0, s, src, flow_v, out, C, H, W, sx, sy, ngroups, src_bstride, flow_bstride, out_bstride);
+    } else {
+      if (C == 3) launch_pdl(warp_px_kernel<3, false>, grid, block, 0, s, src, flow_v, out, C, H, W, sx, sy, ngroups, src_bstride, flow_bstride, out_bstride);
+      else launch_pdl(warp_px_kernel<0, false>, grid, block, 0, s, src, flow_v, out, C, H, W, sx, sy, ngroups, src_bstride, flow_bstride, out_bstride);
+    }
+    RIB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (W % 4 == 0 && flow_bstride % 4 == 0 && out_bstride % 4 == 0 &&
       (((uintptr_t)flow_v & (flow_fp16 ? 7 : 15)) | ((uintptr_t)out & 15)) == 0) {
     const size_t total4 = total / 4;

@@ -60,7 +60,8 @@ struct FrameScratch {
   short f[kEdges][kMaxDim];
   EdgeMeta edge[kEdges];
   JointMeta joint[kJoints];
-  unsigned char flag[kEdges][kKeys];
+  unsigned char flag[kEdges][kKeys];         // end-cap stamps (keys >= kBodyKeys): "hit an older pixel"
+  unsigned long long bodyflag[kEdges];       // the same flag of the 64 body stamps of a limb, bit = key
   float win[kJoints][kWin];
 };
 
@@ -86,8 +87,8 @@ __constant__ unsigned char c_colors[kEdges][3] = {{153, 0, 51}, {153, 0, 0}, {15
                                                   {0, 208, 0}, {0, 208, 208}, {0, 0, 208}};
 
 // ---------------------------------------------------------------------------------------------
-// prep: grid (20, B).  blockIdx.x < 19: the 41x41 response window of joint blockIdx.x (already divided
-// by its maximum); blockIdx.x == 19: limb tables.
+// prep: grid (19 + 18, B).  blockIdx.x < 19: the 41x41 response window of joint blockIdx.x (already divided
+// by its maximum); blockIdx.x >= 19: the table of limb blockIdx.x - 19.
 // ---------------------------------------------------------------------------------------------
 __device__ void heat_window(const double* __restrict__ jp, const GaussTable& tab, double thres, FrameScratch* fs, int j,
                             int H, int W) {
@@ -156,9 +157,10 @@ __device__ void heat_window(const double* __restrict__ jp, const GaussTable& tab
 }
 
 __device__ void limb_tables(const double* __restrict__ joints, double thres, double foot_thres, FrameScratch* fs, int H,
-                            int W) {
+                            int W, int e) {
   __shared__ double s_pts[kJoints][2];
-  for (int i = threadIdx.x; i < kEdges * kKeys; i += blockDim.x) (&fs->flag[0][0])[i] = 0;
+  for (int i = threadIdx.x; i < kKeys; i += blockDim.x) fs->flag[e][i] = 0;
+  if (threadIdx.x == 0) fs->bodyflag[e] = 0ull;
   if (threadIdx.x < kJoints) {  // extract_valid_keypoints (keypoint2img.py:114-130)
     const double* jp = joints + threadIdx.x * 3;
     const int i = threadIdx.x;
@@ -169,7 +171,7 @@ __device__ void limb_tables(const double* __restrict__ joints, double thres, dou
     s_pts[i][1] = ok ? y : 0.0;
   }
   __syncthreads();
-  for (int e = 0; e < kEdges; ++e) {
+  {
     EdgeMeta m;
     memset(&m, 0, sizeof(m));
     const double xa = s_pts[c_edges[e][0]][0], ya = s_pts[c_edges[e][0]][1];
@@ -199,7 +201,7 @@ __device__ void limb_tables(const double* __restrict__ joints, double thres, dou
     }
     if (!draw) {
       if (threadIdx.x == 0) fs->edge[e] = m;
-      continue;
+      return;
     }
     const int dim = swap ? H : W;
     for (int i = threadIdx.x; i < dim; i += blockDim.x) fs->f[e][i] = -1;
@@ -235,18 +237,18 @@ __device__ void limb_tables(const double* __restrict__ joints, double thres, dou
       m.b = (float)icpt;
       fs->edge[e] = m;
     }
-    __syncthreads();
   }
 }
 
 __global__ void __launch_bounds__(256) raster_prep_kernel(const double* __restrict__ joints, GaussTable tab, double thres,
                                                           double foot_thres, FrameScratch* __restrict__ scratch, int H,
                                                           int W) {
+  pdl_wait();   // programmatic dependent launch: nothing above depends on the previous kernel
   const int b = blockIdx.y;
   FrameScratch* fs = scratch + b;
   const double* jf = joints + (size_t)b * kJoints * 3;
   if (blockIdx.x < kJoints) heat_window(jf + blockIdx.x * 3, tab, thres, fs, blockIdx.x, H, W);
-  else limb_tables(jf, thres, foot_thres, fs, H, W);
+  else limb_tables(jf, thres, foot_thres, fs, H, W, blockIdx.x - kJoints);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -265,9 +267,11 @@ __device__ __forceinline__ void src_range(int v, int shift, int n, int* lo, int*
   }
 }
 
-template <typename Visit>
+// Hands the 64-bit set of body stamps of the limb that touch (y, x) (bit = key = stamp order) to `body`, then visits the
+// end-cap stamps, which come after all body stamps of the limb, in order.
+template <typename Body, typename Visit>
 __device__ __forceinline__ void visit_limb(const EdgeMeta& m, const short* __restrict__ f, int y, int x, int H, int W,
-                                           Visit&& visit) {
+                                           Body&& body, Visit&& visit) {
   const bool interior = x > 0 && x < W - 1 && y > 0 && y < H - 1;
   unsigned long long mask = 0ull;
   if (interior) {
@@ -305,17 +309,7 @@ __device__ __forceinline__ void visit_limb(const EdgeMeta& m, const short* __res
       }
     }
   }
-  uint32_t mlo32 = (uint32_t)mask, mhi32 = (uint32_t)(mask >> 32);
-  while (mlo32) {
-    const int bit = __ffs((int)mlo32) - 1;
-    mlo32 &= mlo32 - 1;
-    visit(bit);
-  }
-  while (mhi32) {
-    const int bit = __ffs((int)mhi32) - 1;
-    mhi32 &= mhi32 - 1;
-    visit(32 + bit);
-  }
+  body(mask);
   // end caps (keypoint2img.py:59-64): stamps (i, j), i outer, both end points in one stamp
   if (interior) {
     int k0 = -1, k1 = -1;
@@ -369,6 +363,22 @@ __device__ __forceinline__ uint32_t avg_color(uint32_t old, uint32_t col) {
   const uint32_t g = ((((old >> 8) & 0xffu) + ((col >> 8) & 0xffu)) >> 1);
   const uint32_t b = ((((old >> 16) & 0xffu) + ((col >> 16) & 0xffu)) >> 1);
   return r | (g << 8) | (b << 16);
+}
+
+// m more stamps of the same colour on a touched pixel: ((v + c) >> 1 applied m times) == (v + (2^m - 1) c) >> m per
+// channel, because floor(floor(a / 2) + c) / 2) == floor((a + 2 c) / 4) for integers; m is split into steps of at most 16
+// (255 * 65535 + 255 fits in 32 bits).
+__device__ __forceinline__ uint32_t avg_color_n(uint32_t old, uint32_t col, int m) {
+  while (m > 0) {
+    const int t = m < 16 ? m : 16;
+    const uint32_t k = (1u << t) - 1u;
+    const uint32_t r = ((old & 0xffu) + k * (col & 0xffu)) >> t;
+    const uint32_t g = (((old >> 8) & 0xffu) + k * ((col >> 8) & 0xffu)) >> t;
+    const uint32_t b = (((old >> 16) & 0xffu) + k * ((col >> 16) & 0xffu)) >> t;
+    old = r | (g << 8) | (b << 16);
+    m -= t;
+  }
+  return old;
 }
 
 // Tile of 8 rows x 128 columns per CTA (256 threads x 4 consecutive pixels).
@@ -455,6 +465,7 @@ __global__ void __launch_bounds__(256) raster_mark_kernel(FrameScratch* __restri
                                                           unsigned long long* __restrict__ cache, int H, int W) {
   __shared__ TileEdges te;
   __shared__ EdgeMeta s_meta[kEdges];
+  pdl_wait();
   FrameScratch* fs = scratch + blockIdx.z;
   const int y0 = blockIdx.y * kTileRows, x0 = blockIdx.x * kTileCols;
   tile_edges(fs, y0, x0, H, W, &te, s_meta);
@@ -477,21 +488,50 @@ __global__ void __launch_bounds__(256) raster_mark_kernel(FrameScratch* __restri
     for (int k = 0; k < te.n; ++k) {
       const int lo = __shfl_sync(0xffffffffu, my_lo, k), hi = __shfl_sync(0xffffffffu, my_hi, k);
       if (xs + 31 < lo || xs > hi) continue;   // uniform
-      if (x < lo || x > hi || x >= W) continue;
-      const EdgeMeta& m = s_meta[k];
       const int e = te.idx[k];
-      const uint32_t col = (uint32_t)c_colors[e][0] | ((uint32_t)c_colors[e][1] << 8) | ((uint32_t)c_colors[e][2] << 16);
-      visit_limb(m, fs->f[e], y, x, H, W, [&](int key) {
-        if (count++ == 0) {
-          first = (uint32_t)e | ((uint32_t)key << 5);
-          ca = col;
-          cb = avg_color(0u, col);
-        } else {
-          fs->flag[e][key] = 1;
-          ca = avg_color(ca, col);
-          cb = avg_color(cb, col);
-        }
-      });
+      unsigned long long older = 0ull;         // body stamps of limb e that are not this pixel's first stamp
+      if (x >= lo && x <= hi && x < W) {
+        const EdgeMeta& m = s_meta[k];
+        const uint32_t col = (uint32_t)c_colors[e][0] | ((uint32_t)c_colors[e][1] << 8) | ((uint32_t)c_colors[e][2] << 16);
+        auto visit = [&](int key) {            // one end-cap stamp
+          if (count++ == 0) {
+            first = (uint32_t)e | ((uint32_t)key << 5);
+            ca = col;
+            cb = avg_color(0u, col);
+          } else {
+            fs->flag[e][key] = 1;
+            ca = avg_color(ca, col);
+            cb = avg_color(cb, col);
+          }
+        };
+        // The body stamps come first, in key order; all of them carry the limb's colour, so the averaging chain of the
+        // nb - (first ? 1 : 0) stamps that land on an already touched pixel has a closed form.
+        auto apply_body = [&](unsigned long long mask) {
+          const int nb = __popcll(mask);
+          if (nb == 0) return;
+          int more = nb;
+          older = mask;
+          if (count == 0) {
+            const int bit = __ffsll((long long)mask) - 1;
+            first = (uint32_t)e | ((uint32_t)bit << 5);
+            ca = col;
+            cb = avg_color(0u, col);
+            older = mask & (mask - 1ull);
+            more = nb - 1;
+          }
+          ca = avg_color_n(ca, col, more);
+          cb = avg_color_n(cb, col, more);
+          count += nb;
+        };
+        visit_limb(m, fs->f[e], y, x, H, W, apply_body, visit);
+      }
+      // one atomic per limb and segment: the union of the lanes' sets (most are known already)
+      const uint32_t olo = __reduce_or_sync(0xffffffffu, (uint32_t)older);
+      const uint32_t ohi = __reduce_or_sync(0xffffffffu, (uint32_t)(older >> 32));
+      if (lane == 0) {
+        const unsigned long long u = (unsigned long long)olo | ((unsigned long long)ohi << 32);
+        if (u & ~fs->bodyflag[e]) atomicOr(&fs->bodyflag[e], u);
+      }
     }
     if (x < W)
       crow[x] = count > 0 ? (unsigned long long)ca | ((unsigned long long)cb << 24) | ((unsigned long long)first << 48) | (1ull << 63)
@@ -508,16 +548,29 @@ __global__ void __launch_bounds__(256) raster_paint_kernel(const FrameScratch* _
   __shared__ EdgeMeta s_meta[kEdges];
   __shared__ JointMeta s_joint[kJoints];
   __shared__ float s_lut[256];
+  __shared__ unsigned s_jmask;
+  pdl_wait();
   const int b = blockIdx.z;
   const FrameScratch* fs = scratch + b;
   const int y0 = blockIdx.y * kTileRows, x0 = blockIdx.x * kTileCols;
   // ToTensor: float32(v) / 255, Normalize: (t - 0.5) / 0.5, both in fp32
   s_lut[threadIdx.x] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)threadIdx.x, 255.0f), 0.5f), 0.5f);
-  if (threadIdx.x < kJoints) s_joint[threadIdx.x] = fs->joint[threadIdx.x];
+  if (threadIdx.x < 32) {   // joints whose 41x41 window reaches this tile (bit j of s_jmask); the others are never tested
+    bool in = false;
+    if (threadIdx.x < kJoints) {
+      const JointMeta jm = fs->joint[threadIdx.x];
+      s_joint[threadIdx.x] = jm;
+      in = jm.valid && jm.ix + kRadius >= x0 && jm.ix - kRadius < x0 + kTileCols && jm.iy + kRadius >= y0 &&
+           jm.iy - kRadius < y0 + kTileRows;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, in);
+    if (threadIdx.x == 0) s_jmask = bal;
+  }
   tile_edges(const_cast<FrameScratch*>(fs), y0, x0, H, W, &te, s_meta);
   const int y = y0 + (threadIdx.x >> 5);
   const int xb = x0 + (threadIdx.x & 31) * kPxPerThread;
   if (y >= H || xb >= W) return;
+  const unsigned jmask = s_jmask;   // (written before the barrier inside tile_edges)
   uint32_t rgb[kPxPerThread];
 #pragma unroll
   for (int p = 0; p < kPxPerThread; ++p) rgb[p] = 0u;
@@ -535,7 +588,8 @@ __global__ void __launch_bounds__(256) raster_paint_kernel(const FrameScratch* _
     for (int p = 0; p < kPxPerThread; ++p) {
       if (!(word[p] >> 63)) continue;
       const uint32_t first = (uint32_t)(word[p] >> 48) & 0x7fffu;
-      const bool hit_older = fs->flag[first & 31u][first >> 5] != 0;
+      const uint32_t fe = first & 31u, fkey = first >> 5;
+      const bool hit_older = fkey < (uint32_t)kBodyKeys ? ((fs->bodyflag[fe] >> fkey) & 1ull) != 0ull : fs->flag[fe][fkey] != 0;
       rgb[p] = (uint32_t)(hit_older ? word[p] >> 24 : word[p]) & 0xffffffu;
     }
   }
@@ -557,11 +611,10 @@ __global__ void __launch_bounds__(256) raster_paint_kernel(const FrameScratch* _
         float h = 0.f;
         if (c < 3) {
           h = s_lut[(rgb[p] >> (8 * c)) & 0xffu];
-        } else if (c < 22) {
+        } else if (c < 22 && ((jmask >> (c - 3)) & 1u)) {   // (uniform over the block)
           const JointMeta jm = s_joint[c - 3];
           const int wy = y - jm.iy + kRadius, wx = xb + p - jm.ix + kRadius;
-          if (jm.valid && (unsigned)wy < (unsigned)kTaps && (unsigned)wx < (unsigned)kTaps)
-            h = fs->win[c - 3][wy * kTaps + wx];
+          if ((unsigned)wy < (unsigned)kTaps && (unsigned)wx < (unsigned)kTaps) h = fs->win[c - 3][wy * kTaps + wx];
         }
         v[k][p] = h;
       }
@@ -596,12 +649,14 @@ int launch_rasterize(const double* joints_dev, int B, int H, int W, const double
   for (int i = 0; i < kTaps; ++i) tab.w[i] = wtab41_host[i];
   FrameScratch* fs = static_cast<FrameScratch*>(workspace);
   unsigned long long* cache = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(workspace) + scratch_bytes(B));
-  raster_prep_kernel<<<dim3(kJoints + 1, B), 256, 0, stream>>>(joints_dev, tab, skeleton_thres, foot_thres, fs, H, W);
+  launch_pdl(raster_prep_kernel, dim3(kJoints + kEdges, B), dim3(256), 0, stream, joints_dev, tab, skeleton_thres, foot_thres,
+             fs, H, W);
   RIB_CHECK_CUDA(cudaGetLastError());
   const dim3 grid(ceil_div(W, kTileCols), ceil_div(H, kTileRows), B);
-  raster_mark_kernel<<<grid, 256, 0, stream>>>(fs, cache, H, W);
+  launch_pdl(raster_mark_kernel, grid, dim3(256), 0, stream, fs, cache, H, W);
   RIB_CHECK_CUDA(cudaGetLastError());
-  raster_paint_kernel<<<grid, 256, 0, stream>>>(fs, cache, label, label_planar, H, W);
+  launch_pdl(raster_paint_kernel, grid, dim3(256), 0, stream, static_cast<const FrameScratch*>(fs),
+             static_cast<const unsigned long long*>(cache), label, label_planar, H, W);
   RIB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -17,7 +17,7 @@ SYMBOLS = [
     'rib_debug_set_simt', 'rib_debug_get_simt', 'rib_generator_debug_tensor', 'rib_generator_plan_text', 'rib_act_is_fp16',
     'rib_conv_test_scratch_bytes', 'rib_conv_test', 'rib_profile_enable', 'rib_profile_collect', 'rib_profile_collect_launches',
     'rib_tune_log', 'rib_tune_export', 'rib_tune_import', 'rib_conv_test_ex',
-    'rib_plan_dry_run', 'rib_frames_from_u8', 'rib_resize_cubic_u8',
+    'rib_plan_dry_run', 'rib_frames_from_u8', 'rib_resize_cubic_u8', 'rib_avgpool_test',
 ]
 
 
@@ -92,6 +92,8 @@ def _load():
     lib.rib_plan_dry_run.argtypes = [C.POINTER(GenConfig), i32, i32, i32, C.POINTER(i64), C.c_char_p, i64]
     lib.rib_conv_test_ex.restype = i32
     lib.rib_conv_test_ex.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp]
+    lib.rib_avgpool_test.restype = i32
+    lib.rib_avgpool_test.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
     return lib
 
 

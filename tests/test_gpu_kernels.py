@@ -87,11 +87,13 @@ def test_composite_matches_oracle(dev):
 
 
 # ---------------------------------------------------------------- A3 warp
-def test_warp_matches_grid_sample(dev):
+@pytest.mark.parametrize('shape', [(64, 96), (20, 28), (9, 7)], ids=['px128', 'four', 'scalar'])
+def test_warp_matches_grid_sample(dev, shape):
+    """The three forms of the kernel: one pixel per lane (H * W % 128 == 0), four pixels per thread (W % 4 == 0), scalar."""
     import rib
-    b, h, w = 2, 64, 96
-    src = synth_image(b, h, w, seed=5)
-    flow = synth_flow(b, h, w, seed=5, max_px=8.0)
+    b, (h, w) = 2, shape
+    src = synth_image(b, max(h, 16), max(w, 16), seed=5)[:, :, :h, :w].contiguous()
+    flow = synth_flow(b, max(h, 64), max(w, 64), seed=5, max_px=8.0)[:, :, :h, :w].contiguous()
     flow[0, :, :4, :4] = 50.0          # far out of range -> border clamp
     flow[1, :, -4:, -4:] = -50.0
     ref = go.warp(src, flow)
@@ -377,3 +379,32 @@ def test_warp_accepts_half_precision_flows(dev):
     flow16 = synth_flow(2 * b, h, w, seed=4).to(dev).half()
     assert torch.equal(rib.warp(src, flow16[:b].contiguous()), rib.warp(src, flow16[:b].float()))
     assert torch.equal(rib.warp(src, flow16[1::2]), rib.warp(src, flow16[1::2].float().contiguous()))
+
+
+# ---------------------------------------------------------------- AvgPool2d(3, 2, 1) between the encoder blocks
+@pytest.mark.parametrize('case', [(2, 16, 16, 16), (1, 8, 64, 96), (3, 32, 12, 6), (1, 64, 128, 128), (2, 8, 2, 2),
+                                  (1, 16, 256, 512)], ids=lambda c: 'B%d_C%d_%dx%d' % c)
+def test_avgpool_matches_avg_pool2d(dev, case):
+    """generator.py:203-208 (`AvgPool2d(3, stride=2, padding=1)`, zero padding counted): the strip kernel against
+    F.avg_pool2d on the same 16-bit inputs; outputs within one 16-bit rounding (the summation order differs), statistics
+    of the un-rounded pooled values against float64."""
+    from rib._lib import check, lib
+    b, c, h, w = case
+    dt = _act_dtype()
+    g = torch.Generator().manual_seed(c * 7 + h + w)
+    x = (torch.randn(b, c, h, w, generator=g) * 2.0 + 0.3).to(dt)
+    ref = F.avg_pool2d(x.double(), 3, 2, 1)
+    xp = to_planar(x.float(), dt).to(dev)
+    out = torch.full((b, c // 8, h // 2, w // 2, 8), float('nan'), dtype=dt, device=dev)
+    stats = torch.zeros(b, c, 2, dtype=torch.float64, device=dev)
+    for want_stats in (True, False):
+        check(lib.rib_avgpool_test(xp.data_ptr(), out.data_ptr(), stats.data_ptr() if want_stats else None, b, h, w, c,
+                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)), 'rib_avgpool_test')
+        torch.cuda.synchronize()
+        got = from_planar(out.float().cpu()).double()
+        ulp = 2.0 ** -7 if dt == torch.bfloat16 else 2.0 ** -10   # one unit in the last place, relative
+        assert torch.isfinite(got).all()
+        assert ((got - ref).abs() <= ulp * ref.abs() + 1e-6).all(), float((got - ref).abs().max())
+    st = _decode_stats(stats.cpu())
+    assert torch.allclose(st[..., 0], ref.sum(dim=(2, 3)), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(st[..., 1], (ref * ref).sum(dim=(2, 3)), rtol=1e-5, atol=1e-3)
