@@ -269,83 +269,97 @@ int launch_in_apply(const InApplyParams& p, cudaStream_t s) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// AvgPool 3x3 s2 p1 + statistics.  Grid = (strip blocks, channel plane, image): every thread of a block works on the same
-// 8 channels, so the statistics reduce with warp shuffles.  A warp owns a strip of kPoolR output rows x 31 output columns:
-// lane l > 0 produces column 31 * cg + l - 1 and loads its two centre / right input columns (32 contiguous bytes per
-// row); the left input column is the right column of lane l - 1 (one shuffle per 32-bit word; lane 0 only serves as
-// lane 1's left neighbour).  The horizontal sum of an odd input row is shared by the two output rows that touch it, so
-// an output costs 2.25 row loads of 32 bytes instead of nine 16-byte loads.
+// AvgPool 3x3 s2 p1 + statistics.  Grid = (row bands, channel plane, image).  The 2 RB + 1 input rows behind a band of RB
+// output rows are contiguous in a plane ([H][W][8]), so one bulk copy (cp.async.bulk, completion on an mbarrier) stages
+// them in shared memory: no register staging and no L1 pressure for the 2.25x overlap of the 3x3 windows, and the copies
+// of the other resident blocks run under this block's arithmetic.  A thread then produces kPoolR consecutive output rows of
+// one column; the horizontal sum of an odd input row is shared by the two output rows that touch it.  Every thread of a
+// block works on the same 8 channels, so the statistics reduce with warp shuffles.
 // ---------------------------------------------------------------------------------------------
-static constexpr int kPoolR = 4;       // output rows per thread
-static constexpr int kPoolCols = 31;   // output columns per warp
+static constexpr int kPoolR = 4;                       // output rows per thread
+static constexpr int kPoolSmemTarget = 72 * 1024;      // bytes of staged rows per block (three blocks per SM)
+
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ float div9(float a) {   // a / 9 (reciprocal, one Newton step on the remainder)
+  const float r9 = 1.0f / 9.0f;
+  const float q = a * r9;
+  return fmaf(fmaf(-q, 9.0f, a), r9, q);
+}
 
 __global__ void __launch_bounds__(256) avgpool3s2_kernel(const act_t* __restrict__ src, long long src_bs,
                                                          act_t* __restrict__ dst, long long dst_bs,
-                                                         double* __restrict__ stats, int H, int W, int C) {
-  pdl_wait();   // programmatic dependent launch: nothing above depends on the previous kernel
+                                                         double* __restrict__ stats, int H, int W, int C, int RB) {
+  extern __shared__ __align__(128) uint8_t pool_smem[];   // [2 RB + 1][W] 16-byte vectors; row 0 = input row 2 oy0 - 1
+  __shared__ __align__(8) uint64_t s_bar;
   __shared__ float s_red[8][16];  // one slot per warp: fixed-order (deterministic) block reduction
   const int pl = blockIdx.y, n = blockIdx.z;
   const int Ho = H / 2, Wo = W / 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int ncg = (Wo + kPoolCols - 1) / kPoolCols, nrg = (Ho + kPoolR - 1) / kPoolR;
-  const int strip = blockIdx.x * 8 + warp;
+  const int oy0 = blockIdx.x * RB;
+  const int rb = min(RB, Ho - oy0);                       // output rows of this band
+  const int iy_lo = 2 * oy0 - 1, row_lo = max(iy_lo, 0), row_hi = 2 * (oy0 + rb);   // input rows [row_lo, row_hi)
+  uint4* tile = reinterpret_cast<uint4*>(pool_smem);
   const uint4* sp = reinterpret_cast<const uint4*>(src + (size_t)n * src_bs + (size_t)pl * H * W * 8);
   uint4* dp = reinterpret_cast<uint4*>(dst + (size_t)n * dst_bs + (size_t)pl * Ho * Wo * 8);
+  const uint32_t bar = smem_u32(&s_bar);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  if (iy_lo < 0)   // the padding row above the image
+    for (int i = threadIdx.x; i < W; i += blockDim.x) tile[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  pdl_wait();   // programmatic dependent launch: nothing above depends on the previous kernel
+  if (threadIdx.x == 0) {
+    const uint32_t bytes = (uint32_t)(row_hi - row_lo) * (uint32_t)W * 16u;
+    mbar_arrive_expect_tx(bar, bytes);
+    bulk_load_1d(smem_u32(tile + (size_t)(row_lo - iy_lo) * W), sp + (size_t)row_lo * W, bytes, bar);
+  }
+  mbar_wait(bar, 0);
   float t1[8], t2[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) t1[k] = t2[k] = 0.f;
-  if (strip < ncg * nrg) {   // warp-uniform
-    const int cg = strip % ncg, rg = strip / ncg;
-    const int ox = cg * kPoolCols + lane - 1;
-    const bool ld_ok = ox >= 0 && ox < Wo, out_ok = lane > 0 && ox < Wo;
-    const int oy0 = rg * kPoolR;
-    constexpr int NR = 2 * kPoolR + 1;   // input rows 2 * oy0 - 1 ... 2 * oy0 + 2 * kPoolR - 1
-    uint4 v[NR][2];
-#pragma unroll
-    for (int r = 0; r < NR; ++r) {
-      const int iy = 2 * oy0 - 1 + r;
-      v[r][0] = v[r][1] = make_uint4(0u, 0u, 0u, 0u);
-      if (ld_ok && iy >= 0 && iy < H) {
-        const uint4* rp = sp + (size_t)iy * W + 2 * ox;
-        v[r][0] = rp[0];
-        v[r][1] = rp[1];
-      }
-    }
-    auto hsum = [&](int r, float* h) {   // input columns 2 ox - 1, 2 ox, 2 ox + 1 of row r, added left to right
-      const uint32_t c0[4] = {v[r][0].x, v[r][0].y, v[r][0].z, v[r][0].w};
-      const uint32_t c1[4] = {v[r][1].x, v[r][1].y, v[r][1].z, v[r][1].w};
+  const int nstrip = ((rb + kPoolR - 1) / kPoolR) * Wo;
+  for (int s = threadIdx.x; s < nstrip; s += blockDim.x) {
+    const int sub = s / Wo, ox = s - sub * Wo;
+    const int o0 = sub * kPoolR;                         // first output row of the strip, relative to the band
+    const uint4* col = tile + (size_t)(2 * o0) * W + 2 * ox;   // local row 2 o0 = input row 2 (oy0 + o0) - 1
+    auto hsum = [&](int r, float* h) {   // input columns 2 ox - 1, 2 ox, 2 ox + 1 of local row 2 o0 + r, left to right
+      const uint4* rp = col + (size_t)r * W;
+      const uint4 vl = ox > 0 ? rp[-1] : make_uint4(0u, 0u, 0u, 0u), vc = rp[0], vr = rp[1];
+      const uint32_t lw[4] = {vl.x, vl.y, vl.z, vl.w}, cw[4] = {vc.x, vc.y, vc.z, vc.w}, rw[4] = {vr.x, vr.y, vr.z, vr.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const uint32_t lw = __shfl_up_sync(0xffffffffu, c1[k], 1);
-        float la, lb, ca, cb, ra, rb;
-        unpack2(lw, la, lb);
-        unpack2(c0[k], ca, cb);
-        unpack2(c1[k], ra, rb);
+        float la, lb, ca, cb, ra, rb2;
+        unpack2(lw[k], la, lb);
+        unpack2(cw[k], ca, cb);
+        unpack2(rw[k], ra, rb2);
         h[2 * k] = (la + ca) + ra;
-        h[2 * k + 1] = (lb + cb) + rb;
+        h[2 * k + 1] = (lb + cb) + rb2;
       }
     };
     float h0[8], h1[8], h2[8];
     hsum(0, h0);
 #pragma unroll
     for (int o = 0; o < kPoolR; ++o) {
+      if (o0 + o >= rb) break;
       hsum(2 * o + 1, h1);
       hsum(2 * o + 2, h2);
-      const int oy = oy0 + o;
-      const bool ok = out_ok && oy < Ho;
       float acc[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        acc[k] = ((h0[k] + h1[k]) + h2[k]) / 9.0f;
+        acc[k] = div9((h0[k] + h1[k]) + h2[k]);
         h0[k] = h2[k];
-        if (ok) {
-          t1[k] += acc[k];
-          t2[k] += acc[k] * acc[k];
-        }
+        t1[k] += acc[k];
+        t2[k] = fmaf(acc[k], acc[k], t2[k]);
       }
-      if (ok)
-        dp[(size_t)oy * Wo + ox] =
-            make_uint4(pack2(acc[0], acc[1]), pack2(acc[2], acc[3]), pack2(acc[4], acc[5]), pack2(acc[6], acc[7]));
+      dp[(size_t)(oy0 + o0 + o) * Wo + ox] =
+          make_uint4(pack2(acc[0], acc[1]), pack2(acc[2], acc[3]), pack2(acc[4], acc[5]), pack2(acc[6], acc[7]));
     }
   }
   if (stats != nullptr) {
@@ -378,10 +392,21 @@ __global__ void __launch_bounds__(256) avgpool3s2_kernel(const act_t* __restrict
 int launch_avgpool3s2(const act_t* src, long long src_bs, act_t* dst, long long dst_bs, double* stats, int B, int H,
                       int W, int C, cudaStream_t s) {
   RIB_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "avgpool: bad shape");
-  const int Ho = H / 2, Wo = W / 2;
-  const int nstrips = ((Wo + kPoolCols - 1) / kPoolCols) * ((Ho + kPoolR - 1) / kPoolR);
-  dim3 grid((unsigned)((nstrips + 7) / 8), (unsigned)(C / 8), (unsigned)B);
-  launch_pdl(avgpool3s2_kernel, grid, dim3(256), 0, s, src, src_bs, dst, dst_bs, stats, H, W, C);
+  RIB_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0 && src_bs % 8 == 0 && dst_bs % 8 == 0,
+              "avgpool: maps must be 16-byte aligned");
+  const int Ho = H / 2;
+  const size_t row_bytes = (size_t)W * 16;
+  // output rows per band: a multiple of kPoolR whose 2 RB + 1 input rows stay near the shared-memory target
+  int RB = (int)((kPoolSmemTarget / row_bytes - 1) / 2) / kPoolR * kPoolR;
+  if (RB < kPoolR) RB = kPoolR;
+  const int ho_up = (Ho + kPoolR - 1) / kPoolR * kPoolR;
+  if (RB > ho_up) RB = ho_up;
+  const size_t smem = (size_t)(2 * RB + 1) * row_bytes;
+  RIB_REQUIRE(smem <= 200 * 1024 && smem < (1u << 20), "avgpool: rows wider than 1408 pixels are not supported");
+  if (smem > 48 * 1024)
+    RIB_CHECK_CUDA(cudaFuncSetAttribute((const void*)avgpool3s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  dim3 grid((unsigned)((Ho + RB - 1) / RB), (unsigned)(C / 8), (unsigned)B);
+  launch_pdl(avgpool3s2_kernel, grid, dim3(256), smem, s, src, src_bs, dst, dst_bs, stats, H, W, C, RB);
   RIB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

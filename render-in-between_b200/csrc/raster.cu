@@ -105,6 +105,7 @@ __device__ void heat_window(const double* __restrict__ jp, const GaussTable& tab
   if (!ok) return;  // map stays all-zero
   const int iy = (int)y, ix = (int)x;
   __shared__ double s_ky[kTaps];
+  __shared__ unsigned long long s_hit[kTaps];
   __shared__ double s_max[8];
   // axis-0 pass: ky[o] for o in [iy-20, iy+20]; centre tap first, then pairs from the outside in.
   if (threadIdx.x < kTaps) {
@@ -119,6 +120,17 @@ __device__ void heat_window(const double* __restrict__ jp, const GaussTable& tab
       }
     }
     s_ky[threadIdx.x] = tmp;
+    // which taps of the axis-1 pass see the joint's column from window column threadIdx.x (the pattern does not depend on
+    // the row): bits 0-19 first operand of tap ii, bits 20-39 second operand, bit 40 the centre tap
+    const int ox = ix - kRadius + threadIdx.x;
+    unsigned long long hm = ox == ix ? 1ull << 40 : 0ull;
+    if (ox >= 0 && ox < W) {
+      for (int ii = 0; ii < kRadius; ++ii) {
+        if (reflect_idx(ox - kRadius + ii, W) == ix) hm |= 1ull << ii;
+        if (reflect_idx(ox + kRadius - ii, W) == ix) hm |= 1ull << (20 + ii);
+      }
+    }
+    s_hit[threadIdx.x] = hm;
   }
   __syncthreads();
   // axis-1 pass over the window; each thread keeps up to 7 pixels in registers.
@@ -133,11 +145,14 @@ __device__ void heat_window(const double* __restrict__ jp, const GaussTable& tab
     const int oy = iy - kRadius + wy, ox = ix - kRadius + wx;
     if (oy < 0 || oy >= H || ox < 0 || ox >= W) continue;
     const double ky = s_ky[wy];
-    double tmp = __dmul_rn(ox == ix ? ky : 0.0, tab.w[kRadius]);
-    for (int ii = 0; ii < kRadius; ++ii) {
-      const bool ha = reflect_idx(ox - kRadius + ii, W) == ix;
-      const bool hb = reflect_idx(ox + kRadius - ii, W) == ix;
-      if (ha || hb) tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn(ha ? ky : 0.0, hb ? ky : 0.0), tab.w[ii]));
+    const unsigned long long hm = s_hit[wx];
+    double tmp = __dmul_rn((hm >> 40) & 1ull ? ky : 0.0, tab.w[kRadius]);
+    uint32_t taps = ((uint32_t)hm | (uint32_t)(hm >> 20)) & 0xfffffu;   // taps with a hit, visited in ascending order
+    while (taps) {                                                       // (a tap without a hit adds an exact zero)
+      const int ii = __ffs((int)taps) - 1;
+      taps &= taps - 1u;
+      const bool ha = (hm >> ii) & 1ull, hb = (hm >> (20 + ii)) & 1ull;
+      tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn(ha ? ky : 0.0, hb ? ky : 0.0), tab.w[ii]));
     }
     g[k] = tmp;
     lmax = fmax(lmax, tmp);
@@ -267,11 +282,26 @@ __device__ __forceinline__ void src_range(int v, int shift, int n, int* lo, int*
   }
 }
 
-// Hands the 64-bit set of body stamps of the limb that touch (y, x) (bit = key = stamp order) to `body`, then visits the
-// end-cap stamps, which come after all body stamps of the limb, in order.
-template <typename Body, typename Visit>
+// Hands the 64-bit set of body stamps of the limb that touch (y, x) (bit = key = stamp order) to `body`, then the end-cap
+// stamps, which come after all body stamps of the limb: an interior pixel `visit`s its (at most two) stamps in order; a
+// clamped pixel hands their number and smallest key to `caps` and `flag`s every stamp but the pixel's first one.
+// Body-stamp shifts s in [-4, 3] with clamp(c + s, 0, n - 1) == v (lo > hi: none).
+__device__ __forceinline__ void shift_range(int v, int c, int n, int* lo, int* hi) {
+  if (v > 0 && v < n - 1) {
+    *lo = max(v - c, -4);
+    *hi = min(v - c, 3);
+  } else if (v == 0) {
+    *lo = -4;
+    *hi = min(3, -c);
+  } else {
+    *lo = max(-4, n - 1 - c);
+    *hi = 3;
+  }
+}
+
+template <typename Body, typename Caps, typename Flag, typename Visit>
 __device__ __forceinline__ void visit_limb(const EdgeMeta& m, const short* __restrict__ f, int y, int x, int H, int W,
-                                           Body&& body, Visit&& visit) {
+                                           Body&& body, Caps&& caps, Flag&& flag, Visit&& visit) {
   const bool interior = x > 0 && x < W - 1 && y > 0 && y < H - 1;
   unsigned long long mask = 0ull;
   if (interior) {
@@ -292,21 +322,23 @@ __device__ __forceinline__ void visit_limb(const EdgeMeta& m, const short* __res
       }
     }
   } else {
-    for (int i = -4; i < 4; ++i) {
-      int ylo, yhi;
-      src_range(y, i, H, &ylo, &yhi);
-      for (int j = -4; j < 4; ++j) {
-        int xlo, xhi;
-        src_range(x, j, W, &xlo, &xhi);
-        const int mlo = max(m.swap ? ylo : xlo, m.mlo), mhi = min(m.swap ? yhi : xhi, m.mhi);
-        const int nlo = m.swap ? xlo : ylo, nhi = m.swap ? xhi : yhi;
-        bool hit = false;
-        for (int mm = mlo; mm <= mhi && !hit; ++mm) {
-          const int nn = f[mm];
-          hit = nn >= 0 && nn >= nlo && nn <= nhi;
-        }
-        if (hit) mask |= 1ull << ((i + 4) * 8 + (j + 4));
-      }
+    // Clamped pixel (np.clip in drawEdge): a curve point (mm, f[mm]) reaches it through a RANGE of shifts along every
+    // clamped axis, i.e. through a rectangle of stamps; the candidate points are the same eight as for an interior pixel.
+    const int pm = m.swap ? y : x, pn = m.swap ? x : y;
+    const int Dm = m.swap ? H : W, Dn = m.swap ? W : H;
+    for (int s = -4; s < 4; ++s) {
+      const int mm = pm - s;
+      if (mm < m.mlo || mm > m.mhi || mm < 0 || mm >= Dm) continue;
+      const int nn = f[mm];
+      if (nn < 0) continue;
+      int a0, a1, b0, b1;
+      shift_range(pm, mm, Dm, &a0, &a1);
+      shift_range(pn, nn, Dn, &b0, &b1);
+      if (a0 > a1 || b0 > b1) continue;
+      const int i0 = m.swap ? a0 : b0, i1 = m.swap ? a1 : b1, j0 = m.swap ? b0 : a0, j1 = m.swap ? b1 : a1;
+      const unsigned long long rows = (~0ull >> (8 * (3 - i1))) & (~0ull << (8 * (i0 + 4)));
+      const unsigned long long cols = (unsigned long long)(((1u << (j1 + 5)) - 1u) & ~((1u << (j0 + 4)) - 1u));
+      mask |= rows & (cols * 0x0101010101010101ull);
     }
   }
   body(mask);
@@ -345,15 +377,30 @@ __device__ __forceinline__ void visit_limb(const EdgeMeta& m, const short* __res
       ilo[t] = max(ilo[t], -12), ihi[t] = min(ihi[t], 11);
       jlo[t] = max(jlo[t], -12), jhi[t] = min(jhi[t], 11);
     }
-    const int i_beg = min(ilo[0], ilo[1]), i_end = max(ihi[0], ihi[1]);
-    const int j_beg = min(jlo[0], jlo[1]), j_end = max(jhi[0], jhi[1]);
-    for (int i = i_beg; i <= i_end; ++i)
-      for (int j = j_beg; j <= j_end; ++j) {
-        if (i * i + j * j >= 64) continue;
-        const bool h0 = i >= ilo[0] && i <= ihi[0] && j >= jlo[0] && j <= jhi[0];
-        const bool h1 = i >= ilo[1] && i <= ihi[1] && j >= jlo[1] && j <= jhi[1];
-        if (h0 || h1) visit(kBodyKeys + (i + 12) * 24 + (j + 12));
+    // Both passes walk rectangle 0, then the part of rectangle 1 outside of it (each stamp once; the order only matters
+    // for the smallest key, which is the first one in stamp order).  Pass 0 counts and finds that key, `caps` applies
+    // the count in closed form and says whether the first stamp is this pixel's very first one, pass 1 flags the others.
+    int n = 0, kmin = 1 << 30;
+    int skip = -1;
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int t = 0; t < 2; ++t)
+        for (int i = ilo[t]; i <= ihi[t]; ++i)
+          for (int j = jlo[t]; j <= jhi[t]; ++j) {
+            if (i * i + j * j >= 64) continue;
+            if (t == 1 && i >= ilo[0] && i <= ihi[0] && j >= jlo[0] && j <= jhi[0]) continue;
+            const int key = kBodyKeys + (i + 12) * 24 + (j + 12);
+            if (pass == 0) {
+              ++n;
+              kmin = min(kmin, key);
+            } else if (key != skip) {
+              flag(key);
+            }
+          }
+      if (pass == 0) {
+        if (n == 0) break;
+        skip = caps(n, kmin) ? kmin : -1;
       }
+    }
   }
 }
 
@@ -523,7 +570,22 @@ __global__ void __launch_bounds__(256) raster_mark_kernel(FrameScratch* __restri
           cb = avg_color_n(cb, col, more);
           count += nb;
         };
-        visit_limb(m, fs->f[e], y, x, H, W, apply_body, visit);
+        auto apply_caps = [&](int n, int kmin) {   // n end-cap stamps on a clamped pixel; true: kmin is the pixel's first stamp
+          int more = n;
+          const bool is_first = count == 0;
+          if (is_first) {
+            first = (uint32_t)e | ((uint32_t)kmin << 5);
+            ca = col;
+            cb = avg_color(0u, col);
+            more = n - 1;
+          }
+          ca = avg_color_n(ca, col, more);
+          cb = avg_color_n(cb, col, more);
+          count += n;
+          return is_first;
+        };
+        auto flag_cap = [&](int key) { fs->flag[e][key] = 1; };
+        visit_limb(m, fs->f[e], y, x, H, W, apply_body, apply_caps, flag_cap, visit);
       }
       // one atomic per limb and segment: the union of the lanes' sets (most are known already)
       const uint32_t olo = __reduce_or_sync(0xffffffffu, (uint32_t)older);
@@ -567,35 +629,29 @@ __global__ void __launch_bounds__(256) raster_paint_kernel(const FrameScratch* _
     if (threadIdx.x == 0) s_jmask = bal;
   }
   tile_edges(const_cast<FrameScratch*>(fs), y0, x0, H, W, &te, s_meta);
+  // Pixel p of a thread is column x0 + 32 p + lane: consecutive lanes own consecutive pixels, so every store instruction
+  // of a warp writes one contiguous run (512 bytes of a planar plane, 128 bytes of an fp32 plane) in whole sectors.
   const int y = y0 + (threadIdx.x >> 5);
-  const int xb = x0 + (threadIdx.x & 31) * kPxPerThread;
-  if (y >= H || xb >= W) return;
+  const int xl = x0 + (threadIdx.x & 31);
+  if (y >= H || xl >= W) return;
   const unsigned jmask = s_jmask;   // (written before the barrier inside tile_edges)
   uint32_t rgb[kPxPerThread];
 #pragma unroll
   for (int p = 0; p < kPxPerThread; ++p) rgb[p] = 0u;
   if (te.n > 0) {  // same test as in mark: only then was the cache written
-    const unsigned long long* cp = cache + ((size_t)b * H + y) * W + xb;
-    unsigned long long word[kPxPerThread];
-    if (xb + kPxPerThread <= W && (W & 3) == 0) {
-      const ulonglong2 w0 = *reinterpret_cast<const ulonglong2*>(cp), w1 = *reinterpret_cast<const ulonglong2*>(cp + 2);
-      word[0] = w0.x, word[1] = w0.y, word[2] = w1.x, word[3] = w1.y;
-    } else {
-#pragma unroll
-      for (int p = 0; p < kPxPerThread; ++p) word[p] = xb + p < W ? cp[p] : 0ull;
-    }
+    const unsigned long long* cp = cache + ((size_t)b * H + y) * W + xl;
 #pragma unroll
     for (int p = 0; p < kPxPerThread; ++p) {
-      if (!(word[p] >> 63)) continue;
-      const uint32_t first = (uint32_t)(word[p] >> 48) & 0x7fffu;
+      const unsigned long long word = xl + 32 * p < W ? cp[32 * p] : 0ull;
+      if (!(word >> 63)) continue;
+      const uint32_t first = (uint32_t)(word >> 48) & 0x7fffu;
       const uint32_t fe = first & 31u, fkey = first >> 5;
       const bool hit_older = fkey < (uint32_t)kBodyKeys ? ((fs->bodyflag[fe] >> fkey) & 1ull) != 0ull : fs->flag[fe][fkey] != 0;
-      rgb[p] = (uint32_t)(hit_older ? word[p] >> 24 : word[p]) & 0xffffffu;
+      rgb[p] = (uint32_t)(hit_older ? word >> 24 : word) & 0xffffffu;
     }
   }
   const size_t HW = (size_t)H * W;
-  const size_t pix = (size_t)y * W + xb;
-  const bool full = xb + kPxPerThread <= W && (W & 3) == 0;
+  const size_t pix = (size_t)y * W + xl;
   float* out = label != nullptr ? label + (size_t)b * 22 * HW + pix : nullptr;
   act_t* pout = planar != nullptr ? planar + (size_t)b * 32 * HW + pix * 8 : nullptr;
   // channel c of the label: 0..2 skeleton, 3..21 heat-maps, 22..31 zero padding of the planar copy;
@@ -613,24 +669,22 @@ __global__ void __launch_bounds__(256) raster_paint_kernel(const FrameScratch* _
           h = s_lut[(rgb[p] >> (8 * c)) & 0xffu];
         } else if (c < 22 && ((jmask >> (c - 3)) & 1u)) {   // (uniform over the block)
           const JointMeta jm = s_joint[c - 3];
-          const int wy = y - jm.iy + kRadius, wx = xb + p - jm.ix + kRadius;
+          const int wy = y - jm.iy + kRadius, wx = xl + 32 * p - jm.ix + kRadius;
           if ((unsigned)wy < (unsigned)kTaps && (unsigned)wx < (unsigned)kTaps) h = fs->win[c - 3][wy * kTaps + wx];
         }
         v[k][p] = h;
       }
       if (out != nullptr && c < 22) {
-        if (full) {
-          *reinterpret_cast<float4*>(out + (size_t)c * HW) = make_float4(v[k][0], v[k][1], v[k][2], v[k][3]);
-        } else {
-          for (int p = 0; p < kPxPerThread && xb + p < W; ++p) out[(size_t)c * HW + p] = v[k][p];
-        }
+#pragma unroll
+        for (int p = 0; p < kPxPerThread; ++p)
+          if (xl + 32 * p < W) out[(size_t)c * HW + 32 * p] = v[k][p];
       }
     }
     if (pout != nullptr) {  // [B][4][H][W][8]
 #pragma unroll
       for (int p = 0; p < kPxPerThread; ++p) {
-        if (xb + p >= W) break;
-        *reinterpret_cast<uint4*>(pout + (size_t)pl * HW * 8 + (size_t)p * 8) =
+        if (xl + 32 * p >= W) break;
+        *reinterpret_cast<uint4*>(pout + (size_t)pl * HW * 8 + (size_t)(32 * p) * 8) =
             make_uint4(pack2(v[0][p], v[1][p]), pack2(v[2][p], v[3][p]), pack2(v[4][p], v[5][p]), pack2(v[6][p], v[7][p]));
       }
     }

@@ -188,7 +188,12 @@ def test_strided_composite_and_warp(dev):
 
 def test_render_clips_matches_clip_by_clip(dev, gen):
     """Two 4x clips rendered as ONE batch per AR step (ClipRenderer.render_clips) against the same clips rendered one by
-    one: the same frames up to the 16-bit rounding noise of a different launch plan (batch 2 x (K-1) vs K-1)."""
+    one.  (a) With one clip per call both entries launch the same plan (batch K-1) and must agree bit for bit: the two
+    code paths sequence the same kernels.  (b) With two clips per batch the plan differs (batch 2 x (K-1)): the
+    instance-norm statistics are reduced over other tile ranges, single 16-bit roundings flip, and at this test size the
+    deepest normalised maps have 2 x 3 pixels, which amplifies a flipped rounding into a few grey levels over three
+    dependent AR passes (measured: <= 4 levels on 5-10 % of the values, 56-60 dB).  The gate is the north star's own:
+    >= 45 dB between the two renderings (50 asserted), no value off by more than 8 levels."""
     from rib.clip import ClipRenderer
     h, w, nkey, rate, nclip = 64, 96, 3, 4, 2
     t = (nkey - 1) * rate + 1
@@ -202,7 +207,20 @@ def test_render_clips_matches_clip_by_clip(dev, gen):
         both = r.render_clips(key_u8, joints, flows=flows)
         single = torch.stack([r.render(key_u8[c], joints[c], flows=flows[c], want_u8=True, want_fuse=False)['u8']
                               for c in range(nclip)])
+        one_by_one = torch.cat([r.render_clips(key_u8[c:c + 1], joints[c:c + 1], flows=flows[c:c + 1]) for c in range(nclip)])
     assert both.shape == single.shape == (nclip, t, h, w, 3)
+    assert torch.equal(one_by_one, single)                              # (a) same plan: bit-identical
     assert torch.equal(both[:, 0::rate], single[:, 0::rate])            # key frames: identical
     d = (both.int() - single.int()).abs()
-    assert d.max().item() <= 3 and (d > 0).float().mean().item() < 0.05, (d.max().item(), (d > 0).float().mean().item())
+    gen_mask = torch.tensor([i % rate != 0 for i in range(t)], device=dev)
+    mse = (d[:, gen_mask].float() ** 2).mean().item()
+    psnr = 10.0 * np.log10(255.0 ** 2 / max(mse, 1e-12))
+    line = ('render_clips vs clip by clip (64x96, 4x): max |d| %d levels, %.2f %% of the values differ, %.1f dB'
+            % (d.max().item(), 100.0 * (d > 0).float().mean().item(), psnr))
+    print(line)
+    import os
+    rep = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+    if os.path.isdir(rep):
+        with open(os.path.join(rep, 'parity_report.txt'), 'a') as f:
+            f.write(line + '\n')
+    assert d.max().item() <= 8 and psnr >= 50.0, (d.max().item(), (d > 0).float().mean().item(), psnr)
