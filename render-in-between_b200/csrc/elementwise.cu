@@ -257,7 +257,8 @@ int launch_in_apply(const InApplyParams& p, cudaStream_t s) {
   const size_t nvec = (size_t)p.H * p.W * (p.C / 8);
   const int threads = 256;
   // every block first derives the normalisation coefficients of its image (fp64 divide + sqrt per channel),
-  // so blocks are kept few and fat: about 8 resident blocks per SM over the whole batch
+  // so blocks are kept few and fat: about 8 blocks per SM over the whole batch (measured: a single resident wave of
+  // 3-4 blocks per SM is slower, 348 -> 432 us per forward; so is requesting the first vectors before the prologue)
   unsigned gx = (unsigned)((nvec + threads - 1) / threads);
   unsigned want = (sm_count_current() * 8u + (unsigned)p.B - 1u) / (unsigned)p.B;
   if (want < 1u) want = 1u;
@@ -389,8 +390,101 @@ __global__ void __launch_bounds__(256) avgpool3s2_kernel(const act_t* __restrict
   }
 }
 
+#ifdef RIB_POOL_V0
+// The round-1 form (one output pixel per thread, nine 16-byte loads each), kept as an A/B build (tools/): 346 us per
+// forward against 221 us for the band kernel.
+__global__ void avgpool3s2_v0_kernel(const act_t* __restrict__ src, long long src_bs, act_t* __restrict__ dst,
+                                  long long dst_bs, double* __restrict__ stats, int H, int W, int C) {
+  pdl_wait();   // programmatic dependent launch: nothing above depends on the previous kernel
+  __shared__ float s_red[8][16];  // one slot per warp: fixed-order (deterministic) block reduction
+  const int pl = blockIdx.y, n = blockIdx.z;
+  const int Ho = H / 2, Wo = W / 2;
+  const act_t* sp = src + (size_t)n * src_bs + (size_t)pl * H * W * 8;
+  act_t* dp = dst + (size_t)n * dst_bs + (size_t)pl * Ho * Wo * 8;
+  float t1[8], t2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) t1[k] = t2[k] = 0.f;
+  const int npix = Ho * Wo;
+  for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += gridDim.x * blockDim.x) {
+    const int oy = pix / Wo, ox = pix - oy * Wo;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int iy = 2 * oy + dy;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int ix = 2 * ox + dx;
+        if (ix < 0 || ix >= W) continue;
+        const uint4 v = *reinterpret_cast<const uint4*>(sp + ((size_t)iy * W + ix) * 8);
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float a, b;
+          unpack2(u[k], a, b);
+          acc[2 * k] += a;
+          acc[2 * k + 1] += b;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      acc[k] = acc[k] / 9.0f;
+      t1[k] += acc[k];
+      t2[k] += acc[k] * acc[k];
+    }
+    *reinterpret_cast<uint4*>(dp + (size_t)pix * 8) =
+        make_uint4(pack2(acc[0], acc[1]), pack2(acc[2], acc[3]), pack2(acc[4], acc[5]), pack2(acc[6], acc[7]));
+  }
+  if (stats != nullptr) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        t1[k] += __shfl_xor_sync(0xffffffffu, t1[k], off);
+        t2[k] += __shfl_xor_sync(0xffffffffu, t2[k], off);
+      }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        s_red[threadIdx.x >> 5][k] = t1[k];
+        s_red[threadIdx.x >> 5][8 + k] = t2[k];
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += s_red[w][threadIdx.x];
+      const int c = pl * 8 + (threadIdx.x & 7);
+      stat_add(&stats[((size_t)n * C + c) * 2], threadIdx.x >> 3, t);
+    }
+  }
+}
+
+static int launch_avgpool3s2_v0(const act_t* src, long long src_bs, act_t* dst, long long dst_bs, double* stats, int B, int H,
+                      int W, int C, cudaStream_t s) {
+  RIB_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "avgpool: bad shape");
+  const int npix = (H / 2) * (W / 2);
+  const int threads = 256;
+  unsigned gx = (unsigned)((npix + threads * 4 - 1) / (threads * 4));
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, (unsigned)(C / 8), (unsigned)B);
+  launch_pdl(avgpool3s2_v0_kernel, grid, dim3(threads), 0, s, src, src_bs, dst, dst_bs, stats, H, W, C);
+  RIB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+#endif
+
 int launch_avgpool3s2(const act_t* src, long long src_bs, act_t* dst, long long dst_bs, double* stats, int B, int H,
                       int W, int C, cudaStream_t s) {
+#ifdef RIB_POOL_V0
+  return launch_avgpool3s2_v0(src, src_bs, dst, dst_bs, stats, B, H, W, C, s);
+#endif
   RIB_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "avgpool: bad shape");
   RIB_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0 && src_bs % 8 == 0 && dst_bs % 8 == 0,
               "avgpool: maps must be 16-byte aligned");

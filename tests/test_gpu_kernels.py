@@ -408,3 +408,12 @@ def test_avgpool_matches_avg_pool2d(dev, case):
     st = _decode_stats(stats.cpu())
     assert torch.allclose(st[..., 0], ref.sum(dim=(2, 3)), rtol=1e-5, atol=1e-3)
     assert torch.allclose(st[..., 1], (ref * ref).sum(dim=(2, 3)), rtol=1e-5, atol=1e-3)
+    # a frame's pooled map and statistics do not depend on the batch it is part of (bit for bit)
+    out1 = torch.empty((1,) + tuple(out.shape[1:]), dtype=dt, device=dev)
+    stats1 = torch.zeros(1, c, 2, dtype=torch.float64, device=dev)
+    last = xp[b - 1:b].contiguous()
+    check(lib.rib_avgpool_test(last.data_ptr(), out1.data_ptr(), stats1.data_ptr(), 1, h, w, c,
+                               C.c_void_p(torch.cuda.current_stream().cuda_stream)), 'rib_avgpool_test')
+    torch.cuda.synchronize()
+    assert torch.equal(out1[0].view(torch.int16), out[b - 1].view(torch.int16))
+    assert torch.equal(stats1[0].view(torch.int64), stats[b - 1].view(torch.int64))
