@@ -583,8 +583,20 @@ int launch_composite(const float* img, const float* mask, const float* dain, flo
 // ---------------------------------------------------------------------------------------------
 // out_u8 (optional): the frame tensor2images(out) would give (utils/utils.py:122-147) - what the evaluator saves for a key
 // frame (evaluator.py:240-244, :265-266); it truncates, so it is NOT the input byte for 63 of the 256 levels.
-__global__ void frames_from_u8_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, uint8_t* __restrict__ out_u8,
-                                      int HW4, int HW, size_t total, long long in_bs, long long out_bs, long long u8_bs) {
+__global__ void __launch_bounds__(256) frames_from_u8_kernel(const uint8_t* __restrict__ in, float* __restrict__ out,
+                                                             uint8_t* __restrict__ out_u8, int HW4, int HW, size_t total,
+                                                             long long in_bs, long long out_bs, long long u8_bs) {
+  // Both results are functions of the input byte alone: one table entry per thread (the exact arithmetic, two IEEE
+  // divisions and the float64 truncation of tensor2images), then the pixels are look-ups.
+  __shared__ float s_norm[256];
+  __shared__ uint8_t s_save[256];
+  {
+    const float v = __fdiv_rn(__fsub_rn(__fdiv_rn((float)threadIdx.x, 255.0f), 0.5f), 0.5f);
+    s_norm[threadIdx.x] = v;
+    s_save[threadIdx.x] = to_u8(v);
+  }
+  __syncthreads();
+  pdl_wait();   // programmatic dependent launch: nothing above depends on the previous kernel
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // over B * HW/4
   if (i >= total) return;
   const size_t n = i / HW4, q = i - n * HW4;
@@ -593,22 +605,18 @@ __global__ void frames_from_u8_kernel(const uint8_t* __restrict__ in, float* __r
   const uint8_t px[12] = {(uint8_t)w0, (uint8_t)(w0 >> 8), (uint8_t)(w0 >> 16), (uint8_t)(w0 >> 24),
                           (uint8_t)w1, (uint8_t)(w1 >> 8), (uint8_t)(w1 >> 16), (uint8_t)(w1 >> 24),
                           (uint8_t)w2, (uint8_t)(w2 >> 8), (uint8_t)(w2 >> 16), (uint8_t)(w2 >> 24)};
-  uint8_t qx[12];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    float v[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      v[k] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)px[3 * k + c], 255.0f), 0.5f), 0.5f);
-      qx[3 * k + c] = to_u8(v[k]);
-    }
-    reinterpret_cast<float4*>(out + n * out_bs + (size_t)c * HW)[q] = make_float4(v[0], v[1], v[2], v[3]);
-  }
+  for (int c = 0; c < 3; ++c)
+    reinterpret_cast<float4*>(out + n * out_bs + (size_t)c * HW)[q] =
+        make_float4(s_norm[px[c]], s_norm[px[3 + c]], s_norm[px[6 + c]], s_norm[px[9 + c]]);
   if (out_u8 != nullptr) {
+    uint32_t qx[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) qx[k] = s_save[px[k]];
     uint32_t* o = reinterpret_cast<uint32_t*>(out_u8 + n * u8_bs + q * 12);
-    o[0] = qx[0] | (qx[1] << 8) | (qx[2] << 16) | ((uint32_t)qx[3] << 24);
-    o[1] = qx[4] | (qx[5] << 8) | (qx[6] << 16) | ((uint32_t)qx[7] << 24);
-    o[2] = qx[8] | (qx[9] << 8) | (qx[10] << 16) | ((uint32_t)qx[11] << 24);
+    o[0] = qx[0] | (qx[1] << 8) | (qx[2] << 16) | (qx[3] << 24);
+    o[1] = qx[4] | (qx[5] << 8) | (qx[6] << 16) | (qx[7] << 24);
+    o[2] = qx[8] | (qx[9] << 8) | (qx[10] << 16) | (qx[11] << 24);
   }
 }
 
@@ -624,8 +632,8 @@ int launch_frames_from_u8(const uint8_t* in, float* out, uint8_t* out_u8, int B,
               "frames_from_u8: strides / pointers must be 4-element aligned");
   const size_t total = (size_t)B * (HW / 4);
   const int threads = 256;
-  frames_from_u8_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(in, out, out_u8, HW / 4, HW, total,
-                                                                                         in_bstride, out_bstride, u8_bstride);
+  launch_pdl(frames_from_u8_kernel, dim3((unsigned)((total + threads - 1) / threads)), dim3(threads), 0, s, in, out, out_u8,
+             HW / 4, HW, total, in_bstride, out_bstride, u8_bstride);
   RIB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -820,38 +828,38 @@ __global__ void warp4_kernel(const float* __restrict__ src, const void* __restri
 // each (consecutive lanes read consecutive source pixels displaced by a smooth flow), where the four-consecutive-pixels
 // form above spreads every gather instruction over five lines and is bound by the L1 wavefront rate.  Needs
 // H * W % 128 == 0 (a group of 128 pixels never straddles two frames).  Same float sequence per pixel as warp_kernel.
-template <int CT, bool FH>
+template <int CT, bool FH, int PX>
 __global__ void __launch_bounds__(256) warp_px_kernel(const float* __restrict__ src, const void* __restrict__ flow_v,
                                                       float* __restrict__ out, int Crt, int H, int W, float sx, float sy,
                                                       size_t ngroups, long long src_bs, long long flow_bs,
                                                       long long out_bs) {
   pdl_wait();   // programmatic dependent launch: nothing above depends on the previous kernel
-  const size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // group of 128 pixels (one warp)
+  const size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // group of 32 PX pixels (one warp)
   if (g >= ngroups) return;
   const int lane = threadIdx.x & 31;
-  const int HW = H * W, gpf = HW >> 7;
+  const int HW = H * W, gpf = HW / (32 * PX);
   const size_t n = g / gpf;
-  const int hw0 = (int)(g - n * gpf) * 128 + lane;
-  float fxs[4], fys[4];
+  const int hw0 = (int)(g - n * gpf) * (32 * PX) + lane;
+  float fxs[PX], fys[PX];
   if (FH) {
     const __half* flow = static_cast<const __half*>(flow_v) + n * flow_bs;
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
+    for (int p = 0; p < PX; ++p) {
       fxs[p] = __half2float(flow[hw0 + 32 * p]);
       fys[p] = __half2float(flow[(size_t)HW + hw0 + 32 * p]);
     }
   } else {
     const float* flow = static_cast<const float*>(flow_v) + n * flow_bs;
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
+    for (int p = 0; p < PX; ++p) {
       fxs[p] = __ldg(flow + hw0 + 32 * p);
       fys[p] = __ldg(flow + (size_t)HW + hw0 + 32 * p);
     }
   }
-  int o00[4], dx1[4], dy1[4];
-  float wnw[4], wne[4], wsw[4], wse[4];
+  int o00[PX], dx1[PX], dy1[PX];
+  float wnw[PX], wne[PX], wsw[PX], wse[PX];
 #pragma unroll
-  for (int p = 0; p < 4; ++p) {
+  for (int p = 0; p < PX; ++p) {
     const int hw = hw0 + 32 * p;
     const int y = hw / W, x = hw - y * W;
     const float gx = __fsub_rn(__fmul_rn(__fadd_rn((float)x, fxs[p]), sx), 1.0f);
@@ -872,9 +880,9 @@ __global__ void __launch_bounds__(256) warp_px_kernel(const float* __restrict__ 
 #pragma unroll
   for (int c = 0; c < C; ++c) {
     const float* s = src + n * src_bs + (size_t)c * HW;
-    float acc[4];
+    float acc[PX];
 #pragma unroll
-    for (int p = 0; p < 4; ++p) {
+    for (int p = 0; p < PX; ++p) {
       float a = __ldg(s + o00[p]) * wnw[p];
       if (dx1[p] > 0) a += __ldg(s + o00[p] + 1) * wne[p];
       if (dy1[p] > 0) a += __ldg(s + o00[p] + W) * wsw[p];
@@ -883,7 +891,7 @@ __global__ void __launch_bounds__(256) warp_px_kernel(const float* __restrict__ 
     }
     float* o = out + n * out_bs + (size_t)c * HW + hw0;
 #pragma unroll
-    for (int p = 0; p < 4; ++p) o[32 * p] = acc[p];
+    for (int p = 0; p < PX; ++p) o[32 * p] = acc[p];
   }
 }
 
@@ -899,16 +907,31 @@ int launch_warp(const float* src, const void* flow_v, int flow_fp16, float* out,
   RIB_REQUIRE(!flow_fp16 || (W % 4 == 0 && flow_bstride % 4 == 0 && out_bstride % 4 == 0 &&
                              ((uintptr_t)flow_v & 7) == 0 && ((uintptr_t)out & 15) == 0),
               "warp: half-precision flows need W % 4 == 0 and aligned frames");
+  // pixels per thread: 2 (default), 1, 4.  Measured at the bench shape (tools/bw_bench.py, profiles/r3e_bw_bench.txt):
+  // 90 us with 2 (40 registers, twice the resident warps) against 105 / 108 us with 4 / 1.
+  static const int px_env = getenv("RIB_WARP_PX") ? atoi(getenv("RIB_WARP_PX")) : 2;
   if (((size_t)H * W) % 128 == 0) {
-    const size_t ngroups = total / 128;
+    const int PX = (px_env == 1 || px_env == 4) ? px_env : 2;
+    const size_t ngroups = total / (32 * PX);
     const dim3 grid((unsigned)((ngroups * 32 + threads - 1) / threads)), block(threads);
-    if (flow_fp16) {
-      if (C == 3) launch_pdl(warp_px_kernel<3, true>, grid, block, 0, s, src, flow_v, out, C, H, W, sx, sy, ngroups, src_bstride, flow_bstride, out_bstride);
-      else launch_pdl(warp_px_kernel<0, true>, grid, block, 0, s, src, flow_v, out, C, H, W, sx, sy, ngroups, src_bstride, flow_bstride, out_bstride);
-    } else {
-      if (C == 3) launch_pdl(warp_px_kernel<3, false>, grid, block, 0, s, src, flow_v, out, C, H, W, sx, sy, ngroups, src_bstride, flow_bstride, out_bstride);
-      else launch_pdl(warp_px_kernel<0, false>, grid, block, 0, s, src, flow_v, out, C, H, W, sx, sy, ngroups, src_bstride, flow_bstride, out_bstride);
-    }
+#define RIB_WARP_LAUNCH(CT, FH, PXV)                                                                                  \
+  launch_pdl(warp_px_kernel<CT, FH, PXV>, grid, block, 0, s, src, flow_v, out, C, H, W, sx, sy, ngroups, src_bstride, \
+             flow_bstride, out_bstride)
+#define RIB_WARP_PICK(PXV)                                     \
+  do {                                                         \
+    if (flow_fp16) {                                           \
+      if (C == 3) RIB_WARP_LAUNCH(3, true, PXV);               \
+      else RIB_WARP_LAUNCH(0, true, PXV);                      \
+    } else {                                                   \
+      if (C == 3) RIB_WARP_LAUNCH(3, false, PXV);              \
+      else RIB_WARP_LAUNCH(0, false, PXV);                     \
+    }                                                          \
+  } while (0)
+    if (PX == 1) RIB_WARP_PICK(1);
+    else if (PX == 2) RIB_WARP_PICK(2);
+    else RIB_WARP_PICK(4);
+#undef RIB_WARP_PICK
+#undef RIB_WARP_LAUNCH
     RIB_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
