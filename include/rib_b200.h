@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RIB_ABI_VERSION 5
+#define RIB_ABI_VERSION 6
 
 /* Message of the last failing call on this host thread ("" if none). */
 const char* rib_last_error(void);
@@ -146,6 +146,35 @@ int rib_generator_bind(rib_generator* g, int B, int H, int W, void* workspace, l
 int rib_generator_forward(rib_generator* g, int B, int H, int W, const float* label, const float* img_fake,
                           const float* img_prev, float* out_img, float* out_mask, void* workspace,
                           long long workspace_bytes, void* stream);
+
+/* ---- upstream motion model ------------------------------------------
+ * Replaces Human_Motion_Modelling/models/transformer.py:16-132 (`Transformer`, built by build_transformer :336-350 from
+ * configs/config.yaml:77-94) in eval mode for the shipped options: pre_norm, leaky_relu, two_stage, no intermediate
+ * outputs.  fp32 throughout. */
+typedef struct rib_motion_config {
+  int input_joints;     /* transformer.input_joints  (38: 19 joints x (x, y)) */
+  int hidden_dim;       /* transformer.hidden_dim    (128) */
+  int nheads;           /* transformer.nheads        (8; hidden_dim / nheads must be 16) */
+  int dim_feedforward;  /* transformer.dim_feedforward (256) */
+  int enc_layers, dec_layers;
+} rib_motion_config;
+
+typedef struct rib_motion rib_motion;
+
+/* `tensors`: the reference module's state-dict (oracle/motion_oracle.state_spec lists the 236 keys of the shipped
+ * configuration), device fp32.  The parameters are copied; the caller's tensors may be released afterwards. */
+int rib_motion_create(const rib_motion_config* cfg, const rib_tensor* tensors, int n_tensors, void* stream, rib_motion** out);
+void rib_motion_destroy(rib_motion* m);
+long long rib_motion_workspace_bytes(rib_motion* m, int B, int L);
+
+/* Transformer.forward(src, src_mask, src_pos, tgt, tgt_mask, tgt_pos, rate) -> (joints, reco)  (transformer.py:76-112;
+ * with two_stage the decoder input is interpolate_embedding(reco, rate), `tgt` is not read and therefore not taken).
+ *   src f32 [B][C][L] (C = input_joints, L = rate * n + 1 frames); src_mask / tgt_mask u8 [B][L], non-zero = the frame is
+ *   hidden from attention as a key (key_padding_mask; may be NULL); src_pos / tgt_pos f32 [L][B][hidden_dim];
+ *   joints, reco f32 [L][B][C].  Asynchronous on `stream`; workspace of rib_motion_workspace_bytes(B, L) bytes. */
+int rib_motion_forward(rib_motion* m, int B, int L, const float* src, const uint8_t* src_mask, const float* src_pos,
+                       const uint8_t* tgt_mask, const float* tgt_pos, int rate, float* joints, float* reco,
+                       void* workspace, long long workspace_bytes, void* stream);
 
 /* ---- measurement hooks (bench.py's roofline pass) ---------------------------------------------
  * While enabled, every launch of the implicit-GEMM convolution kernel is bracketed by CUDA events

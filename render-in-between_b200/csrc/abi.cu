@@ -4,6 +4,7 @@
 #include "conv_gemm.cuh"
 #include "elementwise.cuh"
 #include "generator.cuh"
+#include "motion.cuh"
 #include "raster.cuh"
 
 namespace rib {
@@ -122,6 +123,30 @@ int rib_generator_forward(rib_generator* g, int B, int H, int W, const float* la
   RIB_GUARD_BEGIN
   return generator_forward(reinterpret_cast<Generator*>(g), B, H, W, label, img_fake, img_prev, out_img, out_mask,
                            workspace, workspace_bytes, (cudaStream_t)stream);
+  RIB_GUARD_END
+}
+
+int rib_motion_create(const rib_motion_config* cfg, const rib_tensor* tensors, int n_tensors, void* stream, rib_motion** out) {
+  RIB_GUARD_BEGIN
+  return motion_create(cfg, tensors, n_tensors, (cudaStream_t)stream, reinterpret_cast<MotionModel**>(out));
+  RIB_GUARD_END
+}
+
+void rib_motion_destroy(rib_motion* m) { motion_destroy(reinterpret_cast<MotionModel*>(m)); }
+
+long long rib_motion_workspace_bytes(rib_motion* m, int B, int L) {
+  RIB_GUARD_BEGIN
+  RIB_REQUIRE(m && B > 0 && L > 0, "rib_motion_workspace_bytes: bad argument");
+  return motion_workspace_bytes(reinterpret_cast<MotionModel*>(m), B, L);
+  RIB_GUARD_END
+}
+
+int rib_motion_forward(rib_motion* m, int B, int L, const float* src, const uint8_t* src_mask, const float* src_pos,
+                       const uint8_t* tgt_mask, const float* tgt_pos, int rate, float* joints, float* reco,
+                       void* workspace, long long workspace_bytes, void* stream) {
+  RIB_GUARD_BEGIN
+  return motion_forward(reinterpret_cast<MotionModel*>(m), B, L, src, src_mask, src_pos, tgt_mask, tgt_pos, rate, joints, reco,
+                        workspace, workspace_bytes, (cudaStream_t)stream);
   RIB_GUARD_END
 }
 

@@ -1,0 +1,494 @@
+// Motion Transformer of Human_Motion_Modelling on the GPU.
+//
+//   Transformer.forward / encode / decode / interpolate_embedding    Human_Motion_Modelling/models/transformer.py:57-132
+//   TransformerEncoderLayer.forward_pre / DecoderLayer.forward_pre   Human_Motion_Modelling/models/transformer.py:243-254, :316-337
+//   final LayerNorms of TransformerEncoder / TransformerDecoder       Human_Motion_Modelling/models/transformer.py:134-196
+// for the shipped configuration (configs/config.yaml:77-94): pre-norm, leaky_relu, two_stage, eval mode.
+//
+// The model is tiny (d_model 128, 8 heads of 16, feed-forward 256, 6 + 6 layers, at most 321 tokens): ~1.3 GFLOP per
+// sequence.  Everything stays in fp32 on the CUDA cores (the parity target is the reference's fp32 output, and at these
+// sizes a forward is bound by the ~90 dependent launches, not by arithmetic): three kernels,
+//   linear   Y = act(LN?(X) (+ pos for the first n_pos columns) . W^T + b) (+ residual): 32 x 64 output tile per block, the
+//            LayerNorm of the pre-norm blocks and the "+ pos" of q / k are applied to the A tile in shared memory
+//   mha      one block per (16 queries, head, sequence): the head's K and V rows in shared memory, a warp per query
+//            (scores, masks as -inf, softmax, P.V with warp-shuffle reductions)
+//   interp   interpolate_embedding, the exact float sequence of the reference
+// launched back to back with programmatic dependent launch on the caller's stream.
+#include "motion.cuh"
+
+#include <map>
+#include <string>
+#include <vector>
+
+namespace rib {
+
+namespace {
+
+constexpr int kDH = 16;          // head dimension (hidden_dim / nheads of the shipped configuration)
+constexpr int kLinRows = 32, kLinCols = 64, kLinKC = 32, kLinMaxK = 256;
+constexpr int kMhaQ = 16;        // queries per block (4 warps x 4)
+
+struct LinParams {
+  const float* X;                // element (b, r, k) at X[b * xb + r * xr + k * xk]
+  long long xb, xr, xk;
+  const float* W;                // [N][K] row-major (torch nn.Linear weight)
+  const float* bias;             // [N]
+  const float* ln_g;             // LayerNorm over K applied to every row of X first (null: none)
+  const float* ln_b;
+  const float* pos;              // element (b, r, k) at pos[b * pb + r * pr + k]: added to the (normalised) row for the
+  long long pb, pr;              //   output columns < n_pos (q / k projections take x + pos, v takes x)
+  int n_pos;
+  const float* R;                // residual element (b, r, n) at R[b * rb + r * rr + n * rn] (null: none)
+  long long rb, rr, rn;
+  float* Y;                      // element (b, r, n) at Y[b * yb + r * yr + n]
+  long long yb, yr;
+  int L, N, K, act;              // act 1: leaky_relu(0.01)
+};
+
+__global__ void __launch_bounds__(256) motion_linear_kernel(const LinParams p) {
+  __shared__ float As[kLinRows][kLinMaxK + 1];
+  __shared__ __align__(16) float Ws[kLinKC][kLinCols + 4];
+  pdl_wait();   // programmatic dependent launch: everything below reads the previous kernel's output
+  const int b = blockIdx.z, r0 = blockIdx.x * kLinRows, n0 = blockIdx.y * kLinCols;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int K = p.K;
+  // A tile: rows r0 .. r0 + 31, all K columns (zero rows behind the sequence)
+  for (int i = tid; i < kLinRows * K; i += 256) {
+    const int r = i / K, k = i - r * K;
+    As[r][k] = (r0 + r < p.L) ? p.X[(size_t)b * p.xb + (size_t)(r0 + r) * p.xr + (size_t)k * p.xk] : 0.f;
+  }
+  __syncthreads();
+  if (p.ln_g != nullptr) {   // nn.LayerNorm(K), eps 1e-5: mean, biased variance (two passes), affine
+    for (int r = warp * 4; r < warp * 4 + 4; ++r) {
+      float s = 0.f;
+      for (int k = lane; k < K; k += 32) s += As[r][k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s / (float)K;
+      float v = 0.f;
+      for (int k = lane; k < K; k += 32) {
+        const float d = As[r][k] - mean;
+        v = fmaf(d, d, v);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      const float rstd = rsqrtf(v / (float)K + 1e-5f);
+      for (int k = lane; k < K; k += 32) As[r][k] = (As[r][k] - mean) * rstd * p.ln_g[k] + p.ln_b[k];
+    }
+    __syncthreads();
+  }
+  if (p.pos != nullptr && n0 < p.n_pos) {
+    for (int i = tid; i < kLinRows * K; i += 256) {
+      const int r = i / K, k = i - r * K;
+      if (r0 + r < p.L) As[r][k] += p.pos[(size_t)b * p.pb + (size_t)(r0 + r) * p.pr + k];
+    }
+    __syncthreads();
+  }
+  const int tx = tid & 15, ty = tid >> 4;   // columns n0 + 4 tx .. + 3, rows 2 ty, 2 ty + 1
+  float acc[2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += kLinKC) {
+    {   // weight chunk, transposed: Ws[kk][n] = W[n0 + n][k0 + kk]
+      const int n = tid >> 2, kq = (tid & 3) * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = k0 + kq + i;
+        Ws[kq + i][n] = (n0 + n < p.N && k < K) ? p.W[(size_t)(n0 + n) * K + k] : 0.f;
+      }
+    }
+    __syncthreads();
+    const int kc = min(kLinKC, K - k0);
+    for (int kk = 0; kk < kc; ++kk) {
+      const float a0 = As[2 * ty][k0 + kk], a1 = As[2 * ty + 1][k0 + kk];
+      const float4 w = *reinterpret_cast<const float4*>(&Ws[kk][4 * tx]);
+      acc[0][0] = fmaf(a0, w.x, acc[0][0]);
+      acc[0][1] = fmaf(a0, w.y, acc[0][1]);
+      acc[0][2] = fmaf(a0, w.z, acc[0][2]);
+      acc[0][3] = fmaf(a0, w.w, acc[0][3]);
+      acc[1][0] = fmaf(a1, w.x, acc[1][0]);
+      acc[1][1] = fmaf(a1, w.y, acc[1][1]);
+      acc[1][2] = fmaf(a1, w.z, acc[1][2]);
+      acc[1][3] = fmaf(a1, w.w, acc[1][3]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int r = r0 + 2 * ty + i;
+    if (r >= p.L) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + 4 * tx + j;
+      if (n >= p.N) continue;
+      float v = acc[i][j] + p.bias[n];
+      if (p.act == 1) v = v > 0.f ? v : 0.01f * v;
+      if (p.R != nullptr) v += p.R[(size_t)b * p.rb + (size_t)r * p.rr + (size_t)n * p.rn];
+      p.Y[(size_t)b * p.yb + (size_t)r * p.yr + n] = v;
+    }
+  }
+}
+
+// nn.LayerNorm over the last dimension of [B][L][E] (the encoder's final norm: its output is the decoder's memory).
+__global__ void __launch_bounds__(256) motion_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                               const float* __restrict__ be, float* __restrict__ y,
+                                                               int rows, int E) {
+  pdl_wait();
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float* xr = x + (size_t)r * E;
+  float s = 0.f;
+  for (int k = lane; k < E; k += 32) s += xr[k];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)E;
+  float v = 0.f;
+  for (int k = lane; k < E; k += 32) {
+    const float d = xr[k] - mean;
+    v = fmaf(d, d, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const float rstd = rsqrtf(v / (float)E + 1e-5f);
+  for (int k = lane; k < E; k += 32) y[(size_t)r * E + k] = (xr[k] - mean) * rstd * g[k] + be[k];
+}
+
+// nn.MultiheadAttention core (after the in-projection, before the out-projection): q scaled by sqrt(1 / head_dim) first,
+// scores + masks (-inf), softmax over the keys, P . V.  Q / K / V / O rows are `ld*` floats apart (slices of the packed
+// projection buffer); head h owns columns [16 h, 16 h + 16).
+struct MhaParams {
+  const float *Q, *K, *V;
+  long long qb, kb, vb;      // floats between sequences
+  int ldq, ldk, ldv;
+  float* O;
+  long long ob;
+  int ldo;
+  const uint8_t* kpm;        // [B][Lk], non-zero = the key is ignored (null: none)
+  int Lq, Lk, eye;           // eye: query i may not attend to key i (Transformer.encode's mask)
+};
+
+__global__ void __launch_bounds__(128) motion_mha_kernel(const MhaParams p) {
+  extern __shared__ float sm[];
+  const int Lk = p.Lk, lkp = (Lk + 31) & ~31;
+  float* Ks = sm;                          // [Lk][17]
+  float* Vs = Ks + (size_t)Lk * (kDH + 1);
+  float* S = Vs + (size_t)Lk * (kDH + 1);  // [4 warps][lkp]
+  float* qs = S + 4 * lkp;                 // [4 warps][16]
+  pdl_wait();
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kMhaQ;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < Lk * kDH; i += 128) {
+    const int j = i >> 4, d = i & 15;
+    Ks[j * (kDH + 1) + d] = p.K[(size_t)b * p.kb + (size_t)j * p.ldk + h * kDH + d];
+    Vs[j * (kDH + 1) + d] = p.V[(size_t)b * p.vb + (size_t)j * p.ldv + h * kDH + d];
+  }
+  __syncthreads();
+  const uint8_t* kpm = p.kpm != nullptr ? p.kpm + (size_t)b * Lk : nullptr;
+  float* Sw = S + warp * lkp;
+  float* qw = qs + warp * kDH;
+  for (int qi = q0 + warp * 4; qi < q0 + warp * 4 + 4 && qi < p.Lq; ++qi) {
+    if (lane < kDH) qw[lane] = p.Q[(size_t)b * p.qb + (size_t)qi * p.ldq + h * kDH + lane] * 0.25f;   // sqrt(1 / 16)
+    __syncwarp();
+    float q[kDH];
+#pragma unroll
+    for (int d = 0; d < kDH; ++d) q[d] = qw[d];
+    float mx = -INFINITY;
+    for (int j = lane; j < Lk; j += 32) {
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < kDH; ++d) s = fmaf(q[d], Ks[j * (kDH + 1) + d], s);
+      if ((p.eye && j == qi) || (kpm != nullptr && kpm[j])) s = -INFINITY;
+      Sw[j] = s;
+      mx = fmaxf(mx, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f, acc[kDH];
+#pragma unroll
+    for (int d = 0; d < kDH; ++d) acc[d] = 0.f;
+    for (int j = lane; j < Lk; j += 32) {
+      const float e = expf(Sw[j] - mx);   // (all keys masked: -inf - -inf = NaN, as in torch)
+      sum += e;
+#pragma unroll
+      for (int d = 0; d < kDH; ++d) acc[d] = fmaf(e, Vs[j * (kDH + 1) + d], acc[d]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+#pragma unroll
+      for (int d = 0; d < kDH; ++d) acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], o);
+    }
+    float out = 0.f;
+#pragma unroll
+    for (int d = 0; d < kDH; ++d)
+      if (lane == d) out = acc[d];
+    if (lane < kDH) p.O[(size_t)b * p.ob + (size_t)qi * p.ldo + h * kDH + lane] = out / sum;
+    __syncwarp();
+  }
+}
+
+// Transformer.interpolate_embedding (transformer.py:57-73) on reco [L][B][C] -> interp [B][L][C]:
+//   prev / rate * (rate - i % rate) + next / rate * (i % rate), separately rounded operations as in torch.
+__global__ void motion_interp_kernel(const float* __restrict__ reco, float* __restrict__ interp, int B, int L, int C,
+                                     int rate) {
+  pdl_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * L * C) return;
+  const int c = i % C, l = (i / C) % L, b = i / (C * L);
+  const int chunk = l / rate, rem = l - chunk * rate;
+  const int lp = chunk * rate, ln = (l == L - 1) ? L - 1 : (chunk + 1) * rate;
+  const float prev = reco[((size_t)lp * B + b) * C + c], next = reco[((size_t)ln * B + b) * C + c];
+  const float fr = (float)rate;
+  interp[i] = __fadd_rn(__fmul_rn(__fdiv_rn(prev, fr), (float)(rate - rem)), __fmul_rn(__fdiv_rn(next, fr), (float)rem));
+}
+
+struct AttnW {
+  const float *in_w, *in_b, *out_w, *out_b;
+};
+struct LayerW {
+  AttnW self, cross;
+  const float *l1w, *l1b, *l2w, *l2b, *n1g, *n1b, *n2g, *n2b, *n3g, *n3b;
+};
+
+}  // namespace
+
+struct MotionModel {
+  rib_motion_config cfg;
+  float* blob = nullptr;   // one device buffer with every parameter
+  const float *in_w, *in_b, *out_w, *out_b, *enc_ng, *enc_nb, *dec_ng, *dec_nb;
+  std::vector<LayerW> enc, dec;
+};
+
+int motion_create(const rib_motion_config* cfg, const rib_tensor* tensors, int n_tensors, cudaStream_t stream,
+                  MotionModel** out) {
+  RIB_REQUIRE(cfg && tensors && out, "motion_create: null argument");
+  const int J = cfg->input_joints, E = cfg->hidden_dim, FF = cfg->dim_feedforward;
+  RIB_REQUIRE(J > 0 && J <= kLinMaxK && E > 0 && E <= kLinMaxK && FF > 0 && FF <= kLinMaxK,
+              "motion_create: dimensions above 256 are not supported");
+  RIB_REQUIRE(cfg->nheads > 0 && E == cfg->nheads * kDH, "motion_create: head dimension must be 16");
+  RIB_REQUIRE(E % kLinCols == 0, "motion_create: hidden_dim must be a multiple of 64");
+  RIB_REQUIRE(cfg->enc_layers >= 0 && cfg->dec_layers >= 0, "motion_create: bad layer count");
+  std::map<std::string, std::pair<const float*, long long>> src;
+  size_t total = 0;
+  for (int i = 0; i < n_tensors; ++i) {
+    RIB_REQUIRE(tensors[i].name && tensors[i].data && tensors[i].numel > 0, "motion_create: bad tensor entry");
+    src[tensors[i].name] = {tensors[i].data, tensors[i].numel};
+    total += ((size_t)tensors[i].numel + 3) & ~(size_t)3;
+  }
+  MotionModel* m = new MotionModel();
+  m->cfg = *cfg;
+  if (cudaMalloc(&m->blob, total * sizeof(float)) != cudaSuccess) {
+    delete m;
+    set_error("motion_create: cudaMalloc failed");
+    return -2;
+  }
+  size_t off = 0;
+  bool ok = true;
+  std::string missing;
+  auto take = [&](const std::string& key, long long numel) -> const float* {
+    auto it = src.find(key);
+    if (it == src.end() || it->second.second != numel) {
+      ok = false;
+      missing = key;
+      return nullptr;
+    }
+    float* dst = m->blob + off;
+    off += ((size_t)numel + 3) & ~(size_t)3;
+    if (cudaMemcpyAsync(dst, it->second.first, (size_t)numel * sizeof(float), cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
+      ok = false;
+    return dst;
+  };
+  auto attn = [&](const std::string& p) {
+    AttnW a;
+    a.in_w = take(p + ".in_proj_weight", 3LL * E * E);
+    a.in_b = take(p + ".in_proj_bias", 3LL * E);
+    a.out_w = take(p + ".out_proj.weight", (long long)E * E);
+    a.out_b = take(p + ".out_proj.bias", E);
+    return a;
+  };
+  auto layer = [&](const std::string& p, bool dec) {
+    LayerW l = {};
+    l.self = attn(p + ".self_attn");
+    if (dec) l.cross = attn(p + ".multihead_attn");
+    l.l1w = take(p + ".linear1.weight", (long long)FF * E);
+    l.l1b = take(p + ".linear1.bias", FF);
+    l.l2w = take(p + ".linear2.weight", (long long)E * FF);
+    l.l2b = take(p + ".linear2.bias", E);
+    l.n1g = take(p + ".norm1.weight", E);
+    l.n1b = take(p + ".norm1.bias", E);
+    l.n2g = take(p + ".norm2.weight", E);
+    l.n2b = take(p + ".norm2.bias", E);
+    if (dec) {
+      l.n3g = take(p + ".norm3.weight", E);
+      l.n3b = take(p + ".norm3.bias", E);
+    }
+    return l;
+  };
+  m->in_w = take("input_embed.weight", (long long)E * J);
+  m->in_b = take("input_embed.bias", E);
+  for (int i = 0; i < cfg->enc_layers; ++i) m->enc.push_back(layer("encoder.layers." + std::to_string(i), false));
+  m->enc_ng = take("encoder.norm.weight", E);
+  m->enc_nb = take("encoder.norm.bias", E);
+  for (int i = 0; i < cfg->dec_layers; ++i) m->dec.push_back(layer("decoder.layers." + std::to_string(i), true));
+  m->dec_ng = take("decoder.norm.weight", E);
+  m->dec_nb = take("decoder.norm.bias", E);
+  m->out_w = take("joints_embed.weight", (long long)J * E);
+  m->out_b = take("joints_embed.bias", J);
+  if (ok && cudaStreamSynchronize(stream) != cudaSuccess) ok = false;
+  if (!ok) {
+    cudaFree(m->blob);
+    delete m;
+    set_error(missing.empty() ? std::string("motion_create: copying the parameters failed")
+                              : "motion_create: state-dict entry missing or of the wrong size: " + missing);
+    return -1;
+  }
+  *out = m;
+  return 0;
+}
+
+void motion_destroy(MotionModel* m) {
+  if (m == nullptr) return;
+  cudaFree(m->blob);
+  delete m;
+}
+
+// workspace: x, y, att, mem [B L E]; qkv [B L 3E]; ffh [B L FF]; interp [B L J]
+long long motion_workspace_bytes(const MotionModel* m, int B, int L) {
+  const long long E = m->cfg.hidden_dim, FF = m->cfg.dim_feedforward, J = m->cfg.input_joints;
+  return (long long)B * L * (7 * E + FF + ((J + 3) & ~3LL)) * (long long)sizeof(float) + 256;
+}
+
+namespace {
+
+int run_linear(const LinParams& p, int B, cudaStream_t s) {
+  RIB_REQUIRE(p.K <= kLinMaxK, "motion: inner dimension above 256");
+  RIB_REQUIRE(p.pos == nullptr || p.n_pos >= p.N || p.n_pos % kLinCols == 0, "motion: n_pos must fall on a column tile");
+  const dim3 grid((unsigned)ceil_div(p.L, kLinRows), (unsigned)ceil_div(p.N, kLinCols), (unsigned)B);
+  launch_pdl(motion_linear_kernel, grid, dim3(256), 0, s, p);
+  RIB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int run_mha(const MhaParams& p, int B, int H, cudaStream_t s) {
+  const int lkp = (p.Lk + 31) & ~31;
+  const size_t smem = ((size_t)2 * p.Lk * (kDH + 1) + 4 * lkp + 4 * kDH) * sizeof(float);
+  RIB_REQUIRE(smem <= 200 * 1024, "motion: sequences longer than ~1400 frames are not supported");
+  if (smem > 48 * 1024)
+    RIB_CHECK_CUDA(cudaFuncSetAttribute((const void*)motion_mha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  const dim3 grid((unsigned)ceil_div(p.Lq, kMhaQ), (unsigned)H, (unsigned)B);
+  launch_pdl(motion_mha_kernel, grid, dim3(128), smem, s, p);
+  RIB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int motion_forward(MotionModel* m, int B, int L, const float* src, const uint8_t* src_mask, const float* src_pos,
+                   const uint8_t* tgt_mask, const float* tgt_pos, int rate, float* joints, float* reco, void* workspace,
+                   long long workspace_bytes, cudaStream_t stream) {
+  RIB_REQUIRE(m && src && src_pos && tgt_pos && joints && reco && workspace, "motion_forward: null argument");
+  RIB_REQUIRE(B >= 1 && L >= 2 && rate >= 1, "motion_forward: bad shape");
+  RIB_REQUIRE((L - 1) % rate == 0, "motion_forward: the sequence length must be rate * n + 1 (transformer.py:57-73)");
+  RIB_REQUIRE(workspace_bytes >= motion_workspace_bytes(m, B, L), "motion_forward: workspace too small");
+  RIB_REQUIRE(((uintptr_t)workspace & 15) == 0, "motion_forward: workspace must be 16-byte aligned");
+  const int E = m->cfg.hidden_dim, FF = m->cfg.dim_feedforward, J = m->cfg.input_joints, H = m->cfg.nheads;
+  const long long BL = (long long)B * L;
+  float* x = static_cast<float*>(workspace);
+  float* y = x + BL * E;
+  float* att = y + BL * E;
+  float* mem = att + BL * E;
+  float* qkv = mem + BL * E;
+  float* ffh = qkv + BL * 3 * E;
+  float* interp = ffh + BL * FF;
+  const long long sE = (long long)L * E, s3E = (long long)L * 3 * E, sFF = (long long)L * FF, sJ = (long long)L * J;
+
+  auto lin = [&](const float* X, long long xb, long long xr, long long xk, int K, const float* W, const float* bias, int N,
+                 float* Y, long long yb, long long yr) {
+    LinParams p = {};
+    p.X = X, p.xb = xb, p.xr = xr, p.xk = xk;
+    p.W = W, p.bias = bias, p.N = N, p.K = K;
+    p.Y = Y, p.yb = yb, p.yr = yr;
+    p.L = L;
+    return p;
+  };
+  auto with_ln = [](LinParams p, const float* g, const float* b) {
+    p.ln_g = g, p.ln_b = b;
+    return p;
+  };
+  auto with_pos = [&](LinParams p, const float* pos, int n_pos) {   // pos is [L][B][E]
+    p.pos = pos, p.pb = E, p.pr = (long long)B * E, p.n_pos = n_pos;
+    return p;
+  };
+  auto with_res = [](LinParams p, const float* R, long long rb, long long rr, long long rn) {
+    p.R = R, p.rb = rb, p.rr = rr, p.rn = rn;
+    return p;
+  };
+  auto mha = [&](const float* Q, const float* K, const float* V, const uint8_t* kpm, int eye) {
+    MhaParams p = {};
+    p.Q = Q, p.K = K, p.V = V;
+    p.qb = p.kb = p.vb = s3E;
+    p.ldq = p.ldk = p.ldv = 3 * E;
+    p.O = att, p.ob = sE, p.ldo = E;
+    p.kpm = kpm, p.Lq = L, p.Lk = L, p.eye = eye;
+    return run_mha(p, B, H, stream);
+  };
+  int rc;
+#define RIB_MOTION_RUN(expr) \
+  if ((rc = (expr)) != 0) return rc
+
+  // x = input_embed(src^T)            src is [B][J][L]
+  RIB_MOTION_RUN(run_linear(lin(src, (long long)J * L, 1, L, J, m->in_w, m->in_b, E, x, sE, E), B, stream));
+  for (const LayerW& l : m->enc) {
+    // q, k = (norm1(x) + pos) Wq, Wk; v = norm1(x) Wv
+    RIB_MOTION_RUN(run_linear(with_pos(with_ln(lin(x, sE, E, 1, E, l.self.in_w, l.self.in_b, 3 * E, qkv, s3E, 3 * E), l.n1g, l.n1b),
+                                       src_pos, 2 * E), B, stream));
+    RIB_MOTION_RUN(mha(qkv, qkv + E, qkv + 2 * E, src_mask, 1));
+    RIB_MOTION_RUN(run_linear(with_res(lin(att, sE, E, 1, E, l.self.out_w, l.self.out_b, E, x, sE, E), x, sE, E, 1), B, stream));
+    LinParams f1 = with_ln(lin(x, sE, E, 1, E, l.l1w, l.l1b, FF, ffh, sFF, FF), l.n2g, l.n2b);
+    f1.act = 1;
+    RIB_MOTION_RUN(run_linear(f1, B, stream));
+    RIB_MOTION_RUN(run_linear(with_res(lin(ffh, sFF, FF, 1, FF, l.l2w, l.l2b, E, x, sE, E), x, sE, E, 1), B, stream));
+  }
+  {   // memory = encoder.norm(x)
+    launch_pdl(motion_layernorm_kernel, dim3((unsigned)ceil_div((int)BL, 8)), dim3(256), 0, stream, (const float*)x, m->enc_ng,
+               m->enc_nb, mem, (int)BL, E);
+    RIB_CHECK_CUDA(cudaGetLastError());
+  }
+  // reco[L][B][J] = joints_embed(memory) + src^T
+  RIB_MOTION_RUN(run_linear(with_res(lin(mem, sE, E, 1, E, m->out_w, m->out_b, J, reco, J, (long long)B * J), src, (long long)J * L, 1, L),
+                            B, stream));
+  {
+    const int total = B * L * J;
+    launch_pdl(motion_interp_kernel, dim3((unsigned)ceil_div(total, 256)), dim3(256), 0, stream, (const float*)reco, interp, B, L, J,
+               rate);
+    RIB_CHECK_CUDA(cudaGetLastError());
+  }
+  // y = input_embed(interp)
+  RIB_MOTION_RUN(run_linear(lin(interp, sJ, J, 1, J, m->in_w, m->in_b, E, y, sE, E), B, stream));
+  for (const LayerW& l : m->dec) {
+    RIB_MOTION_RUN(run_linear(with_pos(with_ln(lin(y, sE, E, 1, E, l.self.in_w, l.self.in_b, 3 * E, qkv, s3E, 3 * E), l.n1g, l.n1b),
+                                       tgt_pos, 2 * E), B, stream));
+    RIB_MOTION_RUN(mha(qkv, qkv + E, qkv + 2 * E, tgt_mask, 0));
+    RIB_MOTION_RUN(run_linear(with_res(lin(att, sE, E, 1, E, l.self.out_w, l.self.out_b, E, y, sE, E), y, sE, E, 1), B, stream));
+    // cross attention: q = (norm2(y) + tgt_pos) Wq; k = (memory + src_pos) Wk; v = memory Wv
+    RIB_MOTION_RUN(run_linear(with_pos(with_ln(lin(y, sE, E, 1, E, l.cross.in_w, l.cross.in_b, E, qkv, s3E, 3 * E), l.n2g, l.n2b),
+                                       tgt_pos, E), B, stream));
+    RIB_MOTION_RUN(run_linear(with_pos(lin(mem, sE, E, 1, E, l.cross.in_w + (size_t)E * E, l.cross.in_b + E, 2 * E, qkv + E, s3E, 3 * E),
+                                       src_pos, E), B, stream));
+    RIB_MOTION_RUN(mha(qkv, qkv + E, qkv + 2 * E, src_mask, 0));
+    RIB_MOTION_RUN(run_linear(with_res(lin(att, sE, E, 1, E, l.cross.out_w, l.cross.out_b, E, y, sE, E), y, sE, E, 1), B, stream));
+    LinParams f1 = with_ln(lin(y, sE, E, 1, E, l.l1w, l.l1b, FF, ffh, sFF, FF), l.n3g, l.n3b);
+    f1.act = 1;
+    RIB_MOTION_RUN(run_linear(f1, B, stream));
+    RIB_MOTION_RUN(run_linear(with_res(lin(ffh, sFF, FF, 1, FF, l.l2w, l.l2b, E, y, sE, E), y, sE, E, 1), B, stream));
+  }
+  // joints[L][B][J] = joints_embed(decoder.norm(y)) + interp
+  RIB_MOTION_RUN(run_linear(with_res(with_ln(lin(y, sE, E, 1, E, m->out_w, m->out_b, J, joints, J, (long long)B * J), m->dec_ng, m->dec_nb),
+                                     interp, sJ, J, 1), B, stream));
+#undef RIB_MOTION_RUN
+  return 0;
+}
+
+}  // namespace rib

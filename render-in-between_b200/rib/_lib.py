@@ -18,6 +18,7 @@ SYMBOLS = [
     'rib_conv_test_scratch_bytes', 'rib_conv_test', 'rib_profile_enable', 'rib_profile_collect', 'rib_profile_collect_launches',
     'rib_tune_log', 'rib_tune_export', 'rib_tune_import', 'rib_conv_test_ex',
     'rib_plan_dry_run', 'rib_frames_from_u8', 'rib_resize_cubic_u8', 'rib_avgpool_test',
+    'rib_motion_create', 'rib_motion_destroy', 'rib_motion_workspace_bytes', 'rib_motion_forward',
 ]
 
 
@@ -25,6 +26,10 @@ class GenConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         'label_nc', 'img_nc', 'nf', 'maxf', 'n_down', 'n_res', 'emb_nf', 'emb_max', 'emb_down',
         'mask_nf', 'mask_max', 'mask_down', 'mask_res')]
+
+
+class MotionConfig(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ('input_joints', 'hidden_dim', 'nheads', 'dim_feedforward', 'enc_layers', 'dec_layers')]
 
 
 class Tensor(C.Structure):
@@ -92,6 +97,14 @@ def _load():
     lib.rib_plan_dry_run.argtypes = [C.POINTER(GenConfig), i32, i32, i32, C.POINTER(i64), C.c_char_p, i64]
     lib.rib_conv_test_ex.restype = i32
     lib.rib_conv_test_ex.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp]
+    lib.rib_motion_create.restype = i32
+    lib.rib_motion_create.argtypes = [C.POINTER(MotionConfig), C.POINTER(Tensor), i32, vp, C.POINTER(vp)]
+    lib.rib_motion_destroy.restype = None
+    lib.rib_motion_destroy.argtypes = [vp]
+    lib.rib_motion_workspace_bytes.restype = i64
+    lib.rib_motion_workspace_bytes.argtypes = [vp, i32, i32]
+    lib.rib_motion_forward.restype = i32
+    lib.rib_motion_forward.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, i64, vp]
     lib.rib_avgpool_test.restype = i32
     lib.rib_avgpool_test.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
     return lib

@@ -63,7 +63,7 @@ def test_abi_library_exports_every_declared_symbol():
     dll = ctypes.CDLL(_lib.LIB_PATH)
     for s in declared:
         assert hasattr(dll, s), s
-    assert _lib.lib.rib_abi_version() == 5
+    assert _lib.lib.rib_abi_version() == 6
 
 
 def test_synth_is_deterministic():
