@@ -161,7 +161,7 @@ typedef struct rib_motion_config {
 
 typedef struct rib_motion rib_motion;
 
-/* `tensors`: the reference module's state-dict (oracle/motion_oracle.state_spec lists the 236 keys of the shipped
+/* `tensors`: the reference module's state-dict (oracle/motion_oracle.state_spec lists the 188 keys of the shipped
  * configuration), device fp32.  The parameters are copied; the caller's tensors may be released afterwards. */
 int rib_motion_create(const rib_motion_config* cfg, const rib_tensor* tensors, int n_tensors, void* stream, rib_motion** out);
 void rib_motion_destroy(rib_motion* m);

@@ -8,9 +8,10 @@
 // The model is tiny (d_model 128, 8 heads of 16, feed-forward 256, 6 + 6 layers, at most 321 tokens): ~1.3 GFLOP per
 // sequence.  Everything stays in fp32 on the CUDA cores (the parity target is the reference's fp32 output, and at these
 // sizes a forward is bound by the ~90 dependent launches, not by arithmetic): three kernels,
-//   linear   Y = act(LN?(X) (+ pos for the first n_pos columns) . W^T + b) (+ residual): 32 x 64 output tile per block, the
-//            LayerNorm of the pre-norm blocks and the "+ pos" of q / k are applied to the A tile in shared memory
-//   mha      one block per (16 queries, head, sequence): the head's K and V rows in shared memory, a warp per query
+//   linear   Y = act(LN?(X) (+ pos for the first n_pos columns) . W^T + b) (+ residual): 32 x 64 output tile per block, both
+//            operand tiles resident in shared memory over the whole K (all loads of a block issued up front), 4 x 4
+//            outputs per thread; the LayerNorm of the pre-norm blocks and the "+ pos" of q / k are applied to the A tile
+//   mha      one block per (16 or 64 queries, head, sequence): the head's K and V rows in shared memory, a warp per query
 //            (scores, masks as -inf, softmax, P.V with warp-shuffle reductions)
 //   interp   interpolate_embedding, the exact float sequence of the reference
 // launched back to back with programmatic dependent launch on the caller's stream.
@@ -25,13 +26,14 @@ namespace rib {
 namespace {
 
 constexpr int kDH = 16;          // head dimension (hidden_dim / nheads of the shipped configuration)
-constexpr int kLinRows = 32, kLinCols = 64, kLinKC = 32, kLinMaxK = 256;
-constexpr int kMhaQ = 16;        // queries per block (4 warps x 4)
+constexpr int kLinRows = 32, kLinCols = 64, kLinMaxK = 256;
+constexpr int kMhaWarps = 4;     // warps per attention block; a warp serves QW queries, one after the other
 
 struct LinParams {
   const float* X;                // element (b, r, k) at X[b * xb + r * xr + k * xk]
   long long xb, xr, xk;
-  const float* W;                // [N][K] row-major (torch nn.Linear weight)
+  const float* W;                // TRANSPOSED weight: element (k, n) at W[k * ldw + n] (made once by motion_create from the
+  int ldw;                       //   [N][K] nn.Linear weight; ldw a multiple of 4, rows zero-padded), 16-byte aligned
   const float* bias;             // [N]
   const float* ln_g;             // LayerNorm over K applied to every row of X first (null: none)
   const float* ln_b;
@@ -45,79 +47,114 @@ struct LinParams {
   int L, N, K, act;              // act 1: leaky_relu(0.01)
 };
 
-__global__ void __launch_bounds__(256) motion_linear_kernel(const LinParams p) {
-  __shared__ float As[kLinRows][kLinMaxK + 1];
-  __shared__ __align__(16) float Ws[kLinKC][kLinCols + 4];
-  pdl_wait();   // programmatic dependent launch: everything below reads the previous kernel's output
+// Shared memory of the linear kernel (dynamic): As[kLinRows][Kp + 4] (the A tile, row-major) and Wt[Kp][kLinCols + 4] (the
+// weight tile, k-major), Kp = K rounded up to 4.  The whole K extent of both is resident and arrives by 16-byte cp.async
+// copies that are all in flight at once (one memory latency per block, not one per K chunk; the weights, constants, are
+// requested before the wait on the previous kernel); the product loop then runs without barriers, 4 x 4 outputs per thread,
+// four k per step with 16-byte shared-memory loads of both operands.
+constexpr int kLinWP = kLinCols + 4;
+static size_t linear_smem_bytes(int K) {
+  const int Kp = (K + 3) & ~3;
+  return ((size_t)kLinRows * (Kp + 4) + (size_t)Kp * kLinWP) * sizeof(float);
+}
+
+__global__ void __launch_bounds__(128) motion_linear_kernel(const LinParams p) {
+  extern __shared__ __align__(16) float lin_sm[];
+  const int K = p.K, Kp = (K + 3) & ~3, AP = Kp + 4;
+  float* As = lin_sm;                          // [kLinRows][AP]
+  float* Wt = lin_sm + (size_t)kLinRows * AP;  // [Kp][kLinWP]
   const int b = blockIdx.z, r0 = blockIdx.x * kLinRows, n0 = blockIdx.y * kLinCols;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int K = p.K;
-  // A tile: rows r0 .. r0 + 31, all K columns (zero rows behind the sequence)
-  for (int i = tid; i < kLinRows * K; i += 256) {
-    const int r = i / K, k = i - r * K;
-    As[r][k] = (r0 + r < p.L) ? p.X[(size_t)b * p.xb + (size_t)(r0 + r) * p.xr + (size_t)k * p.xk] : 0.f;
+  {   // weight tile: rows k < K of the transposed weight, 16 chunks of 16 bytes each (zero fill behind ldw and for k >= K)
+    const uint32_t wt0 = smem_u32(Wt);
+    for (int i = tid; i < Kp * (kLinCols / 4); i += 128) {
+      const int k = i >> 4, c = (i & 15) * 4;
+      const bool ok = k < K && n0 + c < ((p.N + 3) & ~3);   // (rows are padded to a multiple of 4 columns)
+      cp_async_16(wt0 + (uint32_t)(k * kLinWP + c) * 4u, ok ? p.W + (size_t)k * p.ldw + n0 + c : p.W, ok ? 16u : 0u);
+    }
+    cp_async_commit();
   }
+  pdl_wait();   // programmatic dependent launch: everything below reads the previous kernel's output
+  const bool a_async = p.xk == 1 && (K & 3) == 0 && (p.xr & 3) == 0 && (p.xb & 3) == 0 && ((uintptr_t)p.X & 15) == 0;
+  if (a_async) {
+    const uint32_t as0 = smem_u32(As);
+    const int cpr = K >> 2;   // 16-byte chunks per row
+    for (int i = tid; i < kLinRows * cpr; i += 128) {
+      const int r = i / cpr, c = (i - r * cpr) * 4;
+      const bool ok = r0 + r < p.L;
+      cp_async_16(as0 + (uint32_t)(r * AP + c) * 4u, ok ? p.X + (size_t)b * p.xb + (size_t)(r0 + r) * p.xr + c : p.X, ok ? 16u : 0u);
+    }
+  } else if (p.xk == 1) {
+    for (int i = tid; i < kLinRows * Kp; i += 128) {
+      const int r = i / Kp, k = i - r * Kp;
+      As[r * AP + k] = (r0 + r < p.L && k < K) ? p.X[(size_t)b * p.xb + (size_t)(r0 + r) * p.xr + k] : 0.f;
+    }
+  } else {   // [B][C][L] input: contiguous along the rows
+    for (int i = tid; i < kLinRows * Kp; i += 128) {
+      const int k = i / kLinRows, r = i - k * kLinRows;
+      As[r * AP + k] = (r0 + r < p.L && k < K) ? p.X[(size_t)b * p.xb + (size_t)(r0 + r) * p.xr + (size_t)k * p.xk] : 0.f;
+    }
+  }
+  cp_async_commit();
+  cp_async_wait_group<0>();
   __syncthreads();
   if (p.ln_g != nullptr) {   // nn.LayerNorm(K), eps 1e-5: mean, biased variance (two passes), affine
-    for (int r = warp * 4; r < warp * 4 + 4; ++r) {
+    for (int r = warp * 8; r < warp * 8 + 8; ++r) {
+      float* row = As + r * AP;
       float s = 0.f;
-      for (int k = lane; k < K; k += 32) s += As[r][k];
+      for (int k = lane; k < K; k += 32) s += row[k];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       const float mean = s / (float)K;
       float v = 0.f;
       for (int k = lane; k < K; k += 32) {
-        const float d = As[r][k] - mean;
+        const float d = row[k] - mean;
         v = fmaf(d, d, v);
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       const float rstd = rsqrtf(v / (float)K + 1e-5f);
-      for (int k = lane; k < K; k += 32) As[r][k] = (As[r][k] - mean) * rstd * p.ln_g[k] + p.ln_b[k];
+      for (int k = lane; k < K; k += 32) row[k] = (row[k] - mean) * rstd * p.ln_g[k] + p.ln_b[k];
     }
     __syncthreads();
   }
   if (p.pos != nullptr && n0 < p.n_pos) {
-    for (int i = tid; i < kLinRows * K; i += 256) {
+    for (int i = tid; i < kLinRows * K; i += 128) {
       const int r = i / K, k = i - r * K;
-      if (r0 + r < p.L) As[r][k] += p.pos[(size_t)b * p.pb + (size_t)(r0 + r) * p.pr + k];
+      if (r0 + r < p.L) As[r * AP + k] += p.pos[(size_t)b * p.pb + (size_t)(r0 + r) * p.pr + k];
     }
     __syncthreads();
   }
-  const int tx = tid & 15, ty = tid >> 4;   // columns n0 + 4 tx .. + 3, rows 2 ty, 2 ty + 1
-  float acc[2][4];
+  const int tx = tid & 15, ty = tid >> 4;   // columns n0 + 4 tx .. + 3, rows 4 ty .. + 3
+  float acc[4][4];
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += kLinKC) {
-    {   // weight chunk, transposed: Ws[kk][n] = W[n0 + n][k0 + kk]
-      const int n = tid >> 2, kq = (tid & 3) * 8;
+  const float* arow = As + (4 * ty) * AP;
+  const float* wcol = Wt + 4 * tx;
+#pragma unroll 2
+  for (int k = 0; k < Kp; k += 4) {
+    float4 a[4], w[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int k = k0 + kq + i;
-        Ws[kq + i][n] = (n0 + n < p.N && k < K) ? p.W[(size_t)(n0 + n) * K + k] : 0.f;
+    for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(arow + i * AP + k);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) w[q] = *reinterpret_cast<const float4*>(wcol + (k + q) * kLinWP);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float av[4] = {a[i].x, a[i].y, a[i].z, a[i].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {   // ascending k: one summation order per output
+        acc[i][0] = fmaf(av[q], w[q].x, acc[i][0]);
+        acc[i][1] = fmaf(av[q], w[q].y, acc[i][1]);
+        acc[i][2] = fmaf(av[q], w[q].z, acc[i][2]);
+        acc[i][3] = fmaf(av[q], w[q].w, acc[i][3]);
       }
     }
-    __syncthreads();
-    const int kc = min(kLinKC, K - k0);
-    for (int kk = 0; kk < kc; ++kk) {
-      const float a0 = As[2 * ty][k0 + kk], a1 = As[2 * ty + 1][k0 + kk];
-      const float4 w = *reinterpret_cast<const float4*>(&Ws[kk][4 * tx]);
-      acc[0][0] = fmaf(a0, w.x, acc[0][0]);
-      acc[0][1] = fmaf(a0, w.y, acc[0][1]);
-      acc[0][2] = fmaf(a0, w.z, acc[0][2]);
-      acc[0][3] = fmaf(a0, w.w, acc[0][3]);
-      acc[1][0] = fmaf(a1, w.x, acc[1][0]);
-      acc[1][1] = fmaf(a1, w.y, acc[1][1]);
-      acc[1][2] = fmaf(a1, w.z, acc[1][2]);
-      acc[1][3] = fmaf(a1, w.w, acc[1][3]);
-    }
-    __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int r = r0 + 2 * ty + i;
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + 4 * ty + i;
     if (r >= p.L) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -129,6 +166,14 @@ __global__ void __launch_bounds__(256) motion_linear_kernel(const LinParams p) {
       p.Y[(size_t)b * p.yb + (size_t)r * p.yr + n] = v;
     }
   }
+}
+
+// [N][K] nn.Linear weight -> transposed, zero-padded [K][ld] copy (once, at model creation)
+__global__ void motion_transpose_kernel(const float* __restrict__ w, float* __restrict__ wt, int N, int K, int ld) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K * ld) return;
+  const int k = i / ld, n = i - k * ld;
+  wt[i] = n < N ? w[(size_t)n * K + k] : 0.f;
 }
 
 // nn.LayerNorm over the last dimension of [B][L][E] (the encoder's final norm: its output is the decoder's memory).
@@ -169,6 +214,7 @@ struct MhaParams {
   int Lq, Lk, eye;           // eye: query i may not attend to key i (Transformer.encode's mask)
 };
 
+template <int QW>   // queries per warp: 4 keeps a single sequence spread over the chip, 16 amortises the K / V staging of a batch
 __global__ void __launch_bounds__(128) motion_mha_kernel(const MhaParams p) {
   extern __shared__ float sm[];
   const int Lk = p.Lk, lkp = (Lk + 31) & ~31;
@@ -177,7 +223,7 @@ __global__ void __launch_bounds__(128) motion_mha_kernel(const MhaParams p) {
   float* S = Vs + (size_t)Lk * (kDH + 1);  // [4 warps][lkp]
   float* qs = S + 4 * lkp;                 // [4 warps][16]
   pdl_wait();
-  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kMhaQ;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * (kMhaWarps * QW);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < Lk * kDH; i += 128) {
     const int j = i >> 4, d = i & 15;
@@ -188,7 +234,7 @@ __global__ void __launch_bounds__(128) motion_mha_kernel(const MhaParams p) {
   const uint8_t* kpm = p.kpm != nullptr ? p.kpm + (size_t)b * Lk : nullptr;
   float* Sw = S + warp * lkp;
   float* qw = qs + warp * kDH;
-  for (int qi = q0 + warp * 4; qi < q0 + warp * 4 + 4 && qi < p.Lq; ++qi) {
+  for (int qi = q0 + warp * QW; qi < q0 + warp * QW + QW && qi < p.Lq; ++qi) {
     if (lane < kDH) qw[lane] = p.Q[(size_t)b * p.qb + (size_t)qi * p.ldq + h * kDH + lane] * 0.25f;   // sqrt(1 / 16)
     __syncwarp();
     float q[kDH];
@@ -244,12 +290,18 @@ __global__ void motion_interp_kernel(const float* __restrict__ reco, float* __re
   interp[i] = __fadd_rn(__fmul_rn(__fdiv_rn(prev, fr), (float)(rate - rem)), __fmul_rn(__fdiv_rn(next, fr), (float)rem));
 }
 
+struct WT {               // transposed weight [K][ld]
+  const float* p;
+  int ld;
+};
 struct AttnW {
-  const float *in_w, *in_b, *out_w, *out_b;
+  WT in_w, out_w;
+  const float *in_b, *out_b;
 };
 struct LayerW {
   AttnW self, cross;
-  const float *l1w, *l1b, *l2w, *l2b, *n1g, *n1b, *n2g, *n2b, *n3g, *n3b;
+  WT l1w, l2w;
+  const float *l1b, *l2b, *n1g, *n1b, *n2g, *n2b, *n3g, *n3b;
 };
 
 }  // namespace
@@ -257,7 +309,8 @@ struct LayerW {
 struct MotionModel {
   rib_motion_config cfg;
   float* blob = nullptr;   // one device buffer with every parameter
-  const float *in_w, *in_b, *out_w, *out_b, *enc_ng, *enc_nb, *dec_ng, *dec_nb;
+  WT in_w, out_w;
+  const float *in_b, *out_b, *enc_ng, *enc_nb, *dec_ng, *dec_nb;
   std::vector<LayerW> enc, dec;
 };
 
@@ -275,7 +328,7 @@ int motion_create(const rib_motion_config* cfg, const rib_tensor* tensors, int n
   for (int i = 0; i < n_tensors; ++i) {
     RIB_REQUIRE(tensors[i].name && tensors[i].data && tensors[i].numel > 0, "motion_create: bad tensor entry");
     src[tensors[i].name] = {tensors[i].data, tensors[i].numel};
-    total += ((size_t)tensors[i].numel + 3) & ~(size_t)3;
+    total += (((size_t)tensors[i].numel + 3) & ~(size_t)3) + 4 * (size_t)kLinMaxK;   // room for the row padding of a transposed copy
   }
   MotionModel* m = new MotionModel();
   m->cfg = *cfg;
@@ -300,11 +353,28 @@ int motion_create(const rib_motion_config* cfg, const rib_tensor* tensors, int n
       ok = false;
     return dst;
   };
+  // a 2-D nn.Linear weight [N][K]: kept as its transposed, row-padded copy [K][ld] (what the linear kernel stages)
+  auto take_w = [&](const std::string& key, int N, int K) -> WT {
+    WT r = {nullptr, (N + 3) & ~3};
+    auto it = src.find(key);
+    if (it == src.end() || it->second.second != (long long)N * K) {
+      ok = false;
+      missing = key;
+      return r;
+    }
+    off = (off + 3) & ~(size_t)3;   // 16-byte aligned rows
+    float* dst = m->blob + off;
+    off += (size_t)K * r.ld;
+    motion_transpose_kernel<<<(unsigned)ceil_div(K * r.ld, 256), 256, 0, stream>>>(it->second.first, dst, N, K, r.ld);
+    if (cudaGetLastError() != cudaSuccess) ok = false;
+    r.p = dst;
+    return r;
+  };
   auto attn = [&](const std::string& p) {
     AttnW a;
-    a.in_w = take(p + ".in_proj_weight", 3LL * E * E);
+    a.in_w = take_w(p + ".in_proj_weight", 3 * E, E);
     a.in_b = take(p + ".in_proj_bias", 3LL * E);
-    a.out_w = take(p + ".out_proj.weight", (long long)E * E);
+    a.out_w = take_w(p + ".out_proj.weight", E, E);
     a.out_b = take(p + ".out_proj.bias", E);
     return a;
   };
@@ -312,9 +382,9 @@ int motion_create(const rib_motion_config* cfg, const rib_tensor* tensors, int n
     LayerW l = {};
     l.self = attn(p + ".self_attn");
     if (dec) l.cross = attn(p + ".multihead_attn");
-    l.l1w = take(p + ".linear1.weight", (long long)FF * E);
+    l.l1w = take_w(p + ".linear1.weight", FF, E);
     l.l1b = take(p + ".linear1.bias", FF);
-    l.l2w = take(p + ".linear2.weight", (long long)E * FF);
+    l.l2w = take_w(p + ".linear2.weight", E, FF);
     l.l2b = take(p + ".linear2.bias", E);
     l.n1g = take(p + ".norm1.weight", E);
     l.n1b = take(p + ".norm1.bias", E);
@@ -326,7 +396,7 @@ int motion_create(const rib_motion_config* cfg, const rib_tensor* tensors, int n
     }
     return l;
   };
-  m->in_w = take("input_embed.weight", (long long)E * J);
+  m->in_w = take_w("input_embed.weight", E, J);
   m->in_b = take("input_embed.bias", E);
   for (int i = 0; i < cfg->enc_layers; ++i) m->enc.push_back(layer("encoder.layers." + std::to_string(i), false));
   m->enc_ng = take("encoder.norm.weight", E);
@@ -334,7 +404,7 @@ int motion_create(const rib_motion_config* cfg, const rib_tensor* tensors, int n
   for (int i = 0; i < cfg->dec_layers; ++i) m->dec.push_back(layer("decoder.layers." + std::to_string(i), true));
   m->dec_ng = take("decoder.norm.weight", E);
   m->dec_nb = take("decoder.norm.bias", E);
-  m->out_w = take("joints_embed.weight", (long long)J * E);
+  m->out_w = take_w("joints_embed.weight", J, E);
   m->out_b = take("joints_embed.bias", J);
   if (ok && cudaStreamSynchronize(stream) != cudaSuccess) ok = false;
   if (!ok) {
@@ -365,8 +435,12 @@ namespace {
 int run_linear(const LinParams& p, int B, cudaStream_t s) {
   RIB_REQUIRE(p.K <= kLinMaxK, "motion: inner dimension above 256");
   RIB_REQUIRE(p.pos == nullptr || p.n_pos >= p.N || p.n_pos % kLinCols == 0, "motion: n_pos must fall on a column tile");
+  const size_t smem = linear_smem_bytes(p.K);
+  if (smem > 48 * 1024)
+    RIB_CHECK_CUDA(cudaFuncSetAttribute((const void*)motion_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)linear_smem_bytes(kLinMaxK)));
   const dim3 grid((unsigned)ceil_div(p.L, kLinRows), (unsigned)ceil_div(p.N, kLinCols), (unsigned)B);
-  launch_pdl(motion_linear_kernel, grid, dim3(256), 0, s, p);
+  launch_pdl(motion_linear_kernel, grid, dim3(128), smem, s, p);
   RIB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -375,10 +449,13 @@ int run_mha(const MhaParams& p, int B, int H, cudaStream_t s) {
   const int lkp = (p.Lk + 31) & ~31;
   const size_t smem = ((size_t)2 * p.Lk * (kDH + 1) + 4 * lkp + 4 * kDH) * sizeof(float);
   RIB_REQUIRE(smem <= 200 * 1024, "motion: sequences longer than ~1400 frames are not supported");
-  if (smem > 48 * 1024)
-    RIB_CHECK_CUDA(cudaFuncSetAttribute((const void*)motion_mha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  const dim3 grid((unsigned)ceil_div(p.Lq, kMhaQ), (unsigned)H, (unsigned)B);
-  launch_pdl(motion_mha_kernel, grid, dim3(128), smem, s, p);
+  const bool wide = (long long)B * H * ceil_div(p.Lq, kMhaWarps * 4) > 2048;   // enough blocks: 64 queries per block
+  if (smem > 48 * 1024) {
+    RIB_CHECK_CUDA(cudaFuncSetAttribute((const void*)motion_mha_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    RIB_CHECK_CUDA(cudaFuncSetAttribute((const void*)motion_mha_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  }
+  if (wide) launch_pdl(motion_mha_kernel<16>, dim3((unsigned)ceil_div(p.Lq, kMhaWarps * 16), (unsigned)H, (unsigned)B), dim3(128), smem, s, p);
+  else launch_pdl(motion_mha_kernel<4>, dim3((unsigned)ceil_div(p.Lq, kMhaWarps * 4), (unsigned)H, (unsigned)B), dim3(128), smem, s, p);
   RIB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -404,11 +481,11 @@ int motion_forward(MotionModel* m, int B, int L, const float* src, const uint8_t
   float* interp = ffh + BL * FF;
   const long long sE = (long long)L * E, s3E = (long long)L * 3 * E, sFF = (long long)L * FF, sJ = (long long)L * J;
 
-  auto lin = [&](const float* X, long long xb, long long xr, long long xk, int K, const float* W, const float* bias, int N,
-                 float* Y, long long yb, long long yr) {
+  auto lin = [&](const float* X, long long xb, long long xr, long long xk, int K, WT W, const float* bias, int N, float* Y,
+                 long long yb, long long yr) {
     LinParams p = {};
     p.X = X, p.xb = xb, p.xr = xr, p.xk = xk;
-    p.W = W, p.bias = bias, p.N = N, p.K = K;
+    p.W = W.p, p.ldw = W.ld, p.bias = bias, p.N = N, p.K = K;
     p.Y = Y, p.yb = yb, p.yr = yr;
     p.L = L;
     return p;
@@ -475,7 +552,7 @@ int motion_forward(MotionModel* m, int B, int L, const float* src, const uint8_t
     // cross attention: q = (norm2(y) + tgt_pos) Wq; k = (memory + src_pos) Wk; v = memory Wv
     RIB_MOTION_RUN(run_linear(with_pos(with_ln(lin(y, sE, E, 1, E, l.cross.in_w, l.cross.in_b, E, qkv, s3E, 3 * E), l.n2g, l.n2b),
                                        tgt_pos, E), B, stream));
-    RIB_MOTION_RUN(run_linear(with_pos(lin(mem, sE, E, 1, E, l.cross.in_w + (size_t)E * E, l.cross.in_b + E, 2 * E, qkv + E, s3E, 3 * E),
+    RIB_MOTION_RUN(run_linear(with_pos(lin(mem, sE, E, 1, E, WT{l.cross.in_w.p + E, l.cross.in_w.ld}, l.cross.in_b + E, 2 * E, qkv + E, s3E, 3 * E),
                                        src_pos, E), B, stream));
     RIB_MOTION_RUN(mha(qkv, qkv + E, qkv + 2 * E, src_mask, 0));
     RIB_MOTION_RUN(run_linear(with_res(lin(att, sE, E, 1, E, l.cross.out_w, l.cross.out_b, E, y, sE, E), y, sE, E, 1), B, stream));

@@ -7,6 +7,8 @@ Public surface (mirrors the reference's names for this path):
     evaluate_from_folder                                                evaluator.py:165-269 (folder-driven entry)
     resize_cubic_u8 / frames_from_u8                                    evaluator.py:18-26, HSM_auto_dataset.py:73-75
     get_config / default_gen_cfg                                        utils/utils.py:77-79
+    MotionTransformer / MotionInference / PositionEmbeddingSine1D       Human_Motion_Modelling/models/transformer.py,
+                                                                        position_encoding.py, inference.py (joints upstream)
 """
 from .config import AttrDict, default_gen_cfg, get_config  # noqa: F401
 from .arch import Arch  # noqa: F401
@@ -27,6 +29,9 @@ def __getattr__(name):
     if name in ('ClipRenderer',):
         from .clip import ClipRenderer
         return ClipRenderer
+    if name in ('MotionTransformer', 'MotionInference', 'PositionEmbeddingSine1D'):
+        from . import motion
+        return getattr(motion, name)
     if name == 'lib':
         from ._lib import lib
         return lib

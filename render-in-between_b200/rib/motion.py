@@ -4,7 +4,7 @@
     models.position_encoding.PositionEmbeddingSine_1D   Human_Motion_Modelling/models/position_encoding.py:9-56
     Model_inference.inference                Human_Motion_Modelling/inference.py:21-43
 
-Same constructor arguments as `Transformer(...)` / `build_transformer(args)`, same state-dict keys and shapes (236
+Same constructor arguments as `Transformer(...)` / `build_transformer(args)`, same state-dict keys and shapes (188
 tensors for configs/config.yaml), same positional `forward(src, src_mask, src_pos, tgt, tgt_mask, tgt_pos, rate) ->
 (joints, reco)`, so a checkpoint's `transformer` entry loads unchanged (trainer.resume).  The math runs in the fp32 kernels
 of librib_b200.so (csrc/motion.cu) on the caller's stream: a renderer process can interpolate the joints on the GPU and feed
