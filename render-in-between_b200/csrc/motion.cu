@@ -11,8 +11,8 @@
 //   linear   Y = act(LN?(X) (+ pos for the first n_pos columns) . W^T + b) (+ residual): 32 x 64 output tile per block, both
 //            operand tiles resident in shared memory over the whole K (all loads of a block issued up front), 4 x 4
 //            outputs per thread; the LayerNorm of the pre-norm blocks and the "+ pos" of q / k are applied to the A tile
-//   mha      one block per (16 or 64 queries, head, sequence): the head's K and V rows in shared memory, a warp per query
-//            (scores, masks as -inf, softmax, P.V with warp-shuffle reductions)
+//   mha      one block per (16 or 64 queries, head, sequence): the head's K and V rows in shared memory, a warp per four
+//            queries at a time (scores, masks as -inf, softmax, P.V; recursive-halving shuffle reduction)
 //   interp   interpolate_embedding, the exact float sequence of the reference
 // launched back to back with programmatic dependent launch on the caller's stream.
 #include "motion.cuh"
@@ -214,63 +214,120 @@ struct MhaParams {
   int Lq, Lk, eye;           // eye: query i may not attend to key i (Transformer.encode's mask)
 };
 
+// A warp serves its QW queries four at a time: a lane owns every 32nd key, reads the key's K row once (four 16-byte
+// shared-memory loads) for the four dot products and its V row once for the four weighted sums, so the 64 FMAs of a step
+// cost 4 loads instead of 64.  The 4 x 16 partial outputs of the 32 lanes are combined by recursive halving (a lane sends
+// the half of its values the partner is responsible for: 62 shuffles instead of 320) and every lane ends with two adjacent
+// output values of one query.
+constexpr int kMhaQT = 4;            // queries per step
+constexpr int kMhaKP = kDH + 4;      // K / V row pitch in floats: 16-byte aligned rows, conflict-free 16-byte loads
+
 template <int QW>   // queries per warp: 4 keeps a single sequence spread over the chip, 16 amortises the K / V staging of a batch
 __global__ void __launch_bounds__(128) motion_mha_kernel(const MhaParams p) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int Lk = p.Lk, lkp = (Lk + 31) & ~31;
-  float* Ks = sm;                          // [Lk][17]
-  float* Vs = Ks + (size_t)Lk * (kDH + 1);
-  float* S = Vs + (size_t)Lk * (kDH + 1);  // [4 warps][lkp]
-  float* qs = S + 4 * lkp;                 // [4 warps][16]
+  float* Ks = sm;                                  // [Lk][kMhaKP]
+  float* Vs = Ks + (size_t)Lk * kMhaKP;
+  float* S = Vs + (size_t)Lk * kMhaKP;             // [4 warps][kMhaQT][lkp]
+  float* qs = S + (size_t)kMhaWarps * kMhaQT * lkp;   // [4 warps][kMhaQT][16]
   pdl_wait();
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * (kMhaWarps * QW);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < Lk * kDH; i += 128) {
-    const int j = i >> 4, d = i & 15;
-    Ks[j * (kDH + 1) + d] = p.K[(size_t)b * p.kb + (size_t)j * p.ldk + h * kDH + d];
-    Vs[j * (kDH + 1) + d] = p.V[(size_t)b * p.vb + (size_t)j * p.ldv + h * kDH + d];
+  for (int i = tid; i < Lk * (kDH / 4); i += 128) {
+    const int j = i >> 2, c = (i & 3) * 4;
+    *reinterpret_cast<float4*>(&Ks[j * kMhaKP + c]) =
+        *reinterpret_cast<const float4*>(&p.K[(size_t)b * p.kb + (size_t)j * p.ldk + h * kDH + c]);
+    *reinterpret_cast<float4*>(&Vs[j * kMhaKP + c]) =
+        *reinterpret_cast<const float4*>(&p.V[(size_t)b * p.vb + (size_t)j * p.ldv + h * kDH + c]);
   }
   __syncthreads();
   const uint8_t* kpm = p.kpm != nullptr ? p.kpm + (size_t)b * Lk : nullptr;
-  float* Sw = S + warp * lkp;
-  float* qw = qs + warp * kDH;
-  for (int qi = q0 + warp * QW; qi < q0 + warp * QW + QW && qi < p.Lq; ++qi) {
-    if (lane < kDH) qw[lane] = p.Q[(size_t)b * p.qb + (size_t)qi * p.ldq + h * kDH + lane] * 0.25f;   // sqrt(1 / 16)
+  float* Sw = S + (size_t)warp * kMhaQT * lkp;
+  float* qw = qs + warp * kMhaQT * kDH;
+  for (int qb = q0 + warp * QW; qb < q0 + warp * QW + QW && qb < p.Lq; qb += kMhaQT) {
+    // the four queries of this step (clamped behind the sequence: computed, not stored), scaled by sqrt(1 / 16)
+    for (int i = lane; i < kMhaQT * kDH; i += 32) {
+      const int qi = min(qb + (i >> 4), p.Lq - 1);
+      qw[i] = p.Q[(size_t)b * p.qb + (size_t)qi * p.ldq + h * kDH + (i & 15)] * 0.25f;
+    }
     __syncwarp();
-    float q[kDH];
+    float q[kMhaQT][kDH];
 #pragma unroll
-    for (int d = 0; d < kDH; ++d) q[d] = qw[d];
-    float mx = -INFINITY;
+    for (int g = 0; g < kMhaQT; ++g)
+#pragma unroll
+      for (int d = 0; d < kDH; d += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(&qw[g * kDH + d]);
+        q[g][d] = t.x, q[g][d + 1] = t.y, q[g][d + 2] = t.z, q[g][d + 3] = t.w;
+      }
+    float mx[kMhaQT];
+#pragma unroll
+    for (int g = 0; g < kMhaQT; ++g) mx[g] = -INFINITY;
     for (int j = lane; j < Lk; j += 32) {
-      float s = 0.f;
+      float kr[kDH];
 #pragma unroll
-      for (int d = 0; d < kDH; ++d) s = fmaf(q[d], Ks[j * (kDH + 1) + d], s);
-      if ((p.eye && j == qi) || (kpm != nullptr && kpm[j])) s = -INFINITY;
-      Sw[j] = s;
-      mx = fmaxf(mx, s);
+      for (int d = 0; d < kDH; d += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(&Ks[j * kMhaKP + d]);
+        kr[d] = t.x, kr[d + 1] = t.y, kr[d + 2] = t.z, kr[d + 3] = t.w;
+      }
+      const bool hidden = kpm != nullptr && kpm[j];
+#pragma unroll
+      for (int g = 0; g < kMhaQT; ++g) {
+        float sc = 0.f;
+#pragma unroll
+        for (int d = 0; d < kDH; ++d) sc = fmaf(q[g][d], kr[d], sc);
+        if (hidden || (p.eye && j == qb + g)) sc = -INFINITY;
+        Sw[g * lkp + j] = sc;
+        mx[g] = fmaxf(mx[g], sc);
+      }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float sum = 0.f, acc[kDH];
+    for (int g = 0; g < kMhaQT; ++g)
 #pragma unroll
-    for (int d = 0; d < kDH; ++d) acc[d] = 0.f;
+      for (int o = 16; o > 0; o >>= 1) mx[g] = fmaxf(mx[g], __shfl_xor_sync(0xffffffffu, mx[g], o));
+    float sum[kMhaQT], acc[kMhaQT * kDH];   // acc[g * 16 + d]
+#pragma unroll
+    for (int g = 0; g < kMhaQT; ++g) sum[g] = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMhaQT * kDH; ++i) acc[i] = 0.f;
     for (int j = lane; j < Lk; j += 32) {
-      const float e = expf(Sw[j] - mx);   // (all keys masked: -inf - -inf = NaN, as in torch)
-      sum += e;
+      float vr[kDH];
 #pragma unroll
-      for (int d = 0; d < kDH; ++d) acc[d] = fmaf(e, Vs[j * (kDH + 1) + d], acc[d]);
+      for (int d = 0; d < kDH; d += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(&Vs[j * kMhaKP + d]);
+        vr[d] = t.x, vr[d + 1] = t.y, vr[d + 2] = t.z, vr[d + 3] = t.w;
+      }
+#pragma unroll
+      for (int g = 0; g < kMhaQT; ++g) {
+        const float e = expf(Sw[g * lkp + j] - mx[g]);   // (all keys masked: -inf - -inf = NaN, as in torch)
+        sum[g] += e;
+#pragma unroll
+        for (int d = 0; d < kDH; ++d) acc[g * kDH + d] = fmaf(e, vr[d], acc[g * kDH + d]);
+      }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    for (int g = 0; g < kMhaQT; ++g)
 #pragma unroll
-      for (int d = 0; d < kDH; ++d) acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], o);
+      for (int o = 16; o > 0; o >>= 1) sum[g] += __shfl_xor_sync(0xffffffffu, sum[g], o);
+    // recursive halving over the 64 partial outputs: after the step with partner distance o, a lane keeps the half of its
+    // values whose index bit matches its lane bit; the final lane l owns indices 2 l and 2 l + 1 (query l / 8)
+#pragma unroll
+    for (int o = 16, n = kMhaQT * kDH / 2; o > 0; o >>= 1, n >>= 1) {
+      const bool up = (lane & o) != 0;
+#pragma unroll
+      for (int i = 0; i < n; ++i) {
+        const float send = up ? acc[i] : acc[i + n];
+        const float keep = up ? acc[i + n] : acc[i];
+        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+      }
     }
-    float out = 0.f;
+    const int g = lane >> 3, qi = qb + g;
+    float sg = sum[0];
 #pragma unroll
-    for (int d = 0; d < kDH; ++d)
-      if (lane == d) out = acc[d];
-    if (lane < kDH) p.O[(size_t)b * p.ob + (size_t)qi * p.ldo + h * kDH + lane] = out / sum;
+    for (int t = 1; t < kMhaQT; ++t)
+      if (g == t) sg = sum[t];
+    if (qi < p.Lq && qi < q0 + warp * QW + QW)
+      *reinterpret_cast<float2*>(&p.O[(size_t)b * p.ob + (size_t)qi * p.ldo + h * kDH + 2 * (lane & 7)]) =
+          make_float2(acc[0] / sg, acc[1] / sg);
     __syncwarp();
   }
 }
@@ -447,8 +504,11 @@ int run_linear(const LinParams& p, int B, cudaStream_t s) {
 
 int run_mha(const MhaParams& p, int B, int H, cudaStream_t s) {
   const int lkp = (p.Lk + 31) & ~31;
-  const size_t smem = ((size_t)2 * p.Lk * (kDH + 1) + 4 * lkp + 4 * kDH) * sizeof(float);
-  RIB_REQUIRE(smem <= 200 * 1024, "motion: sequences longer than ~1400 frames are not supported");
+  const size_t smem = ((size_t)2 * p.Lk * kMhaKP + (size_t)kMhaWarps * kMhaQT * (lkp + kDH)) * sizeof(float);
+  RIB_REQUIRE(((uintptr_t)p.K & 15) == 0 && ((uintptr_t)p.V & 15) == 0 && ((uintptr_t)p.O & 7) == 0 && p.ldk % 4 == 0 &&
+                  p.ldv % 4 == 0 && p.kb % 4 == 0 && p.vb % 4 == 0 && p.ldo % 2 == 0 && p.ob % 2 == 0,
+              "motion: attention operands must be 16-byte aligned");
+  RIB_REQUIRE(smem <= 200 * 1024, "motion: sequences longer than ~1100 frames are not supported");
   const bool wide = (long long)B * H * ceil_div(p.Lq, kMhaWarps * 4) > 2048;   // enough blocks: 64 queries per block
   if (smem > 48 * 1024) {
     RIB_CHECK_CUDA(cudaFuncSetAttribute((const void*)motion_mha_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
