@@ -279,7 +279,13 @@ static void define_layers(Generator* G, std::vector<PackJob>& jobs) {
     }
     for (int i = 0; i < c.mask_down; ++i) {
       std::string ln = "mask." + bn + "." + std::to_string(i + 1);
+#ifdef RIB_MASKDOWN_BN64
+      // A/B build: 64-column tiles for the 128-channel level, whose weights (72 KB) then stay resident beside a deep ring of
+      // halo slots (the stride-2 slots of 16 channels carry ~0.6k clocks of MMAs each, far less than a TMA round trip)
+      add_layer(G, ln, mask_nfilt(c, i + 1), mask_nfilt(c, i + 1), mask_nfilt(c, i), 9, 0, mask_nfilt(c, i + 1) == 128 ? 64 : 0, 2);
+#else
       add_layer(G, ln, mask_nfilt(c, i + 1), mask_nfilt(c, i + 1), mask_nfilt(c, i), 9, 0, 0, 2);
+#endif
       jobs.push_back({ln, f + bn + "." + std::to_string(i + 1) + ".layers.conv", true, mask_nfilt(c, i + 1), mask_nfilt(c, i), 9, 0, mask_nfilt(c, i), 0, 0, 0, false});
     }
   }
