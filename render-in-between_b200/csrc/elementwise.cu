@@ -248,7 +248,8 @@ int launch_in_apply(const InApplyParams& p, cudaStream_t s) {
                 "in_apply: the parity-planar input form is single-term, same-size, normal output");
     const size_t npair = (size_t)p.H * (p.W / 2) * (p.C / 8);
     unsigned gx = (unsigned)((npair + 255) / 256);
-    unsigned want = (sm_count_current() * 8u + (unsigned)p.B - 1u) / (unsigned)p.B;
+    static const unsigned bps = getenv("RIB_INAPPLY_BPS") ? (unsigned)atoi(getenv("RIB_INAPPLY_BPS")) : 8u;
+    unsigned want = (sm_count_current() * (bps ? bps : 8u) + (unsigned)p.B - 1u) / (unsigned)p.B;
     if (gx > want) gx = want;
     launch_pdl(in_apply_unparity_kernel, dim3(gx, (unsigned)p.B), dim3(256), 2 * p.C * sizeof(float), s, p);
     RIB_CHECK_CUDA(cudaGetLastError());
@@ -260,7 +261,8 @@ int launch_in_apply(const InApplyParams& p, cudaStream_t s) {
   // so blocks are kept few and fat: about 8 blocks per SM over the whole batch (measured: a single resident wave of
   // 3-4 blocks per SM is slower, 348 -> 432 us per forward; so is requesting the first vectors before the prologue)
   unsigned gx = (unsigned)((nvec + threads - 1) / threads);
-  unsigned want = (sm_count_current() * 8u + (unsigned)p.B - 1u) / (unsigned)p.B;
+  static const unsigned bps = getenv("RIB_INAPPLY_BPS") ? (unsigned)atoi(getenv("RIB_INAPPLY_BPS")) : 8u;   // blocks per SM
+  unsigned want = (sm_count_current() * (bps ? bps : 8u) + (unsigned)p.B - 1u) / (unsigned)p.B;
   if (want < 1u) want = 1u;
   if (gx > want) gx = want;
   dim3 grid(gx, (unsigned)p.B);
