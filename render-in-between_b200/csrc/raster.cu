@@ -602,7 +602,7 @@ __global__ void __launch_bounds__(256) raster_mark_kernel(FrameScratch* __restri
 }
 
 // paint: all 22 channels of every pixel, as fp32 NCHW and / or the generator's 16-bit planar input.
-__global__ void __launch_bounds__(256) raster_paint_kernel(const FrameScratch* __restrict__ scratch,
+__global__ void __launch_bounds__(256, 6) raster_paint_kernel(const FrameScratch* __restrict__ scratch,
                                                            const unsigned long long* __restrict__ cache,
                                                            float* __restrict__ label, act_t* __restrict__ planar,
                                                            int H, int W) {
