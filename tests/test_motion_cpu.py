@@ -53,3 +53,14 @@ def test_host_mirror_state_dict_and_options():
             MotionTransformer(c['input_joints'], **bad)
     with pytest.raises((ValueError, RuntimeError)):                       # no CPU path
         m(torch.zeros(1, 38, 9), None, torch.zeros(9, 1, 128), None, None, torch.zeros(9, 1, 128), 2)
+
+
+def test_host_position_encoding_equals_oracle():
+    """PositionEmbeddingSine_1D (position_encoding.py:26-56) as the host mirror computes it == the oracle (which is pinned to
+    the reference module in tests/test_oracle_vs_reference.py), for the lengths the model is used at."""
+    from rib.motion import PositionEmbeddingSine1D
+    pe = PositionEmbeddingSine1D(mo.CFG['hidden_dim'] // 2)
+    for n, length in [(1, 9), (2, 33), (1, 321)]:
+        got = pe(torch.zeros(n, length, dtype=torch.bool))
+        assert tuple(got.shape) == (length, n, mo.CFG['hidden_dim'])
+        assert torch.equal(got, mo.position_encoding(n, length))
